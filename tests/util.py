@@ -1,0 +1,79 @@
+"""Shared helpers for the parity tests."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star tolerances (BASELINE.json): COO indices bit-exact; KC0v/KGv/Mv/fint
+# 1e-12 relative; assembled CSR 1e-11 relative.  "Relative" is measured against the
+# largest magnitude of the element block (single entries that are exact
+# cancellations have no meaningful entry-wise relative error in either implementation).
+TOL_VALUES = 1e-12
+TOL_CSR = 1e-11
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    case, ref = {}, {}
+    for k in z.files:
+        if k.startswith("in_"):
+            v = z[k]
+            case[k[3:]] = v.item() if v.ndim == 0 and k != "in_kind" else v
+    case["kind"] = str(z["in_kind"])
+    if "stress" in case:
+        case["stress"] = tuple(float(t) for t in case["stress"])
+    case["ndof"] = int(case["ndof"])
+    case.setdefault("props", None)
+    for k in z.files:
+        if k.startswith("ref_"):
+            key = k[4:]
+            if key.endswith(("_r", "_c", "_v")) and key[:-2] in ("KC0", "KG", "KGs", "M0", "M1", "M2"):
+                ref.setdefault(key[:-2], [None, None, None])["rcv".index(key[-1])] = z[k]
+            else:
+                ref[key] = z[k]
+    return case, ref
+
+
+def block_relerr(got, want, ne):
+    """max over elements of max|got-want| / max|want| within the element's block."""
+    if want.size == 0:
+        return 0.0
+    g = np.asarray(got, float).reshape(ne, -1)
+    w = np.asarray(want, float).reshape(ne, -1)
+    sc = np.abs(w).max(1, keepdims=True)
+    sc[sc == 0] = 1.0
+    return float((np.abs(g - w) / sc).max())
+
+
+def vec_relerr(got, want):
+    s = np.abs(want).max()
+    return float(np.abs(np.asarray(got) - want).max() / (s if s > 0 else 1.0))
+
+
+def compare_outputs(got, ref, ne, tol=TOL_VALUES, keys=None):
+    """Assert bit-exact indices and block-relative values for every key in ref."""
+    checked = []
+    for k, want in ref.items():
+        if keys is not None and k not in keys:
+            continue
+        if k in ("R", "m", "xe", "geo"):
+            continue
+        assert k in got, "missing output %s" % k
+        if k == "fint":
+            err = vec_relerr(got[k], want)
+            assert err <= tol, "fint rel err %.2e" % err
+        else:
+            r, c, v = want
+            if got[k][0] is not None:
+                assert np.array_equal(np.asarray(got[k][0]), r), "%s row indices differ" % k
+                assert np.array_equal(np.asarray(got[k][1]), c), "%s col indices differ" % k
+            err = block_relerr(got[k][2], v, ne)
+            assert err <= tol, "%s value rel err %.2e" % (k, err)
+        checked.append(k)
+    return checked
