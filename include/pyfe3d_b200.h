@@ -1,0 +1,203 @@
+/*
+ * pyfe3d_b200 — C ABI of the B200-native element-evaluation + sparse-assembly path.
+ *
+ * This is the drop-in boundary for ONE hot path of saullocastro/pyfe3d
+ * (SURVEY.md §8): the per-element update_KC0 / update_KG / update_KG_given_stress /
+ * update_M / update_fint methods of Quad4, Quad4R, Tria3R, BeamC, BeamLR, Truss and
+ * Spring, and the COO -> CSR sum-duplicates step the reference leaves to scipy.
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types.  All array arguments are DEVICE
+ *    pointers unless the function name ends in `_host`.
+ *  - int return: 0 = ok, <0 = PF3_E_* (bad argument / state), >0 = cudaError_t.
+ *    pf3_error_string(code) explains either.  There is no CPU fallback: every
+ *    compute call needs a CUDA device and fails with PF3_E_NO_DEVICE otherwise.
+ *  - x  : float64[3*nnodes], node p at x[3p..3p+2]          (quad4.pyx:526-537)
+ *    u  : float64[6*nnodes], u v w rx ry rz per node        (quad4.pyx:634-639)
+ *    conn: int64[ne*nn] node POSITIONS p; the reference's c_a attribute is 6*p
+ *  - COO blocks: element e of a batch owns entries [init_k + e*SIZE, +SIZE) in the
+ *    reference's own order (row-major over node_i, dof_i, node_j, dof_j restricted
+ *    to the per-matrix mask).  Offsets are 64-bit (the reference
+ *    overflows its C-int init_k_* beyond 3 728 270 Quad4 elements, quad4.pyx:453).
+ */
+#ifndef PYFE3D_B200_H
+#define PYFE3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define PF3_VERSION 100
+
+/* ---- status codes ------------------------------------------------------- */
+#define PF3_OK 0
+#define PF3_E_BAD_ARG (-1)
+#define PF3_E_NO_DEVICE (-2)
+#define PF3_E_UNSUPPORTED (-3)
+#define PF3_E_CAPACITY (-4)
+
+/* ---- element kinds (pyfe3d/__init__.py:11-17) --------------------------- */
+#define PF3_QUAD4 0   /* pyfe3d/quad4.pyx  */
+#define PF3_QUAD4R 1  /* pyfe3d/quad4r.pyx */
+#define PF3_TRIA3R 2  /* pyfe3d/tria3r.pyx */
+#define PF3_BEAMC 3   /* pyfe3d/beamc.pyx  */
+#define PF3_BEAMLR 4  /* pyfe3d/beamlr.pyx */
+#define PF3_TRUSS 5   /* pyfe3d/truss.pyx  */
+#define PF3_SPRING 6  /* pyfe3d/spring.pyx */
+#define PF3_NKINDS 7
+
+/* ---- which matrices one pf3_eval call produces (bitmask) ---------------- */
+#define PF3_KC0 1        /* update_KC0              e.g. quad4.pyx:1204 */
+#define PF3_KG 2         /* update_KG (from u)      e.g. quad4.pyx:1365 */
+#define PF3_KG_STRESS 4  /* update_KG_given_stress  e.g. quad4.pyx:2259 (shells only) */
+#define PF3_M 8          /* update_M                e.g. quad4.pyx:3083 */
+#define PF3_FINT 16      /* update_fint             e.g. quad4.pyx:1316 */
+
+/* ---- matrix ids for sizes / index fill / assembly plans ----------------- */
+#define PF3_MAT_KC0 0
+#define PF3_MAT_KG 1
+#define PF3_MAT_M 2
+
+/* ---- property tables ---------------------------------------------------- */
+/* ShellProp scalars read by the elements (shellprop.pxd:38-46): row layout
+ *  0..5  A11 A12 A16 A22 A26 A66 | 6..11 B.. | 12..17 D.. | 18..20 E44 E45 E55
+ *  21 scf_k13 | 22 scf_k23 | 23 h | 24 intrho | 25 intrhoz | 26 intrhoz2 | 27..31 pad */
+#define PF3_SHELLPROP_STRIDE 32
+/* BeamProp (beamprop.pxd:1-3): A E G Iyy Izz Iyz J Ay Az intrho intrhoy intrhoz
+ *  intrhoy2 intrhoz2 intrhoyz | pad */
+#define PF3_BEAMPROP_STRIDE 16
+/* per-element parameters (attributes / kwargs of the reference objects):
+ *  shells : 0 K6ROT (default 100, quad4.pyx:481) | 1 alpha_shear_locking (0.7,
+ *           tria3r.pyx:263) | 2..6 hgfactor_u,v,w,rx,ry (1.0, quad4r.pyx:1151-1155)
+ *  spring : 0..5 kxe kye kze krxe krye krze (spring.pyx:117-124) */
+#define PF3_EPARAM_STRIDE 8
+/* per-element explicit state used by the per-element drop-in classes, which keep
+ * r11..r33 / m11..m22 / probe.xe / area|length / probe.ue on the host object exactly
+ * like the reference (quad4.pyx:450-459).  Layout (doubles):
+ *  0..8 R row-major | 9..12 m11 m12 m21 m22 | 13 area or length | 14..25 xe (3*nn)
+ *  | 26..49 ue (6*nn) */
+#define PF3_STATE_STRIDE 50
+
+typedef struct pf3_context pf3_context; /* device, stream, scratch; one host thread at a time */
+typedef struct pf3_plan pf3_plan;       /* symbolic assembly result (pattern + gather map)   */
+
+/* One batch = all elements of ONE kind.  Replaces the Python loop
+ *   for e in elements: e.update_rotation_matrix(...); e.update_probe_xe(x);
+ *                      e.update_probe_ue(u); e.update_KC0(...); ...
+ * (tests/test_quad4_static_point_load.py:53-78). */
+typedef struct pf3_batch {
+  int32_t kind;           /* PF3_QUAD4 ... */
+  int32_t mtype;          /* update_M mtype: shells 0 consistent,1 reduced,2 lumped; lines 0,1 */
+  int64_t ne;
+  int64_t nnodes;
+  const int64_t* conn;    /* [ne*nn] */
+  const double* x;        /* [3*nnodes]; unused by PF3_SPRING and when state != NULL */
+  const double* u;        /* [6*nnodes] or NULL; needed by PF3_KG and PF3_FINT */
+  const double* props;    /* [nprop*stride]; NULL for PF3_SPRING */
+  const int32_t* prop_id; /* [ne] or NULL (all elements use row 0) */
+  int64_t nprop;
+  const double* evec;     /* shells: material direction xmat (update_rotation_matrix kwargs,
+                             quad4.pyx:491); beams: vxy (beamc.pyx:158); spring: xi xj xk vxyi
+                             vxyj vxyk (spring.pyx:147).  NULL => shells: no material axis */
+  int32_t evec_stride;    /* doubles between elements in evec; 0 = one vector for all */
+  const double* eparam;   /* [ne*PF3_EPARAM_STRIDE] or NULL (defaults) */
+  const double* state;    /* [ne*PF3_STATE_STRIDE] or NULL.  When given, frames are NOT
+                             recomputed from x/u: the kernels use this state verbatim */
+  double stress[3];       /* Nxx Nyy Nxy for PF3_KG_STRESS */
+} pf3_batch;
+
+/* Destination COO arrays of one matrix.  r/c may be NULL ("update_*v_only=1");
+ * v may be NULL (indices only).  accumulate!=0 gives the reference's `+=` on values
+ * (quad4.pyx:1313); 0 overwrites, which equals `+=` into zero-initialised arrays and
+ * saves reading 8 B per entry. */
+typedef struct pf3_coo {
+  int64_t* r;
+  int64_t* c;
+  double* v;
+  int64_t init_k;
+  int32_t accumulate;
+} pf3_coo;
+
+/* ---- context / utilities ------------------------------------------------ */
+int pf3_version(void);
+const char* pf3_error_string(int code);
+int pf3_device_count(int* n);
+int pf3_create(int device, pf3_context** ctx);
+int pf3_destroy(pf3_context* ctx);
+int pf3_set_stream(pf3_context* ctx, void* cuda_stream); /* borrow a cudaStream_t (e.g. torch's) */
+int pf3_synchronize(pf3_context* ctx);
+int pf3_malloc(pf3_context* ctx, size_t bytes, void** dptr);
+int pf3_free(pf3_context* ctx, void* dptr);
+int pf3_memcpy_h2d(pf3_context* ctx, void* dst, const void* src, size_t bytes);
+int pf3_memcpy_d2h(pf3_context* ctx, void* dst, const void* src, size_t bytes);
+int pf3_memset(pf3_context* ctx, void* dst, int byte, size_t bytes);
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+int pf3_launch_count(pf3_context* ctx, int64_t* n);
+
+/* ---- static element data (XData classes, e.g. quad4.pyx:142-180) -------- */
+int pf3_num_nodes(int kind);
+/* KC0/KG/M_SPARSE_SIZE; 0 where the element has no such matrix */
+int pf3_sparse_size(int kind, int matrix);
+/* entries actually written for this mtype (lumped mass writes fewer) */
+int pf3_written_size(int kind, int matrix, int mtype);
+
+/* ---- element evaluation ------------------------------------------------- */
+/* what: bitmask of PF3_KC0|PF3_KG|PF3_KG_STRESS|PF3_M|PF3_FINT (KG and KG_STRESS are
+ * exclusive: both write `kg`).  Unused outputs may be NULL.  fint: float64[6*nnodes],
+ * accumulated (`fint[c+i] += ...`, quad4.pyx:1339) deterministically (node gather). */
+int pf3_eval(pf3_context* ctx, const pf3_batch* batch, int what,
+             const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);
+/* COO row/col indices only (the unrolled `KC0r[k]=..; KC0c[k]=..` blocks) */
+int pf3_fill_indices(pf3_context* ctx, int kind, int matrix, int mtype, int64_t ne,
+                     const int64_t* conn, int64_t init_k, int64_t* r, int64_t* c);
+/* per-element state as the reference leaves it on the object/probe after
+ * update_rotation_matrix + update_probe_xe + update_probe_ue: out[ne*PF3_STATE_STRIDE] */
+int pf3_eval_state(pf3_context* ctx, const pf3_batch* batch, double* state_out);
+/* probe.finte (local internal force, update_probe_finte e.g. quad4.pyx:1174): out[ne*6*nn] */
+int pf3_eval_finte(pf3_context* ctx, const pf3_batch* batch, double* finte_out);
+
+/* ---- assembly: replaces scipy.sparse.coo_matrix((v,(r,c))).tocsr() ------- */
+/* (call site tests/test_quad4_static_point_load.py:80).
+ * Structured plan: built from connectivity only (indices are a pure function of it).
+ * groups: ngroups batches contributing to the SAME matrix; only kind, ne, conn, mtype are
+ * read.  coo_offsets[g] = init_k of group g inside the common COO value array.
+ * Rows owned by this plan: DOF rows of nodes [node_begin, node_end) — the multi-GPU
+ * row-ownership shard; use 0, nnodes for everything. */
+int pf3_plan_create(pf3_context* ctx, int matrix, int64_t nnodes, int ngroups,
+                    const pf3_batch* groups, const int64_t* coo_offsets,
+                    int64_t node_begin, int64_t node_end, pf3_plan** plan);
+/* Generic plan from arbitrary COO indices (any element mix / ordering): radix sort of
+ * (row,col) keys + unique.  n = matrix dimension. */
+int pf3_plan_create_coo(pf3_context* ctx, int64_t n, int64_t nnz_coo, const int64_t* r,
+                        const int64_t* c, pf3_plan** plan);
+int pf3_plan_destroy(pf3_plan* plan);
+int pf3_plan_nnz(const pf3_plan* plan, int64_t* nnz);
+int pf3_plan_nrows(const pf3_plan* plan, int64_t* nrows);
+/* CSR pattern: indptr[nrows+1], indices[nnz] (int64, column indices global, sorted) */
+int pf3_plan_pattern(pf3_context* ctx, const pf3_plan* plan, int64_t* indptr, int64_t* indices);
+/* numeric phase: csr_v[nnz] = sum of duplicates of coo_v, deterministic order */
+int pf3_plan_assemble(pf3_context* ctx, const pf3_plan* plan, const double* coo_v, double* csr_v);
+
+/* y = A x for a CSR matrix with int64 indptr/indices (downstream cg / eigsh operators) */
+int pf3_spmv_csr(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                 const double* vals, const double* x, double* y);
+
+/* ---- host-pointer convenience (numpy callers): copies in, runs, copies out -- */
+int pf3_eval_host(pf3_context* ctx, const pf3_batch* host_batch, int what,
+                  const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYFE3D_B200_H */

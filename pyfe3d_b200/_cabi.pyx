@@ -1,0 +1,290 @@
+# cython: language_level=3, boundscheck=False, wraparound=False
+"""Thin Cython layer over the extern "C" ABI of libpyfe3d_b200.so
+(include/pyfe3d_b200.h).  Nothing here computes: it packs plain pointers and
+sizes into the C structs and turns status codes into exceptions.
+
+Pointers are passed as integers (``tensor.data_ptr()`` for device memory,
+``ndarray.ctypes.data`` for the ``*_host`` entry points); 0 means NULL.
+"""
+from libc.stdint cimport int32_t, int64_t, uintptr_t
+from libc.string cimport memset
+
+cdef extern from "pyfe3d_b200.h":
+    ctypedef struct pf3_context:
+        pass
+    ctypedef struct pf3_plan:
+        pass
+    ctypedef struct pf3_batch:
+        int32_t kind
+        int32_t mtype
+        int64_t ne
+        int64_t nnodes
+        const int64_t* conn
+        const double* x
+        const double* u
+        const double* props
+        const int32_t* prop_id
+        int64_t nprop
+        const double* evec
+        int32_t evec_stride
+        const double* eparam
+        const double* state
+        double stress[3]
+    ctypedef struct pf3_coo:
+        int64_t* r
+        int64_t* c
+        double* v
+        int64_t init_k
+        int32_t accumulate
+    int pf3_version()
+    const char* pf3_error_string(int code)
+    int pf3_device_count(int* n)
+    int pf3_create(int device, pf3_context** ctx)
+    int pf3_destroy(pf3_context* ctx)
+    int pf3_set_stream(pf3_context* ctx, void* s)
+    int pf3_synchronize(pf3_context* ctx)
+    int pf3_launch_count(pf3_context* ctx, int64_t* n)
+    int pf3_num_nodes(int kind)
+    int pf3_sparse_size(int kind, int matrix)
+    int pf3_written_size(int kind, int matrix, int mtype)
+    int pf3_eval(pf3_context*, const pf3_batch*, int what, const pf3_coo*, const pf3_coo*, const pf3_coo*, double* fint) nogil
+    int pf3_eval_host(pf3_context*, const pf3_batch*, int what, const pf3_coo*, const pf3_coo*, const pf3_coo*, double* fint) nogil
+    int pf3_fill_indices(pf3_context*, int kind, int matrix, int mtype, int64_t ne, const int64_t* conn,
+                         int64_t init_k, int64_t* r, int64_t* c) nogil
+    int pf3_eval_state(pf3_context*, const pf3_batch*, double* out) nogil
+    int pf3_eval_finte(pf3_context*, const pf3_batch*, double* out) nogil
+    int pf3_plan_create(pf3_context*, int matrix, int64_t nnodes, int ngroups, const pf3_batch* groups,
+                        const int64_t* coo_offsets, int64_t node_begin, int64_t node_end, pf3_plan** plan) nogil
+    int pf3_plan_create_coo(pf3_context*, int64_t n, int64_t nnz, const int64_t* r, const int64_t* c, pf3_plan**) nogil
+    int pf3_plan_destroy(pf3_plan*)
+    int pf3_plan_nnz(const pf3_plan*, int64_t*)
+    int pf3_plan_nrows(const pf3_plan*, int64_t*)
+    int pf3_plan_pattern(pf3_context*, const pf3_plan*, int64_t* indptr, int64_t* indices) nogil
+    int pf3_plan_assemble(pf3_context*, const pf3_plan*, const double* coo_v, double* csr_v) nogil
+    int pf3_spmv_csr(pf3_context*, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                     const double* vals, const double* x, double* y) nogil
+    int pf3_memcpy_h2d(pf3_context*, void* dst, const void* src, size_t n) nogil
+    int pf3_memcpy_d2h(pf3_context*, void* dst, const void* src, size_t n) nogil
+
+KC0, KG, KG_STRESS, M, FINT = 1, 2, 4, 8, 16
+MAT_KC0, MAT_KG, MAT_M = 0, 1, 2
+QUAD4, QUAD4R, TRIA3R, BEAMC, BEAMLR, TRUSS, SPRING = range(7)
+SHELLPROP_STRIDE, BEAMPROP_STRIDE, EPARAM_STRIDE, STATE_STRIDE = 32, 16, 8, 50
+
+
+class Pf3Error(RuntimeError):
+    pass
+
+
+cdef int _check(int rc) except -1:
+    if rc == 0:
+        return 0
+    msg = pf3_error_string(rc).decode()
+    if rc == -1:
+        raise ValueError(msg)
+    raise Pf3Error("%s (code %d)" % (msg, rc))
+
+
+def version():
+    return pf3_version()
+
+
+def device_count():
+    cdef int n = 0
+    pf3_device_count(&n)
+    return n
+
+
+def num_nodes(int kind):
+    return pf3_num_nodes(kind)
+
+
+def sparse_size(int kind, int matrix):
+    return pf3_sparse_size(kind, matrix)
+
+
+def written_size(int kind, int matrix, int mtype=0):
+    return pf3_written_size(kind, matrix, mtype)
+
+
+cdef class Batch:
+    """pf3_batch; every pointer argument is an integer address (0 = NULL)."""
+    cdef pf3_batch b
+
+    def __init__(self, int kind, int64_t ne, int64_t nnodes, uintptr_t conn=0, uintptr_t x=0, uintptr_t u=0,
+                 uintptr_t props=0, uintptr_t prop_id=0, int64_t nprop=0, uintptr_t evec=0, int evec_stride=0,
+                 uintptr_t eparam=0, uintptr_t state=0, int mtype=0, stress=(0., 0., 0.)):
+        memset(&self.b, 0, sizeof(pf3_batch))
+        self.b.kind = kind
+        self.b.mtype = mtype
+        self.b.ne = ne
+        self.b.nnodes = nnodes
+        self.b.conn = <const int64_t*>conn
+        self.b.x = <const double*>x
+        self.b.u = <const double*>u
+        self.b.props = <const double*>props
+        self.b.prop_id = <const int32_t*>prop_id
+        self.b.nprop = nprop
+        self.b.evec = <const double*>evec
+        self.b.evec_stride = evec_stride
+        self.b.eparam = <const double*>eparam
+        self.b.state = <const double*>state
+        self.b.stress[0] = stress[0]
+        self.b.stress[1] = stress[1]
+        self.b.stress[2] = stress[2]
+
+
+cdef class Coo:
+    """pf3_coo destination (r, c, v addresses; 0 = not requested)."""
+    cdef pf3_coo c
+
+    def __init__(self, uintptr_t r=0, uintptr_t c=0, uintptr_t v=0, int64_t init_k=0, int accumulate=0):
+        self.c.r = <int64_t*>r
+        self.c.c = <int64_t*>c
+        self.c.v = <double*>v
+        self.c.init_k = init_k
+        self.c.accumulate = accumulate
+
+
+cdef class Context:
+    cdef pf3_context* ctx
+    cdef public int device
+
+    def __cinit__(self, int device=0):
+        self.ctx = NULL
+        self.device = device
+        _check(pf3_create(device, &self.ctx))
+
+    def __dealloc__(self):
+        if self.ctx != NULL:
+            pf3_destroy(self.ctx)
+            self.ctx = NULL
+
+    def set_stream(self, uintptr_t stream):
+        _check(pf3_set_stream(self.ctx, <void*>stream))
+
+    def synchronize(self):
+        _check(pf3_synchronize(self.ctx))
+
+    def launch_count(self):
+        cdef int64_t n = 0
+        _check(pf3_launch_count(self.ctx, &n))
+        return n
+
+    def eval(self, Batch b, int what, Coo kc0=None, Coo kg=None, Coo m=None, uintptr_t fint=0, bint host=False):
+        cdef const pf3_coo* p0 = &kc0.c if kc0 is not None else NULL
+        cdef const pf3_coo* p1 = &kg.c if kg is not None else NULL
+        cdef const pf3_coo* p2 = &m.c if m is not None else NULL
+        cdef int rc
+        with nogil:
+            if host:
+                rc = pf3_eval_host(self.ctx, &b.b, what, p0, p1, p2, <double*>fint)
+            else:
+                rc = pf3_eval(self.ctx, &b.b, what, p0, p1, p2, <double*>fint)
+        _check(rc)
+
+    def fill_indices(self, int kind, int matrix, int mtype, int64_t ne, uintptr_t conn, int64_t init_k,
+                     uintptr_t r, uintptr_t c):
+        cdef int rc
+        with nogil:
+            rc = pf3_fill_indices(self.ctx, kind, matrix, mtype, ne, <const int64_t*>conn, init_k,
+                                  <int64_t*>r, <int64_t*>c)
+        _check(rc)
+
+    def eval_state(self, Batch b, uintptr_t out):
+        cdef int rc
+        with nogil:
+            rc = pf3_eval_state(self.ctx, &b.b, <double*>out)
+        _check(rc)
+
+    def eval_finte(self, Batch b, uintptr_t out):
+        cdef int rc
+        with nogil:
+            rc = pf3_eval_finte(self.ctx, &b.b, <double*>out)
+        _check(rc)
+
+    def spmv_csr(self, int64_t nrows, uintptr_t indptr, uintptr_t indices, uintptr_t vals, uintptr_t x, uintptr_t y):
+        cdef int rc
+        with nogil:
+            rc = pf3_spmv_csr(self.ctx, nrows, <const int64_t*>indptr, <const int64_t*>indices,
+                              <const double*>vals, <const double*>x, <double*>y)
+        _check(rc)
+
+    def memcpy_h2d(self, uintptr_t dst, uintptr_t src, size_t n):
+        cdef int rc
+        with nogil:
+            rc = pf3_memcpy_h2d(self.ctx, <void*>dst, <const void*>src, n)
+        _check(rc)
+
+    def memcpy_d2h(self, uintptr_t dst, uintptr_t src, size_t n):
+        cdef int rc
+        with nogil:
+            rc = pf3_memcpy_d2h(self.ctx, <void*>dst, <const void*>src, n)
+        _check(rc)
+
+
+cdef class Plan:
+    cdef pf3_plan* plan
+    cdef Context owner
+
+    def __cinit__(self):
+        self.plan = NULL
+
+    def __dealloc__(self):
+        if self.plan != NULL:
+            pf3_plan_destroy(self.plan)
+            self.plan = NULL
+
+    @staticmethod
+    def structured(Context ctx, int matrix, int64_t nnodes, list batches, list coo_offsets,
+                   int64_t node_begin, int64_t node_end):
+        cdef int n = len(batches)
+        if n == 0 or n > 8 or len(coo_offsets) != n:
+            raise ValueError("1..8 element groups with one COO offset each")
+        cdef pf3_batch groups[8]
+        cdef int64_t offs[8]
+        cdef int i
+        for i in range(n):
+            groups[i] = (<Batch>batches[i]).b
+            offs[i] = coo_offsets[i]
+        cdef Plan p = Plan()
+        p.owner = ctx
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_create(ctx.ctx, matrix, nnodes, n, groups, offs, node_begin, node_end, &p.plan)
+        _check(rc)
+        return p
+
+    @staticmethod
+    def from_coo(Context ctx, int64_t n, int64_t nnz, uintptr_t r, uintptr_t c):
+        cdef Plan p = Plan()
+        p.owner = ctx
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_create_coo(ctx.ctx, n, nnz, <const int64_t*>r, <const int64_t*>c, &p.plan)
+        _check(rc)
+        return p
+
+    @property
+    def nnz(self):
+        cdef int64_t n = 0
+        _check(pf3_plan_nnz(self.plan, &n))
+        return n
+
+    @property
+    def nrows(self):
+        cdef int64_t n = 0
+        _check(pf3_plan_nrows(self.plan, &n))
+        return n
+
+    def pattern(self, uintptr_t indptr, uintptr_t indices):
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_pattern(self.owner.ctx, self.plan, <int64_t*>indptr, <int64_t*>indices)
+        _check(rc)
+
+    def assemble(self, uintptr_t coo_v, uintptr_t csr_v):
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_assemble(self.owner.ctx, self.plan, <const double*>coo_v, <double*>csr_v)
+        _check(rc)

@@ -1,0 +1,343 @@
+"""Batched entry points: all elements of one kind in one launch, then a device
+COO -> CSR assembly.  This is the new API the north star asks for; the
+per-element drop-in classes (``pyfe3d_b200.elements``) sit on the same C ABI.
+
+What it replaces in a reference script (tests/test_quad4_static_point_load.py:53-80)::
+
+    for quad in quads:                      ->  b = ElementBatch("quad4", conn, x, prop)
+        quad.update_rotation_matrix(x)          KC0 = b.update_KC0()          # device COO
+        quad.update_probe_xe(x)                 plan = AssemblyPlan("KC0", nnodes, [b])
+        quad.update_KC0(KC0r, KC0c, KC0v, prop) K = plan.assemble(KC0.v)      # device CSR
+    KC0 = coo_matrix(...).tocsc()
+
+torch is used only as the owner of device memory and streams.
+There is no CPU fallback: constructing a batch without a CUDA device raises.
+"""
+import numpy as np
+import torch
+
+from . import _cabi
+
+KINDS = {"quad4": _cabi.QUAD4, "quad4r": _cabi.QUAD4R, "tria3r": _cabi.TRIA3R, "beamc": _cabi.BEAMC,
+         "beamlr": _cabi.BEAMLR, "truss": _cabi.TRUSS, "spring": _cabi.SPRING}
+MATRICES = {"KC0": _cabi.MAT_KC0, "KG": _cabi.MAT_KG, "M": _cabi.MAT_M}
+SHELL_FIELDS = ["A11", "A12", "A16", "A22", "A26", "A66", "B11", "B12", "B16", "B22", "B26", "B66",
+                "D11", "D12", "D16", "D22", "D26", "D66", "E44", "E45", "E55", "scf_k13", "scf_k23", "h",
+                "intrho", "intrhoz", "intrhoz2"]
+BEAM_FIELDS = ["A", "E", "G", "Iyy", "Izz", "Iyz", "J", "Ay", "Az",
+               "intrho", "intrhoy", "intrhoz", "intrhoy2", "intrhoz2", "intrhoyz"]
+
+_CONTEXTS = {}
+
+
+def context(device=None):
+    """The per-device C-ABI context, bound to torch's current stream on that device."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("pyfe3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ctx = _CONTEXTS.get(idx)
+    if ctx is None:
+        ctx = _cabi.Context(idx)
+        _CONTEXTS[idx] = ctx
+    ctx.set_stream(torch.cuda.current_stream(idx).cuda_stream)
+    return ctx
+
+
+def pack_props(kind, props):
+    """ShellProp/BeamProp object(s) or an already packed table -> float64[nprop, stride]."""
+    if props is None:
+        return None
+    if isinstance(props, (np.ndarray, torch.Tensor)):
+        return props
+    shell = KINDS[kind] <= _cabi.TRIA3R
+    fields, stride = (SHELL_FIELDS, _cabi.SHELLPROP_STRIDE) if shell else (BEAM_FIELDS, _cabi.BEAMPROP_STRIDE)
+    objs = list(props) if isinstance(props, (list, tuple)) else [props]
+    out = np.zeros((len(objs), stride))
+    for i, o in enumerate(objs):
+        for j, f in enumerate(fields):
+            out[i, j] = getattr(o, f)
+    return out
+
+
+def _dev(a, dtype, device):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.array(a, copy=True, order="C"), dtype=dtype).to(device)
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class Coo:
+    """Device COO triplets of one matrix (r, c may be None when only values were asked for)."""
+
+    def __init__(self, r, c, v, n):
+        self.r, self.c, self.v, self.n = r, c, v, n
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.coo_matrix((self.v.cpu().numpy(), (self.r.cpu().numpy(), self.c.cpu().numpy())),
+                             shape=(self.n, self.n))
+
+
+class ElementBatch:
+    """All elements of one kind.  Inputs may be numpy arrays or torch tensors (any device);
+    they are moved to the target device once and stay resident."""
+
+    def __init__(self, kind, conn, x=None, props=None, prop_id=None, u=None, xmat=None, vxy=None,
+                 axes=None, k=None, K6ROT=None, alpha_shear_locking=None, hgfactors=None,
+                 nnodes=None, device=None):
+        if kind not in KINDS:
+            raise ValueError("unknown element kind %r" % (kind,))
+        self.kind = kind
+        self.kid = KINDS[kind]
+        self.ctx = context(device)
+        self.device = torch.device("cuda", self.ctx.device)
+        self.nn = _cabi.num_nodes(self.kid)
+        self.conn = _dev(conn, torch.int64, self.device).reshape(-1, self.nn)
+        self.ne = int(self.conn.shape[0])
+        self.x = _dev(x, torch.float64, self.device)
+        if self.x is not None:
+            self.x = self.x.reshape(-1)
+        if nnodes is None:
+            if self.x is None:
+                raise ValueError("nnodes is required when no coordinate array is given")
+            nnodes = self.x.numel() // 3
+        self.nnodes = int(nnodes)
+        self.u = _dev(u, torch.float64, self.device)
+        self.props = _dev(pack_props(kind, props), torch.float64, self.device)
+        if self.props is not None:
+            self.props = self.props.reshape(-1, _cabi.SHELLPROP_STRIDE if self.kid <= _cabi.TRIA3R
+                                            else _cabi.BEAMPROP_STRIDE)
+        self.prop_id = _dev(prop_id, torch.int32, self.device)
+        evec = xmat if self.kid <= _cabi.TRIA3R else (axes if kind == "spring" else vxy)
+        self.evec = _dev(evec, torch.float64, self.device)
+        self.evec_stride = 0
+        if self.evec is not None:
+            w = 6 if kind == "spring" else 3
+            self.evec = self.evec.reshape(-1, w)
+            if self.evec.shape[0] not in (1, self.ne):
+                raise ValueError("per-element vector must have 1 or ne rows")
+            self.evec_stride = w if self.evec.shape[0] == self.ne and self.ne > 1 else 0
+        self.eparam = None
+        if kind == "spring":
+            if k is None:
+                raise ValueError("spring batches need k[ne,6] = (kxe,kye,kze,krxe,krye,krze)")
+            ep = torch.zeros((self.ne, _cabi.EPARAM_STRIDE), dtype=torch.float64, device=self.device)
+            ep[:, :6] = _dev(k, torch.float64, self.device).reshape(self.ne, 6)
+            self.eparam = ep
+        elif K6ROT is not None or alpha_shear_locking is not None or hgfactors is not None:
+            ep = torch.zeros((self.ne, _cabi.EPARAM_STRIDE), dtype=torch.float64, device=self.device)
+            ep[:, 0] = 100. if K6ROT is None else _dev(np.broadcast_to(np.asarray(K6ROT, float), (self.ne,)),
+                                                        torch.float64, self.device)
+            ep[:, 1] = 0.7 if alpha_shear_locking is None else _dev(
+                np.broadcast_to(np.asarray(alpha_shear_locking, float), (self.ne,)), torch.float64, self.device)
+            ep[:, 2:7] = 1. if hgfactors is None else _dev(
+                np.broadcast_to(np.asarray(hgfactors, float), (self.ne, 5)), torch.float64, self.device)
+            self.eparam = ep
+        self.sizes = {m: _cabi.sparse_size(self.kid, i) for m, i in MATRICES.items()}
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def cabi_batch(self, mtype=0, stress=(0., 0., 0.), u=None, state=None):
+        u = self.u if u is None else u
+        return _cabi.Batch(self.kid, self.ne, self.nnodes, _ptr(self.conn), _ptr(self.x), _ptr(u),
+                           _ptr(self.props), _ptr(self.prop_id),
+                           0 if self.props is None else self.props.shape[0], _ptr(self.evec),
+                           self.evec_stride, _ptr(self.eparam), _ptr(state), mtype,
+                           tuple(float(s) for s in stress))
+
+    def _alloc(self, matrix, indices, out):
+        n = self.ne * self.sizes[matrix]
+        if out is not None:
+            return out
+        v = torch.zeros(n, dtype=torch.float64, device=self.device)
+        r = c = None
+        if indices:
+            r = torch.zeros(n, dtype=torch.int64, device=self.device)
+            c = torch.zeros(n, dtype=torch.int64, device=self.device)
+        return Coo(r, c, v, 6 * self.nnodes)
+
+    def evaluate(self, KC0=False, KG=False, KG_given_stress=None, M=False, mtype=0, fint=None, u=None,
+                 indices=True, out=None, accumulate=False):
+        """One fused launch for any subset of {KC0, KG | KG_given_stress, M, fint}.
+
+        Returns a dict name -> Coo.  ``out`` may carry preallocated Coo objects to overwrite
+        (``accumulate=True`` gives the reference's ``+=``).  ``indices=False`` is the
+        reference's ``update_*v_only=1``."""
+        if u is not None:
+            u = _dev(u, torch.float64, self.device)
+        ctx = context(self.device)
+        out = dict(out or {})
+        what = 0
+        coos = {}
+        for name, on in (("KC0", KC0), ("KG", KG or KG_given_stress is not None), ("M", M)):
+            if not on:
+                continue
+            if self.sizes[name] == 0:
+                raise ValueError("%s has no %s matrix" % (self.kind, name))
+            coos[name] = self._alloc(name, indices, out.get(name))
+        if KC0:
+            what |= _cabi.KC0
+        if KG_given_stress is not None:
+            what |= _cabi.KG_STRESS
+        elif KG:
+            what |= _cabi.KG
+        if M:
+            what |= _cabi.M
+        if fint is not None:
+            what |= _cabi.FINT
+            if not (isinstance(fint, torch.Tensor) and fint.is_cuda and fint.dtype == torch.float64):
+                raise TypeError("fint must be a float64 CUDA tensor (it is accumulated in place)")
+
+        def cc(name):
+            k = coos.get(name)
+            if k is None:
+                return None
+            return _cabi.Coo(_ptr(k.r) if indices else 0, _ptr(k.c) if indices else 0, _ptr(k.v), 0,
+                             1 if accumulate else 0)
+
+        b = self.cabi_batch(mtype, KG_given_stress or (0., 0., 0.), u)
+        ctx.eval(b, what, cc("KC0"), cc("KG"), cc("M"), _ptr(fint))
+        return coos
+
+    # -- reference-named conveniences --------------------------------------------------------
+    def update_KC0(self, update_KC0v_only=0, **kw):
+        return self.evaluate(KC0=True, indices=not update_KC0v_only, **kw)["KC0"]
+
+    def update_KG(self, u=None, update_KGv_only=0, **kw):
+        return self.evaluate(KG=True, u=u, indices=not update_KGv_only, **kw)["KG"]
+
+    def update_KG_given_stress(self, Nxx, Nyy, Nxy, update_KGv_only=0, **kw):
+        return self.evaluate(KG_given_stress=(Nxx, Nyy, Nxy), indices=not update_KGv_only, **kw)["KG"]
+
+    def update_M(self, mtype=0, **kw):
+        return self.evaluate(M=True, mtype=mtype, **kw)["M"]
+
+    def update_fint(self, fint, u=None):
+        self.evaluate(fint=fint, u=u)
+        return fint
+
+    def fill_indices(self, matrix, mtype=0, coo=None):
+        coo = coo or self._alloc(matrix, True, None)
+        context(self.device).fill_indices(self.kid, MATRICES[matrix], mtype, self.ne, _ptr(self.conn), 0,
+                                          _ptr(coo.r), _ptr(coo.c))
+        return coo
+
+    def state(self, u=None):
+        """[ne, 50] per-element state (R, m, area|length, xe, ue) as the reference leaves it
+        on the element/probe after update_rotation_matrix + update_probe_xe + update_probe_ue."""
+        if u is not None:
+            u = _dev(u, torch.float64, self.device)
+        out = torch.zeros((self.ne, _cabi.STATE_STRIDE), dtype=torch.float64, device=self.device)
+        context(self.device).eval_state(self.cabi_batch(u=u), _ptr(out))
+        return out
+
+    def finte(self, u=None):
+        """probe.finte of every element: [ne, 6*nn] local internal forces."""
+        if u is not None:
+            u = _dev(u, torch.float64, self.device)
+        out = torch.zeros((self.ne, 6 * self.nn), dtype=torch.float64, device=self.device)
+        context(self.device).eval_finte(self.cabi_batch(u=u), _ptr(out))
+        return out
+
+
+class AssemblyPlan:
+    """Symbolic COO -> CSR assembly of ONE matrix from connectivity only.
+
+    ``batches``: ElementBatch objects contributing to the matrix (<= 8 kinds, e.g. Quad4 skin +
+    BeamC stiffeners); their COO value blocks are expected back to back in one value array, group
+    g starting at ``coo_offsets[g]`` (default: concatenated in order).  ``node_range`` restricts
+    the plan to the DOF rows of nodes [begin, end): the multi-GPU row-ownership shard."""
+
+    def __init__(self, matrix, nnodes, batches, coo_offsets=None, node_range=None, mtype=0):
+        self.matrix = matrix
+        self.nnodes = int(nnodes)
+        self.batches = list(batches)
+        self.device = self.batches[0].device
+        if coo_offsets is None:
+            coo_offsets, o = [], 0
+            for b in self.batches:
+                coo_offsets.append(o)
+                o += b.ne * b.sizes[matrix]
+        self.coo_offsets = [int(o) for o in coo_offsets]
+        self.coo_size = max(o + b.ne * b.sizes[matrix] for o, b in zip(self.coo_offsets, self.batches))
+        nb, ne = node_range if node_range is not None else (0, self.nnodes)
+        self.node_begin, self.node_end = int(nb), int(ne)
+        ctx = context(self.device)
+        self._plan = _cabi.Plan.structured(ctx, MATRICES[matrix], self.nnodes,
+                                           [b.cabi_batch(mtype) for b in self.batches],
+                                           self.coo_offsets, self.node_begin, self.node_end)
+        self.nnz = self._plan.nnz
+        self.nrows = self._plan.nrows
+        self._pattern = None
+
+    def pattern(self):
+        """(indptr[nrows+1], indices[nnz]) int64 device tensors; rows are local to the shard,
+        columns global; column indices sorted within each row."""
+        if self._pattern is None:
+            indptr = torch.empty(self.nrows + 1, dtype=torch.int64, device=self.device)
+            indices = torch.empty(self.nnz, dtype=torch.int64, device=self.device)
+            context(self.device)
+            self._plan.pattern(_ptr(indptr), _ptr(indices))
+            self._pattern = (indptr, indices)
+        return self._pattern
+
+    def assemble(self, coo_v, out=None):
+        """Numeric phase (repeatable): csr values = deterministic sum of duplicates."""
+        if coo_v.numel() < self.coo_size:
+            raise ValueError("COO value array shorter than the plan's layout")
+        if out is None:
+            out = torch.empty(self.nnz, dtype=torch.float64, device=self.device)
+        context(self.device)
+        self._plan.assemble(_ptr(coo_v), _ptr(out))
+        return out
+
+    def to_scipy(self, vals):
+        import scipy.sparse as sp
+        indptr, indices = self.pattern()
+        return sp.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()),
+                             shape=(self.nrows, 6 * self.nnodes))
+
+
+class CooPlan:
+    """Generic plan from arbitrary COO index arrays (what scipy's tocsr does)."""
+
+    def __init__(self, n, r, c, device=None):
+        ctx = context(device)
+        self.device = torch.device("cuda", ctx.device)
+        self.r = _dev(r, torch.int64, self.device)
+        self.c = _dev(c, torch.int64, self.device)
+        self.n = int(n)
+        self._plan = _cabi.Plan.from_coo(ctx, self.n, self.r.numel(), _ptr(self.r), _ptr(self.c))
+        self.nnz = self._plan.nnz
+        self.nrows = self.n
+        self._pattern = None
+
+    pattern = AssemblyPlan.pattern
+
+    def assemble(self, coo_v, out=None):
+        coo_v = _dev(coo_v, torch.float64, self.device)
+        if out is None:
+            out = torch.empty(self.nnz, dtype=torch.float64, device=self.device)
+        context(self.device)
+        self._plan.assemble(_ptr(coo_v), _ptr(out))
+        return out
+
+    def to_scipy(self, vals):
+        import scipy.sparse as sp
+        indptr, indices = self.pattern()
+        return sp.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()),
+                             shape=(self.n, self.n))
+
+
+def spmv(indptr, indices, vals, x, out=None):
+    """y = A @ x on the device for a CSR matrix with int64 indptr/indices."""
+    nrows = indptr.numel() - 1
+    if out is None:
+        out = torch.empty(nrows, dtype=torch.float64, device=vals.device)
+    context(vals.device).spmv_csr(nrows, _ptr(indptr), _ptr(indices), _ptr(vals), _ptr(x), _ptr(out))
+    return out

@@ -1,0 +1,524 @@
+// extern "C" surface of libpyfe3d_b200.so (declared in include/pyfe3d_b200.h).
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+#include "pattern.hpp"
+
+struct pf3_plan;
+
+namespace pf3 {
+cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st);
+cudaError_t launch_tria(const EvalArgs& A, cudaStream_t st);
+cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st);
+int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnodes, int ngroups,
+                           const pf3_batch* groups, const int64_t* coo_offsets, int64_t node_begin,
+                           int64_t node_end, int64_t* launches, pf3_plan** out);
+int plan_create_generic(int device, cudaStream_t st, int64_t n, int64_t nnz_coo, const int64_t* r, const int64_t* c,
+                        int64_t* launches, pf3_plan** out);
+int plan_pattern(const pf3_plan* pl, cudaStream_t st, int64_t* indptr, int64_t* indices, int64_t* launches);
+int plan_assemble(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int64_t* launches);
+int spmv_csr(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
+             const double* x, double* y, int64_t* launches);
+int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64_t* conn, const double* fe,
+                double* fint, int64_t* launches);
+int64_t plan_nnz(const pf3_plan* pl);
+int64_t plan_nrows(const pf3_plan* pl);
+}  // namespace pf3
+
+struct pf3_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  std::map<int, int8_t*> idx_tabs;  // (kind, matrix, mtype) -> device table [4][written]
+  double* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+namespace {
+
+#define PF3_CUDA(x)                        \
+  do {                                     \
+    cudaError_t _e = (x);                  \
+    if (_e != cudaSuccess) return int(_e); \
+  } while (0)
+
+int use_device(pf3_context* ctx) {
+  if (!ctx) return PF3_E_BAD_ARG;
+  PF3_CUDA(cudaSetDevice(ctx->device));
+  return PF3_OK;
+}
+
+int ensure_scratch(pf3_context* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return PF3_OK;
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  ctx->scratch = nullptr;
+  ctx->scratch_bytes = 0;
+  PF3_CUDA(cudaMalloc((void**)&ctx->scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return PF3_OK;
+}
+
+__global__ void k_fill_indices(const int8_t* __restrict__ tab, int written, int size, int nn, int64_t ne,
+                               const int64_t* __restrict__ conn, int64_t* __restrict__ r, int64_t* __restrict__ c) {
+  const int64_t n = ne * written;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t e = t / written;
+    const int l = int(t - e * written);
+    const int a = tab[l], i = tab[written + l], b = tab[2 * written + l], j = tab[3 * written + l];
+    const int64_t k = e * size + l;
+    if (r) r[k] = 6 * conn[e * nn + a] + i;
+    if (c) c[k] = 6 * conn[e * nn + b] + j;
+  }
+}
+
+int check_batch(const pf3_batch* b, int what) {
+  if (!b || b->kind < 0 || b->kind >= PF3_NKINDS || b->ne < 0) return PF3_E_BAD_ARG;
+  if (b->ne == 0) return PF3_OK;
+  if (!b->conn) return PF3_E_BAD_ARG;
+  if (b->kind != PF3_SPRING && !b->props) return PF3_E_BAD_ARG;
+  if (!b->state) {
+    if (b->kind != PF3_SPRING && !b->x) return PF3_E_BAD_ARG;
+    if ((b->kind == PF3_BEAMC || b->kind == PF3_BEAMLR || b->kind == PF3_SPRING) && !b->evec) return PF3_E_BAD_ARG;
+    if ((what & (PF3_KG | PF3_FINT)) && !b->u) return PF3_E_BAD_ARG;
+  }
+  if (b->kind == PF3_SPRING && !b->eparam) return PF3_E_BAD_ARG;
+  if ((what & PF3_KG) && (what & PF3_KG_STRESS)) return PF3_E_BAD_ARG;
+  if ((what & PF3_KG_STRESS) && b->kind > PF3_TRIA3R) return PF3_E_UNSUPPORTED;
+  if ((what & PF3_KG) && pf3::kind_sparse_size(b->kind, PF3_MAT_KG) == 0) return PF3_E_UNSUPPORTED;
+  if ((what & PF3_M) && pf3::kind_sparse_size(b->kind, PF3_MAT_M) == 0) return PF3_E_UNSUPPORTED;
+  if (what & PF3_M) {
+    const int maxm = (b->kind <= PF3_TRIA3R) ? 2 : 1;
+    if (b->mtype < 0 || b->mtype > maxm) return PF3_E_BAD_ARG;
+  }
+  return PF3_OK;
+}
+
+int launch_eval(pf3_context* ctx, const pf3::EvalArgs& A, int kind) {
+  cudaError_t e;
+  if (kind == PF3_QUAD4 || kind == PF3_QUAD4R)
+    e = pf3::launch_quad(kind, A, ctx->stream);
+  else if (kind == PF3_TRIA3R)
+    e = pf3::launch_tria(A, ctx->stream);
+  else
+    e = pf3::launch_line(kind, A, ctx->stream);
+  ++ctx->launches;
+  return int(e);
+}
+
+void base_args(const pf3_batch* b, pf3::EvalArgs& A) {
+  std::memset(&A, 0, sizeof(A));
+  A.ne = b->ne;
+  A.conn = b->conn;
+  A.x = b->x;
+  A.u = b->u;
+  A.props = b->props;
+  A.prop_id = b->prop_id;
+  A.evec = b->evec;
+  A.evec_stride = b->evec_stride;
+  A.eparam = b->eparam;
+  A.state = b->state;
+  A.mtype = b->mtype;
+  A.Nxx = b->stress[0];
+  A.Nyy = b->stress[1];
+  A.Nxy = b->stress[2];
+}
+
+}  // namespace
+
+extern "C" {
+
+int pf3_version(void) { return PF3_VERSION; }
+
+const char* pf3_error_string(int code) {
+  switch (code) {
+    case PF3_OK: return "ok";
+    case PF3_E_BAD_ARG: return "pyfe3d_b200: bad argument";
+    case PF3_E_NO_DEVICE: return "pyfe3d_b200: no CUDA device (this library has no CPU fallback)";
+    case PF3_E_UNSUPPORTED: return "pyfe3d_b200: matrix not defined for this element kind";
+    case PF3_E_CAPACITY: return "pyfe3d_b200: size exceeds a plan/kernel capacity limit";
+    default: return code > 0 ? cudaGetErrorString(cudaError_t(code)) : "pyfe3d_b200: unknown error";
+  }
+}
+
+int pf3_device_count(int* n) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    c = 0;
+  }
+  if (n) *n = c;
+  return PF3_OK;
+}
+
+int pf3_create(int device, pf3_context** out) {
+  if (!out) return PF3_E_BAD_ARG;
+  int c = 0;
+  pf3_device_count(&c);
+  if (c <= 0) return PF3_E_NO_DEVICE;
+  if (device < 0 || device >= c) return PF3_E_BAD_ARG;
+  PF3_CUDA(cudaSetDevice(device));
+  pf3_context* ctx = new pf3_context();
+  ctx->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return int(e);
+  }
+  ctx->own_stream = true;
+  *out = ctx;
+  return PF3_OK;
+}
+
+int pf3_destroy(pf3_context* ctx) {
+  if (!ctx) return PF3_OK;
+  cudaSetDevice(ctx->device);
+  for (auto& kv : ctx->idx_tabs) cudaFree(kv.second);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return PF3_OK;
+}
+
+int pf3_set_stream(pf3_context* ctx, void* s) {
+  if (!ctx) return PF3_E_BAD_ARG;
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = cudaStream_t(s);
+  ctx->own_stream = false;
+  return PF3_OK;
+}
+
+int pf3_synchronize(pf3_context* ctx) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  PF3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PF3_OK;
+}
+
+int pf3_malloc(pf3_context* ctx, size_t bytes, void** p) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!p) return PF3_E_BAD_ARG;
+  PF3_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+  return PF3_OK;
+}
+
+int pf3_free(pf3_context* ctx, void* p) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  PF3_CUDA(cudaFree(p));
+  return PF3_OK;
+}
+
+int pf3_memcpy_h2d(pf3_context* ctx, void* dst, const void* src, size_t bytes) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  PF3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PF3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PF3_OK;
+}
+
+int pf3_memcpy_d2h(pf3_context* ctx, void* dst, const void* src, size_t bytes) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  PF3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PF3_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PF3_OK;
+}
+
+int pf3_memset(pf3_context* ctx, void* dst, int byte, size_t bytes) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  PF3_CUDA(cudaMemsetAsync(dst, byte, bytes, ctx->stream));
+  return PF3_OK;
+}
+
+int pf3_launch_count(pf3_context* ctx, int64_t* n) {
+  if (!ctx || !n) return PF3_E_BAD_ARG;
+  *n = ctx->launches;
+  return PF3_OK;
+}
+
+int pf3_num_nodes(int kind) { return pf3::kind_nodes(kind); }
+int pf3_sparse_size(int kind, int matrix) { return pf3::kind_sparse_size(kind, matrix); }
+int pf3_written_size(int kind, int matrix, int mtype) { return pf3::make_layout(kind, matrix, mtype).written; }
+
+int pf3_fill_indices(pf3_context* ctx, int kind, int matrix, int mtype, int64_t ne, const int64_t* conn,
+                     int64_t init_k, int64_t* r, int64_t* c) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (ne < 0 || (ne > 0 && !conn)) return PF3_E_BAD_ARG;
+  const int key = kind * 100 + matrix * 10 + mtype;
+  pf3::BlockLayout L = pf3::make_layout(kind, matrix, mtype);
+  if (L.written == 0) return PF3_E_UNSUPPORTED;
+  if (ne == 0 || (!r && !c)) return PF3_OK;
+  auto it = ctx->idx_tabs.find(key);
+  if (it == ctx->idx_tabs.end()) {
+    std::vector<int8_t> tab(size_t(4) * L.written);
+    for (int l = 0; l < L.written; ++l) {
+      tab[l] = L.la[l];
+      tab[L.written + l] = L.li[l];
+      tab[2 * L.written + l] = L.lb[l];
+      tab[3 * L.written + l] = L.lj[l];
+    }
+    int8_t* d = nullptr;
+    PF3_CUDA(cudaMalloc((void**)&d, tab.size()));
+    PF3_CUDA(cudaMemcpyAsync(d, tab.data(), tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    PF3_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = ctx->idx_tabs.emplace(key, d).first;
+  }
+  const int64_t n = ne * L.written;
+  const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 64)));
+  k_fill_indices<<<grid, 256, 0, ctx->stream>>>(it->second, L.written, L.size, L.nn, ne, conn,
+                                                 r ? r + init_k : nullptr, c ? c + init_k : nullptr);
+  ++ctx->launches;
+  PF3_CUDA(cudaGetLastError());
+  return PF3_OK;
+}
+
+int pf3_eval(pf3_context* ctx, const pf3_batch* b, int what, const pf3_coo* kc0, const pf3_coo* kg,
+             const pf3_coo* m, double* fint) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  rc = check_batch(b, what);
+  if (rc) return rc;
+  if (b->ne == 0) return PF3_OK;
+  const int nn = pf3::kind_nodes(b->kind);
+  pf3::EvalArgs A;
+  base_args(b, A);
+  int kwhat = 0;
+  if ((what & PF3_KC0) && kc0) {
+    if (kc0->v) {
+      A.kc0v = kc0->v;
+      A.kc0_k0 = kc0->init_k;
+      A.acc_kc0 = kc0->accumulate;
+      kwhat |= PF3_KC0;
+    }
+    if (kc0->r || kc0->c) {
+      rc = pf3_fill_indices(ctx, b->kind, PF3_MAT_KC0, 0, b->ne, b->conn, kc0->init_k, kc0->r, kc0->c);
+      if (rc) return rc;
+    }
+  }
+  if ((what & (PF3_KG | PF3_KG_STRESS)) && kg) {
+    if (kg->v) {
+      A.kgv = kg->v;
+      A.kg_k0 = kg->init_k;
+      A.acc_kg = kg->accumulate;
+      kwhat |= what & (PF3_KG | PF3_KG_STRESS);
+    }
+    if (kg->r || kg->c) {
+      rc = pf3_fill_indices(ctx, b->kind, PF3_MAT_KG, 0, b->ne, b->conn, kg->init_k, kg->r, kg->c);
+      if (rc) return rc;
+    }
+  }
+  if ((what & PF3_M) && m) {
+    if (m->v) {
+      A.mv = m->v;
+      A.m_k0 = m->init_k;
+      A.acc_m = m->accumulate;
+      kwhat |= PF3_M;
+    }
+    if (m->r || m->c) {
+      rc = pf3_fill_indices(ctx, b->kind, PF3_MAT_M, b->mtype, b->ne, b->conn, m->init_k, m->r, m->c);
+      if (rc) return rc;
+    }
+  }
+  if ((what & PF3_FINT) && fint) {
+    rc = ensure_scratch(ctx, size_t(b->ne) * 6 * nn * sizeof(double));
+    if (rc) return rc;
+    A.fe = ctx->scratch;
+    kwhat |= PF3_FINT;
+  }
+  if (kwhat == 0) return PF3_OK;
+  A.what = kwhat;
+  rc = launch_eval(ctx, A, b->kind);
+  if (rc) return rc;
+  if (kwhat & PF3_FINT) {
+    rc = pf3::fint_gather(ctx->stream, b->ne, nn, b->nnodes, b->conn, ctx->scratch, fint, &ctx->launches);
+    if (rc) return rc;
+  }
+  return PF3_OK;
+}
+
+int pf3_eval_state(pf3_context* ctx, const pf3_batch* b, double* state_out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  rc = check_batch(b, 0);
+  if (rc) return rc;
+  if (!state_out) return PF3_E_BAD_ARG;
+  if (b->ne == 0) return PF3_OK;
+  pf3::EvalArgs A;
+  base_args(b, A);
+  A.what = 0;
+  A.state_out = state_out;
+  return launch_eval(ctx, A, b->kind);
+}
+
+int pf3_eval_finte(pf3_context* ctx, const pf3_batch* b, double* finte_out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  rc = check_batch(b, PF3_FINT);
+  if (rc) return rc;
+  if (!finte_out) return PF3_E_BAD_ARG;
+  if (b->ne == 0) return PF3_OK;
+  pf3::EvalArgs A;
+  base_args(b, A);
+  A.what = PF3_FINT;
+  A.finte = finte_out;
+  return launch_eval(ctx, A, b->kind);
+}
+
+int pf3_plan_create(pf3_context* ctx, int matrix, int64_t nnodes, int ngroups, const pf3_batch* groups,
+                    const int64_t* coo_offsets, int64_t node_begin, int64_t node_end, pf3_plan** plan) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!groups || !plan || matrix < 0 || matrix > 2) return PF3_E_BAD_ARG;
+  return pf3::plan_create_structured(ctx->device, ctx->stream, matrix, nnodes, ngroups, groups, coo_offsets,
+                                     node_begin, node_end, &ctx->launches, plan);
+}
+
+int pf3_plan_create_coo(pf3_context* ctx, int64_t n, int64_t nnz_coo, const int64_t* r, const int64_t* c,
+                        pf3_plan** plan) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan) return PF3_E_BAD_ARG;
+  return pf3::plan_create_generic(ctx->device, ctx->stream, n, nnz_coo, r, c, &ctx->launches, plan);
+}
+
+int pf3_plan_nnz(const pf3_plan* plan, int64_t* nnz) {
+  if (!plan || !nnz) return PF3_E_BAD_ARG;
+  *nnz = pf3::plan_nnz(plan);
+  return PF3_OK;
+}
+
+int pf3_plan_nrows(const pf3_plan* plan, int64_t* nrows) {
+  if (!plan || !nrows) return PF3_E_BAD_ARG;
+  *nrows = pf3::plan_nrows(plan);
+  return PF3_OK;
+}
+
+int pf3_plan_pattern(pf3_context* ctx, const pf3_plan* plan, int64_t* indptr, int64_t* indices) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan) return PF3_E_BAD_ARG;
+  return pf3::plan_pattern(plan, ctx->stream, indptr, indices, &ctx->launches);
+}
+
+int pf3_plan_assemble(pf3_context* ctx, const pf3_plan* plan, const double* coo_v, double* csr_v) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan || !coo_v || !csr_v) return PF3_E_BAD_ARG;
+  return pf3::plan_assemble(plan, ctx->stream, coo_v, csr_v, &ctx->launches);
+}
+
+int pf3_spmv_csr(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                 const double* vals, const double* x, double* y) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (nrows < 0 || !indptr || !x || !y) return PF3_E_BAD_ARG;
+  return pf3::spmv_csr(ctx->stream, nrows, indptr, indices, vals, x, y, &ctx->launches);
+}
+
+// Host-pointer convenience: every pointer in host_batch / the pf3_coo structs / fint is a HOST pointer.
+int pf3_eval_host(pf3_context* ctx, const pf3_batch* hb, int what, const pf3_coo* kc0, const pf3_coo* kg,
+                  const pf3_coo* m, double* fint) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  rc = check_batch(hb, what);
+  if (rc) return rc;
+  if (hb->ne == 0) return PF3_OK;
+  const int nn = pf3::kind_nodes(hb->kind);
+  const int pstride = (hb->kind <= PF3_TRIA3R) ? PF3_SHELLPROP_STRIDE : PF3_BEAMPROP_STRIDE;
+  std::vector<void*> owned;
+  auto up = [&](const void* h, size_t bytes, const void** d) -> int {
+    *d = nullptr;
+    if (!h || bytes == 0) return PF3_OK;
+    void* p = nullptr;
+    PF3_CUDA(cudaMalloc(&p, bytes));
+    owned.push_back(p);
+    PF3_CUDA(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *d = p;
+    return PF3_OK;
+  };
+  auto release = [&]() {
+    for (void* p : owned) cudaFree(p);
+  };
+#define PF3_TRYH(x) do { rc = (x); if (rc) { release(); return rc; } } while (0)
+  pf3_batch b = *hb;
+  PF3_TRYH(up(hb->conn, size_t(hb->ne) * nn * 8, (const void**)&b.conn));
+  PF3_TRYH(up(hb->x, size_t(hb->nnodes) * 3 * 8, (const void**)&b.x));
+  PF3_TRYH(up(hb->u, size_t(hb->nnodes) * 6 * 8, (const void**)&b.u));
+  PF3_TRYH(up(hb->props, size_t(hb->nprop) * pstride * 8, (const void**)&b.props));
+  PF3_TRYH(up(hb->prop_id, size_t(hb->ne) * 4, (const void**)&b.prop_id));
+  if (hb->evec) {
+    const int width = (hb->kind == PF3_SPRING) ? 6 : 3;
+    const size_t cnt = hb->evec_stride ? size_t(hb->ne - 1) * hb->evec_stride + width : width;
+    PF3_TRYH(up(hb->evec, cnt * 8, (const void**)&b.evec));
+  }
+  PF3_TRYH(up(hb->eparam, size_t(hb->ne) * PF3_EPARAM_STRIDE * 8, (const void**)&b.eparam));
+  PF3_TRYH(up(hb->state, size_t(hb->ne) * PF3_STATE_STRIDE * 8, (const void**)&b.state));
+  struct DevCoo {
+    pf3_coo d;
+    const pf3_coo* h;
+    int64_t n;
+  };
+  DevCoo dc[3];
+  const pf3_coo* hs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
+                          (what & PF3_M) ? m : nullptr};
+  for (int k = 0; k < 3; ++k) {
+    dc[k].h = hs[k];
+    dc[k].n = hb->ne * pf3::kind_sparse_size(hb->kind, k);
+    std::memset(&dc[k].d, 0, sizeof(pf3_coo));
+    if (!hs[k] || dc[k].n == 0) {
+      dc[k].h = nullptr;
+      continue;
+    }
+    dc[k].d.accumulate = hs[k]->accumulate;
+    dc[k].d.init_k = 0;
+    if (hs[k]->v) {
+      void* p = nullptr;
+      PF3_TRYH(int(cudaMalloc(&p, size_t(dc[k].n) * 8)));
+      owned.push_back(p);
+      dc[k].d.v = (double*)p;
+      // existing values are needed both for `+=` and for the unwritten lumped-mass tail
+      PF3_TRYH(int(cudaMemcpyAsync(p, hs[k]->v + hs[k]->init_k, size_t(dc[k].n) * 8, cudaMemcpyHostToDevice, ctx->stream)));
+    }
+    if (hs[k]->r) {
+      void* p = nullptr;
+      PF3_TRYH(int(cudaMalloc(&p, size_t(dc[k].n) * 8)));
+      owned.push_back(p);
+      dc[k].d.r = (int64_t*)p;
+      PF3_TRYH(int(cudaMemcpyAsync(p, hs[k]->r + hs[k]->init_k, size_t(dc[k].n) * 8, cudaMemcpyHostToDevice, ctx->stream)));
+    }
+    if (hs[k]->c) {
+      void* p = nullptr;
+      PF3_TRYH(int(cudaMalloc(&p, size_t(dc[k].n) * 8)));
+      owned.push_back(p);
+      dc[k].d.c = (int64_t*)p;
+      PF3_TRYH(int(cudaMemcpyAsync(p, hs[k]->c + hs[k]->init_k, size_t(dc[k].n) * 8, cudaMemcpyHostToDevice, ctx->stream)));
+    }
+  }
+  double* dfint = nullptr;
+  if ((what & PF3_FINT) && fint) {
+    PF3_TRYH(up(fint, size_t(hb->nnodes) * 6 * 8, (const void**)&dfint));
+  }
+  PF3_TRYH(pf3_eval(ctx, &b, what, dc[0].h ? &dc[0].d : nullptr, dc[1].h ? &dc[1].d : nullptr,
+                    dc[2].h ? &dc[2].d : nullptr, dfint));
+  for (int k = 0; k < 3; ++k) {
+    if (!dc[k].h) continue;
+    if (dc[k].d.v) PF3_TRYH(int(cudaMemcpyAsync(dc[k].h->v + dc[k].h->init_k, dc[k].d.v, size_t(dc[k].n) * 8, cudaMemcpyDeviceToHost, ctx->stream)));
+    if (dc[k].d.r) PF3_TRYH(int(cudaMemcpyAsync(dc[k].h->r + dc[k].h->init_k, dc[k].d.r, size_t(dc[k].n) * 8, cudaMemcpyDeviceToHost, ctx->stream)));
+    if (dc[k].d.c) PF3_TRYH(int(cudaMemcpyAsync(dc[k].h->c + dc[k].h->init_k, dc[k].d.c, size_t(dc[k].n) * 8, cudaMemcpyDeviceToHost, ctx->stream)));
+  }
+  if (dfint) PF3_TRYH(int(cudaMemcpyAsync(fint, dfint, size_t(hb->nnodes) * 6 * 8, cudaMemcpyDeviceToHost, ctx->stream)));
+  PF3_TRYH(int(cudaStreamSynchronize(ctx->stream)));
+#undef PF3_TRYH
+  release();
+  return PF3_OK;
+}
+
+}  // extern "C"

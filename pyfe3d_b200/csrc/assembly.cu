@@ -1,0 +1,659 @@
+// GPU COO -> CSR sum-duplicates assembly.
+//
+// Replaces the `scipy.sparse.coo_matrix((v,(r,c)),shape=(N,N)).tocsc()/.tocsr()` call every
+// reference script makes right after its element loop (tests/test_quad4_static_point_load.py:80,
+// tests/test_beamc_natural_freq_curved.py:93-94 in /root/reference).
+//
+// Two plans:
+//  * structured: built from connectivity alone.  COO indices are a pure function of connectivity
+//    (SURVEY Appendix B), so the symbolic phase sorts NODE-PAIR keys (16 per quad instead of 576
+//    entry keys), and the numeric phase is a deterministic gather: one warp per node row block reads
+//    the contiguous row slab of every incident element (coalesced) and writes its CSR rows once.
+//  * generic: radix sort of (row, col) keys of arbitrary COO arrays + segmented sum.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
+#include "common.cuh"
+#include "pattern.hpp"
+
+namespace pf3 {
+
+constexpr int kMaxGroups = 8;
+
+struct GroupDev {
+  const int64_t* conn;
+  const uint16_t* tab;  // per slab-local entry: dof_i | node_j<<3 | colrank<<6 (node_j==7: same node)
+  int64_t ne;
+  int64_t coo_offset;
+  int64_t pairbase, incbase;
+  int nn, size, wn, diag, npairs;
+};
+
+struct PlanDev {
+  GroupDev g[kMaxGroups];
+  int ngroups;
+  int64_t nnodes, node_begin, node_end;
+  int cnt[6], rowoff[6], mc;
+};
+
+}  // namespace pf3
+
+struct pf3_plan {
+  int device = 0;
+  int generic = 0;
+  int64_t nrows = 0, nnz = 0;
+  // structured
+  pf3::PlanDev dev{};
+  int8_t colrank[6][6];
+  bool umask[6][6];
+  int64_t nblk = 0, ninc = 0, npair = 0, nown = 0;
+  int max_nb = 0;
+  int degenerate = 0;
+  int64_t* d_brow_ptr = nullptr;
+  int64_t* d_bcol = nullptr;
+  int64_t* d_inc_ptr = nullptr;
+  int64_t* d_inc_src = nullptr;
+  int64_t* d_inc_pair0 = nullptr;
+  int32_t* d_inc_meta = nullptr;
+  int32_t* d_slot = nullptr;
+  std::vector<uint16_t*> d_tabs;
+  // generic
+  int64_t n = 0, nnz_coo = 0;
+  int64_t* d_indptr = nullptr;
+  int64_t* d_indices = nullptr;
+  int64_t* d_perm = nullptr;
+  int64_t* d_seg = nullptr;
+};
+
+namespace pf3 {
+
+#define PF3_CUDA(x)                      \
+  do {                                   \
+    cudaError_t _e = (x);                \
+    if (_e != cudaSuccess) return int(_e); \
+  } while (0)
+
+namespace {
+
+template <class T>
+int dalloc(T** p, int64_t n) {
+  *p = nullptr;
+  if (n <= 0) n = 1;
+  return int(cudaMalloc((void**)p, size_t(n) * sizeof(T)));
+}
+
+__device__ __forceinline__ int find_group_by(const PlanDev& P, int64_t id, bool pair) {
+  int g = 0;
+  for (int k = 1; k < P.ngroups; ++k)
+    if (id >= (pair ? P.g[k].pairbase : P.g[k].incbase)) g = k;
+  return g;
+}
+
+// ---- symbolic kernels ---------------------------------------------------------------------
+__global__ void k_pair_keys(const PlanDev P, int gi, int64_t* keys, uint32_t* vals) {
+  const GroupDev& G = P.g[gi];
+  const int64_t n = G.ne * G.npairs;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t e = t / G.npairs;
+    const int q = int(t - e * G.npairs);
+    const int a = G.diag ? q : q / G.nn, b = G.diag ? q : q % G.nn;
+    const int64_t na = G.conn[e * G.nn + a], nb = G.conn[e * G.nn + b];
+    const bool own = na >= P.node_begin && na < P.node_end;
+    keys[G.pairbase + t] = own ? na * P.nnodes + nb : P.nnodes * P.nnodes;
+    vals[G.pairbase + t] = uint32_t(G.pairbase + t);
+  }
+}
+
+__global__ void k_inc_keys(const PlanDev P, int gi, int64_t* keys, uint32_t* vals, int* degenerate) {
+  const GroupDev& G = P.g[gi];
+  const int64_t n = G.ne * G.nn;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t e = t / G.nn;
+    const int a = int(t - e * G.nn);
+    const int64_t na = G.conn[t];
+    for (int b = 0; b < a; ++b)
+      if (G.conn[e * G.nn + b] == na) *degenerate = 1;
+    const bool own = na >= P.node_begin && na < P.node_end;
+    keys[G.incbase + t] = own ? na : P.nnodes;
+    vals[G.incbase + t] = uint32_t(G.incbase + t);
+  }
+}
+
+__global__ void k_head_flags(const int64_t* keys, int64_t n, int64_t sentinel, int32_t* flags) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x)
+    flags[t] = (keys[t] != sentinel && (t == 0 || keys[t] != keys[t - 1])) ? 1 : 0;
+}
+
+__global__ void k_scatter_unique(const int64_t* keys, const int32_t* flags, const int32_t* incl, int64_t n,
+                                 int64_t* ukeys) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x)
+    if (flags[t]) ukeys[incl[t] - 1] = keys[t];
+}
+
+// lower_bound of target in sorted a[0..n)
+__device__ __forceinline__ int64_t lower_bound_dev(const int64_t* a, int64_t n, int64_t target) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void k_row_ptr(const int64_t* sorted, int64_t n, int64_t first, int64_t count, int64_t scale,
+                          int64_t* ptr) {
+  // ptr[i] = lower_bound(sorted, (first+i)*scale), i in [0, count]
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i <= count; i += int64_t(gridDim.x) * blockDim.x)
+    ptr[i] = lower_bound_dev(sorted, n, (first + i) * scale);
+}
+
+__global__ void k_bcol_maxnb(const int64_t* ukeys, int64_t nblk, int64_t nnodes, int64_t* bcol,
+                             const int64_t* brow_ptr, int64_t nown, int* max_nb) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < max(nblk, nown);
+       t += int64_t(gridDim.x) * blockDim.x) {
+    if (t < nblk) bcol[t] = ukeys[t] % nnodes;
+    if (t < nown) atomicMax(max_nb, int(brow_ptr[t + 1] - brow_ptr[t]));
+  }
+}
+
+__global__ void k_pair_slots(const PlanDev P, const int64_t* keys, const uint32_t* vals, const int32_t* incl,
+                             int64_t n, const int64_t* brow_ptr, int32_t* slot) {
+  const int64_t sentinel = P.nnodes * P.nnodes;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t k = keys[t];
+    if (k == sentinel) {
+      slot[vals[t]] = -1;
+      continue;
+    }
+    const int64_t row = k / P.nnodes - P.node_begin;
+    slot[vals[t]] = int32_t(int64_t(incl[t] - 1) - brow_ptr[row]);
+  }
+}
+
+__global__ void k_inc_fill(const PlanDev P, const uint32_t* vals, int64_t ninc_valid, int64_t* inc_src,
+                           int64_t* inc_pair0, int32_t* inc_meta) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < ninc_valid;
+       t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t id = vals[t];
+    const int gi = find_group_by(P, id, false);
+    const GroupDev& G = P.g[gi];
+    const int64_t loc = id - G.incbase;
+    const int64_t e = loc / G.nn;
+    const int a = int(loc - e * G.nn);
+    inc_src[t] = G.coo_offset + e * G.size + int64_t(a) * G.wn;
+    inc_pair0[t] = G.pairbase + e * G.npairs + (G.diag ? a : a * G.nn);
+    inc_meta[t] = gi | (a << 8);
+  }
+}
+
+// ---- pattern -----------------------------------------------------------------------------
+struct MaskDev {
+  int8_t cols[6][6];  // cols[d][r] = r-th column dof of row d
+};
+
+__global__ void k_pattern(const PlanDev P, const MaskDev M, const int64_t* brow_ptr, const int64_t* bcol,
+                          int64_t nown, int64_t* indptr, int64_t* indices) {
+  // one thread per (owned node, dof row)
+  const int64_t n = nown * 6;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t <= n; t += int64_t(gridDim.x) * blockDim.x) {
+    if (t == n) {
+      if (indptr) indptr[n] = brow_ptr[nown] * P.mc;
+      continue;
+    }
+    const int64_t i = t / 6;
+    const int d = int(t - i * 6);
+    const int64_t b0 = brow_ptr[i], nb = brow_ptr[i + 1] - b0;
+    const int64_t start = b0 * P.mc + int64_t(P.rowoff[d]) * nb;
+    if (indptr) indptr[t] = start;
+    if (indices)
+      for (int64_t s = 0; s < nb; ++s)
+        for (int r = 0; r < P.cnt[d]; ++r) indices[start + s * P.cnt[d] + r] = 6 * bcol[b0 + s] + M.cols[d][r];
+  }
+}
+
+// ---- numeric -----------------------------------------------------------------------------
+// One warp per owned node.  acc lives in shared memory (max_nb * mc doubles per warp).
+template <bool SAFE>
+__global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t* __restrict__ brow_ptr,
+                                                  const int64_t* __restrict__ inc_ptr,
+                                                  const int64_t* __restrict__ inc_src,
+                                                  const int64_t* __restrict__ inc_pair0,
+                                                  const int32_t* __restrict__ inc_meta,
+                                                  const int32_t* __restrict__ slot, int64_t nown, int acc_stride,
+                                                  const double* __restrict__ coo_v, double* __restrict__ csr_v) {
+  extern __shared__ double sacc[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  double* acc = sacc + size_t(warp) * acc_stride;
+  for (int64_t i = int64_t(blockIdx.x) * wpc + warp; i < nown; i += int64_t(gridDim.x) * wpc) {
+    const int64_t b0 = brow_ptr[i];
+    const int nb = int(brow_ptr[i + 1] - b0);
+    const int nout = nb * P.mc;
+    for (int k = lane; k < nout; k += 32) acc[k] = 0.;
+    __syncwarp();
+    const int64_t q0 = inc_ptr[i], q1 = inc_ptr[i + 1];
+    for (int64_t q = q0; q < q1; ++q) {
+      const int meta = inc_meta[q];
+      const GroupDev& G = P.g[meta & 0xff];
+      const int a = meta >> 8;
+      const double* src = coo_v + inc_src[q];
+      const int32_t* sl = slot + inc_pair0[q];
+      const uint16_t* tab = G.tab;
+      for (int l = lane; l < G.wn; l += 32) {
+        const int code = tab[l];
+        const int di = code & 7, bj = (code >> 3) & 7, rk = code >> 6;
+        const int s = G.diag ? sl[0] : sl[bj];
+        (void)a;
+        const int dest = P.rowoff[di] * nb + s * P.cnt[di] + rk;
+        const double v = src[l];
+        if (SAFE) atomicAdd(&acc[dest], v); else acc[dest] += v;
+      }
+      __syncwarp();
+    }
+    double* out = csr_v + b0 * P.mc;
+    for (int k = lane; k < nout; k += 32) out[k] = acc[k];
+    __syncwarp();
+  }
+}
+
+// ---- generic COO plan -----------------------------------------------------------------------
+__global__ void k_coo_keys(const int64_t* r, const int64_t* c, int64_t n, int64_t nnz, int64_t* keys, int64_t* vals) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < nnz; t += int64_t(gridDim.x) * blockDim.x) {
+    keys[t] = r[t] * n + c[t];
+    vals[t] = t;
+  }
+}
+__global__ void k_seg_starts(const int32_t* flags, const int32_t* incl, int64_t n, int64_t* seg) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t <= n; t += int64_t(gridDim.x) * blockDim.x) {
+    if (t == n) {
+      seg[n ? incl[n - 1] : 0] = n;
+    } else if (flags[t]) {
+      seg[incl[t] - 1] = t;
+    }
+  }
+}
+__global__ void k_indices_from_keys(const int64_t* ukeys, int64_t nnz, int64_t n, int64_t* indices) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < nnz; t += int64_t(gridDim.x) * blockDim.x)
+    indices[t] = ukeys[t] % n;
+}
+__global__ void k_segsum(const int64_t* seg, const int64_t* perm, int64_t nnz, const double* v, double* out) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < nnz; t += int64_t(gridDim.x) * blockDim.x) {
+    double s = 0.;
+    for (int64_t k = seg[t]; k < seg[t + 1]; ++k) s += v[perm[k]];
+    out[t] = s;
+  }
+}
+
+// ---- SpMV ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_spmv(int64_t nrows, const int64_t* __restrict__ indptr,
+                                              const int64_t* __restrict__ indices, const double* __restrict__ vals,
+                                              const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = w; row < nrows; row += nw) {
+    double s = 0.;
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) s += vals[k] * x[indices[k]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+  }
+}
+
+inline unsigned grid_for(int64_t n, int block = 256) {
+  int64_t g = (n + block - 1) / block;
+  return unsigned(std::max<int64_t>(1, std::min<int64_t>(g, 148 * 32)));
+}
+
+int bits_for(int64_t maxval) {
+  int b = 1;
+  while (b < 63 && (int64_t(1) << b) <= maxval) ++b;
+  return b;
+}
+
+template <class K, class V>
+int sort_pairs(K* kin, K* kout, V* vin, V* vout, int64_t n, int end_bit, cudaStream_t st) {
+  size_t bytes = 0;
+  PF3_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, end_bit, st));
+  void* tmp = nullptr;
+  PF3_CUDA(cudaMalloc(&tmp, bytes ? bytes : 1));
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, n, 0, end_bit, st);
+  cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  return int(e);
+}
+
+int inclusive_sum(const int32_t* in, int32_t* out, int64_t n, cudaStream_t st) {
+  size_t bytes = 0;
+  PF3_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, in, out, n, st));
+  void* tmp = nullptr;
+  PF3_CUDA(cudaMalloc(&tmp, bytes ? bytes : 1));
+  cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, bytes, in, out, n, st);
+  cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  return int(e);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnodes, int ngroups,
+                           const pf3_batch* groups, const int64_t* coo_offsets, int64_t node_begin,
+                           int64_t node_end, int64_t* launches, pf3_plan** out) {
+  if (ngroups <= 0 || ngroups > kMaxGroups || nnodes <= 0 || node_begin < 0 || node_end > nnodes ||
+      node_begin >= node_end)
+    return PF3_E_BAD_ARG;
+  pf3_plan* pl = new pf3_plan();
+  pl->device = device;
+  PlanDev& P = pl->dev;
+  P.ngroups = ngroups;
+  P.nnodes = nnodes;
+  P.node_begin = node_begin;
+  P.node_end = node_end;
+  pl->nown = node_end - node_begin;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) pl->umask[i][j] = false;
+  std::vector<BlockLayout> lay(ngroups);
+  int64_t pairbase = 0, incbase = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    lay[g] = make_layout(groups[g].kind, matrix, groups[g].mtype);
+    const BlockLayout& L = lay[g];
+    if (L.written == 0 || groups[g].ne < 0 || groups[g].conn == nullptr) {
+      delete pl;
+      return PF3_E_BAD_ARG;
+    }
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) pl->umask[i][j] |= mask_has(L.mask, i, j);
+    GroupDev& G = P.g[g];
+    G.conn = groups[g].conn;
+    G.ne = groups[g].ne;
+    G.coo_offset = coo_offsets ? coo_offsets[g] : 0;
+    G.nn = L.nn;
+    G.size = L.size;
+    G.wn = L.written / L.nn;
+    G.diag = L.diag_pairs ? 1 : 0;
+    G.npairs = L.diag_pairs ? L.nn : L.nn * L.nn;
+    G.pairbase = pairbase;
+    G.incbase = incbase;
+    pairbase += G.ne * G.npairs;
+    incbase += G.ne * G.nn;
+  }
+  pl->npair = pairbase;
+  pl->ninc = incbase;
+  if (pairbase >= (int64_t(1) << 32) || incbase >= (int64_t(1) << 32)) {
+    delete pl;
+    return PF3_E_CAPACITY;
+  }
+  P.mc = 0;
+  MaskDev MD;
+  for (int i = 0; i < 6; ++i) {
+    P.rowoff[i] = P.mc;
+    int c = 0;
+    for (int j = 0; j < 6; ++j) {
+      pl->colrank[i][j] = -1;
+      MD.cols[i][j] = 0;
+      if (pl->umask[i][j]) {
+        pl->colrank[i][j] = int8_t(c);
+        MD.cols[i][c] = int8_t(j);
+        ++c;
+      }
+    }
+    P.cnt[i] = c;
+    P.mc += c;
+  }
+  // per-group slab tables
+  for (int g = 0; g < ngroups; ++g) {
+    const BlockLayout& L = lay[g];
+    std::vector<uint16_t> tab(P.g[g].wn);
+    for (int l = 0; l < P.g[g].wn; ++l) {  // slab of local node 0 (identical for every node)
+      const int di = L.li[l], bj = L.diag_pairs ? 7 : L.lb[l], rk = pl->colrank[di][L.lj[l]];
+      tab[l] = uint16_t(di | (bj << 3) | (rk << 6));
+    }
+    uint16_t* d = nullptr;
+    int rc = dalloc(&d, int64_t(tab.size()));
+    if (rc) { pf3_plan_destroy(pl); return rc; }
+    cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+    pl->d_tabs.push_back(d);
+    P.g[g].tab = d;
+  }
+
+  int rc = 0;
+  int64_t *keys = nullptr, *keys2 = nullptr, *ukeys = nullptr;
+  uint32_t *vals = nullptr, *vals2 = nullptr;
+  int32_t *flags = nullptr, *incl = nullptr;
+  int* d_flagsmall = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(keys); cudaFree(keys2); cudaFree(ukeys); cudaFree(vals); cudaFree(vals2);
+    cudaFree(flags); cudaFree(incl); cudaFree(d_flagsmall);
+  };
+#define PF3_TRY(x) do { rc = (x); if (rc) { cleanup(); pf3_plan_destroy(pl); return rc; } } while (0)
+  const int64_t NP = pl->npair, NI = pl->ninc, NMAX = std::max(NP, NI);
+  PF3_TRY(dalloc(&keys, NMAX));
+  PF3_TRY(dalloc(&keys2, NMAX));
+  PF3_TRY(dalloc(&vals, NMAX));
+  PF3_TRY(dalloc(&vals2, NMAX));
+  PF3_TRY(dalloc(&flags, NMAX));
+  PF3_TRY(dalloc(&incl, NMAX));
+  PF3_TRY(dalloc(&d_flagsmall, 2));
+  PF3_TRY(int(cudaMemsetAsync(d_flagsmall, 0, 2 * sizeof(int), st)));
+
+  // ---- node-pair blocks
+  for (int g = 0; g < ngroups; ++g) {
+    k_pair_keys<<<grid_for(P.g[g].ne * P.g[g].npairs), 256, 0, st>>>(P, g, keys, vals);
+    ++*launches;
+  }
+  const int64_t sentinel = nnodes * nnodes;
+  PF3_TRY(sort_pairs(keys, keys2, vals, vals2, NP, bits_for(sentinel), st));
+  k_head_flags<<<grid_for(NP), 256, 0, st>>>(keys2, NP, sentinel, flags);
+  PF3_TRY(inclusive_sum(flags, incl, NP, st));
+  int32_t nblk32 = 0;
+  if (NP > 0) PF3_TRY(int(cudaMemcpyAsync(&nblk32, incl + NP - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st)));
+  cudaStreamSynchronize(st);
+  pl->nblk = nblk32;
+  PF3_TRY(dalloc(&ukeys, pl->nblk));
+  k_scatter_unique<<<grid_for(NP), 256, 0, st>>>(keys2, flags, incl, NP, ukeys);
+  PF3_TRY(dalloc(&pl->d_brow_ptr, pl->nown + 1));
+  PF3_TRY(dalloc(&pl->d_bcol, pl->nblk));
+  k_row_ptr<<<grid_for(pl->nown + 1), 256, 0, st>>>(ukeys, pl->nblk, node_begin, pl->nown, nnodes, pl->d_brow_ptr);
+  k_bcol_maxnb<<<grid_for(std::max(pl->nblk, pl->nown)), 256, 0, st>>>(ukeys, pl->nblk, nnodes, pl->d_bcol,
+                                                                         pl->d_brow_ptr, pl->nown, d_flagsmall);
+  PF3_TRY(dalloc(&pl->d_slot, NP));
+  k_pair_slots<<<grid_for(NP), 256, 0, st>>>(P, keys2, vals2, incl, NP, pl->d_brow_ptr, pl->d_slot);
+  *launches += 5;
+
+  // ---- node -> (element, local node) incidences
+  for (int g = 0; g < ngroups; ++g) {
+    k_inc_keys<<<grid_for(P.g[g].ne * P.g[g].nn), 256, 0, st>>>(P, g, keys, vals, d_flagsmall + 1);
+    ++*launches;
+  }
+  PF3_TRY(sort_pairs(keys, keys2, vals, vals2, NI, bits_for(nnodes), st));
+  PF3_TRY(dalloc(&pl->d_inc_ptr, pl->nown + 1));
+  k_row_ptr<<<grid_for(pl->nown + 1), 256, 0, st>>>(keys2, NI, node_begin, pl->nown, 1, pl->d_inc_ptr);
+  // incidences of owned nodes occupy sorted positions [inc_ptr[0], inc_ptr[nown]); store them rebased
+  int64_t h_first = 0, h_last = 0;
+  PF3_TRY(int(cudaMemcpyAsync(&h_first, pl->d_inc_ptr, sizeof(int64_t), cudaMemcpyDeviceToHost, st)));
+  PF3_TRY(int(cudaMemcpyAsync(&h_last, pl->d_inc_ptr + pl->nown, sizeof(int64_t), cudaMemcpyDeviceToHost, st)));
+  int h_small[2] = {0, 0};
+  PF3_TRY(int(cudaMemcpyAsync(h_small, d_flagsmall, 2 * sizeof(int), cudaMemcpyDeviceToHost, st)));
+  cudaStreamSynchronize(st);
+  pl->max_nb = h_small[0];
+  pl->degenerate = h_small[1];
+  const int64_t nvalid = h_last;  // sorted keys < nnodes come first; owned range may start after 0
+  PF3_TRY(dalloc(&pl->d_inc_src, nvalid));
+  PF3_TRY(dalloc(&pl->d_inc_pair0, nvalid));
+  PF3_TRY(dalloc(&pl->d_inc_meta, nvalid));
+  k_inc_fill<<<grid_for(nvalid), 256, 0, st>>>(P, vals2, nvalid, pl->d_inc_src, pl->d_inc_pair0, pl->d_inc_meta);
+  *launches += 2;
+  (void)h_first;
+  PF3_TRY(int(cudaStreamSynchronize(st)));
+  PF3_TRY(int(cudaGetLastError()));
+  cleanup();
+#undef PF3_TRY
+  pl->nrows = 6 * pl->nown;
+  pl->nnz = pl->nblk * P.mc;
+  *out = pl;
+  return PF3_OK;
+}
+
+int plan_pattern(const pf3_plan* pl, cudaStream_t st, int64_t* indptr, int64_t* indices, int64_t* launches) {
+  if (pl->generic) {
+    if (indptr) PF3_CUDA(cudaMemcpyAsync(indptr, pl->d_indptr, size_t(pl->nrows + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    if (indices) PF3_CUDA(cudaMemcpyAsync(indices, pl->d_indices, size_t(pl->nnz) * 8, cudaMemcpyDeviceToDevice, st));
+    return PF3_OK;
+  }
+  MaskDev MD;
+  for (int i = 0; i < 6; ++i) {
+    int c = 0;
+    for (int j = 0; j < 6; ++j) {
+      MD.cols[i][j] = 0;
+      if (pl->umask[i][j]) MD.cols[i][c++] = int8_t(j);
+    }
+  }
+  k_pattern<<<grid_for(pl->nown * 6 + 1), 256, 0, st>>>(pl->dev, MD, pl->d_brow_ptr, pl->d_bcol, pl->nown, indptr, indices);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+
+int plan_assemble(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int64_t* launches) {
+  if (pl->generic) {
+    k_segsum<<<grid_for(pl->nnz), 256, 0, st>>>(pl->d_seg, pl->d_perm, pl->nnz, coo_v, csr_v);
+    ++*launches;
+    return int(cudaGetLastError());
+  }
+  const int acc_stride = std::max(1, pl->max_nb * pl->dev.mc);
+  int wpc = 8;
+  while (wpc > 1 && size_t(wpc) * acc_stride * sizeof(double) > 200 * 1024) wpc >>= 1;
+  const size_t smem = size_t(wpc) * acc_stride * sizeof(double);
+  if (smem > 220 * 1024) return PF3_E_CAPACITY;
+  const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((pl->nown + wpc - 1) / wpc, 148 * 64)));
+  if (pl->degenerate) {
+    if (smem > 48 * 1024) PF3_CUDA(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    k_assemble<true><<<grid, wpc * 32, smem, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
+                                                   pl->d_inc_meta, pl->d_slot, pl->nown, acc_stride, coo_v, csr_v);
+  } else {
+    if (smem > 48 * 1024) PF3_CUDA(cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    k_assemble<false><<<grid, wpc * 32, smem, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
+                                                    pl->d_inc_meta, pl->d_slot, pl->nown, acc_stride, coo_v, csr_v);
+  }
+  ++*launches;
+  return int(cudaGetLastError());
+}
+
+int plan_create_generic(int device, cudaStream_t st, int64_t n, int64_t nnz_coo, const int64_t* r, const int64_t* c,
+                        int64_t* launches, pf3_plan** out) {
+  if (n <= 0 || nnz_coo < 0 || (nnz_coo > 0 && (!r || !c))) return PF3_E_BAD_ARG;
+  if (nnz_coo >= (int64_t(1) << 31)) return PF3_E_CAPACITY;
+  pf3_plan* pl = new pf3_plan();
+  pl->device = device;
+  pl->generic = 1;
+  pl->n = n;
+  pl->nrows = n;
+  pl->nnz_coo = nnz_coo;
+  int rc = 0;
+  int64_t *keys = nullptr, *keys2 = nullptr, *vals = nullptr, *ukeys = nullptr;
+  int32_t *flags = nullptr, *incl = nullptr;
+  auto cleanup = [&]() { cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(ukeys); cudaFree(flags); cudaFree(incl); };
+#define PF3_TRY(x) do { rc = (x); if (rc) { cleanup(); pf3_plan_destroy(pl); return rc; } } while (0)
+  PF3_TRY(dalloc(&keys, nnz_coo));
+  PF3_TRY(dalloc(&keys2, nnz_coo));
+  PF3_TRY(dalloc(&vals, nnz_coo));
+  PF3_TRY(dalloc(&pl->d_perm, nnz_coo));
+  PF3_TRY(dalloc(&flags, nnz_coo));
+  PF3_TRY(dalloc(&incl, nnz_coo));
+  k_coo_keys<<<grid_for(nnz_coo), 256, 0, st>>>(r, c, n, nnz_coo, keys, vals);
+  PF3_TRY(sort_pairs(keys, keys2, vals, pl->d_perm, nnz_coo, bits_for(n * n), st));
+  k_head_flags<<<grid_for(nnz_coo), 256, 0, st>>>(keys2, nnz_coo, int64_t(-1), flags);
+  PF3_TRY(inclusive_sum(flags, incl, nnz_coo, st));
+  int32_t nu = 0;
+  if (nnz_coo > 0) PF3_TRY(int(cudaMemcpyAsync(&nu, incl + nnz_coo - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st)));
+  cudaStreamSynchronize(st);
+  pl->nnz = nu;
+  PF3_TRY(dalloc(&ukeys, pl->nnz));
+  PF3_TRY(dalloc(&pl->d_seg, pl->nnz + 1));
+  PF3_TRY(dalloc(&pl->d_indptr, n + 1));
+  PF3_TRY(dalloc(&pl->d_indices, pl->nnz));
+  k_scatter_unique<<<grid_for(nnz_coo), 256, 0, st>>>(keys2, flags, incl, nnz_coo, ukeys);
+  k_seg_starts<<<grid_for(nnz_coo + 1), 256, 0, st>>>(flags, incl, nnz_coo, pl->d_seg);
+  k_row_ptr<<<grid_for(n + 1), 256, 0, st>>>(ukeys, pl->nnz, 0, n, n, pl->d_indptr);
+  k_indices_from_keys<<<grid_for(pl->nnz), 256, 0, st>>>(ukeys, pl->nnz, n, pl->d_indices);
+  *launches += 6;
+  PF3_TRY(int(cudaStreamSynchronize(st)));
+  PF3_TRY(int(cudaGetLastError()));
+  cleanup();
+#undef PF3_TRY
+  *out = pl;
+  return PF3_OK;
+}
+
+int spmv_csr(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
+             const double* x, double* y, int64_t* launches) {
+  if (nrows <= 0) return PF3_OK;
+  const int64_t blocks = (nrows * 32 + 255) / 256;
+  k_spmv<<<unsigned(std::min<int64_t>(blocks, 148 * 64)), 256, 0, st>>>(nrows, indptr, indices, vals, x, y);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+
+// deterministic fint gather: fint[6*node + d] += sum over incident (element, local node) of fe
+__global__ void k_fint_gather(const uint32_t* __restrict__ sorted_inc, const int64_t* __restrict__ inc_ptr,
+                              int64_t nnodes, const double* __restrict__ fe, double* __restrict__ fint) {
+  const int64_t n = nnodes * 6;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t node = t / 6;
+    const int d = int(t - node * 6);
+    double s = 0.;
+    for (int64_t q = inc_ptr[node]; q < inc_ptr[node + 1]; ++q) s += fe[int64_t(sorted_inc[q]) * 6 + d];
+    fint[t] += s;
+  }
+}
+__global__ void k_simple_inc_keys(const int64_t* conn, int64_t n, int64_t* keys, uint32_t* vals) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n; t += int64_t(gridDim.x) * blockDim.x) {
+    keys[t] = conn[t];
+    vals[t] = uint32_t(t);
+  }
+}
+
+int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64_t* conn, const double* fe,
+                double* fint, int64_t* launches) {
+  const int64_t NI = ne * nn;
+  if (NI >= (int64_t(1) << 32)) return PF3_E_CAPACITY;
+  int64_t *keys = nullptr, *keys2 = nullptr, *ptr = nullptr;
+  uint32_t *vals = nullptr, *vals2 = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() { cudaFree(keys); cudaFree(keys2); cudaFree(ptr); cudaFree(vals); cudaFree(vals2); };
+#define PF3_TRY(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+  PF3_TRY(dalloc(&keys, NI));
+  PF3_TRY(dalloc(&keys2, NI));
+  PF3_TRY(dalloc(&vals, NI));
+  PF3_TRY(dalloc(&vals2, NI));
+  PF3_TRY(dalloc(&ptr, nnodes + 1));
+  k_simple_inc_keys<<<grid_for(NI), 256, 0, st>>>(conn, NI, keys, vals);
+  PF3_TRY(sort_pairs(keys, keys2, vals, vals2, NI, bits_for(nnodes), st));
+  k_row_ptr<<<grid_for(nnodes + 1), 256, 0, st>>>(keys2, NI, 0, nnodes, 1, ptr);
+  // fe is [ne][nn][6]: incidence id t = e*nn + a addresses fe[t*6 .. t*6+5]
+  k_fint_gather<<<grid_for(nnodes * 6), 256, 0, st>>>(vals2, ptr, nnodes, fe, fint);
+  *launches += 3;
+  PF3_TRY(int(cudaStreamSynchronize(st)));
+  PF3_TRY(int(cudaGetLastError()));
+  cleanup();
+#undef PF3_TRY
+  return PF3_OK;
+}
+
+int64_t plan_nnz(const pf3_plan* pl) { return pl->nnz; }
+int64_t plan_nrows(const pf3_plan* pl) { return pl->nrows; }
+
+}  // namespace pf3
+
+extern "C" int pf3_plan_destroy(pf3_plan* pl) {
+  if (!pl) return PF3_OK;
+  cudaFree(pl->d_brow_ptr); cudaFree(pl->d_bcol); cudaFree(pl->d_inc_ptr); cudaFree(pl->d_inc_src);
+  cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot);
+  for (auto* t : pl->d_tabs) cudaFree(t);
+  cudaFree(pl->d_indptr); cudaFree(pl->d_indices); cudaFree(pl->d_perm); cudaFree(pl->d_seg);
+  delete pl;
+  return PF3_OK;
+}

@@ -1,0 +1,129 @@
+// Shared device helpers for the element-evaluation kernels (sm_100a, FP64).
+//
+// Execution shape: ONE ELEMENT PER THREAD for the arithmetic, so the
+// frame / Jacobian / shape-gradient set-up is never replicated across lanes, and a
+// per-warp shared-memory stage so that every global store instruction writes one
+// contiguous >=256 B run of the caller's COO value array (an element's block is
+// contiguous: 576 / 144 / 480 doubles).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/pyfe3d_b200.h"
+
+namespace pf3 {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreads = 32 * kWarpsPerCta;
+constexpr int kChunk = 72;     // doubles one thread stages between flushes (3 rows x 24)
+constexpr int kStageLd = 73;   // odd leading dimension: conflict-free row writes
+constexpr size_t kStageBytes = size_t(kWarpsPerCta) * 32 * kStageLd * sizeof(double);
+
+struct EvalArgs {
+  int64_t ne;
+  const int64_t* __restrict__ conn;
+  const double* __restrict__ x;
+  const double* __restrict__ u;
+  const double* __restrict__ props;
+  const int32_t* __restrict__ prop_id;
+  const double* __restrict__ evec;
+  int evec_stride;
+  const double* __restrict__ eparam;
+  const double* __restrict__ state;
+  int what;
+  int mtype;
+  double Nxx, Nyy, Nxy;
+  double* kc0v;
+  double* kgv;
+  double* mv;
+  double* fe;        // [ne][6*nn] element force in global axes (PF3_FINT scratch)
+  double* finte;     // [ne][6*nn] local internal force (probe.finte), optional
+  double* state_out; // [ne][PF3_STATE_STRIDE], optional
+  int64_t kc0_k0, kg_k0, m_k0;
+  int acc_kc0, acc_kg, acc_m;
+};
+
+struct Mat3 {
+  double a[3][3];
+};
+
+__device__ __forceinline__ double dot3(const double* a, const double* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double normalize3(double* v) {
+  double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  v[0] /= n;
+  v[1] /= n;
+  v[2] /= n;
+  return n;
+}
+
+// out = R * L * R^T for a local 3x3 block L = [[l00,l01,0],[l10,l11,0],[0,0,l22]]
+// (translation-translation and rotation-rotation shell blocks).
+__device__ __forceinline__ void rot_block_diag5(const Mat3& R, double l00, double l01, double l10,
+                                                double l11, double l22, double (*o)[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double t0 = R.a[i][0] * l00 + R.a[i][1] * l10;
+    double t1 = R.a[i][0] * l01 + R.a[i][1] * l11;
+    double t2 = R.a[i][2] * l22;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o[i][j] = t0 * R.a[j][0] + t1 * R.a[j][1] + t2 * R.a[j][2];
+  }
+}
+// out = R * L * R^T for L with only l22 == 0 (translation-rotation couplings).
+__device__ __forceinline__ void rot_block_8(const Mat3& R, double l00, double l01, double l02,
+                                            double l10, double l11, double l12, double l20,
+                                            double l21, double (*o)[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double t0 = R.a[i][0] * l00 + R.a[i][1] * l10 + R.a[i][2] * l20;
+    double t1 = R.a[i][0] * l01 + R.a[i][1] * l11 + R.a[i][2] * l21;
+    double t2 = R.a[i][0] * l02 + R.a[i][1] * l12;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o[i][j] = t0 * R.a[j][0] + t1 * R.a[j][1] + t2 * R.a[j][2];
+  }
+}
+// generic dense 3x3 (line elements)
+__device__ __forceinline__ void rot_block_full(const Mat3& R, const double (*l)[3], double (*o)[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double t[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) t[q] = R.a[i][0] * l[0][q] + R.a[i][1] * l[1][q] + R.a[i][2] * l[2][q];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o[i][j] = t[0] * R.a[j][0] + t[1] * R.a[j][1] + t[2] * R.a[j][2];
+  }
+}
+
+// Every lane has written `len` doubles of ITS element at stage[lane*kStageLd + k].
+// Write them to out[(e0+lane)*estride + off + k] with warp-contiguous stores.
+template <int LEN>
+__device__ __forceinline__ void flush_chunk(const double* stage, double* __restrict__ out, int64_t e0,
+                                            int nvalid, int64_t estride, int off, bool accumulate,
+                                            int lane) {
+  __syncwarp();
+  const int total = nvalid * LEN;
+  double* base = out + e0 * estride + off;
+  if (accumulate) {
+    for (int idx = lane; idx < total; idx += 32) {
+      int el = idx / LEN, k = idx - el * LEN;
+      double* p = base + int64_t(el) * estride + k;
+      *p += stage[el * kStageLd + k];
+    }
+  } else {
+#pragma unroll 4
+    for (int idx = lane; idx < total; idx += 32) {
+      int el = idx / LEN, k = idx - el * LEN;
+      base[int64_t(el) * estride + k] = stage[el * kStageLd + k];
+    }
+  }
+  __syncwarp();
+}
+
+}  // namespace pf3

@@ -1,0 +1,461 @@
+// BeamC, BeamLR, Truss, Spring: KC0 / KG / M / fint, one element per thread.
+//
+// Replaces (reference, /root/reference/pyfe3d):
+//   beamc.pyx : update_rotation_matrix :158, update_probe_ue :234, update_probe_xe :287,
+//               update_probe_finte :352, update_KC0 :489, update_fint :1354, update_KG :1392, update_M :2181
+//   beamlr.pyx: :160, :236, :289, :354, update_KC0 :407, update_fint :1188, update_KG :1226, update_M :1464
+//   truss.pyx : update_rotation_matrix :203, update_KC0 :386, update_fint :802, update_M :838
+//   spring.pyx: update_rotation_matrix :147, update_KC0 :295, update_fint :708
+//
+// These elements are tiny (72..144 values each) and purely store-bound; the local 12x12
+// matrix lives in per-thread local memory and is rotated block by block.
+#include "common.cuh"
+
+namespace pf3 {
+
+namespace {
+
+struct BeamP {
+  double A, E, G, Iyy, Izz, Iyz, J, Ay, Az, r0, ry, rz, ry2, rz2, ryz;
+};
+
+__device__ __forceinline__ void sym(double (*K)[12], int i, int j, double v) {
+  K[i][j] = v;
+  K[j][i] = v;
+}
+__device__ __forceinline__ void zero12(double (*K)[12]) {
+  for (int i = 0; i < 12; ++i)
+    for (int j = 0; j < 12; ++j) K[i][j] = 0.;
+}
+
+// Timoshenko beam with consistent shape functions (Luo 2008); beamc.pyx:543-624
+__device__ void beamc_Ke(const BeamP& p, double L, double (*K)[12]) {
+  zero12(K);
+  const double L2 = L * L, L3 = L2 * L;
+  const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
+  const double by = 1 / (1. - ay), bz = 1 / (1. - az);
+  const double Ky = by * by * (p.A * p.G * L2 * ay * ay + 12 * p.E * p.Izz);
+  const double Kz = bz * bz * (p.A * p.G * L2 * az * az + 12 * p.E * p.Iyy);
+  const double Kyz = p.E * p.Iyz * by * bz;
+  const double Sy = p.Az * p.G * ay * by, Sz = p.Ay * p.G * az * bz;
+  const double cz = p.Az * p.E * bz * (1 - az) / L, cy = p.Ay * p.E * by * (ay - 1) / L;
+  const double EA = p.A * p.E / L, GJ = p.G * p.J / L;
+  sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
+  sym(K, 0, 4, cz); sym(K, 6, 10, cz); sym(K, 0, 10, -cz); sym(K, 4, 6, -cz);
+  sym(K, 0, 5, cy); sym(K, 6, 11, cy); sym(K, 0, 11, -cy); sym(K, 5, 6, -cy);
+  sym(K, 1, 1, Ky / L3); sym(K, 7, 7, Ky / L3); sym(K, 1, 7, -Ky / L3);
+  sym(K, 1, 5, Ky / (2 * L2)); sym(K, 1, 11, Ky / (2 * L2)); sym(K, 5, 7, -Ky / (2 * L2)); sym(K, 7, 11, -Ky / (2 * L2));
+  sym(K, 2, 2, Kz / L3); sym(K, 8, 8, Kz / L3); sym(K, 2, 8, -Kz / L3);
+  sym(K, 2, 4, -Kz / (2 * L2)); sym(K, 2, 10, -Kz / (2 * L2)); sym(K, 4, 8, Kz / (2 * L2)); sym(K, 8, 10, Kz / (2 * L2));
+  sym(K, 1, 2, 12 * Kyz / L3); sym(K, 7, 8, 12 * Kyz / L3); sym(K, 1, 8, -12 * Kyz / L3); sym(K, 2, 7, -12 * Kyz / L3);
+  sym(K, 1, 4, -6 * Kyz / L2); sym(K, 1, 10, -6 * Kyz / L2); sym(K, 5, 8, -6 * Kyz / L2); sym(K, 8, 11, -6 * Kyz / L2);
+  sym(K, 2, 5, 6 * Kyz / L2); sym(K, 2, 11, 6 * Kyz / L2); sym(K, 4, 7, 6 * Kyz / L2); sym(K, 7, 10, 6 * Kyz / L2);
+  sym(K, 3, 3, GJ); sym(K, 9, 9, GJ); sym(K, 3, 9, -GJ);
+  sym(K, 1, 3, Sy / L); sym(K, 7, 9, Sy / L); sym(K, 1, 9, -Sy / L); sym(K, 3, 7, -Sy / L);
+  sym(K, 3, 5, Sy / 2); sym(K, 3, 11, Sy / 2); sym(K, 5, 9, -Sy / 2); sym(K, 9, 11, -Sy / 2);
+  sym(K, 2, 3, -Sz / L); sym(K, 8, 9, -Sz / L); sym(K, 2, 9, Sz / L); sym(K, 3, 8, Sz / L);
+  sym(K, 3, 4, Sz / 2); sym(K, 3, 10, Sz / 2); sym(K, 4, 9, -Sz / 2); sym(K, 9, 10, -Sz / 2);
+  const double EIy = p.E * p.Iyy, EIz = p.E * p.Izz, AGL2 = p.A * p.G * L2;
+  const double k44 = bz * bz * (AGL2 * az * az / 4 + EIy * az * az - 2 * EIy * az + 4 * EIy) / L;
+  const double k55 = by * by * (AGL2 * ay * ay / 4 + EIz * ay * ay - 2 * EIz * ay + 4 * EIz) / L;
+  sym(K, 4, 4, k44); sym(K, 10, 10, k44);
+  sym(K, 4, 10, bz * bz * (AGL2 * az * az / 4 - EIy * az * az + 2 * EIy * az + 2 * EIy) / L);
+  sym(K, 5, 5, k55); sym(K, 11, 11, k55);
+  sym(K, 5, 11, by * by * (AGL2 * ay * ay / 4 - EIz * ay * ay + 2 * EIz * ay + 2 * EIz) / L);
+  const double k45 = Kyz * (-ay * az + ay + az - 4) / L, k411 = Kyz * (ay * az - ay - az - 2) / L;
+  sym(K, 4, 5, k45); sym(K, 10, 11, k45); sym(K, 4, 11, k411); sym(K, 5, 10, k411);
+}
+
+// beamc.pyx:1889-2179
+__device__ void beamc_KGe(const BeamP& p, double L, const double* ue, double (*K)[12]) {
+  zero12(K);
+  const double L2 = L * L;
+  const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
+  const double by = 1 / (1. - ay), bz = 1 / (1. - az);
+  const double N = p.A * p.E * (-ue[0] + ue[6]) / L;
+  double v = N * by * by * (5 * ay * ay - 10 * ay + 6) / (5 * L);
+  sym(K, 1, 1, v); sym(K, 7, 7, v); sym(K, 1, 7, -v);
+  v = N * bz * bz * (5 * az * az - 10 * az + 6) / (5 * L);
+  sym(K, 2, 2, v); sym(K, 8, 8, v); sym(K, 2, 8, -v);
+  v = N * by * bz * (5 * ay * az - 5 * ay - 5 * az + 6) / (5 * L);
+  sym(K, 1, 2, v); sym(K, 7, 8, v); sym(K, 1, 8, -v); sym(K, 2, 7, -v);
+  v = N * by * by / 10;
+  sym(K, 1, 5, v); sym(K, 1, 11, v); sym(K, 5, 7, -v); sym(K, 7, 11, -v);
+  v = -N * bz * bz / 10;
+  sym(K, 2, 4, v); sym(K, 2, 10, v); sym(K, 4, 8, -v); sym(K, 8, 10, -v);
+  v = -N * by * bz / 10;
+  sym(K, 1, 4, v); sym(K, 1, 10, v); sym(K, 4, 7, -v); sym(K, 7, 10, -v);
+  v = N * by * bz / 10;
+  sym(K, 2, 5, v); sym(K, 2, 11, v); sym(K, 5, 8, -v); sym(K, 8, 11, -v);
+  v = L * N * bz * bz * (5 * az * az - 10 * az + 8) / 60;
+  sym(K, 4, 4, v); sym(K, 10, 10, v);
+  v = L * N * by * by * (5 * ay * ay - 10 * ay + 8) / 60;
+  sym(K, 5, 5, v); sym(K, 11, 11, v);
+  sym(K, 4, 10, L * N * bz * bz * (-5 * az * az + 10 * az - 2) / 60);
+  sym(K, 5, 11, L * N * by * by * (-5 * ay * ay + 10 * ay - 2) / 60);
+  v = L * N * by * bz * (-5 * ay * az + 5 * ay + 5 * az - 8) / 60;
+  sym(K, 4, 5, v); sym(K, 10, 11, v);
+  v = L * N * by * bz * (5 * ay * az - 5 * ay - 5 * az + 2) / 60;
+  sym(K, 4, 11, v); sym(K, 5, 10, v);
+}
+
+// beamc.pyx:2246-3152; mtype 0 consistent, 1 lumped
+__device__ void beamc_Me(const BeamP& p, double L, int mtype, double (*K)[12]) {
+  zero12(K);
+  const double L2 = L * L;
+  const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
+  const double by = 1 / (1. - ay), bz = 1 / (1. - az);
+  const double r0 = p.r0, ry = p.ry, rz = p.rz, ry2 = p.ry2, rz2 = p.rz2, ryz = p.ryz;
+  if (mtype == 1) {
+    const double d[6] = {L * r0 / 2, L * by * by * r0 * (ay - 1) * (ay - 1) / 2, L * bz * bz * r0 * (az - 1) * (az - 1) / 2,
+                         L * (ry2 + rz2) / 2, L * bz * bz * rz2 * (az - 1) * (az - 1) / 2,
+                         L * by * by * ry2 * (ay - 1) * (ay - 1) / 2};
+    for (int i = 0; i < 6; ++i) {
+      K[i][i] = d[i];
+      K[i + 6][i + 6] = d[i];
+    }
+    return;
+  }
+  const double by2 = by * by, bz2 = bz * bz, ay2 = ay * ay, az2 = az * az, bb = by * bz;
+  double v;
+  sym(K, 0, 0, L * r0 / 3); sym(K, 6, 6, L * r0 / 3); sym(K, 0, 6, L * r0 / 6);
+  v = by * ry / 2; sym(K, 0, 1, v); sym(K, 1, 6, v); sym(K, 0, 7, -v); sym(K, 6, 7, -v);
+  v = bz * rz / 2; sym(K, 0, 2, v); sym(K, 2, 6, v); sym(K, 0, 8, -v); sym(K, 6, 8, -v);
+  v = L * bz * rz * (1 - 4 * az) / 12; sym(K, 0, 4, v); sym(K, 6, 10, v);
+  v = L * by * ry * (4 * ay - 1) / 12; sym(K, 0, 5, v); sym(K, 6, 11, v);
+  v = -L * bz * rz * (2 * az + 1) / 12; sym(K, 0, 10, v); sym(K, 4, 6, v);
+  v = L * by * ry * (2 * ay + 1) / 12; sym(K, 0, 11, v); sym(K, 5, 6, v);
+  v = by2 * (70 * L2 * ay2 * r0 - 147 * L2 * ay * r0 + 78 * L2 * r0 + 252 * ry2) / (210 * L); sym(K, 1, 1, v); sym(K, 7, 7, v);
+  sym(K, 1, 7, by2 * (35 * L2 * ay2 * r0 - 63 * L2 * ay * r0 + 27 * L2 * r0 - 252 * ry2) / (210 * L));
+  v = bz2 * (70 * L2 * az2 * r0 - 147 * L2 * az * r0 + 78 * L2 * r0 + 252 * rz2) / (210 * L); sym(K, 2, 2, v); sym(K, 8, 8, v);
+  sym(K, 2, 8, bz2 * (35 * L2 * az2 * r0 - 63 * L2 * az * r0 + 27 * L2 * r0 - 252 * rz2) / (210 * L));
+  v = 6 * bb * ryz / (5 * L); sym(K, 1, 2, v); sym(K, 7, 8, v); sym(K, 1, 8, -v); sym(K, 2, 7, -v);
+  v = L * by * rz * (20 * ay - 21) / 60; sym(K, 1, 3, v); sym(K, 7, 9, v);
+  v = L * by * rz * (10 * ay - 9) / 60; sym(K, 1, 9, v); sym(K, 3, 7, v);
+  v = L * bz * ry * (21 - 20 * az) / 60; sym(K, 2, 3, v); sym(K, 8, 9, v);
+  v = L * bz * ry * (9 - 10 * az) / 60; sym(K, 2, 9, v); sym(K, 3, 8, v);
+  v = -bb * ryz * (5 * az + 1) / 10; sym(K, 1, 4, v); sym(K, 1, 10, v); sym(K, 4, 7, -v); sym(K, 7, 10, -v);
+  v = bb * ryz * (5 * ay + 1) / 10; sym(K, 2, 5, v); sym(K, 2, 11, v); sym(K, 5, 8, -v); sym(K, 8, 11, -v);
+  v = by2 * (35 * L2 * ay2 * r0 - 77 * L2 * ay * r0 + 44 * L2 * r0 + 420 * ay * ry2 + 84 * ry2) / 840; sym(K, 1, 5, v); sym(K, 7, 11, -v);
+  v = by2 * (-35 * L2 * ay2 * r0 + 63 * L2 * ay * r0 - 26 * L2 * r0 + 420 * ay * ry2 + 84 * ry2) / 840; sym(K, 1, 11, v); sym(K, 5, 7, -v);
+  v = bz2 * (-35 * L2 * az2 * r0 + 77 * L2 * az * r0 - 44 * L2 * r0 - 420 * az * rz2 - 84 * rz2) / 840; sym(K, 2, 4, v); sym(K, 8, 10, -v);
+  v = bz2 * (35 * L2 * az2 * r0 - 63 * L2 * az * r0 + 26 * L2 * r0 - 420 * az * rz2 - 84 * rz2) / 840; sym(K, 2, 10, v); sym(K, 4, 8, -v);
+  v = L * (ry2 + rz2) / 3; sym(K, 3, 3, v); sym(K, 9, 9, v); sym(K, 3, 9, L * (ry2 + rz2) / 6);
+  v = L2 * bz * ry * (5 * az - 6) / 120; sym(K, 3, 4, v); sym(K, 9, 10, -v);
+  v = L2 * by * rz * (5 * ay - 6) / 120; sym(K, 3, 5, v); sym(K, 9, 11, -v);
+  v = L2 * bz * ry * (4 - 5 * az) / 120; sym(K, 3, 10, v); sym(K, 4, 9, -v);
+  v = L2 * by * rz * (4 - 5 * ay) / 120; sym(K, 3, 11, v); sym(K, 5, 9, -v);
+  v = L * bz2 * (7 * L2 * az2 * r0 - 14 * L2 * az * r0 + 8 * L2 * r0 + 280 * az2 * rz2 - 140 * az * rz2 + 112 * rz2) / 840; sym(K, 4, 4, v); sym(K, 10, 10, v);
+  v = L * by2 * (7 * L2 * ay2 * r0 - 14 * L2 * ay * r0 + 8 * L2 * r0 + 280 * ay2 * ry2 - 140 * ay * ry2 + 112 * ry2) / 840; sym(K, 5, 5, v); sym(K, 11, 11, v);
+  sym(K, 4, 10, L * bz2 * (-7 * L2 * az2 * r0 + 14 * L2 * az * r0 - 6 * L2 * r0 + 140 * az2 * rz2 + 140 * az * rz2 - 28 * rz2) / 840);
+  sym(K, 5, 11, L * by2 * (-7 * L2 * ay2 * r0 + 14 * L2 * ay * r0 - 6 * L2 * r0 + 140 * ay2 * ry2 + 140 * ay * ry2 - 28 * ry2) / 840);
+  v = L * bb * ryz * (-20 * ay * az + 5 * ay + 5 * az - 8) / 60; sym(K, 4, 5, v); sym(K, 10, 11, v);
+  v = L * bb * ryz * (-10 * ay * az - 5 * ay - 5 * az + 2) / 60; sym(K, 4, 11, v); sym(K, 5, 10, v);
+}
+
+// linear Timoshenko beam, one-point reduced integration; beamlr.pyx:460-1186
+__device__ void beamlr_Ke(const BeamP& p, double L, double (*K)[12]) {
+  zero12(K);
+  const double EA = p.E * p.A / L, EAz = p.E * p.Az / L, EAy = p.E * p.Ay / L;
+  const double GA = p.G * p.A, GAy = p.G * p.Ay, GAz = p.G * p.Az, GJ = p.G * p.J / L;
+  sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
+  sym(K, 0, 4, EAz); sym(K, 6, 10, EAz); sym(K, 0, 10, -EAz); sym(K, 4, 6, -EAz);
+  sym(K, 0, 5, -EAy); sym(K, 6, 11, -EAy); sym(K, 0, 11, EAy); sym(K, 5, 6, EAy);
+  sym(K, 1, 1, GA / L); sym(K, 7, 7, GA / L); sym(K, 2, 2, GA / L); sym(K, 8, 8, GA / L);
+  sym(K, 1, 7, -GA / L); sym(K, 2, 8, -GA / L);
+  sym(K, 1, 3, -GAz / L); sym(K, 7, 9, -GAz / L); sym(K, 1, 9, GAz / L); sym(K, 3, 7, GAz / L);
+  sym(K, 1, 5, GA / 2); sym(K, 1, 11, GA / 2); sym(K, 5, 7, -GA / 2); sym(K, 7, 11, -GA / 2);
+  sym(K, 2, 3, GAy / L); sym(K, 8, 9, GAy / L); sym(K, 2, 9, -GAy / L); sym(K, 3, 8, -GAy / L);
+  sym(K, 2, 4, -GA / 2); sym(K, 2, 10, -GA / 2); sym(K, 4, 8, GA / 2); sym(K, 8, 10, GA / 2);
+  sym(K, 3, 3, GJ); sym(K, 9, 9, GJ); sym(K, 3, 9, -GJ);
+  sym(K, 3, 4, -GAy / 2); sym(K, 3, 10, -GAy / 2); sym(K, 4, 9, GAy / 2); sym(K, 9, 10, GAy / 2);
+  sym(K, 3, 5, -GAz / 2); sym(K, 3, 11, -GAz / 2); sym(K, 5, 9, GAz / 2); sym(K, 9, 11, GAz / 2);
+  sym(K, 4, 4, GA * L / 4 + p.E * p.Iyy / L); sym(K, 10, 10, GA * L / 4 + p.E * p.Iyy / L);
+  sym(K, 4, 10, GA * L / 4 - p.E * p.Iyy / L);
+  sym(K, 5, 5, GA * L / 4 + p.E * p.Izz / L); sym(K, 11, 11, GA * L / 4 + p.E * p.Izz / L);
+  sym(K, 5, 11, GA * L / 4 - p.E * p.Izz / L);
+  sym(K, 4, 5, -p.E * p.Iyz / L); sym(K, 10, 11, -p.E * p.Iyz / L);
+  sym(K, 4, 11, p.E * p.Iyz / L); sym(K, 5, 10, p.E * p.Iyz / L);
+}
+
+// beamlr.pyx:1388-1462 (literal 0.333.. / 0.1666.. constants of the reference kept)
+__device__ void beamlr_KGe(const BeamP& p, double L, const double* ue, double (*K)[12]) {
+  zero12(K);
+  const double N = p.A * p.E * (-ue[0] + ue[6]) / L;
+  const double t = 0.333333333333333 * L * N, s = 0.166666666666667 * L * N;
+  sym(K, 4, 4, t); sym(K, 5, 5, t); sym(K, 10, 10, t); sym(K, 11, 11, t);
+  sym(K, 4, 5, -t); sym(K, 10, 11, -t);
+  sym(K, 4, 10, s); sym(K, 5, 11, s);
+  sym(K, 4, 11, -s); sym(K, 5, 10, -s);
+}
+
+// beamlr.pyx:1518-2424; truss.pyx:894-1800 (same with the ry/rz inertia removed)
+__device__ void beamlr_Me(const BeamP& p, double L, int mtype, bool truss, double (*K)[12]) {
+  zero12(K);
+  double mb[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) mb[i][j] = 0.;
+  mb[0][0] = mb[1][1] = mb[2][2] = p.r0;
+  mb[0][4] = mb[4][0] = p.rz;
+  mb[0][5] = mb[5][0] = -p.ry;
+  mb[1][3] = mb[3][1] = -p.rz;
+  mb[2][3] = mb[3][2] = p.ry;
+  mb[3][3] = p.ry2 + p.rz2;
+  mb[4][4] = p.rz2;
+  mb[5][5] = p.ry2;
+  mb[4][5] = mb[5][4] = -p.ryz;
+  if (truss)
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j)
+        if (i >= 4 || j >= 4) mb[i][j] = 0.;
+  if (mtype == 0) {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) K[6 * a + i][6 * b + j] = ((a == b) ? L / 3 : L / 6) * mb[i][j];
+  } else {
+    for (int a = 0; a < 2; ++a)
+      for (int i = 0; i < 6; ++i) K[6 * a + i][6 * a + i] = L / 2 * mb[i][i];
+  }
+}
+
+__device__ void truss_Ke(const BeamP& p, double L, double (*K)[12]) {
+  zero12(K);
+  const double EA = p.E * p.A / L, GJ = p.G * p.J / L;
+  sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
+  sym(K, 3, 3, GJ); sym(K, 9, 9, GJ); sym(K, 3, 9, -GJ);
+}
+
+__device__ void spring_Ke(const double* k, double (*K)[12]) {
+  zero12(K);
+  for (int i = 0; i < 6; ++i) {
+    K[i][i] = k[i];
+    K[i + 6][i + 6] = k[i];
+    K[i][i + 6] = -k[i];
+    K[i + 6][i] = -k[i];
+  }
+}
+
+// mask ids
+constexpr int MK_FULL = 0, MK_D18 = 1, MK_RR = 2;
+__device__ __forceinline__ bool in_mask(int mk, int i, int j) {
+  if (mk == MK_FULL) return true;
+  if (mk == MK_D18) return (i < 3) == (j < 3);
+  return i >= 3 && j >= 3;
+}
+
+// Rotate the local 12x12 matrix block by block and emit one node-row slab per flush, in the
+// reference's (node_i, dof_i, node_j, dof_j) order restricted to the mask.
+template <int MK, bool DIAG, int SLAB>
+__device__ void emit_line_matrix(const Mat3& R, const double (*K)[12], double* stage, double* my, double* out,
+                                 int64_t e0, int nvalid, int esize, bool acc, int lane) {
+  for (int a = 0; a < 2; ++a) {
+    double Gb[2][6][6];
+    for (int b = 0; b < 2; ++b) {
+      if (DIAG && a != b) continue;
+      for (int s = 0; s < 2; ++s)
+        for (int t = 0; t < 2; ++t) {
+          if (MK == MK_D18 && s != t) continue;
+          if (MK == MK_RR && !(s == 1 && t == 1)) continue;
+          double l[3][3], o[3][3];
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) l[i][j] = K[6 * a + 3 * s + i][6 * b + 3 * t + j];
+          rot_block_full(R, l, o);
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Gb[b][3 * s + i][3 * t + j] = o[i][j];
+        }
+    }
+    int cnt = 0;
+    for (int i = 0; i < 6; ++i)
+      for (int b = 0; b < 2; ++b) {
+        if (DIAG && a != b) continue;
+        for (int j = 0; j < 6; ++j)
+          if (in_mask(MK, i, j)) my[cnt++] = Gb[b][i][j];
+      }
+    flush_chunk<SLAB>(stage, out, e0, nvalid, esize, a * SLAB, acc, lane);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e0 = (int64_t(blockIdx.x) * kWarpsPerCta + warp) * 32;
+  if (e0 >= A.ne) return;
+  const int nvalid = int(min(int64_t(32), A.ne - e0));
+  const int64_t e = e0 + min(lane, nvalid - 1);
+  double* stage = smem + warp * 32 * kStageLd;
+  double* my = stage + lane * kStageLd;
+
+  Mat3 R;
+  double xe[6] = {0, 0, 0, 0, 0, 0}, L = 0., ue[12];
+  const bool have_u = (A.u != nullptr || A.state != nullptr);
+  if (A.state != nullptr) {
+    const double* s = A.state + e * PF3_STATE_STRIDE;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R.a[i][j] = s[3 * i + j];
+    L = s[13];
+    for (int i = 0; i < 6; ++i) xe[i] = s[14 + i];
+    for (int i = 0; i < 12; ++i) ue[i] = s[26 + i];
+  } else {
+    const int64_t n0 = A.conn[2 * e], n1 = A.conn[2 * e + 1];
+    double xh[3], yh[3], zh[3], v[3], P0[3] = {0, 0, 0}, P1[3] = {0, 0, 0};
+    const double* ev = A.evec ? A.evec + e * int64_t(A.evec_stride) : nullptr;
+    if (KIND == PF3_SPRING) {
+      // axis given directly (spring.pyx:147-206)
+      for (int i = 0; i < 3; ++i) {
+        xh[i] = ev[i];
+        v[i] = ev[3 + i];
+      }
+      normalize3(xh);
+    } else {
+      for (int i = 0; i < 3; ++i) {
+        P0[i] = A.x[3 * n0 + i];
+        P1[i] = A.x[3 * n1 + i];
+        xh[i] = P1[i] - P0[i];
+      }
+      normalize3(xh);
+      if (KIND == PF3_TRUSS) {  // arbitrary off-axis vector: cyclic shift (truss.pyx:243-245)
+        v[0] = xh[1];
+        v[1] = xh[2];
+        v[2] = xh[0];
+      } else {
+        for (int i = 0; i < 3; ++i) v[i] = ev[i];
+      }
+    }
+    cross3(xh, v, zh);   // z = x X vxy   (beamc.pyx:207-214)
+    normalize3(zh);
+    cross3(zh, xh, yh);  // y = z X x
+    normalize3(yh);
+    for (int i = 0; i < 3; ++i) {
+      R.a[i][0] = xh[i];
+      R.a[i][1] = yh[i];
+      R.a[i][2] = zh[i];
+    }
+    if (KIND != PF3_SPRING) {
+      for (int a = 0; a < 2; ++a) {
+        const double* P = a ? P1 : P0;
+        xe[3 * a + 0] = xh[0] * P[0] + xh[1] * P[1] + xh[2] * P[2];
+        xe[3 * a + 1] = yh[0] * P[0] + yh[1] * P[1] + yh[2] * P[2];
+        xe[3 * a + 2] = zh[0] * P[0] + zh[1] * P[1] + zh[2] * P[2];
+      }
+      const double dx = xe[3] - xe[0], dy = xe[4] - xe[1], dz = xe[5] - xe[2];
+      L = sqrt(dx * dx + dy * dy + dz * dz);  // update_length, beamc.pyx:336-349
+    }
+    if (have_u) {
+      for (int a = 0; a < 2; ++a)
+        for (int t = 0; t < 2; ++t) {
+          const double* ug = A.u + 6 * (a ? n1 : n0) + 3 * t;
+          ue[6 * a + 3 * t + 0] = xh[0] * ug[0] + xh[1] * ug[1] + xh[2] * ug[2];
+          ue[6 * a + 3 * t + 1] = yh[0] * ug[0] + yh[1] * ug[1] + yh[2] * ug[2];
+          ue[6 * a + 3 * t + 2] = zh[0] * ug[0] + zh[1] * ug[1] + zh[2] * ug[2];
+        }
+    }
+  }
+  if (A.state_out != nullptr) {
+    if (lane < nvalid) {
+      double* s = A.state_out + e * PF3_STATE_STRIDE;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) s[3 * i + j] = R.a[i][j];
+      s[9] = 1.;
+      s[10] = 0.;
+      s[11] = 0.;
+      s[12] = 1.;
+      s[13] = L;
+      for (int i = 0; i < 12; ++i) s[14 + i] = (i < 6) ? xe[i] : 0.;
+      for (int i = 0; i < 24; ++i) s[26 + i] = (i < 12 && have_u) ? ue[i] : 0.;
+    }
+    if (A.what == 0) return;
+  }
+
+  BeamP p;
+  double kspr[6];
+  if (KIND == PF3_SPRING) {
+    for (int i = 0; i < 6; ++i) kspr[i] = A.eparam[e * PF3_EPARAM_STRIDE + i];
+  } else {
+    const int pid = A.prop_id ? A.prop_id[e] : 0;
+    const double* q = A.props + int64_t(pid) * PF3_BEAMPROP_STRIDE;
+    p.A = q[0]; p.E = q[1]; p.G = q[2]; p.Iyy = q[3]; p.Izz = q[4]; p.Iyz = q[5]; p.J = q[6]; p.Ay = q[7];
+    p.Az = q[8]; p.r0 = q[9]; p.ry = q[10]; p.rz = q[11]; p.ry2 = q[12]; p.rz2 = q[13]; p.ryz = q[14];
+  }
+
+  double K[12][12];
+  if (A.what & (PF3_KC0 | PF3_FINT)) {
+    if (KIND == PF3_BEAMC) beamc_Ke(p, L, K);
+    if (KIND == PF3_BEAMLR) beamlr_Ke(p, L, K);
+    if (KIND == PF3_TRUSS) truss_Ke(p, L, K);
+    if (KIND == PF3_SPRING) spring_Ke(kspr, K);
+    if (A.what & PF3_KC0) {
+      double* out = A.kc0v + A.kc0_k0;
+      if (KIND == PF3_BEAMC || KIND == PF3_BEAMLR)
+        emit_line_matrix<MK_FULL, false, 72>(R, K, stage, my, out, e0, nvalid, 144, A.acc_kc0 != 0, lane);
+      else
+        emit_line_matrix<MK_D18, false, 36>(R, K, stage, my, out, e0, nvalid, 72, A.acc_kc0 != 0, lane);
+    }
+    if (A.what & PF3_FINT) {
+      double f[12];
+      for (int i = 0; i < 12; ++i) {
+        double s = 0.;
+        for (int j = 0; j < 12; ++j) s += K[i][j] * ue[j];
+        f[i] = s;
+      }
+      if (A.finte != nullptr) {
+        for (int i = 0; i < 12; ++i) my[i] = f[i];
+        flush_chunk<12>(stage, A.finte, e0, nvalid, 12, 0, false, lane);
+      }
+      if (A.fe != nullptr) {
+        for (int t = 0; t < 4; ++t)
+          for (int i = 0; i < 3; ++i)
+            my[3 * t + i] = R.a[i][0] * f[3 * t] + R.a[i][1] * f[3 * t + 1] + R.a[i][2] * f[3 * t + 2];
+        flush_chunk<12>(stage, A.fe, e0, nvalid, 12, 0, false, lane);
+      }
+    }
+  }
+  if ((A.what & PF3_KG) && (KIND == PF3_BEAMC || KIND == PF3_BEAMLR)) {
+    double* out = A.kgv + A.kg_k0;
+    if (KIND == PF3_BEAMC) {
+      beamc_KGe(p, L, ue, K);
+      emit_line_matrix<MK_FULL, false, 72>(R, K, stage, my, out, e0, nvalid, 144, A.acc_kg != 0, lane);
+    } else {
+      beamlr_KGe(p, L, ue, K);
+      emit_line_matrix<MK_RR, false, 18>(R, K, stage, my, out, e0, nvalid, 36, A.acc_kg != 0, lane);
+    }
+  }
+  if ((A.what & PF3_M) && KIND != PF3_SPRING) {
+    double* out = A.mv + A.m_k0;
+    if (KIND == PF3_BEAMC)
+      beamc_Me(p, L, A.mtype, K);
+    else
+      beamlr_Me(p, L, A.mtype, KIND == PF3_TRUSS, K);
+    if (A.mtype == 0)
+      emit_line_matrix<MK_FULL, false, 72>(R, K, stage, my, out, e0, nvalid, 144, A.acc_m != 0, lane);
+    else  // lumped: two diagonal node blocks only, 36 of 144 entries written (beamc.pyx:2970)
+      emit_line_matrix<MK_D18, true, 18>(R, K, stage, my, out, e0, nvalid, 144, A.acc_m != 0, lane);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st) {
+  if (A.ne <= 0) return cudaSuccess;
+  const int64_t per_cta = 32 * kWarpsPerCta;
+  const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(line_eval_kernel<PF3_BEAMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    cudaFuncSetAttribute(line_eval_kernel<PF3_BEAMLR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    cudaFuncSetAttribute(line_eval_kernel<PF3_TRUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    cudaFuncSetAttribute(line_eval_kernel<PF3_SPRING>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    once = true;
+  }
+  switch (kind) {
+    case PF3_BEAMC: line_eval_kernel<PF3_BEAMC><<<grid, kThreads, kStageBytes, st>>>(A); break;
+    case PF3_BEAMLR: line_eval_kernel<PF3_BEAMLR><<<grid, kThreads, kStageBytes, st>>>(A); break;
+    case PF3_TRUSS: line_eval_kernel<PF3_TRUSS><<<grid, kThreads, kStageBytes, st>>>(A); break;
+    case PF3_SPRING: line_eval_kernel<PF3_SPRING><<<grid, kThreads, kStageBytes, st>>>(A); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace pf3

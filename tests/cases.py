@@ -121,12 +121,15 @@ def shell_mesh(kind, nx, ny, seed, a=1.3, b=0.8, distort=0.25, curved=True):
     return _finish(case, nx * ny, rng)
 
 
-def line_soup(kind, ne, seed, full=True):
+def line_soup(kind, ne, seed, full=True, logL=(-1.5, 0.5)):
+    """Disconnected random line elements.  BeamC divides by (1 - alpha), alpha = 12EI/(GAL^2)
+    (beamc.pyx:543-546): stubby random beams with alpha ~ 1 are ill-conditioned in the reference
+    itself, so large random sweeps use a longer ``logL`` range."""
     rng = np.random.default_rng(seed)
     X = np.zeros((2 * ne, 3))
     vxy = np.zeros((ne, 3))
     for e in range(ne):
-        L = 10 ** rng.uniform(-1.5, 0.5)
+        L = 10 ** rng.uniform(*logL)
         d = rng.normal(size=3)
         d /= np.linalg.norm(d)
         p0 = rng.normal(size=3)

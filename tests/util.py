@@ -77,3 +77,54 @@ def compare_outputs(got, ref, ne, tol=TOL_VALUES, keys=None):
             assert err <= tol, "%s value rel err %.2e" % (k, err)
         checked.append(k)
     return checked
+
+
+# ---------------------------------------------------------------------------- GPU side
+def batch_from_case(case, device=None):
+    """ElementBatch for a case dict (see oracle/driver.py for the fields)."""
+    from pyfe3d_b200.batch import ElementBatch
+    kind = case["kind"]
+    kw = dict(x=case.get("x"), props=case.get("props"), prop_id=case.get("prop_id"), u=case.get("u"),
+              nnodes=case["ndof"] // 6, device=device)
+    if kind in ("quad4", "quad4r", "tria3r"):
+        kw.update(xmat=case.get("xmat"), K6ROT=case.get("K6ROT"), alpha_shear_locking=case.get("alpha"),
+                  hgfactors=case.get("hg"))
+    elif kind in ("beamc", "beamlr"):
+        kw.update(vxy=case["vxy"])
+    elif kind == "spring":
+        kw.update(axes=case["axes"], k=case["k"])
+    return ElementBatch(kind, case["conn"], **kw)
+
+
+def run_gpu(case, what=("KC0", "KG", "KGs", "M0", "M1", "M2", "fint"), fused=True):
+    """Same output dict as oracle.driver.run / ref_loop.run, computed by the CUDA path."""
+    import torch
+    b = batch_from_case(case)
+    kind = case["kind"]
+    shell = kind in ("quad4", "quad4r", "tria3r")
+    out = {}
+
+    def cpu(coo):
+        return [None if coo.r is None else coo.r.cpu().numpy(), None if coo.c is None else coo.c.cpu().numpy(),
+                coo.v.cpu().numpy()]
+    mts = [mt for mt in (0, 1, 2) if "M%d" % mt in what and b.sizes["M"] and (shell or mt < 2)]
+    if fused and "KC0" in what and "KG" in what and b.sizes["KG"] and mts:
+        fint = torch.zeros(case["ndof"], dtype=torch.float64, device=b.device) if "fint" in what else None
+        res = b.evaluate(KC0=True, KG=True, M=True, mtype=mts[0], fint=fint)
+        out["KC0"], out["KG"], out["M%d" % mts[0]] = cpu(res["KC0"]), cpu(res["KG"]), cpu(res["M"])
+        if fint is not None:
+            out["fint"] = fint.cpu().numpy()
+        mts = mts[1:]
+    else:
+        if "KC0" in what:
+            out["KC0"] = cpu(b.update_KC0())
+        if "KG" in what and b.sizes["KG"]:
+            out["KG"] = cpu(b.update_KG())
+        if "fint" in what:
+            fint = torch.zeros(case["ndof"], dtype=torch.float64, device=b.device)
+            out["fint"] = b.update_fint(fint).cpu().numpy()
+    if "KGs" in what and shell:
+        out["KGs"] = cpu(b.update_KG_given_stress(*case.get("stress", (0., 0., 0.))))
+    for mt in mts:
+        out["M%d" % mt] = cpu(b.update_M(mtype=mt))
+    return out
