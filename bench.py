@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py — Quad4 KC0+KG+M evaluation + CSR assembly throughput (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference Cython loop on host cores
+
+One step = one pass of the hot path over the whole mesh: ONE fused element kernel writing the
+KC0/KG/M COO value arrays (values only — the steady-state `update_*v_only` case; the index
+arrays are a function of connectivity and are not re-written) + three numeric CSR assemblies
+through a precomputed plan.  N>1 (torchrun): weak scaling, the mesh grows to N x (side x side)
+elements, node rows are strip-partitioned, each rank evaluates the elements touching its
+rows (halo duplicated) and assembles its own CSR row block: no collective on the data path.
+Prints one JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "quad4_kc0_kg_m_eval_plus_csr_assembly_throughput"
+UNIT = "elements/s"
+# SURVEY §8(d) algorithmic bytes per Quad4 element (values-only steady state)
+BYTES_EVAL = (576 + 144 + 480) * 8 + 108            # 9600 B of COO values + connectivity/coords/u reads
+BYTES_CSR = (324 + 81 + 270) * 8                    # 5400 B of CSR values (amortised per element)
+BYTES_ASM_READ = (576 + 144 + 480) * 8              # assembly re-reads the COO values
+BYTES_PATH = BYTES_EVAL + BYTES_CSR                 # 15.1 kB: fused lower bound of the whole step
+
+
+def clocks_sampler(index, stop, out):
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    def reader():
+        for line in p.stdout:
+            out.append(line.strip())
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    stop.wait()
+    p.terminate()
+    t.join(timeout=2)
+
+
+def summarize_clocks(lines):
+    sm, mx, reasons = [], 0, set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for ln in lines:
+        f = [t.strip() for t in ln.split(",")]
+        if len(f) < 6:
+            continue
+        try:
+            sm.append(float(f[0]))
+            mx = max(mx, float(f[1]))
+        except ValueError:
+            continue
+        for n, v in zip(names, f[2:6]):
+            if v.lower().startswith("active"):
+                reasons.add(n)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    sm.sort()
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref_loop
+    if not ref_loop.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (python oracle/build_ref.py)"}))
+        return 0
+    from oracle.cpu_bench import ReferenceBench
+    rb = ReferenceBench(side=args.cpu_side)
+    for _ in range(args.warmup):
+        rb.step()
+    t = [rb.step() for _ in range(args.steps)]
+    rb.close()
+    total = sum(t)
+    value = rb.ne * args.steps / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "Quad4 KC0+KG+M + CSR assembly, structured rotated unit plate, laminate [30,-45,0]",
+                       "elements_per_step": rb.ne, "note": "bounded sample of the 4M-element workload; the reference "
+                       "cannot hold 4M Quad4 in one COO array (int32 init_k, quad4.pyx:453)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": rb.nproc, "kind": "reference", "sample": rb.describe()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pyfe3d_b200 import meshes
+    from pyfe3d_b200.batch import AssemblyPlan, ElementBatch, context
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    side = args.side
+    nx, ny = side * world, side
+    i0 = rank * side + (1 if rank > 0 else 0)
+    i1 = (rank + 1) * side + 1
+    case = meshes.plate_quad4(nx, ny, a=float(world), b=1.0, i0=i0 if world > 1 else None,
+                              i1=i1 if world > 1 else None)
+    nnodes = case["ndof"] // 6
+    ne_local = case["conn"].shape[0]
+    ne_unique_total = nx * ny
+    batch = ElementBatch("quad4", case["conn"], case["x"], case["props"], u=case["u"], device=dev)
+    ctx = context(dev)
+    mats = ("KC0", "KG", "M")
+    t_sym0 = time.perf_counter()
+    plans = {m: AssemblyPlan(m, nnodes, [batch], node_range=case["owned_nodes"]) for m in mats}
+    torch.cuda.synchronize()
+    t_symbolic = time.perf_counter() - t_sym0
+    coos = batch.evaluate(KC0=True, KG=True, M=True, indices=False)          # allocates the value arrays
+    csr = {m: torch.empty(plans[m].nnz, dtype=torch.float64, device=dev) for m in mats}
+
+    def step(ev=None):
+        if ev is not None:
+            ev[0].record()
+        batch.evaluate(KC0=True, KG=True, M=True, indices=False, out=coos)
+        if ev is not None:
+            ev[1].record()
+        for i, m in enumerate(mats):
+            plans[m].assemble(coos[m].v, out=csr[m])
+            if ev is not None:
+                ev[2 + i].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    clk_lines, stop = [], threading.Event()
+    th = threading.Thread(target=clocks_sampler, args=(local, stop, clk_lines), daemon=True)
+    th.start()
+    time.sleep(0.25)
+    l0 = ctx.launch_count()
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    end.record()
+    barrier()
+    launches = ctx.launch_count() - l0
+    stop.set()
+    th.join(timeout=3)
+    ms_total = start.elapsed_time(end)
+    kern = np.zeros(4)
+    for ev in evs:
+        for i in range(4):
+            kern[i] += ev[i].elapsed_time(ev[i + 1])
+    kern /= args.steps                                         # ms per launch: eval, asm KC0, asm KG, asm M
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = ne_unique_total / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers --------------------------------------
+    e2e = None
+    if args.e2e_steps > 0:
+        try:
+            xh = torch.as_tensor(case["x"]).pin_memory()
+            uh = torch.as_tensor(case["u"]).pin_memory()
+            outh = {m: torch.empty(plans[m].nnz, dtype=torch.float64).pin_memory() for m in mats}
+            h2d = xh.numel() * 8 + uh.numel() * 8
+            d2h = sum(o.numel() * 8 for o in outh.values())
+
+            def e2e_step():
+                batch.x.copy_(xh, non_blocking=True)
+                batch.u.copy_(uh, non_blocking=True)
+                step()
+                for m in mats:
+                    outh[m].copy_(csr[m], non_blocking=True)
+                torch.cuda.synchronize()
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            e2e = {"value": ne_unique_total * args.e2e_steps / float(dt.item()), "unit": UNIT,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "what": "H2D of x,u from pinned host memory -> fused eval -> 3 CSR assemblies -> D2H of the three "
+                           "CSR value arrays into pinned host memory (pattern is static), per step"}
+            del outh
+        except RuntimeError as exc:   # e.g. pinned allocation refused
+            e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    names = ["quad_eval_kernel<QUAD4> (KC0+KG+M values)", "k_assemble (KC0)", "k_assemble (KG)", "k_assemble (M)"]
+    alg = [BYTES_EVAL * ne_local,
+           (576 * 8) * ne_local + 324 * 8 * ne_local, (144 * 8) * ne_local + 81 * 8 * ne_local,
+           (480 * 8) * ne_local + 270 * 8 * ne_local]
+    dom = int(np.argmax(kern))
+    achieved = alg[dom] / (kern[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": {n: float(k) for n, k in zip(names, kern)},
+                "kernel_gbs": {n: float(a / (k * 1e-3) / 1e9) for n, a, k in zip(names, alg, kern)},
+                "path_frac": BYTES_PATH * (ne_local / (ms_step * 1e-3)) / 1e9 / peak,
+                "path_bytes_per_element": BYTES_PATH}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            roofline["traffic"] = json.load(f).get(names[dom].split(" ")[0])
+
+    cpu = None
+    if world == 1 and args.cpu_side > 0:
+        try:
+            from oracle import ref_loop
+            if ref_loop.available():
+                from oracle.cpu_bench import ReferenceBench
+                rb = ReferenceBench(side=args.cpu_side)
+                rb.step()
+                dt = rb.step()
+                rb.close()
+                cpu = {"value": rb.ne / dt, "unit": UNIT, "cores": rb.nproc, "kind": "reference", "sample": rb.describe()}
+        except Exception as exc:  # the CPU leg is reporting only
+            cpu = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1..] north-star mesh: %dx%d Quad4 structured plate per GPU (%d elements/GPU), "
+                                   "rigidly rotated, coupled laminate [30,-45,0] offset 0.5 mm, u=1e-4 N(0,1); "
+                                   "KC0+KG(from u)+M(mtype 0) values + CSR assembly" % (side, side, side * side),
+                       "elements_total": ne_unique_total, "elements_evaluated_per_gpu": ne_local,
+                       "halo": "row-ownership strips, halo elements duplicated, no collective on the data path",
+                       "l2": "COO+CSR outputs are %.1f GB per step, far larger than the 126 MB L2 (no flush needed)"
+                             % ((BYTES_ASM_READ + BYTES_CSR) * ne_local / 1e9),
+                       "symbolic_plan_s": t_symbolic, "indices": "values only (update_*v_only=1); plan built once"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": summarize_clocks(clk_lines)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--side", type=int, default=2000, help="elements per side per GPU (2000 -> 4.0M Quad4)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-side", type=int, default=256, help="side of the sub-plate the CPU arm evaluates")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

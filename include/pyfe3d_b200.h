@@ -77,14 +77,19 @@ extern "C" {
 /* per-element parameters (attributes / kwargs of the reference objects):
  *  shells : 0 K6ROT (default 100, quad4.pyx:481) | 1 alpha_shear_locking (0.7,
  *           tria3r.pyx:263) | 2..6 hgfactor_u,v,w,rx,ry (1.0, quad4r.pyx:1151-1155)
+ *           | 7 != 0: slots 8..11 hold the element's PREVIOUS m11 m12 m21 m22, which
+ *           update_rotation_matrix leaves untouched when xmat is null or normal to the
+ *           element (sticky state, quad4.pyx:588,598); 0: start from identity
  *  spring : 0..5 kxe kye kze krxe krye krze (spring.pyx:117-124) */
-#define PF3_EPARAM_STRIDE 8
+#define PF3_EPARAM_STRIDE 12
 /* per-element explicit state used by the per-element drop-in classes, which keep
  * r11..r33 / m11..m22 / probe.xe / area|length / probe.ue on the host object exactly
  * like the reference (quad4.pyx:450-459).  Layout (doubles):
  *  0..8 R row-major | 9..12 m11 m12 m21 m22 | 13 area or length | 14..25 xe (3*nn)
  *  | 26..49 ue (6*nn) */
 #define PF3_STATE_STRIDE 50
+#define PF3_STATE_REFRESH_XE 1
+#define PF3_STATE_REFRESH_UE 2
 
 typedef struct pf3_context pf3_context; /* device, stream, scratch; one host thread at a time */
 typedef struct pf3_plan pf3_plan;       /* symbolic assembly result (pattern + gather map)   */
@@ -111,6 +116,9 @@ typedef struct pf3_batch {
   const double* eparam;   /* [ne*PF3_EPARAM_STRIDE] or NULL (defaults) */
   const double* state;    /* [ne*PF3_STATE_STRIDE] or NULL.  When given, frames are NOT
                              recomputed from x/u: the kernels use this state verbatim */
+  int32_t state_flags;    /* with state: PF3_STATE_REFRESH_XE recomputes xe and area|length from
+                             x with the state's R (update_probe_xe, quad4.pyx:682);
+                             PF3_STATE_REFRESH_UE recomputes ue from u (update_probe_ue, :627) */
   double stress[3];       /* Nxx Nyy Nxy for PF3_KG_STRESS */
 } pf3_batch;
 

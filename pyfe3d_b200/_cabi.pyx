@@ -29,6 +29,7 @@ cdef extern from "pyfe3d_b200.h":
         int32_t evec_stride
         const double* eparam
         const double* state
+        int32_t state_flags
         double stress[3]
     ctypedef struct pf3_coo:
         int64_t* r
@@ -69,7 +70,8 @@ cdef extern from "pyfe3d_b200.h":
 KC0, KG, KG_STRESS, M, FINT = 1, 2, 4, 8, 16
 MAT_KC0, MAT_KG, MAT_M = 0, 1, 2
 QUAD4, QUAD4R, TRIA3R, BEAMC, BEAMLR, TRUSS, SPRING = range(7)
-SHELLPROP_STRIDE, BEAMPROP_STRIDE, EPARAM_STRIDE, STATE_STRIDE = 32, 16, 8, 50
+SHELLPROP_STRIDE, BEAMPROP_STRIDE, EPARAM_STRIDE, STATE_STRIDE = 32, 16, 12, 50
+STATE_REFRESH_XE, STATE_REFRESH_UE = 1, 2
 
 
 class Pf3Error(RuntimeError):
@@ -113,7 +115,7 @@ cdef class Batch:
 
     def __init__(self, int kind, int64_t ne, int64_t nnodes, uintptr_t conn=0, uintptr_t x=0, uintptr_t u=0,
                  uintptr_t props=0, uintptr_t prop_id=0, int64_t nprop=0, uintptr_t evec=0, int evec_stride=0,
-                 uintptr_t eparam=0, uintptr_t state=0, int mtype=0, stress=(0., 0., 0.)):
+                 uintptr_t eparam=0, uintptr_t state=0, int mtype=0, stress=(0., 0., 0.), int state_flags=0):
         memset(&self.b, 0, sizeof(pf3_batch))
         self.b.kind = kind
         self.b.mtype = mtype
@@ -129,6 +131,7 @@ cdef class Batch:
         self.b.evec_stride = evec_stride
         self.b.eparam = <const double*>eparam
         self.b.state = <const double*>state
+        self.b.state_flags = state_flags
         self.b.stress[0] = stress[0]
         self.b.stress[1] = stress[1]
         self.b.stress[2] = stress[2]

@@ -85,6 +85,8 @@ int check_batch(const pf3_batch* b, int what) {
     if ((b->kind == PF3_BEAMC || b->kind == PF3_BEAMLR || b->kind == PF3_SPRING) && !b->evec) return PF3_E_BAD_ARG;
     if ((what & (PF3_KG | PF3_FINT)) && !b->u) return PF3_E_BAD_ARG;
   }
+  if (b->state && (b->state_flags & PF3_STATE_REFRESH_XE) && b->kind != PF3_SPRING && !b->x) return PF3_E_BAD_ARG;
+  if (b->state && (b->state_flags & PF3_STATE_REFRESH_UE) && !b->u) return PF3_E_BAD_ARG;
   if (b->kind == PF3_SPRING && !b->eparam) return PF3_E_BAD_ARG;
   if ((what & PF3_KG) && (what & PF3_KG_STRESS)) return PF3_E_BAD_ARG;
   if ((what & PF3_KG_STRESS) && b->kind > PF3_TRIA3R) return PF3_E_UNSUPPORTED;
@@ -121,6 +123,7 @@ void base_args(const pf3_batch* b, pf3::EvalArgs& A) {
   A.evec_stride = b->evec_stride;
   A.eparam = b->eparam;
   A.state = b->state;
+  A.state_flags = b->state_flags;
   A.mtype = b->mtype;
   A.Nxx = b->stress[0];
   A.Nyy = b->stress[1];

@@ -30,6 +30,7 @@ struct EvalArgs {
   int evec_stride;
   const double* __restrict__ eparam;
   const double* __restrict__ state;
+  int state_flags;
   int what;
   int mtype;
   double Nxx, Nyy, Nxy;

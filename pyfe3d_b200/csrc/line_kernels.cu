@@ -290,16 +290,30 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
   Mat3 R;
   double xe[6] = {0, 0, 0, 0, 0, 0}, L = 0., ue[12];
   const bool have_u = (A.u != nullptr || A.state != nullptr);
-  if (A.state != nullptr) {
+  const bool from_state = A.state != nullptr;
+  const bool need_x = KIND != PF3_SPRING && (!from_state || (A.state_flags & PF3_STATE_REFRESH_XE));
+  const bool need_u = have_u && (!from_state || (A.state_flags & PF3_STATE_REFRESH_UE));
+  const int64_t n0 = A.conn[2 * e], n1 = A.conn[2 * e + 1];
+  double xh[3], yh[3], zh[3], P0[3] = {0, 0, 0}, P1[3] = {0, 0, 0};
+  if (need_x)
+    for (int i = 0; i < 3; ++i) {
+      P0[i] = A.x[3 * n0 + i];
+      P1[i] = A.x[3 * n1 + i];
+    }
+  if (from_state) {
     const double* s = A.state + e * PF3_STATE_STRIDE;
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) R.a[i][j] = s[3 * i + j];
     L = s[13];
     for (int i = 0; i < 6; ++i) xe[i] = s[14 + i];
     for (int i = 0; i < 12; ++i) ue[i] = s[26 + i];
+    for (int i = 0; i < 3; ++i) {
+      xh[i] = R.a[i][0];
+      yh[i] = R.a[i][1];
+      zh[i] = R.a[i][2];
+    }
   } else {
-    const int64_t n0 = A.conn[2 * e], n1 = A.conn[2 * e + 1];
-    double xh[3], yh[3], zh[3], v[3], P0[3] = {0, 0, 0}, P1[3] = {0, 0, 0};
+    double v[3];
     const double* ev = A.evec ? A.evec + e * int64_t(A.evec_stride) : nullptr;
     if (KIND == PF3_SPRING) {
       // axis given directly (spring.pyx:147-206)
@@ -309,11 +323,7 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
       }
       normalize3(xh);
     } else {
-      for (int i = 0; i < 3; ++i) {
-        P0[i] = A.x[3 * n0 + i];
-        P1[i] = A.x[3 * n1 + i];
-        xh[i] = P1[i] - P0[i];
-      }
+      for (int i = 0; i < 3; ++i) xh[i] = P1[i] - P0[i];
       normalize3(xh);
       if (KIND == PF3_TRUSS) {  // arbitrary off-axis vector: cyclic shift (truss.pyx:243-245)
         v[0] = xh[1];
@@ -332,25 +342,25 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
       R.a[i][1] = yh[i];
       R.a[i][2] = zh[i];
     }
-    if (KIND != PF3_SPRING) {
-      for (int a = 0; a < 2; ++a) {
-        const double* P = a ? P1 : P0;
-        xe[3 * a + 0] = xh[0] * P[0] + xh[1] * P[1] + xh[2] * P[2];
-        xe[3 * a + 1] = yh[0] * P[0] + yh[1] * P[1] + yh[2] * P[2];
-        xe[3 * a + 2] = zh[0] * P[0] + zh[1] * P[1] + zh[2] * P[2];
+  }
+  if (need_x) {
+    for (int a = 0; a < 2; ++a) {
+      const double* P = a ? P1 : P0;
+      xe[3 * a + 0] = xh[0] * P[0] + xh[1] * P[1] + xh[2] * P[2];
+      xe[3 * a + 1] = yh[0] * P[0] + yh[1] * P[1] + yh[2] * P[2];
+      xe[3 * a + 2] = zh[0] * P[0] + zh[1] * P[1] + zh[2] * P[2];
+    }
+    const double dx = xe[3] - xe[0], dy = xe[4] - xe[1], dz = xe[5] - xe[2];
+    L = sqrt(dx * dx + dy * dy + dz * dz);  // update_length, beamc.pyx:336-349
+  }
+  if (need_u) {
+    for (int a = 0; a < 2; ++a)
+      for (int t = 0; t < 2; ++t) {
+        const double* ug = A.u + 6 * (a ? n1 : n0) + 3 * t;
+        ue[6 * a + 3 * t + 0] = xh[0] * ug[0] + xh[1] * ug[1] + xh[2] * ug[2];
+        ue[6 * a + 3 * t + 1] = yh[0] * ug[0] + yh[1] * ug[1] + yh[2] * ug[2];
+        ue[6 * a + 3 * t + 2] = zh[0] * ug[0] + zh[1] * ug[1] + zh[2] * ug[2];
       }
-      const double dx = xe[3] - xe[0], dy = xe[4] - xe[1], dz = xe[5] - xe[2];
-      L = sqrt(dx * dx + dy * dy + dz * dz);  // update_length, beamc.pyx:336-349
-    }
-    if (have_u) {
-      for (int a = 0; a < 2; ++a)
-        for (int t = 0; t < 2; ++t) {
-          const double* ug = A.u + 6 * (a ? n1 : n0) + 3 * t;
-          ue[6 * a + 3 * t + 0] = xh[0] * ug[0] + xh[1] * ug[1] + xh[2] * ug[2];
-          ue[6 * a + 3 * t + 1] = yh[0] * ug[0] + yh[1] * ug[1] + yh[2] * ug[2];
-          ue[6 * a + 3 * t + 2] = zh[0] * ug[0] + zh[1] * ug[1] + zh[2] * ug[2];
-        }
-    }
   }
   if (A.state_out != nullptr) {
     if (lane < nvalid) {

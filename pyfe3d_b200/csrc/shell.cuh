@@ -43,11 +43,18 @@ __device__ __forceinline__ double f_qq(const double* S, double gxx, double gxy, 
 // Material-axis state, reference quad4.pyx:583-624 (same block in tria3r.pyx).
 // m is left at identity when xmat is absent, null, or parallel to the normal.
 template <int NN>
-__device__ __forceinline__ void material_axes(ShellGeom<NN>& g, const double* xm, double znorm) {
+__device__ __forceinline__ void material_axes(ShellGeom<NN>& g, const double* xm, double znorm,
+                                              const double* mprev) {
   g.m11 = 1.;
   g.m12 = 0.;
   g.m21 = 0.;
   g.m22 = 1.;
+  if (mprev != nullptr) {  // sticky state of a per-element object (quad4.pyx:485-488, 588, 598)
+    g.m11 = mprev[0];
+    g.m12 = mprev[1];
+    g.m21 = mprev[2];
+    g.m22 = mprev[3];
+  }
   if (xm == nullptr) return;
   const double tol = znorm / 1e10;
   double v[3] = {xm[0], xm[1], xm[2]};
@@ -78,7 +85,21 @@ __device__ __forceinline__ void material_axes(ShellGeom<NN>& g, const double* xm
 // (quad4.pyx:491-624, 682-752); Tria3R: tria3r.pyx:294-424, 480-547.
 template <int NN>
 __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGeom<NN>& g, double* ue) {
-  if (A.state != nullptr) {
+  const bool from_state = A.state != nullptr;
+  const bool need_x = !from_state || (A.state_flags & PF3_STATE_REFRESH_XE);
+  const bool need_u = ue != nullptr && (!from_state || (A.state_flags & PF3_STATE_REFRESH_UE));
+  int64_t cn[NN];
+  double P[NN][3];
+#pragma unroll
+  for (int a = 0; a < NN; ++a) {
+    cn[a] = A.conn[e * NN + a];
+    if (need_x) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) P[a][i] = A.x[3 * cn[a] + i];
+    }
+  }
+  double xh[3], yh[3], zh[3];
+  if (from_state) {
     const double* s = A.state + e * PF3_STATE_STRIDE;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -98,65 +119,67 @@ __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGe
     if (ue != nullptr)
 #pragma unroll
       for (int i = 0; i < 6 * NN; ++i) ue[i] = s[26 + i];
-    return;
-  }
-  int64_t cn[NN];
-  double P[NN][3];
-#pragma unroll
-  for (int a = 0; a < NN; ++a) {
-    cn[a] = A.conn[e * NN + a];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) P[a][i] = A.x[3 * cn[a] + i];
-  }
-  double xh[3], yh[3], zh[3], znorm;
-  if (NN == 4) {
-    double v13[3], v42[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      v13[i] = P[2][i] - P[0][i];
-      v42[i] = P[1][i] - P[NN - 1][i];
+      xh[i] = g.R.a[i][0];
+      yh[i] = g.R.a[i][1];
+      zh[i] = g.R.a[i][2];
     }
-    cross3(v42, v13, zh);
-    znorm = normalize3(zh);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) xh[i] = (v13[i] + v42[i]) / 2.;
-    normalize3(xh);
   } else {
-    double v12[3], v13[3];
+    double znorm;
+    if (NN == 4) {
+      double v13[3], v42[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        v13[i] = P[2][i] - P[0][i];
+        v42[i] = P[1][i] - P[NN - 1][i];
+      }
+      cross3(v42, v13, zh);
+      znorm = normalize3(zh);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) xh[i] = (v13[i] + v42[i]) / 2.;
+      normalize3(xh);
+    } else {
+      double v12[3], v13[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        v12[i] = P[1][i] - P[0][i];
+        v13[i] = P[2][i] - P[0][i];
+        xh[i] = v12[i];
+      }
+      cross3(v12, v13, zh);
+      znorm = normalize3(zh);
+      normalize3(xh);
+    }
+    cross3(zh, xh, yh);
+    normalize3(yh);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      v12[i] = P[1][i] - P[0][i];
-      v13[i] = P[2][i] - P[0][i];
-      xh[i] = v12[i];
+      g.R.a[i][0] = xh[i];
+      g.R.a[i][1] = yh[i];
+      g.R.a[i][2] = zh[i];
     }
-    cross3(v12, v13, zh);
-    znorm = normalize3(zh);
-    normalize3(xh);
+    const double* xm = nullptr;
+    if (A.evec != nullptr) xm = A.evec + e * int64_t(A.evec_stride);
+    const double* mprev = nullptr;
+    if (A.eparam != nullptr && A.eparam[e * PF3_EPARAM_STRIDE + 7] != 0.) mprev = A.eparam + e * PF3_EPARAM_STRIDE + 8;
+    material_axes<NN>(g, xm, znorm, mprev);
   }
-  cross3(zh, xh, yh);
-  normalize3(yh);
+  if (need_x) {
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    g.R.a[i][0] = xh[i];
-    g.R.a[i][1] = yh[i];
-    g.R.a[i][2] = zh[i];
+    for (int a = 0; a < NN; ++a) {
+      g.X[a] = xh[0] * P[a][0] + xh[1] * P[a][1] + xh[2] * P[a][2];
+      g.Y[a] = yh[0] * P[a][0] + yh[1] * P[a][1] + yh[2] * P[a][2];
+      g.Z[a] = zh[0] * P[a][0] + zh[1] * P[a][1] + zh[2] * P[a][2];
+    }
+    if (NN == 4) {
+      g.area = 0.5 * fabs((g.X[0] * g.Y[1] + g.X[1] * g.Y[2] + g.X[2] * g.Y[NN - 1] + g.X[NN - 1] * g.Y[0]) -
+                          (g.X[1] * g.Y[0] + g.X[2] * g.Y[1] + g.X[NN - 1] * g.Y[2] + g.X[0] * g.Y[NN - 1]));
+    } else {
+      g.area = fabs((-g.X[0] + g.X[1]) * (-g.Y[0] + g.Y[2]) / 2. + (g.X[0] - g.X[2]) * (-g.Y[0] + g.Y[1]) / 2.);
+    }
   }
-  const double* xm = nullptr;
-  if (A.evec != nullptr) xm = A.evec + e * int64_t(A.evec_stride);
-  material_axes<NN>(g, xm, znorm);
-#pragma unroll
-  for (int a = 0; a < NN; ++a) {
-    g.X[a] = xh[0] * P[a][0] + xh[1] * P[a][1] + xh[2] * P[a][2];
-    g.Y[a] = yh[0] * P[a][0] + yh[1] * P[a][1] + yh[2] * P[a][2];
-    g.Z[a] = zh[0] * P[a][0] + zh[1] * P[a][1] + zh[2] * P[a][2];
-  }
-  if (NN == 4) {
-    g.area = 0.5 * fabs((g.X[0] * g.Y[1] + g.X[1] * g.Y[2] + g.X[2] * g.Y[NN - 1] + g.X[NN - 1] * g.Y[0]) -
-                        (g.X[1] * g.Y[0] + g.X[2] * g.Y[1] + g.X[NN - 1] * g.Y[2] + g.X[0] * g.Y[NN - 1]));
-  } else {
-    g.area = fabs((-g.X[0] + g.X[1]) * (-g.Y[0] + g.Y[2]) / 2. + (g.X[0] - g.X[2]) * (-g.Y[0] + g.Y[1]) / 2.);
-  }
-  if (ue != nullptr) {
+  if (need_u) {
     // update_probe_ue (quad4.pyx:627-679): local = R^T global, per 3-DOF triplet
 #pragma unroll
     for (int a = 0; a < NN; ++a)
