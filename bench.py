@@ -143,10 +143,17 @@ def run_ours(args):
     t_symbolic = time.perf_counter() - t_sym0
     coos = batch.evaluate(KC0=True, KG=True, M=True, indices=False)          # allocates the value arrays
     csr = {m: torch.empty(plans[m].nnz, dtype=torch.float64, device=dev) for m in mats}
+    fused = args.path == "fused"
 
     def step(ev=None):
         if ev is not None:
             ev[0].record()
+        if fused:
+            plans["KC0"].evaluate_assemble(KC0=True, KG=True, M=True, coo=coos, csr=csr)
+            if ev is not None:
+                for i in range(1, 5):
+                    ev[i].record()
+            return
         batch.evaluate(KC0=True, KG=True, M=True, indices=False, out=coos)
         if ev is not None:
             ev[1].record()
@@ -236,6 +243,9 @@ def run_ours(args):
     alg = [BYTES_EVAL * ne_local,
            (576 * 8) * ne_local + 324 * 8 * ne_local, (144 * 8) * ne_local + 81 * 8 * ne_local,
            (480 * 8) * ne_local + 270 * 8 * ne_local]
+    if fused:
+        names[0] = "quad_fused_kernel<QUAD4> (KC0+KG+M COO values + CSR values, one launch)"
+        alg[0] = BYTES_PATH * ne_local
     dom = int(np.argmax(kern))
     achieved = alg[dom] / (kern[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -273,7 +283,8 @@ def run_ours(args):
                        "halo": "row-ownership strips, halo elements duplicated, no collective on the data path",
                        "l2": "COO+CSR outputs are %.1f GB per step, far larger than the 126 MB L2 (no flush needed)"
                              % ((BYTES_ASM_READ + BYTES_CSR) * ne_local / 1e9),
-                       "symbolic_plan_s": t_symbolic, "indices": "values only (update_*v_only=1); plan built once"},
+                       "symbolic_plan_s": t_symbolic, "indices": "values only (update_*v_only=1); plan built once",
+                       "path": args.path},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": summarize_clocks(clk_lines)}
     print(json.dumps(line))
@@ -290,6 +301,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=2000, help="elements per side per GPU (2000 -> 4.0M Quad4)")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--path", default="fused", choices=["fused", "twopass"],
+                    help="fused: one node-centric kernel writes COO + CSR; twopass: eval kernel then 3 assemblies")
     ap.add_argument("--cpu-side", type=int, default=256, help="side of the sub-plate the CPU arm evaluates")
     args = ap.parse_args()
     if args.impl == "reference":

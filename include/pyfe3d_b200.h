@@ -194,6 +194,19 @@ int pf3_plan_pattern(pf3_context* ctx, const pf3_plan* plan, int64_t* indptr, in
 /* numeric phase: csr_v[nnz] = sum of duplicates of coo_v, deterministic order */
 int pf3_plan_assemble(pf3_context* ctx, const pf3_plan* plan, const double* coo_v, double* csr_v);
 
+int pf3_plan_nblocks(const pf3_plan* plan, int64_t* nblk); /* 6x6 node-pair blocks of a structured plan */
+
+/* Fused evaluate + assemble for ONE Quad4/Quad4R batch and the structured PF3_MAT_KC0 plan built from
+ * it: a single kernel writes the COO value arrays (kc0/kg/m, any may be NULL or have v == NULL: that
+ * COO array is then not produced) AND the assembled CSR values, without re-reading the COO arrays
+ * (DRAM traffic = SURVEY §8(d)'s 15.1 kB/element lower bound).  CSR layouts are those of structured plans
+ * of the same batch: csr_kc0[nblk*36], csr_kg[nblk*9], csr_m[nblk*30] (mtype 2: nblk*18).  Replaces the
+ * element loop + scipy tocsr pair of tests/test_quad4_static_point_load.py:53-80 in one call.
+ * PF3_E_UNSUPPORTED for other kinds / multi-group plans (use pf3_eval + pf3_plan_assemble). */
+int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* batch, const pf3_plan* plan, int what,
+                      const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* csr_kc0,
+                      double* csr_kg, double* csr_m);
+
 /* y = A x for a CSR matrix with int64 indptr/indices (downstream cg / eigsh operators) */
 int pf3_spmv_csr(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
                  const double* vals, const double* x, double* y);

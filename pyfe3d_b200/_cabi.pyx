@@ -61,6 +61,9 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_nnz(const pf3_plan*, int64_t*)
     int pf3_plan_nrows(const pf3_plan*, int64_t*)
     int pf3_plan_pattern(pf3_context*, const pf3_plan*, int64_t* indptr, int64_t* indices) nogil
+    int pf3_plan_nblocks(const pf3_plan*, int64_t*)
+    int pf3_eval_assemble(pf3_context*, const pf3_batch*, const pf3_plan*, int what, const pf3_coo*, const pf3_coo*,
+                          const pf3_coo*, double*, double*, double*) nogil
     int pf3_plan_assemble(pf3_context*, const pf3_plan*, const double* coo_v, double* csr_v) nogil
     int pf3_spmv_csr(pf3_context*, int64_t nrows, const int64_t* indptr, const int64_t* indices,
                      const double* vals, const double* x, double* y) nogil
@@ -279,6 +282,23 @@ cdef class Plan:
         cdef int64_t n = 0
         _check(pf3_plan_nrows(self.plan, &n))
         return n
+
+    @property
+    def nblocks(self):
+        cdef int64_t n = 0
+        _check(pf3_plan_nblocks(self.plan, &n))
+        return n
+
+    def eval_assemble(self, Batch b, int what, Coo kc0=None, Coo kg=None, Coo m=None, uintptr_t csr_kc0=0,
+                      uintptr_t csr_kg=0, uintptr_t csr_m=0):
+        cdef const pf3_coo* p0 = &kc0.c if kc0 is not None else NULL
+        cdef const pf3_coo* p1 = &kg.c if kg is not None else NULL
+        cdef const pf3_coo* p2 = &m.c if m is not None else NULL
+        cdef int rc
+        with nogil:
+            rc = pf3_eval_assemble(self.owner.ctx, &b.b, self.plan, what, p0, p1, p2, <double*>csr_kc0,
+                                   <double*>csr_kg, <double*>csr_m)
+        _check(rc)
 
     def pattern(self, uintptr_t indptr, uintptr_t indices):
         cdef int rc

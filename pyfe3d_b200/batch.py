@@ -302,6 +302,57 @@ class AssemblyPlan:
         return sp.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()),
                              shape=(self.nrows, 6 * self.nnodes))
 
+    # -- fused evaluate + assemble (Quad4 / Quad4R, single batch) ---------------------------------
+    def csr_sizes(self, mtype=0):
+        """nnz of the KC0 / KG / M CSR value arrays the fused kernel fills (same layouts as the
+        structured plans of the same batch for those matrices)."""
+        nblk = self._plan.nblocks
+        return {"KC0": nblk * 36, "KG": nblk * 9, "M": nblk * (18 if mtype == 2 else 30)}
+
+    def evaluate_assemble(self, KC0=False, KG=False, KG_given_stress=None, M=False, mtype=0, u=None,
+                          coo=None, csr=None, write_coo=True, indices=False):
+        """ONE kernel: element matrices -> COO value arrays AND assembled CSR values, with no re-read
+        of the COO arrays.  Requires this plan to be the "KC0" plan of a single Quad4/Quad4R batch.
+
+        ``coo`` / ``csr``: optional dicts of preallocated outputs (name -> Coo / tensor).  With
+        ``write_coo=False`` only the CSR values are produced.  Returns (coo, csr) dicts."""
+        if self.matrix != "KC0" or len(self.batches) != 1:
+            raise ValueError("evaluate_assemble needs the KC0 plan of a single batch")
+        b = self.batches[0]
+        if u is not None:
+            u = _dev(u, torch.float64, self.device)
+        sizes = self.csr_sizes(mtype)
+        coo = dict(coo or {})
+        csr = dict(csr or {})
+        what = 0
+        for name, on in (("KC0", KC0), ("KG", KG or KG_given_stress is not None), ("M", M)):
+            if not on:
+                continue
+            if name not in csr:
+                csr[name] = torch.empty(sizes[name], dtype=torch.float64, device=self.device)
+            if write_coo and name not in coo:
+                coo[name] = b._alloc(name, indices, None)
+        if KC0:
+            what |= _cabi.KC0
+        if KG_given_stress is not None:
+            what |= _cabi.KG_STRESS
+        elif KG:
+            what |= _cabi.KG
+        if M:
+            what |= _cabi.M
+
+        def cc(name):
+            k = coo.get(name) if write_coo else None
+            if k is None:
+                return None
+            return _cabi.Coo(_ptr(k.r) if indices else 0, _ptr(k.c) if indices else 0, _ptr(k.v), 0, 0)
+
+        context(self.device)
+        self._plan.eval_assemble(b.cabi_batch(mtype, KG_given_stress or (0., 0., 0.), u), what, cc("KC0"),
+                                 cc("KG"), cc("M"), _ptr(csr.get("KC0")), _ptr(csr.get("KG")),
+                                 _ptr(csr.get("M")))
+        return coo, csr
+
 
 class CooPlan:
     """Generic plan from arbitrary COO index arrays (what scipy's tocsr does)."""

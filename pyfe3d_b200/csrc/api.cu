@@ -25,6 +25,10 @@ int spmv_csr(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_
 int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64_t* conn, const double* fe,
                 double* fint, int64_t* launches);
 int64_t plan_nnz(const pf3_plan* pl);
+int64_t plan_nblocks(const pf3_plan* pl);
+int64_t plan_group_ne(const pf3_plan* pl);
+int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F);
+cudaError_t launch_quad_fused(int kind, const FusedArgs& F, cudaStream_t st);
 int64_t plan_nrows(const pf3_plan* pl);
 }  // namespace pf3
 
@@ -401,6 +405,51 @@ int pf3_plan_nnz(const pf3_plan* plan, int64_t* nnz) {
 int pf3_plan_nrows(const pf3_plan* plan, int64_t* nrows) {
   if (!plan || !nrows) return PF3_E_BAD_ARG;
   *nrows = pf3::plan_nrows(plan);
+  return PF3_OK;
+}
+
+int pf3_plan_nblocks(const pf3_plan* plan, int64_t* nblk) {
+  if (!plan || !nblk) return PF3_E_BAD_ARG;
+  *nblk = pf3::plan_nblocks(plan);
+  return PF3_OK;
+}
+
+int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan, int what, const pf3_coo* kc0,
+                      const pf3_coo* kg, const pf3_coo* m, double* csr_kc0, double* csr_kg, double* csr_m) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan) return PF3_E_BAD_ARG;
+  rc = check_batch(b, what);
+  if (rc) return rc;
+  if (b->state || (what & PF3_FINT)) return PF3_E_UNSUPPORTED;
+  if (b->ne != pf3::plan_group_ne(plan)) return PF3_E_BAD_ARG;
+  if (((what & PF3_KC0) && !csr_kc0) || ((what & (PF3_KG | PF3_KG_STRESS)) && !csr_kg) || ((what & PF3_M) && !csr_m))
+    return PF3_E_BAD_ARG;
+  for (const pf3_coo* c : {kc0, kg, m})
+    if (c && c->accumulate) return PF3_E_UNSUPPORTED;
+  if (b->ne == 0) return PF3_OK;
+  pf3::FusedArgs F;
+  std::memset(&F, 0, sizeof(F));
+  rc = pf3::plan_fused_args(plan, b->kind, &F);
+  if (rc) return rc;
+  base_args(b, F.A);
+  F.A.what = what & (PF3_KC0 | PF3_KG | PF3_KG_STRESS | PF3_M);
+  if (kc0 && kc0->v) { F.A.kc0v = kc0->v; F.A.kc0_k0 = kc0->init_k; }
+  if (kg && kg->v) { F.A.kgv = kg->v; F.A.kg_k0 = kg->init_k; }
+  if (m && m->v) { F.A.mv = m->v; F.A.m_k0 = m->init_k; }
+  F.csr_kc0 = csr_kc0;
+  F.csr_kg = csr_kg;
+  F.csr_m = csr_m;
+  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->stream);
+  ++ctx->launches;
+  if (e != cudaSuccess) return int(e);
+  const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
+                          (what & PF3_M) ? m : nullptr};
+  for (int k = 0; k < 3; ++k)
+    if (cs[k] && (cs[k]->r || cs[k]->c)) {
+      rc = pf3_fill_indices(ctx, b->kind, k, k == 2 ? b->mtype : 0, b->ne, b->conn, cs[k]->init_k, cs[k]->r, cs[k]->c);
+      if (rc) return rc;
+    }
   return PF3_OK;
 }
 

@@ -643,6 +643,23 @@ int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64
   return PF3_OK;
 }
 
+int fused_max_slots();
+// Fill the plan part of FusedArgs; PF3_E_UNSUPPORTED when the plan cannot drive the fused kernel.
+int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F) {
+  if (pl->generic || pl->dev.ngroups != 1 || pl->degenerate) return PF3_E_UNSUPPORTED;
+  const GroupDev& G = pl->dev.g[0];
+  if (G.nn != 4 || G.diag || G.npairs != 16 || G.pairbase != 0) return PF3_E_UNSUPPORTED;
+  if (kind != PF3_QUAD4 && kind != PF3_QUAD4R) return PF3_E_UNSUPPORTED;
+  if (pl->max_nb > fused_max_slots()) return PF3_E_CAPACITY;
+  F->brow_ptr = pl->d_brow_ptr;
+  F->inc_ptr = pl->d_inc_ptr;
+  F->inc_pair0 = pl->d_inc_pair0;
+  F->slot = pl->d_slot;
+  F->nown = pl->nown;
+  return PF3_OK;
+}
+int64_t plan_nblocks(const pf3_plan* pl) { return pl->generic ? 0 : pl->nblk; }
+int64_t plan_group_ne(const pf3_plan* pl) { return pl->generic ? 0 : pl->dev.g[0].ne; }
 int64_t plan_nnz(const pf3_plan* pl) { return pl->nnz; }
 int64_t plan_nrows(const pf3_plan* pl) { return pl->nrows; }
 

@@ -44,6 +44,19 @@ struct EvalArgs {
   int acc_kc0, acc_kg, acc_m;
 };
 
+// fused evaluate + assemble (quad_fused.cu): element inputs + the plan's block structure
+struct FusedArgs {
+  EvalArgs A;
+  const int64_t* __restrict__ brow_ptr;   // [nown+1] first block of each owned node row
+  const int64_t* __restrict__ inc_ptr;    // [nown+1] incident (element, local node) pairs per node
+  const int64_t* __restrict__ inc_pair0;  // [ninc]   e*16 + a*4
+  const int32_t* __restrict__ slot;       // [ne*16]  column-block slot of node pair (e, a, b) in a's row
+  int64_t nown;
+  double* csr_kc0;
+  double* csr_kg;
+  double* csr_m;
+};
+
 struct Mat3 {
   double a[3][3];
 };

@@ -1,0 +1,76 @@
+"""GPU: the fused node-centric evaluate+assemble kernel against the reference goldens (COO values)
+and scipy's sum-duplicates of the reference COO (CSR values)."""
+import numpy as np
+import pytest
+
+from oracle import driver
+from tests import cases, util
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(case, ref, mtype=0, stress=None, node_range=None):
+    import scipy.sparse as sp
+    from pyfe3d_b200.batch import AssemblyPlan
+    b = util.batch_from_case(case)
+    n = case["ndof"]
+    nn = n // 6
+    plan = AssemblyPlan("KC0", nn, [b], node_range=node_range)
+    kw = dict(KC0=True, M=True, mtype=mtype, indices=True)
+    if stress is None:
+        kw["KG"] = True
+    else:
+        kw["KG_given_stress"] = stress
+    coo, csr = plan.evaluate_assemble(**kw)
+    ne = case["conn"].shape[0]
+    keys = {"KC0": "KC0", "KG": "KG" if stress is None else "KGs", "M": "M%d" % mtype}
+    lo, hi = (0, nn) if node_range is None else node_range
+    for name, rk in keys.items():
+        r, c, v = ref[rk]
+        if node_range is None:   # with a shard only the owned nodes' slabs are written
+            assert np.array_equal(coo[name].r.cpu().numpy(), r) and np.array_equal(coo[name].c.cpu().numpy(), c)
+            assert util.block_relerr(coo[name].v.cpu().numpy(), v, ne) <= util.TOL_VALUES, name
+        p = AssemblyPlan(name, nn, [b], node_range=node_range, mtype=mtype)
+        A = p.to_scipy(csr[name])
+        S = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+        S.sum_duplicates()
+        S.sort_indices()
+        S = S[6 * lo:6 * hi]
+        assert np.array_equal(A.indptr, S.indptr) and np.array_equal(A.indices, S.indices), name
+        assert np.abs(A.data - S.data).max() <= util.TOL_CSR * np.abs(S.data).max(), name
+
+
+@pytest.mark.parametrize("name", ["quad4_mesh", "quad4r_mesh", "quad4_soup", "quad4r_soup", "quad4_soup_thick"])
+@pytest.mark.parametrize("mtype", [0, 1, 2])
+def test_fused_matches_reference_golden(name, mtype):
+    case, ref = util.load_golden(name)
+    _check(case, ref, mtype=mtype)
+
+
+def test_fused_given_stress_and_shard():
+    case, ref = util.load_golden("quad4r_mesh")
+    _check(case, ref, stress=case["stress"])
+    nn = case["ndof"] // 6
+    _check(case, ref, node_range=(nn // 3, nn - 2))
+
+
+@pytest.mark.parametrize("kind", ["quad4", "quad4r"])
+def test_fused_large_mesh_matches_oracle_and_twopass(kind):
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    case = cases.shell_mesh(kind, 61, 47, seed=404)
+    want = driver.run(case, what=("KC0", "KG", "M0"))
+    _check(case, want)
+    b = util.batch_from_case(case)
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan("KC0", nn, [b])
+    coo, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True)
+    two = b.evaluate(KC0=True, KG=True, M=True)
+    for m in ("KC0", "KG", "M"):
+        assert util.block_relerr(coo[m].v.cpu().numpy(), two[m].v.cpu().numpy(), case["conn"].shape[0]) <= 1e-13
+        ref_csr = AssemblyPlan(m, nn, [b]).assemble(two[m].v)
+        assert np.abs((csr[m] - ref_csr).cpu().numpy()).max() <= 1e-12 * float(ref_csr.abs().max())
+    # CSR only (no COO arrays written)
+    _, csr2 = plan.evaluate_assemble(KC0=True, KG=True, M=True, write_coo=False)
+    for m in ("KC0", "KG", "M"):
+        assert torch.equal(csr2[m], csr[m])
