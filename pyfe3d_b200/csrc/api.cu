@@ -28,7 +28,8 @@ int64_t plan_nnz(const pf3_plan* pl);
 int64_t plan_nblocks(const pf3_plan* pl);
 int64_t plan_group_ne(const pf3_plan* pl);
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F);
-cudaError_t launch_quad_fused(int kind, const FusedArgs& F, cudaStream_t st);
+cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
+int fused_record_stride(const EvalArgs& A);
 int64_t plan_nrows(const pf3_plan* pl);
 }  // namespace pf3
 
@@ -440,8 +441,9 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
   F.csr_kc0 = csr_kc0;
   F.csr_kg = csr_kg;
   F.csr_m = csr_m;
-  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->stream);
-  ++ctx->launches;
+  rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
+  if (rc) return rc;
+  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
   if (e != cudaSuccess) return int(e);
   const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
                           (what & PF3_M) ? m : nullptr};
