@@ -191,7 +191,10 @@ __device__ __forceinline__ void stage9(double* my, const double (*o)[3], int row
 
 struct NodeWork {   // what a lane needs to know about its node / incidence before touching any double
   int64_t b0, pair0;
-  int v, nb, myslot;
+  int packed;       // v | nb << 8 | (myslot + 1) << 16
+  __device__ __forceinline__ int v() const { return packed & 0xff; }
+  __device__ __forceinline__ int nb() const { return (packed >> 8) & 0xff; }
+  __device__ __forceinline__ int myslot() const { return (packed >> 16) - 1; }
 };
 
 __device__ __forceinline__ NodeWork fetch_work(const FusedArgs& F, int64_t np, int64_t npairs, int h, int k, int b,
@@ -199,23 +202,25 @@ __device__ __forceinline__ NodeWork fetch_work(const FusedArgs& F, int64_t np, i
   NodeWork w;
   w.b0 = 0;
   w.pair0 = 0;
-  w.v = 0;
-  w.nb = 0;
-  w.myslot = -1;
+  w.packed = 0;
   const int64_t n = 2 * np + h;
   if (np < npairs && n < F.nown) {
     const int64_t q0 = F.inc_ptr[n];
-    w.v = int(F.inc_ptr[n + 1] - q0);
+    const int v = int(F.inc_ptr[n + 1] - q0);
     w.b0 = F.brow_ptr[n];
-    w.nb = int(F.brow_ptr[n + 1] - w.b0);
+    const int nb = int(F.brow_ptr[n + 1] - w.b0);
     const int kk = 4 * round + k;
-    if (kk < w.v) {
+    int ms = -1;
+    if (kk < v) {
       w.pair0 = F.inc_pair0[q0 + kk];
-      w.myslot = F.slot[w.pair0 + b];
+      ms = F.slot[w.pair0 + b];
     }
+    w.packed = v | (nb << 8) | ((ms + 1) << 16);
   }
   return w;
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <int KIND>
 __global__ void __launch_bounds__(32 * kFusedWarps, 4) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
@@ -239,24 +244,31 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 4) quad_fused_kernel(const F
   I33.init(lane);
   const int64_t stride_np = int64_t(gridDim.x) * kFusedWarps;
   int64_t np = int64_t(blockIdx.x) * kFusedWarps + warp;
+  // software pipeline: index chain two node pairs ahead, element record lines one pair ahead (L1 prefetch)
   NodeWork nxt = fetch_work(F, np, npairs, h, k, b, 0);
+  NodeWork nxt2 = fetch_work(F, np + stride_np, npairs, h, k, b, 0);
 
   for (; np < npairs; np += stride_np) {
     const NodeWork cur0 = nxt;
-    nxt = fetch_work(F, np + stride_np, npairs, h, k, b, 0);   // index chain of the NEXT node pair, in flight
-    const int vmax = max(__shfl_sync(0xffffffffu, cur0.v, 0), __shfl_sync(0xffffffffu, cur0.v, 16));
+    nxt = nxt2;
+    nxt2 = fetch_work(F, np + 2 * stride_np, npairs, h, k, b, 0);
+    if (nxt.myslot() >= 0) {
+      const char* pr = reinterpret_cast<const char*>(rec + (nxt.pair0 >> 4) * rstride);
+      for (int off = b * 128; off < rstride * 8; off += 512) prefetch_l1(pr + off);
+    }
+    const int vmax = max(__shfl_sync(0xffffffffu, cur0.v(), 0), __shfl_sync(0xffffffffu, cur0.v(), 16));
     const int rounds = (vmax + 3) >> 2;
 
     for (int r = 0; r < rounds; ++r) {
       const NodeWork cur = (r == 0) ? cur0 : fetch_work(F, np, npairs, h, k, b, r);
-      const bool act = cur.myslot >= 0;
+      const bool act = cur.myslot() >= 0;
       const int64_t e = cur.pair0 >> 4;
       const int a = int(cur.pair0 >> 2) & 3;
       const int64_t b0 = cur.b0;
-      const int nb = cur.nb;
+      const int nb = cur.nb();
       for (int i = lane; i < 8 * kMaxSlots; i += 32) inv[i] = -1;
       __syncwarp();
-      if (act) inv[(h * 4 + k) * kMaxSlots + cur.myslot] = (signed char)b;
+      if (act) inv[(h * 4 + k) * kMaxSlots + cur.myslot()] = (signed char)b;
       const bool first = (r == 0);
       const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
 
