@@ -223,7 +223,7 @@ __device__ __forceinline__ NodeWork fetch_work(const FusedArgs& F, int64_t np, i
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 template <int KIND>
-__global__ void __launch_bounds__(32 * kFusedWarps, 4) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
+__global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
                                                                          int rstride) {
   extern __shared__ double smem[];
   const EvalArgs& A = F.A;
@@ -501,7 +501,7 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   const size_t smem = fused_smem_bytes();
   const int64_t npairs = (F.nown + 1) / 2;
   const int64_t want = (npairs + kFusedWarps - 1) / kFusedWarps;
-  const int64_t cap = 148 * 4 * 8;
+  const int64_t cap = 148 * 3 * 8;
   const unsigned grid = unsigned(want < cap ? (want < 1 ? 1 : want) : cap);
   static bool once = false;
   if (!once) {
