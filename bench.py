@@ -239,17 +239,20 @@ def run_ours(args):
         return 0
 
     peak, peak_src = measured_peak()
-    names = ["quad_eval_kernel<QUAD4> (KC0+KG+M values)", "k_assemble (KC0)", "k_assemble (KG)", "k_assemble (M)"]
-    alg = [BYTES_EVAL * ne_local,
-           (576 * 8) * ne_local + 324 * 8 * ne_local, (144 * 8) * ne_local + 81 * 8 * ne_local,
-           (480 * 8) * ne_local + 270 * 8 * ne_local]
     if fused:
-        names[0] = "quad_fused_kernel<QUAD4> (KC0+KG+M COO values + CSR values, one launch)"
-        alg[0] = BYTES_PATH * ne_local
+        names = ["quad_record_kernel + quad_fused_kernel<QUAD4> (COO values of KC0,KG,M + their CSR values; 2 launches)"]
+        alg = [BYTES_PATH * ne_local]
+        kern = kern[:1]
+    else:
+        names = ["quad_eval_kernel<QUAD4> (KC0+KG+M values)", "k_assemble (KC0)", "k_assemble (KG)", "k_assemble (M)"]
+        alg = [BYTES_EVAL * ne_local,
+               (576 * 8) * ne_local + 324 * 8 * ne_local, (144 * 8) * ne_local + 81 * 8 * ne_local,
+               (480 * 8) * ne_local + 270 * 8 * ne_local]
     dom = int(np.argmax(kern))
     achieved = alg[dom] / (kern[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg[dom]),
                 "kernel_ms": {n: float(k) for n, k in zip(names, kern)},
                 "kernel_gbs": {n: float(a / (k * 1e-3) / 1e9) for n, a, k in zip(names, alg, kern)},
                 "path_frac": BYTES_PATH * (ne_local / (ms_step * 1e-3)) / 1e9 / peak,
@@ -257,7 +260,10 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         with open(prof) as f:
-            roofline["traffic"] = json.load(f).get(names[dom].split(" ")[0])
+            t = json.load(f).get("fused" if fused else "twopass")
+        if t and t.get("elements") == ne_local:
+            roofline["traffic"] = t["dram_bytes_per_launch"]
+            roofline["traffic_source"] = t.get("source")
 
     cpu = None
     if world == 1 and args.cpu_side > 0:
