@@ -27,7 +27,7 @@ int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64
 int64_t plan_nnz(const pf3_plan* pl);
 int64_t plan_nblocks(const pf3_plan* pl);
 int64_t plan_group_ne(const pf3_plan* pl);
-int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F);
+int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches);
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
 int fused_record_stride(const EvalArgs& A);
 int64_t plan_nrows(const pf3_plan* pl);
@@ -426,12 +426,16 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
   if (b->ne != pf3::plan_group_ne(plan)) return PF3_E_BAD_ARG;
   if (((what & PF3_KC0) && !csr_kc0) || ((what & (PF3_KG | PF3_KG_STRESS)) && !csr_kg) || ((what & PF3_M) && !csr_m))
     return PF3_E_BAD_ARG;
-  for (const pf3_coo* c : {kc0, kg, m})
+  for (const pf3_coo* c : {kc0, kg, m}) {
     if (c && c->accumulate) return PF3_E_UNSUPPORTED;
+    // COO slabs leave shared memory as 16-byte-aligned bulk copies
+    if (c && c->v && (((uintptr_t)c->v & 15) != 0 || (c->init_k & 1) != 0)) return PF3_E_UNSUPPORTED;
+  }
+  if ((((uintptr_t)csr_kc0) | ((uintptr_t)csr_kg) | ((uintptr_t)csr_m)) & 15) return PF3_E_UNSUPPORTED;
   if (b->ne == 0) return PF3_OK;
   pf3::FusedArgs F;
   std::memset(&F, 0, sizeof(F));
-  rc = pf3::plan_fused_args(plan, b->kind, &F);
+  rc = pf3::plan_fused_args(plan, b->kind, &F, ctx->stream, &ctx->launches);
   if (rc) return rc;
   base_args(b, F.A);
   F.A.what = what & (PF3_KC0 | PF3_KG | PF3_KG_STRESS | PF3_M);

@@ -44,6 +44,17 @@ struct EvalArgs {
   int acc_kc0, acc_kg, acc_m;
 };
 
+// Per-node work record of the fused kernel, built once per plan (one 64-B load replaces the
+// inc_ptr -> inc_pair0 -> slot pointer chase).  One record per (node, round of 4 incidences).
+struct alignas(16) NodeRec {
+  int64_t b0;          // first 6x6 block of the node's CSR row block
+  int32_t inc[4];      // e*16 + a*4 of the incident (element, local node) pairs of this round, -1: none
+  uint16_t gmap[16];   // per column-block slot: nibble k -> local node b of incidence k feeding it, 0xF: none
+  uint8_t v, nb;       // incidences in this round, column blocks of the node row
+  uint8_t pad[6];
+};
+static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
+
 // fused evaluate + assemble (quad_fused.cu): element inputs + the plan's block structure
 struct FusedArgs {
   EvalArgs A;
@@ -51,6 +62,8 @@ struct FusedArgs {
   const int64_t* __restrict__ inc_ptr;    // [nown+1] incident (element, local node) pairs per node
   const int64_t* __restrict__ inc_pair0;  // [ninc]   e*16 + a*4
   const int32_t* __restrict__ slot;       // [ne*16]  column-block slot of node pair (e, a, b) in a's row
+  const NodeRec* __restrict__ noderec;    // [nown*rmax]
+  int rmax;                               // rounds of 4 incidences per node (1 when every valence <= 4)
   int64_t nown;
   double* csr_kc0;
   double* csr_kg;

@@ -114,375 +114,400 @@ __global__ void __launch_bounds__(128) quad_record_kernel(const EvalArgs A, doub
 }
 
 // ------------------------------------------------------------------------------------------ K2
+// Shared-memory staging uses the COO slab layout itself (row d, node b, masked column r) with a padded,
+// even slab stride, so that (i) a slab leaves as ONE bulk async copy (TMA, cp.async.bulk shared->global)
+// issued by the incidence's first lane and (ii) staging stores are conflict-free.
 template <int NR, int CNT>
-struct EmitIdx {
-  static constexpr int kSlab = NR * 4 * CNT;           // doubles per (element, node) COO slab
-  static constexpr int kCooIt = (kSlab + 31) / 32;
-  static constexpr int kCsrIt = (kMaxSlots * CNT + 15) / 16;
-  int coo_src[kCooIt];   // staging offset of slab entry p = lane + 32 i (without the incidence column)
-  __device__ __forceinline__ void init(int lane) {
-#pragma unroll
-    for (int i = 0; i < kCooIt; ++i) {
-      const int p = lane + 32 * i;
-      const int d = p / (4 * CNT), rem = p - d * (4 * CNT);
-      const int bb = rem / CNT, rr = rem - bb * CNT;
-      coo_src[i] = (d * CNT + rr) * kLd + bb;
-    }
-  }
+struct SlabShape {
+  static constexpr int kSlab = NR * 4 * CNT;   // doubles per (element, node) COO slab
+  static constexpr int kLd = kSlab + 2;        // padded stride: 146 / 122 / 74 / 38 doubles
 };
-
-// The lanes have staged their block at st[t*kLd + lane], t = d*CNT + r.  Stream the 8 slabs to the COO
-// array and reduce the 4 incidences of each half-warp's node into its CSR rows.
-template <int NR, int CNT>
-__device__ __forceinline__ void emit_staged(const EmitIdx<NR, CNT>& I, const double* st, const signed char* inv,
-                                            double* __restrict__ coo, int64_t slab_base, bool act,
-                                            double* __restrict__ csr, int64_t csr_base, int nb, bool first_round,
-                                            int lane) {
-  const int h = lane >> 4, l16 = lane & 15;
-  __syncwarp();
-  if (coo != nullptr) {
-#pragma unroll 1
-    for (int idx = 0; idx < 8; ++idx) {
-      const int64_t base = __shfl_sync(0xffffffffu, slab_base, idx * 4);
-      const int on = __shfl_sync(0xffffffffu, act ? 1 : 0, idx * 4);
-      if (on) {
-        double* dst = coo + base + lane;
-        const double* src = st + idx * 4;
-#pragma unroll
-        for (int i = 0; i < EmitIdx<NR, CNT>::kCooIt; ++i)
-          if (lane + 32 * i < EmitIdx<NR, CNT>::kSlab) dst[32 * i] = src[I.coo_src[i]];
-      }
-    }
-  }
-  if (nb > 0 && csr != nullptr) {
-    const int w = nb * CNT;
-    const signed char* iv = inv + h * 4 * kMaxSlots;
-    const double* sh = st + h * 16;
-    double* out = csr + csr_base + l16;
-#pragma unroll 1
-    for (int x = l16; x < w; x += 16) {
-      const int s = x / CNT, rr = x - s * CNT;
-      int off[4];
-#pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) {
-        const int bs = iv[k2 * kMaxSlots + s];
-        off[k2] = (bs >= 0) ? (k2 * 4 + bs + rr * kLd) : -1;
-      }
-#pragma unroll
-      for (int d = 0; d < NR; ++d) {
-        double sum = 0.;
-#pragma unroll
-        for (int k2 = 0; k2 < 4; ++k2)
-          if (off[k2] >= 0) sum += sh[d * CNT * kLd + off[k2]];
-        double* o = out + d * w + (x - l16);
-        if (first_round) *o = sum; else *o += sum;
-      }
-    }
-  }
-  __syncwarp();
-}
-
-__device__ __forceinline__ void stage9(double* my, const double (*o)[3], int row0, int col0, int cnt) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) my[((row0 + i) * cnt + col0 + j) * kLd] = o[i][j];
-}
-
-struct NodeWork {   // what a lane needs to know about its node / incidence before touching any double
-  int64_t b0, pair0;
-  int packed;       // v | nb << 8 | (myslot + 1) << 16
-  __device__ __forceinline__ int v() const { return packed & 0xff; }
-  __device__ __forceinline__ int nb() const { return (packed >> 8) & 0xff; }
-  __device__ __forceinline__ int myslot() const { return (packed >> 16) - 1; }
-};
-
-__device__ __forceinline__ NodeWork fetch_work(const FusedArgs& F, int64_t np, int64_t npairs, int h, int k, int b,
-                                               int round) {
-  NodeWork w;
-  w.b0 = 0;
-  w.pair0 = 0;
-  w.packed = 0;
-  const int64_t n = 2 * np + h;
-  if (np < npairs && n < F.nown) {
-    const int64_t q0 = F.inc_ptr[n];
-    const int v = int(F.inc_ptr[n + 1] - q0);
-    w.b0 = F.brow_ptr[n];
-    const int nb = int(F.brow_ptr[n + 1] - w.b0);
-    const int kk = 4 * round + k;
-    int ms = -1;
-    if (kk < v) {
-      w.pair0 = F.inc_pair0[q0 + kk];
-      ms = F.slot[w.pair0 + b];
-    }
-    w.packed = v | (nb << 8) | ((ms + 1) << 16);
-  }
-  return w;
-}
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+// Lanes have written their block into slab (lane>>2).  Ship the slabs to the COO array and reduce the (up to)
+// 4 incidences of each half-warp's node into its CSR rows in the fixed order k = 0..3.
+template <int NR, int CNT>
+__device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, double* __restrict__ coo,
+                                           int64_t slab_base, bool act, double* __restrict__ csr, int64_t csr_base,
+                                           int nb, bool first_round, int lane) {
+  constexpr int kSlab = SlabShape<NR, CNT>::kSlab, kLd = SlabShape<NR, CNT>::kLd;
+  const int h = lane >> 4, l16 = lane & 15;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (coo != nullptr && act && (lane & 3) == 0) {
+    const uint32_t src = smem_u32(st + (lane >> 2) * kLd);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(coo + slab_base), "r"(src),
+                 "r"(kSlab * 8)
+                 : "memory");
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  if (nb > 0 && csr != nullptr) {
+    const int w = nb * CNT;
+    const double* sh = st + h * 4 * kLd;
+    if (CNT % 2 == 0) {
+      double* out = csr + csr_base;
+#pragma unroll 1
+      for (int y = l16; 2 * y < w; y += 16) {
+        const int x = 2 * y, s = x / CNT, rr = x - s * CNT;
+        const unsigned gm = nr->gmap[s];
+        int off[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const int nib = (gm >> (4 * k2)) & 0xF;
+          off[k2] = (nib != 0xF) ? (k2 * kLd + nib * CNT + rr) : -1;
+        }
+#pragma unroll
+        for (int d = 0; d < NR; ++d) {
+          double2 sum = make_double2(0., 0.);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2)
+            if (off[k2] >= 0) {
+              const double2 t = *reinterpret_cast<const double2*>(sh + d * 4 * CNT + off[k2]);
+              sum.x += t.x;
+              sum.y += t.y;
+            }
+          double2* o = reinterpret_cast<double2*>(out + d * w + x);
+          if (!first_round) {
+            const double2 t = *o;
+            sum.x += t.x;
+            sum.y += t.y;
+          }
+          *o = sum;
+        }
+      }
+    } else {
+      double* out = csr + csr_base;
+#pragma unroll 1
+      for (int x = l16; x < w; x += 16) {
+        const int s = x / CNT, rr = x - s * CNT;
+        const unsigned gm = nr->gmap[s];
+        int off[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const int nib = (gm >> (4 * k2)) & 0xF;
+          off[k2] = (nib != 0xF) ? (k2 * kLd + nib * CNT + rr) : -1;
+        }
+#pragma unroll
+        for (int d = 0; d < NR; ++d) {
+          double sum = 0.;
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2)
+            if (off[k2] >= 0) sum += sh[d * 4 * CNT + off[k2]];
+          double* o = out + d * w + x;
+          if (first_round) *o = sum; else *o += sum;
+        }
+      }
+    }
+  }
+  // the staging area is reused by the next matrix: wait until the bulk copies have READ shared memory
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
+constexpr int kRing = 3;                                   // node-record prefetch ring (records of 2 nodes each)
+constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1168 doubles: the largest matrix (KC0)
+constexpr int kWarpSmemV4 = kStageV4 + kRing * 2 * 8;      // + 3 x 2 x 64 B
+
+// Bring the NodeRec of node pair `np`, round r into ring slot `slot` (8 x 16-B cp.async by lanes 0..7).
+__device__ __forceinline__ void ring_fetch(const FusedArgs& F, NodeRec* ring, int slot, int64_t np, int r,
+                                           int64_t npairs, int lane) {
+  if (lane < 8) {
+    const int hh = lane >> 2, q = lane & 3;
+    const int64_t n = 2 * np + hh;
+    char* dst = reinterpret_cast<char*>(ring + slot * 2 + hh) + 16 * q;
+    if (np < npairs && n < F.nown) {
+      const char* src = reinterpret_cast<const char*>(F.noderec + n * F.rmax + r) + 16 * q;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    } else {
+      // empty record: no incidences, no blocks
+      // bytes 0-15: b0, inc[0..1] | 16-47: inc[2..3], gmap[0..11] | 48-63: gmap[12..15], v, nb, pad
+      int4 z = make_int4(-1, -1, -1, -1);
+      if (q == 0) z = make_int4(0, 0, -1, -1);
+      if (q == 3) z = make_int4(-1, -1, 0, 0);
+      *reinterpret_cast<int4*>(dst) = z;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
                                                                          int rstride) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const EvalArgs& A = F.A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* st = smem + warp * kWarpSmemDoubles;
-  double* my = st + lane;
-  signed char* inv = reinterpret_cast<signed char*>(st + kStageDoubles);
+  double* st = smem + warp * kWarpSmemV4;
+  NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
   const int64_t npairs = (F.nown + 1) >> 1;
+  const int rmax = F.rmax;
   const double xib = (b == 1 || b == 2) ? 1. : -1., etab = (b >= 2) ? 1. : -1.;
-  EmitIdx<6, 6> I66;
-  EmitIdx<6, 5> I65;
-  EmitIdx<6, 3> I63;
-  EmitIdx<3, 3> I33;
-  I66.init(lane);
-  I65.init(lane);
-  I63.init(lane);
-  I33.init(lane);
   const int64_t stride_np = int64_t(gridDim.x) * kFusedWarps;
-  int64_t np = int64_t(blockIdx.x) * kFusedWarps + warp;
-  // software pipeline: index chain two node pairs ahead, element record lines one pair ahead (L1 prefetch)
-  NodeWork nxt = fetch_work(F, np, npairs, h, k, b, 0);
-  NodeWork nxt2 = fetch_work(F, np + stride_np, npairs, h, k, b, 0);
+  const int64_t np0 = int64_t(blockIdx.x) * kFusedWarps + warp;
+  // flattened work items j = (node pair, round); ring slot j % 3 holds item j
+  auto item_np = [&](int64_t j) { return np0 + (j / rmax) * stride_np; };
+  ring_fetch(F, ring, 0, item_np(0), 0, npairs, lane);
+  ring_fetch(F, ring, 1, item_np(1), int(1 % rmax), npairs, lane);
 
-  for (; np < npairs; np += stride_np) {
-    const NodeWork cur0 = nxt;
-    nxt = nxt2;
-    nxt2 = fetch_work(F, np + 2 * stride_np, npairs, h, k, b, 0);
-    if (nxt.myslot() >= 0) {
-      const char* pr = reinterpret_cast<const char*>(rec + (nxt.pair0 >> 4) * rstride);
-      for (int off = b * 128; off < rstride * 8; off += 512) prefetch_l1(pr + off);
+  for (int64_t j = 0;; ++j) {
+    const int64_t np = item_np(j);
+    if (np >= npairs) break;
+    const int r = int(j % rmax);
+    ring_fetch(F, ring, int((j + 2) % kRing), item_np(j + 2), int((j + 2) % rmax), npairs, lane);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // items j and j+1 have landed
+    __syncwarp();
+    const NodeRec* nr = ring + int(j % kRing) * 2 + h;
+    {   // L1-prefetch the element records of the next item
+      const int p0n = (ring + int((j + 1) % kRing) * 2 + h)->inc[k];
+      if (p0n >= 0) {
+        const char* pr = reinterpret_cast<const char*>(rec + int64_t(p0n >> 4) * rstride);
+        for (int off = b * 128; off < rstride * 8; off += 512) prefetch_l1(pr + off);
+      }
     }
-    const int vmax = max(__shfl_sync(0xffffffffu, cur0.v(), 0), __shfl_sync(0xffffffffu, cur0.v(), 16));
-    const int rounds = (vmax + 3) >> 2;
-
-    for (int r = 0; r < rounds; ++r) {
-      const NodeWork cur = (r == 0) ? cur0 : fetch_work(F, np, npairs, h, k, b, r);
-      const bool act = cur.myslot() >= 0;
-      const int64_t e = cur.pair0 >> 4;
-      const int a = int(cur.pair0 >> 2) & 3;
-      const int64_t b0 = cur.b0;
-      const int nb = cur.nb();
-      for (int i = lane; i < 8 * kMaxSlots; i += 32) inv[i] = -1;
+    const int64_t b0 = nr->b0;
+    const int nb = nr->nb;
+    const int pair0 = nr->inc[k];
+    const bool act = pair0 >= 0;
+    if (__ballot_sync(0xffffffffu, act) == 0u) {
       __syncwarp();
-      if (act) inv[(h * 4 + k) * kMaxSlots + cur.myslot()] = (signed char)b;
-      const bool first = (r == 0);
-      const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
+      continue;
+    }
+    const int64_t e = act ? (pair0 >> 4) : 0;
+    const int a = act ? ((pair0 >> 2) & 3) : 0;
+    const bool first = (r == 0);
+    const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
 
-      // ---------------- element record (K1) and property row
-      const double* re = rec + e * rstride;
-      Mat3 R;
+    // ---------------- element record (K1) and property row
+    const double2* re2 = reinterpret_cast<const double2*>(rec + e * rstride);
+    double rr_[24];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const double2 t = re2[i];
+      rr_[2 * i] = t.x;
+      rr_[2 * i + 1] = t.y;
+    }
+    Mat3 R;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj) R.a[i][jj] = rr_[3 * i + jj];
+    const double dX10 = rr_[9], dX23 = rr_[10], dX30 = rr_[11], dX21 = rr_[12];
+    const double dY10 = rr_[13], dY23 = rr_[14], dY30 = rr_[15], dY21 = rr_[16];
+    const double idJ[4] = {rr_[17], rr_[18], rr_[19], rr_[20]};
+    const double idJ0 = rr_[21], area = rr_[22];
+    const double* re = rec + e * rstride;
+    const double* prow = A.props + int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE;
+    const double* abd = (rstride == kRecRot) ? re + 36 : prow;
+
+    // Jacobian rows: J11,J12 depend on eta only, J21,J22 on xi only (index 0: -p, 1: +p)
+    double J11e[2], J12e[2], J21x[2], J22x[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double t = i ? kGpF : -kGpF;
+      J11e[i] = 0.25 * ((1. - t) * dX10 + (1. + t) * dX23);
+      J12e[i] = 0.25 * ((1. - t) * dY10 + (1. + t) * dY23);
+      J21x[i] = 0.25 * ((1. - t) * dX30 + (1. + t) * dX21);
+      J22x[i] = 0.25 * ((1. - t) * dY30 + (1. + t) * dY21);
+    }
+    const bool kg_u = (A.what & PF3_KG) != 0;
+
+    // gradient Gram of the pair over the 2x2 Gauss points, the mixed N / N,x sums, and Ge_ab
+    double gxx = 0., gxy = 0., gyx = 0., gyy = 0., pyab = 0., pxab = 0., pyba = 0., pxba = 0., hab = 0., ge = 0.;
+#pragma unroll
+    for (int gp = 0; gp < 4; ++gp) {
+      const int ix = gp >> 1, ie = gp & 1;
+      const double xg = ix ? kGpF : -kGpF, eg = ie ? kGpF : -kGpF;
+      const double dxa = 0.25 * xia * (1. + etaa * eg), dea = 0.25 * etaa * (1. + xia * xg);
+      const double dxb = 0.25 * xib * (1. + etab * eg), deb = 0.25 * etab * (1. + xib * xg);
+      const double wxa = J22x[ix] * dxa - J12e[ie] * dea, wya = -J21x[ix] * dxa + J11e[ie] * dea;
+      const double wxb = J22x[ix] * dxb - J12e[ie] * deb, wyb = -J21x[ix] * dxb + J11e[ie] * deb;
+      const double na = 0.25 * (1. + xia * xg) * (1. + etaa * eg), nbv = 0.25 * (1. + xib * xg) * (1. + etab * eg);
+      const double vax = wxa * idJ[gp], vay = wya * idJ[gp];
+      gxx += vax * wxb;
+      gxy += vax * wyb;
+      gyx += vay * wxb;
+      gyy += vay * wyb;
+      pyab += wya * nbv;
+      pxab += wxa * nbv;
+      pyba += wyb * na;
+      pxba += wxb * na;
+      hab += (na * nbv) * (J11e[ie] * J22x[ix] - J12e[ie] * J21x[ix]);
+      if (kg_u) {
+        const double nxx = re[24 + gp], nyy = re[28 + gp], nxy = re[32 + gp];
+        ge += wxb * (vax * nxx + vay * nxy) + wyb * (vax * nxy + vay * nyy);
+      }
+    }
+    if (A.what & PF3_KG_STRESS) ge = A.Nxx * gxx + A.Nxy * (gxy + gyx) + A.Nyy * gyy;
+
+    // ---------------- KG : Ge_ab * z z^T on the translations
+    if (A.what & (PF3_KG | PF3_KG_STRESS)) {
+      double* sl = st + (lane >> 2) * SlabShape<3, 3>::kLd + b * 3;
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) R.a[i][j] = re[3 * i + j];
-      const double dX10 = re[9], dX23 = re[10], dX30 = re[11], dX21 = re[12];
-      const double dY10 = re[13], dY23 = re[14], dY30 = re[15], dY21 = re[16];
-      double idJ[4];
-#pragma unroll
-      for (int gp = 0; gp < 4; ++gp) idJ[gp] = re[17 + gp];
-      const double idJ0 = re[21], area = re[22];
-      const double* prow = A.props + int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE;
-      const double* abd = (rstride == kRecRot) ? re + 36 : prow;
+        for (int jj = 0; jj < 3; ++jj) sl[i * 12 + jj] = (R.a[i][2] * R.a[jj][2]) * ge;
+      emit_slabs<3, 3>(st, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg, b0 * 9, nb, first,
+                       lane);
+    }
 
-      // Jacobian rows: J11,J12 depend on eta only, J21,J22 on xi only (index 0: -p, 1: +p)
-      double J11e[2], J12e[2], J21x[2], J22x[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const double t = i ? kGpF : -kGpF;
-        J11e[i] = 0.25 * ((1. - t) * dX10 + (1. + t) * dX23);
-        J12e[i] = 0.25 * ((1. - t) * dY10 + (1. + t) * dY23);
-        J21x[i] = 0.25 * ((1. - t) * dX30 + (1. + t) * dX21);
-        J22x[i] = 0.25 * ((1. - t) * dY30 + (1. + t) * dY21);
+    // ---------------- M : H_ab * (T6 m_l T6^T)
+    if (A.what & PF3_M) {
+      double H;
+      if (A.mtype == 0) {
+        H = hab;
+      } else if (A.mtype == 1) {
+        H = 0.0625 * area;
+      } else {
+        // Gauss-Lobatto: detJ at node a on the diagonal, zero elsewhere (quad4.pyx:8873)
+        const double J11n = 0.25 * ((1. - etaa) * dX10 + (1. + etaa) * dX23), J12n = 0.25 * ((1. - etaa) * dY10 + (1. + etaa) * dY23);
+        const double J21n = 0.25 * ((1. - xia) * dX30 + (1. + xia) * dX21), J22n = 0.25 * ((1. - xia) * dY30 + (1. + xia) * dY21);
+        H = (a == b) ? (J11n * J22n - J12n * J21n) : 0.;
       }
-      const bool kg_u = (A.what & PF3_KG) != 0;
-
-      // gradient Gram of the pair over the 2x2 Gauss points, the mixed N / N,x sums, and Ge_ab
-      double gxx = 0., gxy = 0., gyx = 0., gyy = 0., pyab = 0., pxab = 0., pyba = 0., pxba = 0., hab = 0., ge = 0.;
+      const double r0 = prow[24], r1 = prow[25], r2 = prow[26];
+      double* coo = A.mv ? A.mv + A.m_k0 : nullptr;
+      if (A.mtype != 2) {
+        double* sl = st + (lane >> 2) * SlabShape<6, 5>::kLd + b * 5;
 #pragma unroll
-      for (int gp = 0; gp < 4; ++gp) {
-        const int ix = gp >> 1, ie = gp & 1;
-        const double xg = ix ? kGpF : -kGpF, eg = ie ? kGpF : -kGpF;
-        const double dxa = 0.25 * xia * (1. + etaa * eg), dea = 0.25 * etaa * (1. + xia * xg);
-        const double dxb = 0.25 * xib * (1. + etab * eg), deb = 0.25 * etab * (1. + xib * xg);
-        const double wxa = J22x[ix] * dxa - J12e[ie] * dea, wya = -J21x[ix] * dxa + J11e[ie] * dea;
-        const double wxb = J22x[ix] * dxb - J12e[ie] * deb, wyb = -J21x[ix] * dxb + J11e[ie] * deb;
-        const double na = 0.25 * (1. + xia * xg) * (1. + etaa * eg), nbv = 0.25 * (1. + xib * xg) * (1. + etab * eg);
-        const double vax = wxa * idJ[gp], vay = wya * idJ[gp];
-        gxx += vax * wxb;
-        gxy += vax * wyb;
-        gyx += vay * wxb;
-        gyy += vay * wyb;
-        pyab += wya * nbv;
-        pxab += wxa * nbv;
-        pyba += wyb * na;
-        pxba += wxb * na;
-        hab += (na * nbv) * (J11e[ie] * J22x[ix] - J12e[ie] * J21x[ix]);
-        if (kg_u) {
-          const double nxx = re[24 + gp], nyy = re[28 + gp], nxy = re[32 + gp];
-          ge += wxb * (vax * nxx + vay * nxy) + wyb * (vax * nxy + vay * nyy);
+        for (int i = 0; i < 3; ++i) {
+          double tt[3], tr[3], rq[3];
+#pragma unroll
+          for (int jj = 0; jj < 3; ++jj) {
+            tt[jj] = r0 * R.a[i][0] * R.a[jj][0] + r0 * R.a[i][1] * R.a[jj][1] + r0 * R.a[i][2] * R.a[jj][2];
+            tr[jj] = r1 * R.a[i][0] * R.a[jj][1] - r1 * R.a[i][1] * R.a[jj][0];
+            rq[jj] = r2 * R.a[i][0] * R.a[jj][0] + r2 * R.a[i][1] * R.a[jj][1];
+          }
+          sl[i * 20 + 0] = H * tt[0];
+          sl[i * 20 + 1] = H * tt[1];
+          sl[i * 20 + 2] = H * tt[2];
+          sl[i * 20 + 3] = H * tr[(i == 0) ? 1 : 0];
+          sl[i * 20 + 4] = H * tr[(i == 2) ? 1 : 2];
+          // row 3+i: rt = tr^T = -tr (columns j != i), then rr
+          sl[(3 + i) * 20 + 0] = -(H * tr[(i == 0) ? 1 : 0]);
+          sl[(3 + i) * 20 + 1] = -(H * tr[(i == 2) ? 1 : 2]);
+          sl[(3 + i) * 20 + 2] = H * rq[0];
+          sl[(3 + i) * 20 + 3] = H * rq[1];
+          sl[(3 + i) * 20 + 4] = H * rq[2];
         }
-      }
-      if (A.what & PF3_KG_STRESS) ge = A.Nxx * gxx + A.Nxy * (gxy + gyx) + A.Nyy * gyy;
-
-      // ---------------- KG : Ge_ab * z z^T on the translations
-      if (A.what & (PF3_KG | PF3_KG_STRESS)) {
+        emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, b0 * 30, nb, first, lane);
+      } else {
+        double* sl = st + (lane >> 2) * SlabShape<6, 3>::kLd + b * 3;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) my[(i * 3 + j) * kLd] = (R.a[i][2] * R.a[j][2]) * ge;
-        emit_staged<3, 3>(I33, st, inv, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg, b0 * 9,
-                          nb, first, lane);
-      }
-
-      // ---------------- M : H_ab * (T6 m_l T6^T)
-      if (A.what & PF3_M) {
-        double H;
-        if (A.mtype == 0) {
-          H = hab;
-        } else if (A.mtype == 1) {
-          H = 0.0625 * area;
-        } else {
-          // Gauss-Lobatto: detJ at node a on the diagonal, zero elsewhere (quad4.pyx:8873)
-          const double J11n = 0.25 * ((1. - etaa) * dX10 + (1. + etaa) * dX23), J12n = 0.25 * ((1. - etaa) * dY10 + (1. + etaa) * dY23);
-          const double J21n = 0.25 * ((1. - xia) * dX30 + (1. + xia) * dX21), J22n = 0.25 * ((1. - xia) * dY30 + (1. + xia) * dY21);
-          H = (a == b) ? (J11n * J22n - J12n * J21n) : 0.;
-        }
-        const double r0 = prow[24], r1 = prow[25], r2 = prow[26];
-        double* coo = A.mv ? A.mv + A.m_k0 : nullptr;
-        if (A.mtype != 2) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            double tt[3], tr[3], rr[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              tt[j] = r0 * R.a[i][0] * R.a[j][0] + r0 * R.a[i][1] * R.a[j][1] + r0 * R.a[i][2] * R.a[j][2];
-              tr[j] = r1 * R.a[i][0] * R.a[j][1] - r1 * R.a[i][1] * R.a[j][0];
-              rr[j] = r2 * R.a[i][0] * R.a[j][0] + r2 * R.a[i][1] * R.a[j][1];
-            }
-            my[(i * 5 + 0) * kLd] = H * tt[0];
-            my[(i * 5 + 1) * kLd] = H * tt[1];
-            my[(i * 5 + 2) * kLd] = H * tt[2];
-            my[(i * 5 + 3) * kLd] = H * tr[(i == 0) ? 1 : 0];
-            my[(i * 5 + 4) * kLd] = H * tr[(i == 2) ? 1 : 2];
-            // row 3+i: rt = tr^T = -tr (columns j != i), then rr
-            my[((3 + i) * 5 + 0) * kLd] = -(H * tr[(i == 0) ? 1 : 0]);
-            my[((3 + i) * 5 + 1) * kLd] = -(H * tr[(i == 2) ? 1 : 2]);
-            my[((3 + i) * 5 + 2) * kLd] = H * rr[0];
-            my[((3 + i) * 5 + 3) * kLd] = H * rr[1];
-            my[((3 + i) * 5 + 4) * kLd] = H * rr[2];
+          for (int jj = 0; jj < 3; ++jj) {
+            sl[i * 12 + jj] = H * (r0 * R.a[i][0] * R.a[jj][0] + r0 * R.a[i][1] * R.a[jj][1] + r0 * R.a[i][2] * R.a[jj][2]);
+            sl[(3 + i) * 12 + jj] = H * (r2 * R.a[i][0] * R.a[jj][0] + r2 * R.a[i][1] * R.a[jj][1]);
           }
-          emit_staged<6, 5>(I65, st, inv, coo, e * 480 + a * 120, act, F.csr_m, b0 * 30, nb, first, lane);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              my[(i * 3 + j) * kLd] = H * (r0 * R.a[i][0] * R.a[j][0] + r0 * R.a[i][1] * R.a[j][1] + r0 * R.a[i][2] * R.a[j][2]);
-              my[((3 + i) * 3 + j) * kLd] = H * (r2 * R.a[i][0] * R.a[j][0] + r2 * R.a[i][1] * R.a[j][1]);
-            }
-          emit_staged<6, 3>(I63, st, inv, coo, e * 480 + a * 72, act, F.csr_m, b0 * 18, nb, first, lane);
-        }
-      }
-
-      // ---------------- KC0 : the 6x6 block (a, b)
-      if (A.what & PF3_KC0) {
-        double cA[6], cB[6], cD[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          cA[i] = abd[i];
-          cB[i] = abd[6 + i];
-          cD[i] = abd[12 + i];
-        }
-        const double J11c = 0.25 * (dX10 + dX23), J12c = 0.25 * (dY10 + dY23);
-        const double J21c = 0.25 * (dX30 + dX21), J22c = 0.25 * (dY30 + dY21);
-        const double w0 = 4. * (J11c * J22c - J12c * J21c);
-        const double N0xa = (J22c * 0.25 * xia - J12c * 0.25 * etaa) * idJ0;
-        const double N0ya = (-J21c * 0.25 * xia + J11c * 0.25 * etaa) * idJ0;
-        const double N0xb = (J22c * 0.25 * xib - J12c * 0.25 * etab) * idJ0;
-        const double N0yb = (-J21c * 0.25 * xib + J11c * 0.25 * etab) * idJ0;
-        const double k13 = prow[21], k23 = prow[22], hh = prow[23];
-        const double E44 = prow[18] * k23, E45 = prow[19] * 0.5 * (k13 + k23), E55 = prow[20] * k13;
-        const double sgn = ((a ^ b) & 1) ? -1. : 1.;
-        double kd = 1., hg0 = 0., hg1 = 0., hg2 = 0., hg3 = 0., hg4 = 0.;
-        if (KIND == PF3_QUAD4R) {
-          double K6ROT = 100., hgf[5] = {1., 1., 1., 1., 1.};
-          if (A.eparam != nullptr) {
-            const double* ep = A.eparam + e * PF3_EPARAM_STRIDE;
-            K6ROT = ep[0];
-#pragma unroll
-            for (int d = 0; d < 5; ++d) hgf[d] = ep[2 + d];
-          }
-          kd = 1e-6 * K6ROT * cA[5];
-          const double den = -cA[0] * cA[3] * cA[5] + cA[0] * cA[4] * cA[4] + cA[1] * cA[1] * cA[5] -
-                             2 * cA[1] * cA[2] * cA[4] + cA[2] * cA[2] * cA[3];
-          const double a11 = (-cA[3] * cA[5] + cA[4] * cA[4]) / den, a22 = (-cA[0] * cA[5] + cA[2] * cA[2]) / den;
-          const double E1eq = 1. / (hh * a11), E2eq = 1. / (hh * a22);
-          const double dd = 1.0 + 1.0 / area;
-          const double Eu = hgf[0] * 0.1 * E1eq * hh / dd, Ev = hgf[1] * 0.1 * E2eq * hh / dd;
-          const double Erx = hgf[3] * 0.1 * E2eq * hh * hh * hh / dd, Ery = hgf[4] * 0.1 * E1eq * hh * hh * hh / dd;
-          const double Ew = hgf[2] * 0.5 * (Erx + Ery);
-          // gamma_a = +-(j11 j22 + j12 j21)/4 with j = J0^-1 (quad4r.pyx:3116)
-          const double gam = 0.25 * (J22c * J11c + J12c * J21c) * idJ0 * idJ0;
-          const double wg2 = sgn * w0 * gam * gam;
-          hg0 = wg2 * Eu;
-          hg1 = wg2 * Ev;
-          hg2 = wg2 * Ew;
-          hg3 = wg2 * Erx;
-          hg4 = wg2 * Ery;
-        }
-        const bool thick = (KIND == PF3_QUAD4) && (hh / sqrt(area) >= 1.);
-        // constitutive Gram: 2x2 Gauss (Quad4) or centre point with weight 4 detJ0 (Quad4R)
-        double cxx = gxx, cxy = gxy, cyx = gyx, cyy = gyy;
-        if (KIND == PF3_QUAD4R) {
-          const double wa = w0 * N0xa, wb = w0 * N0ya;
-          cxx = wa * N0xb;
-          cxy = wa * N0yb;
-          cyx = wb * N0xb;
-          cyy = wb * N0yb;
-        }
-        const double tSa = w0 * (E44 * N0ya + E45 * N0xa), sSa = w0 * (E45 * N0ya + E55 * N0xa);
-        const double tSb = w0 * (E44 * N0yb + E45 * N0xb), sSb = w0 * (E45 * N0yb + E55 * N0xb);
-        double o[3][3];
-        {
-          const double uu = f_pp(cA, cxx, cxy, cyx, cyy) + 0.25 * kd * gyy + hg0;
-          const double uv = f_pq(cA, cxx, cxy, cyx, cyy) - 0.25 * kd * gyx;
-          const double vu = f_qp(cA, cxx, cxy, cyx, cyy) - 0.25 * kd * gxy;
-          const double vv = f_qq(cA, cxx, cxy, cyx, cyy) + 0.25 * kd * gxx + hg1;
-          const double ww = (thick ? (E44 * gyy + E45 * (gxy + gyx) + E55 * gxx) : (tSa * N0yb + sSa * N0xb)) + hg2;
-          rot_block_diag5(R, uu, uv, vu, vv, ww, o);
-          stage9(my, o, 0, 0, 6);
-        }
-        rot_block_8(R, -f_pq(cB, cxx, cxy, cyx, cyy), f_pp(cB, cxx, cxy, cyx, cyy), 0.5 * kd * pyab,
-                    -f_qq(cB, cxx, cxy, cyx, cyy), f_qp(cB, cxx, cxy, cyx, cyy), -0.5 * kd * pxab, -0.25 * tSa,
-                    0.25 * sSa, o);
-        stage9(my, o, 0, 3, 6);
-        rot_block_8(R, -f_qp(cB, cxx, cxy, cyx, cyy), -f_qq(cB, cxx, cxy, cyx, cyy), -0.25 * tSb,
-                    f_pp(cB, cxx, cxy, cyx, cyy), f_pq(cB, cxx, cxy, cyx, cyy), 0.25 * sSb, 0.5 * kd * pyba,
-                    -0.5 * kd * pxba, o);
-        stage9(my, o, 3, 0, 6);
-        {
-          const double c44 = w0 * E44 * 0.0625, c45 = w0 * E45 * 0.0625, c55 = w0 * E55 * 0.0625;
-          const double rxrx = f_qq(cD, cxx, cxy, cyx, cyy) + c44 + hg3;
-          const double rxry = -f_qp(cD, cxx, cxy, cyx, cyy) - c45;
-          const double ryrx = -f_pq(cD, cxx, cxy, cyx, cyy) - c45;
-          const double ryry = f_pp(cD, cxx, cxy, cyx, cyy) + c55 + hg4;
-          rot_block_diag5(R, rxrx, rxry, ryrx, ryry, kd * hab, o);
-          stage9(my, o, 3, 3, 6);
-        }
-        emit_staged<6, 6>(I66, st, inv, A.kc0v ? A.kc0v + A.kc0_k0 : nullptr, e * 576 + a * 144, act, F.csr_kc0,
-                          b0 * 36, nb, first, lane);
+        emit_slabs<6, 3>(st, nr, coo, e * 480 + a * 72, act, F.csr_m, b0 * 18, nb, first, lane);
       }
     }
+
+    // ---------------- KC0 : the 6x6 block (a, b)
+    if (A.what & PF3_KC0) {
+      double cA[6], cB[6], cD[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        cA[i] = abd[i];
+        cB[i] = abd[6 + i];
+        cD[i] = abd[12 + i];
+      }
+      const double J11c = 0.25 * (dX10 + dX23), J12c = 0.25 * (dY10 + dY23);
+      const double J21c = 0.25 * (dX30 + dX21), J22c = 0.25 * (dY30 + dY21);
+      const double w0 = 4. * (J11c * J22c - J12c * J21c);
+      const double N0xa = (J22c * 0.25 * xia - J12c * 0.25 * etaa) * idJ0;
+      const double N0ya = (-J21c * 0.25 * xia + J11c * 0.25 * etaa) * idJ0;
+      const double N0xb = (J22c * 0.25 * xib - J12c * 0.25 * etab) * idJ0;
+      const double N0yb = (-J21c * 0.25 * xib + J11c * 0.25 * etab) * idJ0;
+      const double k13 = prow[21], k23 = prow[22], hh = prow[23];
+      const double E44 = prow[18] * k23, E45 = prow[19] * 0.5 * (k13 + k23), E55 = prow[20] * k13;
+      const double sgn = ((a ^ b) & 1) ? -1. : 1.;
+      double kd = 1., hg0 = 0., hg1 = 0., hg2 = 0., hg3 = 0., hg4 = 0.;
+      if (KIND == PF3_QUAD4R) {
+        double K6ROT = 100., hgf[5] = {1., 1., 1., 1., 1.};
+        if (A.eparam != nullptr) {
+          const double* ep = A.eparam + e * PF3_EPARAM_STRIDE;
+          K6ROT = ep[0];
+#pragma unroll
+          for (int d = 0; d < 5; ++d) hgf[d] = ep[2 + d];
+        }
+        kd = 1e-6 * K6ROT * cA[5];
+        const double den = -cA[0] * cA[3] * cA[5] + cA[0] * cA[4] * cA[4] + cA[1] * cA[1] * cA[5] -
+                           2 * cA[1] * cA[2] * cA[4] + cA[2] * cA[2] * cA[3];
+        const double a11 = (-cA[3] * cA[5] + cA[4] * cA[4]) / den, a22 = (-cA[0] * cA[5] + cA[2] * cA[2]) / den;
+        const double E1eq = 1. / (hh * a11), E2eq = 1. / (hh * a22);
+        const double dd = 1.0 + 1.0 / area;
+        const double Eu = hgf[0] * 0.1 * E1eq * hh / dd, Ev = hgf[1] * 0.1 * E2eq * hh / dd;
+        const double Erx = hgf[3] * 0.1 * E2eq * hh * hh * hh / dd, Ery = hgf[4] * 0.1 * E1eq * hh * hh * hh / dd;
+        const double Ew = hgf[2] * 0.5 * (Erx + Ery);
+        // gamma_a = +-(j11 j22 + j12 j21)/4 with j = J0^-1 (quad4r.pyx:3116)
+        const double gam = 0.25 * (J22c * J11c + J12c * J21c) * idJ0 * idJ0;
+        const double wg2 = sgn * w0 * gam * gam;
+        hg0 = wg2 * Eu;
+        hg1 = wg2 * Ev;
+        hg2 = wg2 * Ew;
+        hg3 = wg2 * Erx;
+        hg4 = wg2 * Ery;
+      }
+      const bool thick = (KIND == PF3_QUAD4) && (hh / sqrt(area) >= 1.);
+      // constitutive Gram: 2x2 Gauss (Quad4) or centre point with weight 4 detJ0 (Quad4R)
+      double cxx = gxx, cxy = gxy, cyx = gyx, cyy = gyy;
+      if (KIND == PF3_QUAD4R) {
+        const double wa = w0 * N0xa, wb = w0 * N0ya;
+        cxx = wa * N0xb;
+        cxy = wa * N0yb;
+        cyx = wb * N0xb;
+        cyy = wb * N0yb;
+      }
+      const double tSa = w0 * (E44 * N0ya + E45 * N0xa), sSa = w0 * (E45 * N0ya + E55 * N0xa);
+      const double tSb = w0 * (E44 * N0yb + E45 * N0xb), sSb = w0 * (E45 * N0yb + E55 * N0xb);
+      double2* sl2 = reinterpret_cast<double2*>(st + (lane >> 2) * SlabShape<6, 6>::kLd + b * 6);
+      double o1[3][3], o2[3][3];
+      {
+        const double uu = f_pp(cA, cxx, cxy, cyx, cyy) + 0.25 * kd * gyy + hg0;
+        const double uv = f_pq(cA, cxx, cxy, cyx, cyy) - 0.25 * kd * gyx;
+        const double vu = f_qp(cA, cxx, cxy, cyx, cyy) - 0.25 * kd * gxy;
+        const double vv = f_qq(cA, cxx, cxy, cyx, cyy) + 0.25 * kd * gxx + hg1;
+        const double ww = (thick ? (E44 * gyy + E45 * (gxy + gyx) + E55 * gxx) : (tSa * N0yb + sSa * N0xb)) + hg2;
+        rot_block_diag5(R, uu, uv, vu, vv, ww, o1);
+      }
+      rot_block_8(R, -f_pq(cB, cxx, cxy, cyx, cyy), f_pp(cB, cxx, cxy, cyx, cyy), 0.5 * kd * pyab,
+                  -f_qq(cB, cxx, cxy, cyx, cyy), f_qp(cB, cxx, cxy, cyx, cyy), -0.5 * kd * pxab, -0.25 * tSa,
+                  0.25 * sSa, o2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {   // rows u v w of node a: 6 columns of node b, 24 doubles per COO row
+        sl2[i * 12 + 0] = make_double2(o1[i][0], o1[i][1]);
+        sl2[i * 12 + 1] = make_double2(o1[i][2], o2[i][0]);
+        sl2[i * 12 + 2] = make_double2(o2[i][1], o2[i][2]);
+      }
+      rot_block_8(R, -f_qp(cB, cxx, cxy, cyx, cyy), -f_qq(cB, cxx, cxy, cyx, cyy), -0.25 * tSb,
+                  f_pp(cB, cxx, cxy, cyx, cyy), f_pq(cB, cxx, cxy, cyx, cyy), 0.25 * sSb, 0.5 * kd * pyba,
+                  -0.5 * kd * pxba, o1);
+      {
+        const double c44 = w0 * E44 * 0.0625, c45 = w0 * E45 * 0.0625, c55 = w0 * E55 * 0.0625;
+        const double rxrx = f_qq(cD, cxx, cxy, cyx, cyy) + c44 + hg3;
+        const double rxry = -f_qp(cD, cxx, cxy, cyx, cyy) - c45;
+        const double ryrx = -f_pq(cD, cxx, cxy, cyx, cyy) - c45;
+        const double ryry = f_pp(cD, cxx, cxy, cyx, cyy) + c55 + hg4;
+        rot_block_diag5(R, rxrx, rxry, ryrx, ryry, kd * hab, o2);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        sl2[(3 + i) * 12 + 0] = make_double2(o1[i][0], o1[i][1]);
+        sl2[(3 + i) * 12 + 1] = make_double2(o1[i][2], o2[i][0]);
+        sl2[(3 + i) * 12 + 2] = make_double2(o2[i][1], o2[i][2]);
+      }
+      emit_slabs<6, 6>(st, nr, A.kc0v ? A.kc0v + A.kc0_k0 : nullptr, e * 576 + a * 144, act, F.csr_kc0, b0 * 36, nb,
+                       first, lane);
+    }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace
 
-size_t fused_smem_bytes() { return size_t(kFusedWarps) * kWarpSmemDoubles * sizeof(double); }
+size_t fused_smem_bytes() { return size_t(kFusedWarps) * kWarpSmemV4 * sizeof(double); }
 int fused_max_slots() { return kMaxSlots; }
 int fused_record_stride(const EvalArgs& A) { return A.evec != nullptr ? kRecRot : kRecPlain; }
 
