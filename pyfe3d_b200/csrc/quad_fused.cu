@@ -208,7 +208,22 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
 
 constexpr int kRing = 3;                                   // node-record prefetch ring (records of 2 nodes each)
 constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1168 doubles: the largest matrix (KC0)
-constexpr int kWarpSmemV4 = kStageV4 + kRing * 2 * 8;      // + 3 x 2 x 64 B
+constexpr int kErecLd = kRecRot + 2;                        // staged element-record stride (58: conflict-free, 16-B aligned)
+constexpr int kErecDoubles = 2 * 8 * kErecLd;               // double buffer x 8 incidences
+constexpr int kWarpSmemV4 = kStageV4 + kRing * 2 * 8 + kErecDoubles;
+
+// Stage the element records of the 8 incidences of an item into shared memory with 16-B cp.async; the 4 lanes
+// of an incidence split the record's chunks.
+__device__ __forceinline__ void erec_fetch(const double* __restrict__ rec, int rstride, double* buf, int pair0,
+                                           int lane) {
+  if (pair0 >= 0) {
+    const char* src = reinterpret_cast<const char*>(rec + int64_t(pair0 >> 4) * rstride);
+    char* dst = reinterpret_cast<char*>(buf + (lane >> 2) * kErecLd);
+    for (int c = (lane & 3) * 16; c < rstride * 8; c += 64)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 // Bring the NodeRec of node pair `np`, round r into ring slot `slot` (8 x 16-B cp.async by lanes 0..7).
 __device__ __forceinline__ void ring_fetch(const FusedArgs& F, NodeRec* ring, int slot, int64_t np, int r,
@@ -240,6 +255,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* st = smem + warp * kWarpSmemV4;
   NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
+  double* erec = st + kStageV4 + kRing * 2 * 8;
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
   const int64_t npairs = (F.nown + 1) >> 1;
   const int rmax = F.rmax;
@@ -250,22 +266,20 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
   auto item_np = [&](int64_t j) { return np0 + (j / rmax) * stride_np; };
   ring_fetch(F, ring, 0, item_np(0), 0, npairs, lane);
   ring_fetch(F, ring, 1, item_np(1), int(1 % rmax), npairs, lane);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  erec_fetch(rec, rstride, erec, (ring + h)->inc[k], lane);   // element records of item 0
 
   for (int64_t j = 0;; ++j) {
     const int64_t np = item_np(j);
     if (np >= npairs) break;
     const int r = int(j % rmax);
     ring_fetch(F, ring, int((j + 2) % kRing), item_np(j + 2), int((j + 2) % rmax), npairs, lane);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");   // items j and j+1 have landed
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j, j+1 and element records j have landed
     __syncwarp();
     const NodeRec* nr = ring + int(j % kRing) * 2 + h;
-    {   // L1-prefetch the element records of the next item
-      const int p0n = (ring + int((j + 1) % kRing) * 2 + h)->inc[k];
-      if (p0n >= 0) {
-        const char* pr = reinterpret_cast<const char*>(rec + int64_t(p0n >> 4) * rstride);
-        for (int off = b * 128; off < rstride * 8; off += 512) prefetch_l1(pr + off);
-      }
-    }
+    // element records of the next item start flowing now
+    erec_fetch(rec, rstride, erec + int((j + 1) & 1) * 8 * kErecLd, (ring + int((j + 1) % kRing) * 2 + h)->inc[k], lane);
     const int64_t b0 = nr->b0;
     const int nb = nr->nb;
     const int pair0 = nr->inc[k];
@@ -280,7 +294,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
     const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
 
     // ---------------- element record (K1) and property row
-    const double2* re2 = reinterpret_cast<const double2*>(rec + e * rstride);
+    const double* re = erec + int(j & 1) * 8 * kErecLd + (lane >> 2) * kErecLd;
+    const double2* re2 = reinterpret_cast<const double2*>(re);
     double rr_[24];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
@@ -297,7 +312,6 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
     const double dY10 = rr_[13], dY23 = rr_[14], dY30 = rr_[15], dY21 = rr_[16];
     const double idJ[4] = {rr_[17], rr_[18], rr_[19], rr_[20]};
     const double idJ0 = rr_[21], area = rr_[22];
-    const double* re = rec + e * rstride;
     const double* prow = A.props + int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE;
     const double* abd = (rstride == kRecRot) ? re + 36 : prow;
 
