@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Throughput of the other BASELINE.json configurations (device-resident, values only, CUDA events).
+Not the headline metric (bench.py is); prints one JSON line per config."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pyfe3d_b200 import meshes  # noqa: E402
+from pyfe3d_b200.batch import AssemblyPlan, ElementBatch  # noqa: E402
+from tests import util  # noqa: E402
+
+
+def timeit(fn, steps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def run(name, case, mats, fused, scale=1.0):
+    b = util.batch_from_case(case)
+    nn = case["ndof"] // 6
+    ne = case["conn"].shape[0]
+    kw = {}
+    for m in mats:
+        if m == "KGs":
+            kw["KG_given_stress"] = case.get("stress", (0., 0., 1.))
+        elif m.startswith("M"):
+            kw["M"] = True
+            kw["mtype"] = int(m[1])
+        else:
+            kw[m] = True
+    names = sorted(set("KG" if m == "KGs" else ("M" if m.startswith("M") else m) for m in mats))
+    mtype = kw.get("mtype", 0)
+    plans = {m: AssemblyPlan(m, nn, [b], mtype=mtype) for m in names}
+    if fused:
+        coo, csr = plans["KC0"].evaluate_assemble(**kw)
+        ms = timeit(lambda: plans["KC0"].evaluate_assemble(coo=coo, csr=csr, **kw))
+    else:
+        coo = b.evaluate(indices=False, **kw)
+        csr = {m: torch.empty(plans[m].nnz, dtype=torch.float64, device=b.device) for m in names}
+
+        def step():
+            b.evaluate(indices=False, out=coo, **kw)
+            for m in names:
+                plans[m].assemble(coo[m].v, out=csr[m])
+        ms = timeit(step)
+    bytes_el = sum(b.sizes[m] * 8 for m in names)
+    nnz = sum(plans[m].nnz for m in names)
+    alg = ne * bytes_el + nnz * 8
+    print(json.dumps({"config": name, "kind": case["kind"], "elements": ne, "matrices": list(mats),
+                      "path": "fused" if fused else "two-pass", "ms_per_step": ms, "elements_per_s": ne / ms * 1e3,
+                      "algorithmic_GBps": alg / ms / 1e6, "frac_of_6538.9": alg / ms / 1e6 / 6538.9}))
+    del plans, coo, csr, b
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    small = "--small" in sys.argv
+    f = 0.1 if small else 1.0
+    run("config2 BeamC arc 100k, KC0+M", meshes.arc_beamc(int(100001 * f)), ("KC0", "M0"), False)
+    run("config3 Quad4R cylinder 1M, KC0+KG_given_stress", meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)),
+        ("KC0", "KGs"), True)
+    run("config3 (two-pass)", meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)), ("KC0", "KGs"), False)
+    run("config4 Tria3R distorted plate 4M, KC0+M(mtype1)", meshes.plate_tria3r(int(1415 * f ** 0.5), int(1415 * f ** 0.5)),
+        ("KC0", "M1"), False)
