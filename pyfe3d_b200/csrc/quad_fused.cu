@@ -25,6 +25,9 @@ namespace pf3 {
 
 namespace {
 
+#ifndef PF3_COO_TMA
+#define PF3_COO_TMA 1   // 1: COO slabs leave as TMA bulk copies; 0: 16-B stores by the incidence's 4 lanes
+#endif
 constexpr double kGpF = 0.5773502691896257645092;
 constexpr int kFusedWarps = 4;
 constexpr int kLd = 36;                     // staging leading dimension: 36 mod 16 = 4 -> <=2-way LDS conflicts
@@ -134,6 +137,7 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
                                            int nb, bool first_round, int lane) {
   constexpr int kSlab = SlabShape<NR, CNT>::kSlab, kLd = SlabShape<NR, CNT>::kLd;
   const int h = lane >> 4, l16 = lane & 15;
+#if PF3_COO_TMA
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
   if (coo != nullptr && act && (lane & 3) == 0) {
@@ -143,6 +147,17 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
                  : "memory");
   }
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#else
+  __syncwarp();
+  if (coo != nullptr && act) {
+    // the 4 lanes of an incidence stream their own slab: 16-B loads/stores, immediate offsets, no index math
+    const double2* src = reinterpret_cast<const double2*>(st + (lane >> 2) * kLd) + (lane & 3);
+    double2* dst = reinterpret_cast<double2*>(coo + slab_base) + (lane & 3);
+#pragma unroll
+    for (int i = 0; i < (kSlab / 2 + 3) / 4; ++i)
+      if ((kSlab / 2) % 4 == 0 || 4 * i + (lane & 3) < kSlab / 2) dst[4 * i] = src[4 * i];
+  }
+#endif
   if (nb > 0 && csr != nullptr) {
     const int w = nb * CNT;
     const double* sh = st + h * 4 * kLd;
@@ -201,9 +216,16 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
       }
     }
   }
-  // the staging area is reused by the next matrix: wait until the bulk copies have READ shared memory
+  __syncwarp();
+}
+
+// The staging area is reused by the next matrix: before writing it again, wait until the bulk copies issued
+// from it have READ shared memory.  Called as late as possible so the copies drain behind arithmetic.
+__device__ __forceinline__ void stage_reuse_wait() {
+#if PF3_COO_TMA
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
+#endif
 }
 
 constexpr int kRing = 3;                                   // node-record prefetch ring (records of 2 nodes each)
@@ -358,6 +380,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
     // ---------------- KG : Ge_ab * z z^T on the translations
     if (A.what & (PF3_KG | PF3_KG_STRESS)) {
       double* sl = st + (lane >> 2) * SlabShape<3, 3>::kLd + b * 3;
+      stage_reuse_wait();
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -383,6 +406,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
       double* coo = A.mv ? A.mv + A.m_k0 : nullptr;
       if (A.mtype != 2) {
         double* sl = st + (lane >> 2) * SlabShape<6, 5>::kLd + b * 5;
+        stage_reuse_wait();
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           double tt[3], tr[3], rq[3];
@@ -407,6 +431,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
         emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, b0 * 30, nb, first, lane);
       } else {
         double* sl = st + (lane >> 2) * SlabShape<6, 3>::kLd + b * 3;
+        stage_reuse_wait();
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -489,6 +514,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
       rot_block_8(R, -f_pq(cB, cxx, cxy, cyx, cyy), f_pp(cB, cxx, cxy, cyx, cyy), 0.5 * kd * pyab,
                   -f_qq(cB, cxx, cxy, cyx, cyy), f_qp(cB, cxx, cxy, cyx, cyy), -0.5 * kd * pxab, -0.25 * tSa,
                   0.25 * sSa, o2);
+      stage_reuse_wait();
 #pragma unroll
       for (int i = 0; i < 3; ++i) {   // rows u v w of node a: 6 columns of node b, 24 doubles per COO row
         sl2[i * 12 + 0] = make_double2(o1[i][0], o1[i][1]);
