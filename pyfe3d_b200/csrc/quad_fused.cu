@@ -254,9 +254,17 @@ __device__ __forceinline__ void ring_fetch(const FusedArgs& F, NodeRec* ring, in
     const int hh = lane >> 2, q = lane & 3;
     const int64_t n = 2 * np + hh;
     char* dst = reinterpret_cast<char*>(ring + slot * 2 + hh) + 16 * q;
-    if (np < npairs && n < F.nown) {
+    if (np < npairs && n < F.nown && F.noderec != nullptr) {
       const char* src = reinterpret_cast<const char*>(F.noderec + n * F.rmax + r) + 16 * q;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    } else if (np < npairs && n < F.nown) {
+      // element mode (COO only, no plan): "node" n is element n, its 4 incidences are its own 4 row slabs
+      const int p0 = int(n) * 16;
+      int4 z = make_int4(-1, -1, -1, -1);
+      if (q == 0) z = make_int4(0, 0, p0, p0 + 4);
+      if (q == 1) z = make_int4(p0 + 8, p0 + 12, -1, -1);
+      if (q == 3) z = make_int4(-1, -1, 4, 0);   // v = 4, nb = 0
+      *reinterpret_cast<int4*>(dst) = z;
     } else {
       // empty record: no incidences, no blocks
       // bytes 0-15: b0, inc[0..1] | 16-47: inc[2..3], gmap[0..11] | 48-63: gmap[12..15], v, nb, pad

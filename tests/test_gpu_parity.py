@@ -50,7 +50,9 @@ def test_values_only_and_accumulate():
     assert torch.equal(k1.v, k2.v)
     # accumulate=True reproduces the reference's `+=` (quad4.pyx:1313)
     b.evaluate(KC0=True, out={"KC0": k1}, accumulate=True)
-    assert torch.allclose(k1.v, 2 * k2.v, rtol=1e-15, atol=0)
+    # (the `+=` path runs the thread-per-element kernel, the overwrite path the pair-lane kernel: same
+    # mathematics, different rounding order)
+    assert util.block_relerr(k1.v.cpu().numpy(), 2 * k2.v.cpu().numpy(), case["conn"].shape[0]) <= 1e-13
 
 
 @pytest.mark.parametrize("name", ["quad4_mesh", "quad4r_mesh", "tria3r_mesh", "beamc_chain", "truss_chain",
