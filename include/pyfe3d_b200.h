@@ -172,6 +172,11 @@ int pf3_eval_state(pf3_context* ctx, const pf3_batch* batch, double* state_out);
 /* probe.finte (local internal force, update_probe_finte e.g. quad4.pyx:1174): out[ne*6*nn] */
 int pf3_eval_finte(pf3_context* ctx, const pf3_batch* batch, double* finte_out);
 
+/* Quad4Probe.update_BL(xi, eta) (quad4.pyx:273-395): the 11 strain-interpolation rows (BLexx BLeyy BLgxy
+ * BLkxx BLkyy BLkxy BLgyz_grad BLgyz_rot BLgxz_grad BLgxz_rot BLdrilling, 24 doubles each) of n probes from
+ * their local coordinates xe[n*12]; out[n*264]. */
+int pf3_quad4_update_BL(pf3_context* ctx, int64_t n, const double* xe, double xi, double eta, double* out);
+
 /* ---- assembly: replaces scipy.sparse.coo_matrix((v,(r,c))).tocsr() ------- */
 /* (call site tests/test_quad4_static_point_load.py:80).
  * Structured plan: built from connectivity only (indices are a pure function of it).

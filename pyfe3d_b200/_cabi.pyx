@@ -62,6 +62,7 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_nrows(const pf3_plan*, int64_t*)
     int pf3_plan_pattern(pf3_context*, const pf3_plan*, int64_t* indptr, int64_t* indices) nogil
     int pf3_plan_nblocks(const pf3_plan*, int64_t*)
+    int pf3_quad4_update_BL(pf3_context*, int64_t n, const double* xe, double xi, double eta, double* out) nogil
     int pf3_eval_assemble(pf3_context*, const pf3_batch*, const pf3_plan*, int what, const pf3_coo*, const pf3_coo*,
                           const pf3_coo*, double*, double*, double*) nogil
     int pf3_plan_assemble(pf3_context*, const pf3_plan*, const double* coo_v, double* csr_v) nogil
@@ -201,6 +202,12 @@ cdef class Context:
         cdef int rc
         with nogil:
             rc = pf3_eval_state(self.ctx, &b.b, <double*>out)
+        _check(rc)
+
+    def quad4_update_BL(self, int64_t n, uintptr_t xe, double xi, double eta, uintptr_t out):
+        cdef int rc
+        with nogil:
+            rc = pf3_quad4_update_BL(self.ctx, n, <const double*>xe, xi, eta, <double*>out)
         _check(rc)
 
     def eval_finte(self, Batch b, uintptr_t out):

@@ -12,6 +12,7 @@ struct pf3_plan;
 namespace pf3 {
 cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st);
 cudaError_t launch_tria(const EvalArgs& A, cudaStream_t st);
+cudaError_t launch_quad4_BL(int64_t n, const double* xe, double xi, double eta, double* out, cudaStream_t st);
 cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st);
 int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnodes, int ngroups,
                            const pf3_batch* groups, const int64_t* coo_offsets, int64_t node_begin,
@@ -395,6 +396,15 @@ int pf3_eval_finte(pf3_context* ctx, const pf3_batch* b, double* finte_out) {
   A.what = PF3_FINT;
   A.finte = finte_out;
   return launch_eval(ctx, A, b->kind);
+}
+
+int pf3_quad4_update_BL(pf3_context* ctx, int64_t n, const double* xe, double xi, double eta, double* out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!xe || !out))) return PF3_E_BAD_ARG;
+  cudaError_t e = pf3::launch_quad4_BL(n, xe, xi, eta, out, ctx->stream);
+  ++ctx->launches;
+  return int(e);
 }
 
 int pf3_plan_create(pf3_context* ctx, int matrix, int64_t nnodes, int ngroups, const pf3_batch* groups,

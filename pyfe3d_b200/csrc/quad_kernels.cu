@@ -544,6 +544,46 @@ __global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
 
 }  // namespace
 
+// Quad4Probe.update_BL (quad4.pyx:273-395): the 11 strain-interpolation rows at one natural point.
+// out[11][24] in the reference's attribute order: BLexx BLeyy BLgxy BLkxx BLkyy BLkxy BLgyz_grad BLgyz_rot
+// BLgxz_grad BLgxz_rot BLdrilling.  One thread per probe (n probes: xe[n][12], out[n][264]).
+__global__ void quad4_BL_kernel(int64_t n, const double* __restrict__ xe, double xi, double eta, double* __restrict__ out) {
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const double* p = xe + 12 * t;
+  const double X[4] = {p[0], p[3], p[6], p[9]}, Y[4] = {p[1], p[4], p[7], p[10]};
+  double wx[4], wy[4], dJ;
+  jac_at(X, Y, xi, eta, wx, wy, dJ);
+  const double xs[4] = {-1., 1., 1., -1.}, es[4] = {-1., -1., 1., 1.};
+  double* o = out + 264 * t;
+  for (int i = 0; i < 264; ++i) o[i] = 0.;
+  for (int a = 0; a < 4; ++a) {
+    const double Nx = wx[a] / dJ, Ny = wy[a] / dJ, N = 0.25 * (1. + xs[a] * xi) * (1. + es[a] * eta);
+    const int c = 6 * a;
+    o[0 * 24 + c + 0] = Nx;            // exx
+    o[1 * 24 + c + 1] = Ny;            // eyy
+    o[2 * 24 + c + 0] = Ny;            // gxy
+    o[2 * 24 + c + 1] = Nx;
+    o[3 * 24 + c + 4] = Nx;            // kxx
+    o[4 * 24 + c + 3] = -Ny;           // kyy
+    o[5 * 24 + c + 3] = -Nx;           // kxy
+    o[5 * 24 + c + 4] = Ny;
+    o[6 * 24 + c + 2] = Ny;            // gyz_grad
+    o[7 * 24 + c + 3] = -N;            // gyz_rot
+    o[8 * 24 + c + 2] = Nx;            // gxz_grad
+    o[9 * 24 + c + 4] = N;             // gxz_rot
+    o[10 * 24 + c + 0] = Ny / 2.;      // drilling
+    o[10 * 24 + c + 1] = -Nx / 2.;
+    o[10 * 24 + c + 5] = N;
+  }
+}
+
+cudaError_t launch_quad4_BL(int64_t n, const double* xe, double xi, double eta, double* out, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  quad4_BL_kernel<<<unsigned((n + 127) / 128), 128, 0, st>>>(n, xe, xi, eta, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st) {
   if (A.ne <= 0) return cudaSuccess;
   const int64_t per_cta = 32 * kWarpsPerCta;

@@ -330,11 +330,52 @@ class Quad4Data(_Data):
 
 
 class Quad4Probe(_Probe):
+    """Quad4Probe (quad4.pyx:183-395): besides xe/ue/finte it carries the 11 strain-interpolation rows
+    filled by ``update_BL(xi, eta)`` and the local stiffness ``KC0ve`` of the last element evaluated."""
     KIND = _cabi.QUAD4
+    _BL = ("BLexx", "BLeyy", "BLgxy", "BLkxx", "BLkyy", "BLkxy", "BLgyz_grad", "BLgyz_rot", "BLgxz_grad",
+           "BLgxz_rot", "BLdrilling")
+
+    def __init__(self):
+        super().__init__()
+        self.KC0ve = np.zeros(576)
+        for n in self._BL:
+            setattr(self, n, np.zeros(24))
+
+    def update_BL(self, xi, eta):
+        import torch
+        ctx = _ctx()
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        xe = torch.as_tensor(np.ascontiguousarray(self.xe)).cuda()
+        out = torch.zeros(264, dtype=torch.float64, device="cuda")
+        ctx.quad4_update_BL(1, xe.data_ptr(), float(xi), float(eta), out.data_ptr())
+        rows = out.cpu().numpy().reshape(11, 24)
+        for i, n in enumerate(self._BL):
+            getattr(self, n)[:] = rows[i]
 
 
 class Quad4(_Shell):
     KIND = _cabi.QUAD4
+
+    def _refresh_KC0ve(self, prop):
+        """probe.KC0ve = the local 24x24 stiffness (quad4.pyx:755): the same kernel evaluated with R = I."""
+        save = (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33)
+        (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = (1., 0., 0., 0., 1., 0., 0., 0., 1.)
+        try:
+            r = np.zeros(576, np.int64)
+            v = np.zeros(576)
+            self._run(_cabi.KC0, prop, (0, (r, r.copy(), v, 0, 576)), values_only=True)
+            self.probe.KC0ve[:] = v
+        finally:
+            (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = save
+
+    def update_KC0(self, KC0r, KC0c, KC0v, prop, update_KC0v_only=0):
+        super().update_KC0(KC0r, KC0c, KC0v, prop, update_KC0v_only)
+        self._refresh_KC0ve(prop)
+
+    def _finte(self, prop, hg=None):   # update_probe_finte recomputes KC0ve in the reference (quad4.pyx:1196)
+        super()._finte(prop, hg)
+        self._refresh_KC0ve(prop)
 
     # Quad4.update_KG / update_KG_given_stress take no update_KGv_only (quad4.pyx:1365, 2259):
     # indices are always written

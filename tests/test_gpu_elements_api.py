@@ -148,3 +148,28 @@ def test_array_contract():
     el = pf.Quad4(probe)
     with pytest.raises(ValueError):
         el.update_probe_xe(np.zeros(12, dtype=np.float32))
+
+
+def test_quad4_probe_BL_and_KC0ve():
+    """Quad4Probe.update_BL (quad4.pyx:273-395) and probe.KC0ve (quad4.pyx:755) against the reference."""
+    import os
+    z = np.load(os.path.join(util.GOLDEN_DIR, "quad4_probe.npz"))
+    case, _ = util.load_golden("quad4_soup")
+    e = int(z["element"])
+    x = np.ascontiguousarray(case["x"], float)
+    probe = pf.Quad4Probe()
+    q = pf.Quad4(probe)
+    for a in range(4):
+        setattr(q, "c%d" % (a + 1), int(6 * case["conn"][e, a]))
+    q.update_rotation_matrix(x, *[float(t) for t in case["xmat"][e]])
+    q.update_probe_xe(x)
+    np.testing.assert_allclose(probe.xe, z["xe"], rtol=0, atol=1e-14 * np.abs(z["xe"]).max())
+    prop = _props("quad4", case["props"])[int(case["prop_id"][e])]
+    r, c, v = np.zeros(576, pf.INT), np.zeros(576, pf.INT), np.zeros(576)
+    q.update_KC0(r, c, v, prop)
+    assert np.abs(probe.KC0ve - z["KC0ve"]).max() <= 1e-12 * np.abs(z["KC0ve"]).max()
+    probe.update_BL(float(z["xi"]), float(z["eta"]))
+    names = ("BLexx", "BLeyy", "BLgxy", "BLkxx", "BLkyy", "BLkxy", "BLgyz_grad", "BLgyz_rot", "BLgxz_grad",
+             "BLgxz_rot", "BLdrilling")
+    for i, n in enumerate(names):
+        assert np.abs(getattr(probe, n) - z["BL"][i]).max() <= 1e-12 * max(np.abs(z["BL"][i]).max(), 1.0), n
