@@ -130,7 +130,7 @@ def run_ours(args):
     i0 = rank * side + (1 if rank > 0 else 0)
     i1 = (rank + 1) * side + 1
     case = meshes.plate_quad4(nx, ny, a=float(world), b=1.0, i0=i0 if world > 1 else None,
-                              i1=i1 if world > 1 else None)
+                              i1=i1 if world > 1 else None, local=True)
     nnodes = case["ndof"] // 6
     ne_local = case["conn"].shape[0]
     ne_unique_total = nx * ny

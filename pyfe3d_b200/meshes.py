@@ -35,33 +35,38 @@ def north_star_laminate():
                            offset=0.5e-3)
 
 
-def plate_quad4(nx, ny, a=1.0, b=1.0, i0=None, i1=None, kind="quad4", seed=0, with_u=True):
+def plate_quad4(nx, ny, a=1.0, b=1.0, i0=None, i1=None, kind="quad4", seed=0, with_u=True, local=False):
     """nx x ny Quad4 elements on an a x b plate, rigidly rotated (R != I), u = 1e-4 N(0,1).
 
     ``i0, i1``: return only the elements that touch node columns [i0, i1) ("halo elements
-    duplicated"); node arrays stay global.  Returns the case plus
-    ``owned_nodes = (begin, end)`` and ``owned_elements`` (elements whose first node is owned,
-    a disjoint cover used to count unique elements)."""
+    duplicated").  With ``local=False`` node arrays stay global; with ``local=True`` only the
+    node columns those elements touch are generated and numbered from 0 (what one rank of a row-ownership
+    shard holds: memory and host<->device traffic independent of the number of ranks); global node
+    position = local + ``node_offset``.  Returns the case plus ``owned_nodes = (begin, end)`` and
+    ``owned_elements`` (elements whose first node is owned: a disjoint cover used to count unique elements)."""
     nnx, nny = nx + 1, ny + 1
-    xs = np.linspace(0., a, nnx)
+    lo = 0 if i0 is None else max(i0 - 1, 0)
+    hi = nx if i1 is None else min(i1, nx)
+    c0, c1 = (lo, hi) if local else (0, nx)          # node columns generated: c0..c1 inclusive
+    xs = np.linspace(0., a, nnx)[c0:c1 + 1]
     ys = np.linspace(0., b, nny)
-    X = np.empty((nnx, nny, 3))
+    ncol = xs.size
+    X = np.empty((ncol, nny, 3))
     X[:, :, 0] = xs[:, None]
     X[:, :, 1] = ys[None, :]
     X[:, :, 2] = 0.
     X = X.reshape(-1, 3) @ fixed_rotation(seed).T
-    lo = 0 if i0 is None else max(i0 - 1, 0)
-    hi = nx if i1 is None else min(i1, nx)
     ii, jj = np.meshgrid(np.arange(lo, hi), np.arange(ny), indexing="ij")
-    n1 = (ii * nny + jj).ravel()
+    n1 = ((ii - c0) * nny + jj).ravel()
     conn = np.stack([n1, n1 + nny, n1 + nny + 1, n1 + 1], 1).astype(np.int64)
+    nn_local = ncol * nny
     case = dict(kind=kind, x=X.ravel(), conn=conn, props=shellprop_row(north_star_laminate())[None, :],
-                ndof=6 * nnx * nny)
+                ndof=6 * nn_local, node_offset=c0 * nny)
     if with_u:
-        case["u"] = 1e-4 * np.random.default_rng(seed).normal(size=6 * nnx * nny)
+        case["u"] = 1e-4 * np.random.default_rng(seed + 7919 * c0).normal(size=6 * nn_local)
     b0 = 0 if i0 is None else i0
     b1 = nnx if i1 is None else i1
-    case["owned_nodes"] = (b0 * nny, b1 * nny)
+    case["owned_nodes"] = ((b0 - c0) * nny, (b1 - c0) * nny)
     case["owned_elements"] = int(((ii >= b0) & (ii < b1)).sum())
     return case
 
