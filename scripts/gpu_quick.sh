@@ -1,1 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -30
+python -m pytest tests/test_gpu_fullsize.py -x -q 2>&1 | tail -25

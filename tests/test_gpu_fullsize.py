@@ -1,0 +1,125 @@
+"""GPU, BASELINE.json full size (4.0 M Quad4): size-independent properties of the evaluated and assembled
+matrices, plus the empty / single-element / ragged edge cases.  The oracle cannot run at this size in
+seconds, so parity here is through invariants of the domain:
+  * checksum conservation: sum(COO values) == sum(CSR values) for KC0, KG, M (assembly only adds)
+  * symmetry: x.(K y) == y.(K x) through the device SpMV
+  * self-consistency: K u == fint(u)  (Quad4: quad4.pyx:1174-1201 computes finte = KC0ve.ue)
+  * rigid-body translation: K t == 0;  total mass: t.(M t) == intrho * area
+  * linearity of KG in u;  fused path == two-pass path
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIDE = 2000
+
+
+@pytest.fixture(scope="module")
+def big():
+    import torch
+    from pyfe3d_b200 import meshes
+    from pyfe3d_b200.batch import AssemblyPlan, ElementBatch
+    case = meshes.plate_quad4(SIDE, SIDE)
+    b = ElementBatch("quad4", case["conn"], case["x"], case["props"], u=case["u"])
+    nn = case["ndof"] // 6
+    plans = {m: AssemblyPlan(m, nn, [b]) for m in ("KC0", "KG", "M")}
+    coo, csr = plans["KC0"].evaluate_assemble(KC0=True, KG=True, M=True)
+    torch.cuda.synchronize()
+    return dict(case=case, b=b, nn=nn, plans=plans, coo=coo, csr=csr)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def test_full_size_shapes(big):
+    ne = SIDE * SIDE
+    assert big["b"].ne == ne == 4_000_000
+    assert big["coo"]["KC0"].v.numel() == 576 * ne          # > 2^31: beyond the reference's int32 init_k
+    assert big["plans"]["KC0"].nnz == big["csr"]["KC0"].numel()
+    # structured plate: interior nodes couple to 9 nodes, edges 6, corners 4
+    n = SIDE + 1
+    nblk = 9 * (n - 2) ** 2 + 6 * 4 * (n - 2) + 4 * 4
+    assert big["plans"]["KC0"].nnz == 36 * nblk and big["csr"]["KG"].numel() == 9 * nblk
+    assert big["csr"]["M"].numel() == 30 * nblk
+
+
+@pytest.mark.parametrize("m", ["KC0", "KG", "M"])
+def test_checksum_conservation(big, m):
+    s_coo = big["coo"][m].v.sum(dtype=__import__("torch").float64)
+    s_csr = big["csr"][m].sum()
+    scale = big["coo"][m].v.abs().sum()
+    assert abs(float(s_coo - s_csr)) <= 1e-11 * float(scale)
+
+
+def test_symmetry_and_fint_and_rigid_body(big):
+    import torch
+    from pyfe3d_b200.batch import spmv
+    case, b, nn = big["case"], big["b"], big["nn"]
+    indptr, indices = big["plans"]["KC0"].pattern()
+    K = big["csr"]["KC0"]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(6 * nn, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.randn(6 * nn, dtype=torch.float64, device="cuda", generator=g)
+    Kx, Ky = spmv(indptr, indices, K, x), spmv(indptr, indices, K, y)
+    assert abs(float(torch.dot(y, Kx) - torch.dot(x, Ky))) <= 1e-10 * float(torch.dot(x, Kx).abs())
+    # K u == fint(u)
+    fint = torch.zeros(6 * nn, dtype=torch.float64, device="cuda")
+    b.update_fint(fint)
+    Ku = spmv(indptr, indices, K, b.u)
+    assert _rel(Ku, fint) <= 1e-9
+    # rigid translation produces no force
+    t = torch.zeros(6 * nn, dtype=torch.float64, device="cuda")
+    t[0::6], t[1::6], t[2::6] = 0.3, -0.2, 0.7
+    Kt = spmv(indptr, indices, K, t)
+    assert float(Kt.abs().max()) <= 1e-9 * float(Kx.abs().max())
+    # total mass of the consistent mass matrix = intrho * plate area (unit plate)
+    mp, mi = big["plans"]["M"].pattern()
+    Mt = spmv(mp, mi, big["csr"]["M"], t)
+    rho0 = float(case["props"][0, 24])
+    want = rho0 * 1.0 * (0.3 ** 2 + 0.2 ** 2 + 0.7 ** 2)
+    assert abs(float(torch.dot(t, Mt)) - want) <= 1e-10 * want
+
+
+def test_kg_linear_in_u_and_fused_equals_twopass(big):
+    import torch
+    b, plans = big["b"], big["plans"]
+    _, csr2 = plans["KC0"].evaluate_assemble(KG=True, u=2.0 * b.u, write_coo=False)
+    assert _rel(csr2["KG"], 2.0 * big["csr"]["KG"]) <= 1e-12
+    del csr2
+    two = b.evaluate(KG=True, indices=False)
+    ref = plans["KG"].assemble(two["KG"].v)
+    assert _rel(big["csr"]["KG"], ref) <= 1e-12
+    assert _rel(big["coo"]["KG"].v, two["KG"].v) <= 1e-12
+
+
+def test_edge_cases_empty_single_and_ragged():
+    import torch
+    from pyfe3d_b200 import meshes
+    from pyfe3d_b200.batch import AssemblyPlan, ElementBatch
+    case = meshes.plate_quad4(1, 1)
+    # empty batch: every call is a no-op
+    b0 = ElementBatch("quad4", np.zeros((0, 4), np.int64), case["x"], case["props"], u=case["u"])
+    out = b0.evaluate(KC0=True, KG=True, M=True)
+    assert all(v.v.numel() == 0 for v in out.values())
+    # single element: one 24x24 dense block, 16 node-pair blocks
+    b1 = ElementBatch("quad4", case["conn"], case["x"], case["props"], u=case["u"])
+    p1 = AssemblyPlan("KC0", 4, [b1])
+    coo, csr = p1.evaluate_assemble(KC0=True)
+    assert p1.nnz == 576
+    A = p1.to_scipy(csr["KC0"]).toarray()
+    assert np.abs(A - A.T).max() <= 1e-12 * np.abs(A).max()
+    assert abs(float(coo["KC0"].v.sum()) - A.sum()) <= 1e-11 * np.abs(A).sum()
+    # ragged valence: an L-shaped patch (nodes with 1, 2, 3 and 4 incident elements) incl. unused nodes
+    c = meshes.plate_quad4(3, 3)
+    keep = np.array([0, 1, 2, 3, 4, 6])        # drop three elements -> ragged, one node without elements
+    br = ElementBatch("quad4", c["conn"][keep], c["x"], c["props"], u=c["u"])
+    pr = AssemblyPlan("KC0", c["ndof"] // 6, [br])
+    coo, csr = pr.evaluate_assemble(KC0=True)
+    two = br.update_KC0(update_KC0v_only=1)
+    ref = pr.assemble(two.v)
+    assert float((csr["KC0"] - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    indptr, _ = pr.pattern()
+    rows = (indptr[1:] - indptr[:-1]).cpu().numpy().reshape(-1, 6)
+    assert (rows == 0).all(axis=1).sum() >= 1       # the orphan node has empty rows
