@@ -61,6 +61,9 @@ struct pf3_plan {
   int32_t* d_slot = nullptr;
   mutable pf3::NodeRec* d_noderec = nullptr;   // built on first fused use
   mutable int rmax = 0;
+  mutable std::vector<pf3::NodeRec*> d_grecs;  // per-group records of the slab assembly (built on first use)
+  mutable std::vector<int> grmax;
+  std::vector<int> gmask;                      // MaskId of every group
   std::vector<uint16_t*> d_tabs;
   // generic
   int64_t n = 0, nnz_coo = 0;
@@ -368,6 +371,7 @@ int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnod
     }
     for (int i = 0; i < 6; ++i)
       for (int j = 0; j < 6; ++j) pl->umask[i][j] |= mask_has(L.mask, i, j);
+    pl->gmask.push_back(L.mask);
     GroupDev& G = P.g[g];
     G.conn = groups[g].conn;
     G.ne = groups[g].ne;
@@ -519,7 +523,235 @@ int plan_pattern(const pf3_plan* pl, cudaStream_t st, int64_t* indptr, int64_t* 
   return int(cudaGetLastError());
 }
 
+// ---- slab assembly ------------------------------------------------------------------------------
+// Per group: node records (4 incidences per round) + a kernel that stages the incident elements' COO row
+// slabs in shared memory with cp.async (each slab is contiguous in the COO array) and reduces them into the
+// node's CSR rows in the fixed order k = 0..3.  A half-warp per node, 8 slabs in flight per warp.
+namespace {
+__global__ void k_group_valence(const PlanDev P, int gi, const int64_t* inc_ptr, const int32_t* inc_meta,
+                                int64_t nown, int* out) {
+  for (int64_t n = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; n < nown; n += int64_t(gridDim.x) * blockDim.x) {
+    int c = 0;
+    for (int64_t q = inc_ptr[n]; q < inc_ptr[n + 1]; ++q) c += ((inc_meta[q] & 0xff) == gi);
+    atomicMax(out, c);
+  }
+}
+__global__ void k_group_records(const PlanDev P, int gi, const int64_t* __restrict__ brow_ptr,
+                                const int64_t* __restrict__ inc_ptr, const int64_t* __restrict__ inc_pair0,
+                                const int32_t* __restrict__ inc_meta, const int32_t* __restrict__ slot,
+                                int64_t nown, int rmax, NodeRec* __restrict__ out) {
+  const GroupDev& G = P.g[gi];
+  const int64_t total = nown * rmax;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t n = t / rmax;
+    const int r = int(t - n * rmax);
+    NodeRec R;
+    R.b0 = brow_ptr[n];
+    R.nb = uint8_t(brow_ptr[n + 1] - R.b0);
+    for (int s = 0; s < 16; ++s) R.gmap[s] = 0xFFFF;
+    for (int k = 0; k < 4; ++k) R.inc[k] = -1;
+    int seen = 0, cnt = 0;
+    for (int64_t q = inc_ptr[n]; q < inc_ptr[n + 1]; ++q) {
+      const int meta = inc_meta[q];
+      if ((meta & 0xff) != gi) continue;
+      const int k = seen - 4 * r;
+      ++seen;
+      if (k < 0 || k >= 4) continue;
+      const int a = meta >> 8;
+      const int64_t p0 = inc_pair0[q];
+      const int64_t e = (p0 - G.pairbase) / G.npairs;
+      R.inc[k] = int32_t(e * G.nn + a);
+      ++cnt;
+      if (G.diag) {
+        const int sl = slot[p0];
+        if (sl >= 0 && sl < 16) R.gmap[sl] = uint16_t(R.gmap[sl] & ~(0xF << (4 * k)));
+      } else {
+        for (int b = 0; b < G.nn; ++b) {
+          const int sl = slot[p0 + b];
+          if (sl >= 0 && sl < 16) R.gmap[sl] = uint16_t((R.gmap[sl] & ~(0xF << (4 * k))) | (b << (4 * k)));
+        }
+      }
+    }
+    R.v = uint8_t(cnt);
+    for (int i = 0; i < 6; ++i) R.pad[i] = 0;
+    out[t] = R;
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+// NNS: node blocks per slab row (element nodes, or 1 for diagonal-pair-only groups); NR x CNT: masked rows/cols
+template <int NNS, int NR, int CNT>
+__global__ void __launch_bounds__(256) k_assemble_slabs(const NodeRec* __restrict__ recs, int rmax, int64_t nown,
+                                                        const double* __restrict__ coo, int nn, int size,
+                                                        double* __restrict__ csr, int accumulate, int vec16) {
+  constexpr int kSlab = NR * NNS * CNT;
+  constexpr int kLd = kSlab + 2 - (kSlab & 1);      // even (16-B aligned rows for the paired path), != 0 mod 16
+  constexpr bool kVec = (kSlab % 2 == 0);            // slab start is 16-B aligned iff size and wn are even
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  double* st = smem + warp * (8 * kLd);
+  const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, qd = l16 & 3;
+  const int64_t npairs = (nown + 1) >> 1;
+  for (int64_t np = int64_t(blockIdx.x) * wpc + warp; np < npairs; np += int64_t(gridDim.x) * wpc) {
+    const int64_t n = 2 * np + h;
+    for (int r = 0; r < rmax; ++r) {
+      int inc = -1, nb = 0;
+      int64_t b0 = 0;
+      const NodeRec* nr = nullptr;
+      if (n < nown) {
+        nr = recs + n * rmax + r;
+        inc = nr->inc[k];
+        nb = nr->nb;
+        b0 = nr->b0;
+      }
+      const bool any = __ballot_sync(0xffffffffu, inc >= 0) != 0u;
+      const bool first = (r == 0) && !accumulate;
+      if (!any && !first) continue;
+      if (inc >= 0) {
+        const int e = inc / nn, a = inc - e * nn;
+        const double* src = coo + int64_t(e) * size + int64_t(a) * kSlab;
+        double* dst = st + (lane >> 2) * kLd;
+        if (kVec && vec16) {
+          for (int c = qd; c < kSlab / 2; c += 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + 2 * c)), "l"(src + 2 * c) : "memory");
+        } else {
+          for (int c = qd; c < kSlab; c += 4)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst + c)), "l"(src + c) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      if (nb > 0) {
+        const int w = nb * CNT;
+        const double* sh = st + h * 4 * kLd;
+        double* out = csr + b0 * (NR * CNT);
+        for (int x = l16; x < w; x += 16) {
+          const int s = x / CNT, rr = x - s * CNT;
+          const unsigned gm = nr->gmap[s];
+          int off[4];
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const int nib = (gm >> (4 * k2)) & 0xF;
+            off[k2] = (nib != 0xF) ? (k2 * kLd + nib * CNT + rr) : -1;
+          }
+#pragma unroll
+          for (int d = 0; d < NR; ++d) {
+            double sum = 0.;
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2)
+              if (off[k2] >= 0) sum += sh[d * NNS * CNT + off[k2]];
+            double* o = out + d * w + x;
+            if (first) *o = sum; else *o += sum;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int NR, int CNT>
+int launch_slabs(int nns, const NodeRec* recs, int rmax, int64_t nown, const double* coo, int nn, int size,
+                 double* csr, int accumulate, cudaStream_t st) {
+  const int wpc = 8;
+  const int64_t npairs = (nown + 1) / 2;
+  const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((npairs + wpc - 1) / wpc, 148 * 16)));
+  const int vec16 = int((((uintptr_t)coo) & 15) == 0 && (size % 2) == 0);   // 16-B cp.async needs aligned slabs
+#define PF3_SLAB_CASE(N)                                                                                       \
+  case N: {                                                                                                    \
+    constexpr int kSlab = NR * N * CNT, kLd = kSlab + 2 - (kSlab & 1);                                          \
+    const size_t smem = size_t(wpc) * 8 * kLd * sizeof(double);                                                 \
+    if (smem > 48 * 1024)                                                                                       \
+      cudaFuncSetAttribute(k_assemble_slabs<N, NR, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
+    k_assemble_slabs<N, NR, CNT><<<grid, wpc * 32, smem, st>>>(recs, rmax, nown, coo, nn, size, csr, accumulate, vec16); \
+    break;                                                                                                      \
+  }
+  switch (nns) {
+    PF3_SLAB_CASE(1)
+    PF3_SLAB_CASE(2)
+    PF3_SLAB_CASE(3)
+    PF3_SLAB_CASE(4)
+    default: return PF3_E_UNSUPPORTED;
+  }
+#undef PF3_SLAB_CASE
+  return int(cudaGetLastError());
+}
+
+// (NR, CNT) of the plan's union mask when every row has the same count (0 rows allowed at one end)
+bool uniform_shape(const PlanDev& P, int* nr, int* cnt) {
+  int c = 0, rows = 0;
+  for (int i = 0; i < 6; ++i) {
+    if (P.cnt[i] == 0) continue;
+    if (c == 0) c = P.cnt[i];
+    if (P.cnt[i] != c) return false;
+    ++rows;
+  }
+  if (!((rows == 6) || (rows == 3 && (P.cnt[0] == 0 || P.cnt[5] == 0)))) return false;
+  *nr = rows;
+  *cnt = c;
+  return (rows == 6 && (c == 6 || c == 5 || c == 3)) || (rows == 3 && c == 3);
+}
+}  // namespace
+
+int plan_assemble_slabs(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int64_t* launches,
+                        bool* done) {
+  *done = false;
+  const PlanDev& P = pl->dev;
+  int nr = 0, cnt = 0;
+  if (pl->degenerate || pl->max_nb > 16 || !uniform_shape(P, &nr, &cnt)) return PF3_OK;
+  for (int g = 0; g < P.ngroups; ++g) {   // every group must write exactly the plan's mask
+    for (int i = 0; i < 6; ++i) {
+      int c = 0;
+      for (int j = 0; j < 6; ++j) c += mask_has(pl->gmask[g], i, j) ? 1 : 0;
+      if (c != P.cnt[i]) return PF3_OK;
+    }
+    if (P.g[g].ne * P.g[g].nn >= (int64_t(1) << 31)) return PF3_OK;
+  }
+  if (pl->d_grecs.empty()) {
+    pl->d_grecs.assign(P.ngroups, nullptr);
+    pl->grmax.assign(P.ngroups, 1);
+    for (int g = 0; g < P.ngroups; ++g) {
+      int* d_mv = nullptr;
+      PF3_CUDA(cudaMalloc((void**)&d_mv, sizeof(int)));
+      PF3_CUDA(cudaMemsetAsync(d_mv, 0, sizeof(int), st));
+      k_group_valence<<<grid_for(pl->nown), 256, 0, st>>>(P, g, pl->d_inc_ptr, pl->d_inc_meta, pl->nown, d_mv);
+      int mv = 0;
+      PF3_CUDA(cudaMemcpyAsync(&mv, d_mv, sizeof(int), cudaMemcpyDeviceToHost, st));
+      PF3_CUDA(cudaStreamSynchronize(st));
+      cudaFree(d_mv);
+      pl->grmax[g] = std::max(1, (mv + 3) / 4);
+      PF3_CUDA(cudaMalloc((void**)&pl->d_grecs[g], size_t(pl->nown) * pl->grmax[g] * sizeof(NodeRec)));
+      k_group_records<<<grid_for(pl->nown * pl->grmax[g]), 256, 0, st>>>(P, g, pl->d_brow_ptr, pl->d_inc_ptr,
+                                                                         pl->d_inc_pair0, pl->d_inc_meta, pl->d_slot,
+                                                                         pl->nown, pl->grmax[g], pl->d_grecs[g]);
+      *launches += 2;
+      PF3_CUDA(cudaGetLastError());
+    }
+  }
+  for (int g = 0; g < P.ngroups; ++g) {
+    const GroupDev& G = P.g[g];
+    const int nns = G.diag ? 1 : G.nn;
+    int rc;
+    const double* coo = coo_v + G.coo_offset;
+    if (nr == 6 && cnt == 6) rc = launch_slabs<6, 6>(nns, pl->d_grecs[g], pl->grmax[g], pl->nown, coo, G.nn, G.size, csr_v, g > 0, st);
+    else if (nr == 6 && cnt == 5) rc = launch_slabs<6, 5>(nns, pl->d_grecs[g], pl->grmax[g], pl->nown, coo, G.nn, G.size, csr_v, g > 0, st);
+    else if (nr == 6 && cnt == 3) rc = launch_slabs<6, 3>(nns, pl->d_grecs[g], pl->grmax[g], pl->nown, coo, G.nn, G.size, csr_v, g > 0, st);
+    else rc = launch_slabs<3, 3>(nns, pl->d_grecs[g], pl->grmax[g], pl->nown, coo, G.nn, G.size, csr_v, g > 0, st);
+    ++*launches;
+    if (rc) return rc;
+  }
+  *done = true;
+  return PF3_OK;
+}
+
 int plan_assemble(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int64_t* launches) {
+  if (!pl->generic) {
+    bool done = false;
+    int rc = plan_assemble_slabs(pl, st, coo_v, csr_v, launches, &done);
+    if (rc || done) return rc;
+  }
   if (pl->generic) {
     k_segsum<<<grid_for(pl->nnz), 256, 0, st>>>(pl->d_seg, pl->d_perm, pl->nnz, coo_v, csr_v);
     ++*launches;
@@ -730,6 +962,7 @@ extern "C" int pf3_plan_destroy(pf3_plan* pl) {
   if (!pl) return PF3_OK;
   cudaFree(pl->d_brow_ptr); cudaFree(pl->d_bcol); cudaFree(pl->d_inc_ptr); cudaFree(pl->d_inc_src);
   cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot); cudaFree(pl->d_noderec);
+  for (auto* r : pl->d_grecs) cudaFree(r);
   for (auto* t : pl->d_tabs) cudaFree(t);
   cudaFree(pl->d_indptr); cudaFree(pl->d_indices); cudaFree(pl->d_perm); cudaFree(pl->d_seg);
   delete pl;
