@@ -168,3 +168,34 @@ def test_state_and_finte():
     np.testing.assert_allclose(st[:, 14:26].reshape(ne, 4, 3), ref["xe"], rtol=0, atol=1e-14 * np.abs(ref["xe"]).max())
     fe = b.finte().cpu().numpy()
     assert fe.shape == (ne, 24) and np.isfinite(fe).all()
+
+
+def test_two_group_plan_with_odd_offset():
+    """Two Tria3R batches in ONE KG matrix: group 1 starts at an odd COO offset (81 * odd), so its slabs are
+    only 8-byte aligned (the slab assembly must not use 16-byte async copies there)."""
+    import scipy.sparse as sp
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    case = cases.shell_mesh("tria3r", 6, 5, seed=91)
+    ne = case["conn"].shape[0]
+    cut = 7
+    parts = []
+    for sel in (slice(0, cut), slice(cut, ne)):
+        c = dict(case)
+        c["conn"] = case["conn"][sel]
+        c["prop_id"] = case["prop_id"][sel]
+        c["xmat"] = case["xmat"][sel]
+        parts.append(c)
+    bs = [util.batch_from_case(c) for c in parts]
+    coos = [b.update_KG() for b in bs]
+    v = torch.cat([c.v for c in coos])
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan("KG", nn, bs)
+    assert plan.coo_offsets[1] % 2 == 1
+    A = plan.to_scipy(plan.assemble(v))
+    want = driver.run(case, what=("KG",))["KG"]
+    n = case["ndof"]
+    S = sp.coo_matrix((want[2], (want[0], want[1])), shape=(n, n)).tocsr()
+    S.sum_duplicates()
+    assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max()
+    assert A.nnz == S.nnz
