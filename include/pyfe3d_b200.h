@@ -199,6 +199,10 @@ int pf3_plan_pattern(pf3_context* ctx, const pf3_plan* plan, int64_t* indptr, in
 /* numeric phase: csr_v[nnz] = sum of duplicates of coo_v, deterministic order */
 int pf3_plan_assemble(pf3_context* ctx, const pf3_plan* plan, const double* coo_v, double* csr_v);
 
+/* update_fint for every element of `batch` (= group `group` of the structured plan) using the plan's
+ * node -> incident element lists: fint[6*nnodes] += ..., fixed summation order, no sort, no atomics; only
+ * the plan's owned node rows are updated (e.g. quad4.pyx:1316-1362). */
+int pf3_plan_fint(pf3_context* ctx, const pf3_plan* plan, int group, const pf3_batch* batch, double* fint);
 int pf3_plan_nblocks(const pf3_plan* plan, int64_t* nblk); /* 6x6 node-pair blocks of a structured plan */
 
 /* Fused evaluate + assemble for ONE Quad4/Quad4R batch and the structured PF3_MAT_KC0 plan built from

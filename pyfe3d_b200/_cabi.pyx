@@ -62,6 +62,7 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_nrows(const pf3_plan*, int64_t*)
     int pf3_plan_pattern(pf3_context*, const pf3_plan*, int64_t* indptr, int64_t* indices) nogil
     int pf3_plan_nblocks(const pf3_plan*, int64_t*)
+    int pf3_plan_fint(pf3_context*, const pf3_plan*, int group, const pf3_batch*, double* fint) nogil
     int pf3_quad4_update_BL(pf3_context*, int64_t n, const double* xe, double xi, double eta, double* out) nogil
     int pf3_eval_assemble(pf3_context*, const pf3_batch*, const pf3_plan*, int what, const pf3_coo*, const pf3_coo*,
                           const pf3_coo*, double*, double*, double*) nogil
@@ -305,6 +306,12 @@ cdef class Plan:
         with nogil:
             rc = pf3_eval_assemble(self.owner.ctx, &b.b, self.plan, what, p0, p1, p2, <double*>csr_kc0,
                                    <double*>csr_kg, <double*>csr_m)
+        _check(rc)
+
+    def fint(self, int group, Batch b, uintptr_t fint):
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_fint(self.owner.ctx, self.plan, group, &b.b, <double*>fint)
         _check(rc)
 
     def pattern(self, uintptr_t indptr, uintptr_t indices):

@@ -302,6 +302,18 @@ class AssemblyPlan:
         return sp.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()),
                              shape=(self.nrows, 6 * self.nnodes))
 
+    def update_fint(self, fint, u=None):
+        """fint += internal forces of every batch of the plan (update_fint of the reference), gathered per
+        node through the plan's incidence lists: deterministic, no per-call sort, owned rows only."""
+        if not (isinstance(fint, torch.Tensor) and fint.is_cuda and fint.dtype == torch.float64):
+            raise TypeError("fint must be a float64 CUDA tensor (it is accumulated in place)")
+        if u is not None:
+            u = _dev(u, torch.float64, self.device)
+        context(self.device)
+        for g, b in enumerate(self.batches):
+            self._plan.fint(g, b.cabi_batch(u=u), _ptr(fint))
+        return fint
+
     # -- fused evaluate + assemble (Quad4 / Quad4R, single batch) ---------------------------------
     def csr_sizes(self, mtype=0):
         """nnz of the KC0 / KG / M CSR value arrays the fused kernel fills (same layouts as the

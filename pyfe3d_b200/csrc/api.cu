@@ -27,6 +27,9 @@ int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64
                 double* fint, int64_t* launches);
 int64_t plan_nnz(const pf3_plan* pl);
 int64_t plan_nblocks(const pf3_plan* pl);
+int plan_fint_gather(const pf3_plan* pl, cudaStream_t st, int group, const double* fe, double* fint, int64_t* launches);
+int plan_group_kind_nn(const pf3_plan* pl, int group);
+int64_t plan_group_ne_of(const pf3_plan* pl, int group);
 int64_t plan_group_ne(const pf3_plan* pl);
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches);
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
@@ -434,6 +437,26 @@ int pf3_plan_nrows(const pf3_plan* plan, int64_t* nrows) {
   if (!plan || !nrows) return PF3_E_BAD_ARG;
   *nrows = pf3::plan_nrows(plan);
   return PF3_OK;
+}
+
+int pf3_plan_fint(pf3_context* ctx, const pf3_plan* plan, int group, const pf3_batch* b, double* fint) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan || !fint) return PF3_E_BAD_ARG;
+  rc = check_batch(b, PF3_FINT);
+  if (rc) return rc;
+  const int nn = pf3::kind_nodes(b->kind);
+  if (pf3::plan_group_kind_nn(plan, group) != nn || pf3::plan_group_ne_of(plan, group) != b->ne) return PF3_E_BAD_ARG;
+  if (b->ne == 0) return PF3_OK;
+  rc = ensure_scratch(ctx, size_t(b->ne) * 6 * nn * sizeof(double));
+  if (rc) return rc;
+  pf3::EvalArgs A;
+  base_args(b, A);
+  A.what = PF3_FINT;
+  A.fe = ctx->scratch;
+  rc = launch_eval(ctx, A, b->kind);
+  if (rc) return rc;
+  return pf3::plan_fint_gather(plan, ctx->stream, group, ctx->scratch, fint, &ctx->launches);
 }
 
 int pf3_plan_nblocks(const pf3_plan* plan, int64_t* nblk) {

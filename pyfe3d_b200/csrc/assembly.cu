@@ -393,16 +393,13 @@ int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnod
     return PF3_E_CAPACITY;
   }
   P.mc = 0;
-  MaskDev MD;
   for (int i = 0; i < 6; ++i) {
     P.rowoff[i] = P.mc;
     int c = 0;
     for (int j = 0; j < 6; ++j) {
       pl->colrank[i][j] = -1;
-      MD.cols[i][j] = 0;
       if (pl->umask[i][j]) {
         pl->colrank[i][j] = int8_t(c);
-        MD.cols[i][c] = int8_t(j);
         ++c;
       }
     }
@@ -950,6 +947,45 @@ int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st,
   F->slot = pl->d_slot;
   F->nown = pl->nown;
   return PF3_OK;
+}
+// fint[6*node + d] += sum over the node's incident (element, local node) pairs of group `group` of fe, in the
+// plan's fixed incidence order: no sort, no atomics (update_fint, e.g. quad4.pyx:1339-1362).
+namespace {
+__global__ void k_plan_fint(const PlanDev P, int gi, const int64_t* __restrict__ inc_ptr,
+                            const int64_t* __restrict__ inc_pair0, const int32_t* __restrict__ inc_meta, int64_t nown,
+                            const double* __restrict__ fe, double* __restrict__ fint) {
+  const GroupDev& G = P.g[gi];
+  const int64_t n6 = nown * 6;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < n6; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t i = t / 6;
+    const int d = int(t - i * 6);
+    double s = 0.;
+    bool any = false;
+    for (int64_t q = inc_ptr[i]; q < inc_ptr[i + 1]; ++q) {
+      const int meta = inc_meta[q];
+      if ((meta & 0xff) != gi) continue;
+      const int64_t e = (inc_pair0[q] - G.pairbase) / G.npairs;
+      s += fe[(e * G.nn + (meta >> 8)) * 6 + d];
+      any = true;
+    }
+    if (any) fint[6 * (P.node_begin + i) + d] += s;
+  }
+}
+}  // namespace
+
+int plan_fint_gather(const pf3_plan* pl, cudaStream_t st, int group, const double* fe, double* fint,
+                     int64_t* launches) {
+  if (pl->generic || group < 0 || group >= pl->dev.ngroups) return PF3_E_BAD_ARG;
+  k_plan_fint<<<grid_for(pl->nown * 6), 256, 0, st>>>(pl->dev, group, pl->d_inc_ptr, pl->d_inc_pair0, pl->d_inc_meta,
+                                                     pl->nown, fe, fint);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+int plan_group_kind_nn(const pf3_plan* pl, int group) {
+  return (pl->generic || group < 0 || group >= pl->dev.ngroups) ? 0 : pl->dev.g[group].nn;
+}
+int64_t plan_group_ne_of(const pf3_plan* pl, int group) {
+  return (pl->generic || group < 0 || group >= pl->dev.ngroups) ? -1 : pl->dev.g[group].ne;
 }
 int64_t plan_nblocks(const pf3_plan* pl) { return pl->generic ? 0 : pl->nblk; }
 int64_t plan_group_ne(const pf3_plan* pl) { return pl->generic ? 0 : pl->dev.g[0].ne; }

@@ -30,10 +30,7 @@ namespace {
 #endif
 constexpr double kGpF = 0.5773502691896257645092;
 constexpr int kFusedWarps = 4;
-constexpr int kLd = 36;                     // staging leading dimension: 36 mod 16 = 4 -> <=2-way LDS conflicts
-constexpr int kStageDoubles = 36 * kLd;     // one 6x6 block per lane
-constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path
-constexpr int kWarpSmemDoubles = kStageDoubles + (8 * kMaxSlots) / 8;
+constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path (NodeRec::gmap)
 constexpr int kRecPlain = 36;               // record doubles without / with rotated A,B,D
 constexpr int kRecRot = 56;
 
@@ -126,7 +123,6 @@ struct SlabShape {
   static constexpr int kLd = kSlab + 2;        // padded stride: 146 / 122 / 74 / 38 doubles
 };
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 // Lanes have written their block into slab (lane>>2).  Ship the slabs to the COO array and reduce the (up to)

@@ -199,3 +199,25 @@ def test_two_group_plan_with_odd_offset():
     S.sum_duplicates()
     assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max()
     assert A.nnz == S.nnz
+
+
+@pytest.mark.parametrize("name", ["quad4_mesh", "tria3r_mesh", "beamc_chain", "spring_chain"])
+def test_plan_fint_matches_reference(name):
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    case, ref = util.load_golden(name)
+    b = util.batch_from_case(case)
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan("KC0", nn, [b])
+    fint = torch.zeros(case["ndof"], dtype=torch.float64, device=b.device)
+    plan.update_fint(fint)
+    assert util.vec_relerr(fint.cpu().numpy(), ref["fint"]) <= util.TOL_VALUES
+    # row shard: only owned rows are touched
+    lo, hi = nn // 4, nn - 1
+    ps = AssemblyPlan("KC0", nn, [b], node_range=(lo, hi))
+    f2 = torch.zeros(case["ndof"], dtype=torch.float64, device=b.device)
+    ps.update_fint(f2)
+    f2 = f2.cpu().numpy()
+    assert np.all(f2[:6 * lo] == 0) and np.all(f2[6 * hi:] == 0)
+    assert util.vec_relerr(f2[6 * lo:6 * hi], ref["fint"][6 * lo:6 * hi]) <= util.TOL_VALUES * (
+        np.abs(ref["fint"]).max() / max(np.abs(ref["fint"][6 * lo:6 * hi]).max(), 1e-300))
