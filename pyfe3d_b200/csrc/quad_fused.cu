@@ -29,7 +29,11 @@ namespace {
 #define PF3_COO_TMA 1   // 1: COO slabs leave as TMA bulk copies; 0: 16-B stores by the incidence's 4 lanes
 #endif
 constexpr double kGpF = 0.5773502691896257645092;
-constexpr int kFusedWarps = 4;
+#ifndef PF3_FUSED_WARPS
+#define PF3_FUSED_WARPS 4   // warps per CTA and CTAs per SM of the fused kernel: 12 warps/SM at 168 registers
+#define PF3_FUSED_CTAS 3    // measured best; the staging shared memory allows at most 15 warps
+#endif
+constexpr int kFusedWarps = PF3_FUSED_WARPS;
 constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path (NodeRec::gmap)
 constexpr int kRecPlain = 36;               // record doubles without / with rotated A,B,D
 constexpr int kRecRot = 56;
@@ -226,9 +230,8 @@ __device__ __forceinline__ void stage_reuse_wait() {
 
 constexpr int kRing = 3;                                   // node-record prefetch ring (records of 2 nodes each)
 constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1168 doubles: the largest matrix (KC0)
-constexpr int kErecLd = kRecRot + 2;                        // staged element-record stride (58: conflict-free, 16-B aligned)
-constexpr int kErecDoubles = 2 * 8 * kErecLd;               // double buffer x 8 incidences
-constexpr int kWarpSmemV4 = kStageV4 + kRing * 2 * 8 + kErecDoubles;
+// staged element records: stride rstride + 2 doubles (38 / 58: conflict-free, 16-B aligned), double buffer x 8
+__host__ __device__ constexpr int warp_smem_doubles(int rstride) { return kStageV4 + kRing * 2 * 8 + 2 * 8 * (rstride + 2); }
 
 // Stage the element records of the 8 incidences of an item into shared memory with 16-B cp.async; the 4 lanes
 // of an incidence split the record's chunks.
@@ -236,7 +239,7 @@ __device__ __forceinline__ void erec_fetch(const double* __restrict__ rec, int r
                                            int lane) {
   if (pair0 >= 0) {
     const char* src = reinterpret_cast<const char*>(rec + int64_t(pair0 >> 4) * rstride);
-    char* dst = reinterpret_cast<char*>(buf + (lane >> 2) * kErecLd);
+    char* dst = reinterpret_cast<char*>(buf + (lane >> 2) * (rstride + 2));
     for (int c = (lane & 3) * 16; c < rstride * 8; c += 64)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
   }
@@ -274,12 +277,13 @@ __device__ __forceinline__ void ring_fetch(const FusedArgs& F, NodeRec* ring, in
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
+__global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
                                                                          int rstride) {
   extern __shared__ __align__(16) double smem[];
   const EvalArgs& A = F.A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* st = smem + warp * kWarpSmemV4;
+  const int eld = rstride + 2;
+  double* st = smem + warp * warp_smem_doubles(rstride);
   NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
   double* erec = st + kStageV4 + kRing * 2 * 8;
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
     __syncwarp();
     const NodeRec* nr = ring + int(j % kRing) * 2 + h;
     // element records of the next item start flowing now
-    erec_fetch(rec, rstride, erec + int((j + 1) & 1) * 8 * kErecLd, (ring + int((j + 1) % kRing) * 2 + h)->inc[k], lane);
+    erec_fetch(rec, rstride, erec + int((j + 1) & 1) * 8 * eld, (ring + int((j + 1) % kRing) * 2 + h)->inc[k], lane);
     const int64_t b0 = nr->b0;
     const int nb = nr->nb;
     const int pair0 = nr->inc[k];
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
     const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
 
     // ---------------- element record (K1) and property row
-    const double* re = erec + int(j & 1) * 8 * kErecLd + (lane >> 2) * kErecLd;
+    const double* re = erec + int(j & 1) * 8 * eld + (lane >> 2) * eld;
     const double2* re2 = reinterpret_cast<const double2*>(re);
     double rr_[24];
 #pragma unroll
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, 3) quad_fused_kernel(const F
 
 }  // namespace
 
-size_t fused_smem_bytes() { return size_t(kFusedWarps) * kWarpSmemV4 * sizeof(double); }
+size_t fused_smem_bytes(int rstride) { return size_t(kFusedWarps) * warp_smem_doubles(rstride) * sizeof(double); }
 int fused_max_slots() { return kMaxSlots; }
 int fused_record_stride(const EvalArgs& A) { return A.evec != nullptr ? kRecRot : kRecPlain; }
 
@@ -567,15 +571,16 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   ++*launches;
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) return e1;
-  const size_t smem = fused_smem_bytes();
+  const size_t smem = fused_smem_bytes(stride);
   const int64_t npairs = (F.nown + 1) / 2;
   const int64_t want = (npairs + kFusedWarps - 1) / kFusedWarps;
-  const int64_t cap = 148 * 3 * 8;
+  const int64_t cap = 148 * PF3_FUSED_CTAS * 8;
   const unsigned grid = unsigned(want < cap ? (want < 1 ? 1 : want) : cap);
   static bool once = false;
   if (!once) {
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    const int maxs = int(fused_smem_bytes(kRecRot));
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
     once = true;
   }
   if (kind == PF3_QUAD4)
