@@ -220,6 +220,15 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* batch, const pf3_plan* 
 int pf3_spmv_csr(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
                  const double* vals, const double* x, double* y);
 
+/* y = P A P x, P = diag(free_dof != 0): the boundary-condition partition KC0[bu,:][:,bu] every reference script
+ * forms right after assembly (tests/test_quad4_static_point_load.py:84-99), applied on the fly (square A). */
+int pf3_spmv_csr_masked(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                        const double* vals, const unsigned char* free_dof, const double* x, double* y);
+/* diag[r] = A[r, r + row0]: Jacobi scaling used by the reference's preconditioned cg calls
+ * (tests/test_quad4r_linear_buckling_plate.py:135-146) */
+int pf3_csr_diagonal(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                     const double* vals, int64_t row0, double* diag);
+
 /* ---- host-pointer convenience (numpy callers): copies in, runs, copies out -- */
 int pf3_eval_host(pf3_context* ctx, const pf3_batch* host_batch, int what,
                   const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);

@@ -69,6 +69,10 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_assemble(pf3_context*, const pf3_plan*, const double* coo_v, double* csr_v) nogil
     int pf3_spmv_csr(pf3_context*, int64_t nrows, const int64_t* indptr, const int64_t* indices,
                      const double* vals, const double* x, double* y) nogil
+    int pf3_spmv_csr_masked(pf3_context*, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                            const double* vals, const unsigned char* free_dof, const double* x, double* y) nogil
+    int pf3_csr_diagonal(pf3_context*, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                         const double* vals, int64_t row0, double* diag) nogil
     int pf3_memcpy_h2d(pf3_context*, void* dst, const void* src, size_t n) nogil
     int pf3_memcpy_d2h(pf3_context*, void* dst, const void* src, size_t n) nogil
 
@@ -222,6 +226,22 @@ cdef class Context:
         with nogil:
             rc = pf3_spmv_csr(self.ctx, nrows, <const int64_t*>indptr, <const int64_t*>indices,
                               <const double*>vals, <const double*>x, <double*>y)
+        _check(rc)
+
+    def spmv_csr_masked(self, int64_t nrows, uintptr_t indptr, uintptr_t indices, uintptr_t vals, uintptr_t free_dof,
+                        uintptr_t x, uintptr_t y):
+        cdef int rc
+        with nogil:
+            rc = pf3_spmv_csr_masked(self.ctx, nrows, <const int64_t*>indptr, <const int64_t*>indices,
+                                     <const double*>vals, <const unsigned char*>free_dof, <const double*>x, <double*>y)
+        _check(rc)
+
+    def csr_diagonal(self, int64_t nrows, uintptr_t indptr, uintptr_t indices, uintptr_t vals, int64_t row0,
+                     uintptr_t diag):
+        cdef int rc
+        with nogil:
+            rc = pf3_csr_diagonal(self.ctx, nrows, <const int64_t*>indptr, <const int64_t*>indices,
+                                  <const double*>vals, row0, <double*>diag)
         _check(rc)
 
     def memcpy_h2d(self, uintptr_t dst, uintptr_t src, size_t n):

@@ -23,6 +23,10 @@ int plan_pattern(const pf3_plan* pl, cudaStream_t st, int64_t* indptr, int64_t* 
 int plan_assemble(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int64_t* launches);
 int spmv_csr(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
              const double* x, double* y, int64_t* launches);
+int spmv_csr_masked(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
+                    const unsigned char* free_, const double* x, double* y, int64_t* launches);
+int csr_diagonal(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
+                 int64_t row0, double* d, int64_t* launches);
 int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64_t* conn, const double* fe,
                 double* fint, int64_t* launches);
 int64_t plan_nnz(const pf3_plan* pl);
@@ -529,6 +533,22 @@ int pf3_spmv_csr(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const i
   if (rc) return rc;
   if (nrows < 0 || !indptr || !x || !y) return PF3_E_BAD_ARG;
   return pf3::spmv_csr(ctx->stream, nrows, indptr, indices, vals, x, y, &ctx->launches);
+}
+
+int pf3_spmv_csr_masked(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                        const double* vals, const unsigned char* free_dof, const double* x, double* y) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (nrows < 0 || !indptr || !x || !y || !free_dof) return PF3_E_BAD_ARG;
+  return pf3::spmv_csr_masked(ctx->stream, nrows, indptr, indices, vals, free_dof, x, y, &ctx->launches);
+}
+
+int pf3_csr_diagonal(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
+                     const double* vals, int64_t row0, double* diag) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (nrows < 0 || !indptr || !diag) return PF3_E_BAD_ARG;
+  return pf3::csr_diagonal(ctx->stream, nrows, indptr, indices, vals, row0, diag, &ctx->launches);
 }
 
 // Host-pointer convenience: every pointer in host_batch / the pf3_coo structs / fint is a HOST pointer.

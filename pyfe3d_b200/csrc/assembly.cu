@@ -819,6 +819,54 @@ int plan_create_generic(int device, cudaStream_t st, int64_t n, int64_t nnz_coo,
   return PF3_OK;
 }
 
+// y = P A P x with P = diag(free): the boundary-condition partition K[bu,:][:,bu] of the reference scripts
+// (tests/test_quad4_static_point_load.py:84-99) applied on the fly, without extracting a sub-matrix.
+__global__ void __launch_bounds__(256) k_spmv_masked(int64_t nrows, const int64_t* __restrict__ indptr,
+                                                     const int64_t* __restrict__ indices,
+                                                     const double* __restrict__ vals,
+                                                     const unsigned char* __restrict__ free_,
+                                                     const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = w; row < nrows; row += nw) {
+    double s = 0.;
+    if (free_[row])
+      for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+        const int64_t c = indices[k];
+        if (free_[c]) s += vals[k] * x[c];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) y[row] = s;
+  }
+}
+__global__ void k_csr_diag(int64_t nrows, const int64_t* __restrict__ indptr, const int64_t* __restrict__ indices,
+                           const double* __restrict__ vals, int64_t row0, double* __restrict__ d) {
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < nrows; r += int64_t(gridDim.x) * blockDim.x) {
+    double v = 0.;
+    for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k)
+      if (indices[k] == r + row0) v += vals[k];
+    d[r] = v;
+  }
+}
+
+int spmv_csr_masked(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
+                    const unsigned char* free_, const double* x, double* y, int64_t* launches) {
+  if (nrows <= 0) return PF3_OK;
+  const int64_t blocks = (nrows * 32 + 255) / 256;
+  k_spmv_masked<<<unsigned(std::min<int64_t>(blocks, 148 * 64)), 256, 0, st>>>(nrows, indptr, indices, vals, free_, x, y);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+int csr_diagonal(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
+                 int64_t row0, double* d, int64_t* launches) {
+  if (nrows <= 0) return PF3_OK;
+  k_csr_diag<<<grid_for(nrows), 256, 0, st>>>(nrows, indptr, indices, vals, row0, d);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+
 int spmv_csr(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
              const double* x, double* y, int64_t* launches) {
   if (nrows <= 0) return PF3_OK;
