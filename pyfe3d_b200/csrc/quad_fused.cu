@@ -41,13 +41,22 @@ constexpr int kRecRot = 56;
 // ------------------------------------------------------------------------------------------ K1
 template <int KIND>
 __global__ void __launch_bounds__(128) quad_record_kernel(const EvalArgs A, double* __restrict__ rec, int stride) {
-  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (e >= A.ne) return;
+  // records are staged per warp in shared memory (odd leading dimension) and written out as one contiguous
+  // run of 32 x stride doubles
+  extern __shared__ double k1_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+  if (e0 >= A.ne) return;
+  const int nvalid = int(min(int64_t(32), A.ne - e0));
+  const int64_t e = e0 + min(lane, nvalid - 1);
+  const int ld = stride + 1;
+  double* stage = k1_smem + warp * 32 * ld;
   const bool kg_u = (A.what & PF3_KG) != 0;
   double ue[24];
   ShellGeom<4> g;
   shell_geom<4>(A, e, g, kg_u ? ue : nullptr);
-  double* r = rec + e * stride;
+  double* r = stage + lane * ld;
+  for (int i = 23; i < stride; ++i) r[i] = 0.;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -114,6 +123,14 @@ __global__ void __launch_bounds__(128) quad_record_kernel(const EvalArgs A, doub
         r[32 + gp] = c.A[2] * exx + c.A[4] * eyy + c.A[5] * gxy + c.B[2] * kxx + c.B[4] * kyy + c.B[5] * kxy;
       }
     }
+  }
+  __syncwarp();
+  double* out = rec + e0 * stride;
+  const int total = nvalid * stride;
+  if (stride == kRecPlain) {
+    for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / kRecPlain) * ld + idx % kRecPlain];
+  } else {
+    for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / stride) * ld + idx % stride];
   }
 }
 
@@ -564,10 +581,18 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   if (F.nown <= 0 || F.A.ne <= 0) return cudaSuccess;
   const int stride = fused_record_stride(F.A);
   const unsigned g1 = unsigned((F.A.ne + 127) / 128);
+  const size_t smem1 = size_t(4) * 32 * (stride + 1) * sizeof(double);
+  static bool once1 = false;
+  if (!once1) {
+    const int maxs = int(size_t(4) * 32 * (kRecRot + 1) * sizeof(double));
+    cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+    cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+    once1 = true;
+  }
   if (kind == PF3_QUAD4)
-    quad_record_kernel<PF3_QUAD4><<<g1, 128, 0, st>>>(F.A, rec, stride);
+    quad_record_kernel<PF3_QUAD4><<<g1, 128, smem1, st>>>(F.A, rec, stride);
   else
-    quad_record_kernel<PF3_QUAD4R><<<g1, 128, 0, st>>>(F.A, rec, stride);
+    quad_record_kernel<PF3_QUAD4R><<<g1, 128, smem1, st>>>(F.A, rec, stride);
   ++*launches;
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) return e1;
