@@ -57,6 +57,10 @@ def run(name, case, mats, fused, scale=1.0):
             for m in names:
                 plans[m].assemble(coo[m].v, out=csr[m])
         ms = timeit(step)
+        parts = {"eval": timeit(lambda: b.evaluate(indices=False, out=coo, **kw))}
+        for m in names:
+            parts["assemble_" + m] = timeit(lambda m=m: plans[m].assemble(coo[m].v, out=csr[m]))
+        print(json.dumps({"config": name, "kernel_ms": parts}))
     bytes_el = sum(b.sizes[m] * 8 for m in names)
     nnz = sum(plans[m].nnz for m in names)
     alg = ne * bytes_el + nnz * 8
