@@ -323,16 +323,22 @@ class AssemblyPlan:
 
     def evaluate_assemble(self, KC0=False, KG=False, KG_given_stress=None, M=False, mtype=0, u=None,
                           coo=None, csr=None, write_coo=True, indices=False):
-        """ONE kernel: element matrices -> COO value arrays AND assembled CSR values, with no re-read
-        of the COO arrays.  Requires this plan to be the "KC0" plan of a single Quad4/Quad4R batch.
+        """Element matrices -> COO value arrays AND assembled CSR values.
+
+        For the "KC0" plan of a single Quad4/Quad4R batch this is ONE fused kernel that never re-reads the
+        COO arrays; for every other element kind (or when a node couples to more than 16 nodes) it runs the
+        two-pass path (one evaluation launch + one slab assembly per matrix) with the same outputs.
 
         ``coo`` / ``csr``: optional dicts of preallocated outputs (name -> Coo / tensor).  With
-        ``write_coo=False`` only the CSR values are produced.  Returns (coo, csr) dicts."""
+        ``write_coo=False`` only the CSR values are returned.  Returns (coo, csr) dicts."""
         if self.matrix != "KC0" or len(self.batches) != 1:
             raise ValueError("evaluate_assemble needs the KC0 plan of a single batch")
         b = self.batches[0]
         if u is not None:
             u = _dev(u, torch.float64, self.device)
+        if b.kind not in ("quad4", "quad4r") or getattr(self, "_fused_unsupported", False):
+            return self._evaluate_assemble_two_pass(KC0, KG, KG_given_stress, M, mtype, u, coo, csr, write_coo,
+                                                    indices)
         sizes = self.csr_sizes(mtype)
         coo = dict(coo or {})
         csr = dict(csr or {})
@@ -360,10 +366,39 @@ class AssemblyPlan:
             return _cabi.Coo(_ptr(k.r) if indices else 0, _ptr(k.c) if indices else 0, _ptr(k.v), 0, 0)
 
         context(self.device)
-        self._plan.eval_assemble(b.cabi_batch(mtype, KG_given_stress or (0., 0., 0.), u), what, cc("KC0"),
-                                 cc("KG"), cc("M"), _ptr(csr.get("KC0")), _ptr(csr.get("KG")),
-                                 _ptr(csr.get("M")))
+        try:
+            self._plan.eval_assemble(b.cabi_batch(mtype, KG_given_stress or (0., 0., 0.), u), what, cc("KC0"),
+                                     cc("KG"), cc("M"), _ptr(csr.get("KC0")), _ptr(csr.get("KG")),
+                                     _ptr(csr.get("M")))
+        except _cabi.Pf3Error as exc:
+            if "capacity" not in str(exc) and "not defined" not in str(exc):
+                raise
+            self._fused_unsupported = True      # e.g. a node coupled to more than 16 nodes
+            return self._evaluate_assemble_two_pass(KC0, KG, KG_given_stress, M, mtype, u, coo, csr, write_coo,
+                                                    indices)
         return coo, csr
+
+    def _sibling(self, matrix, mtype):
+        """Plan of another matrix of the same batches / row shard (cached)."""
+        if matrix == self.matrix and mtype == 0:
+            return self
+        cache = self.__dict__.setdefault("_siblings", {})
+        key = (matrix, mtype if matrix == "M" else 0)
+        if key not in cache:
+            cache[key] = AssemblyPlan(matrix, self.nnodes, self.batches,
+                                      node_range=(self.node_begin, self.node_end), mtype=key[1])
+        return cache[key]
+
+    def _evaluate_assemble_two_pass(self, KC0, KG, KG_given_stress, M, mtype, u, coo, csr, write_coo, indices):
+        b = self.batches[0]
+        coo = dict(coo or {})
+        csr = dict(csr or {})
+        res = b.evaluate(KC0=KC0, KG=KG, KG_given_stress=KG_given_stress, M=M, mtype=mtype, u=u, indices=indices,
+                         out=coo)
+        for name, k in res.items():
+            plan = self._sibling(name, mtype)
+            csr[name] = plan.assemble(k.v, out=csr.get(name))
+        return (res if write_coo else {}), csr
 
 
 class CooPlan:

@@ -1,1 +1,1 @@
-python scripts/bench_configs.py 2>&1 | grep kernel_ms
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8

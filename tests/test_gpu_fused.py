@@ -74,3 +74,45 @@ def test_fused_large_mesh_matches_oracle_and_twopass(kind):
     _, csr2 = plan.evaluate_assemble(KC0=True, KG=True, M=True, write_coo=False)
     for m in ("KC0", "KG", "M"):
         assert torch.equal(csr2[m], csr[m])
+
+
+def _fan_case(kind, nquads=6, seed=7):
+    """nquads quads around one centre node: the centre has valence nquads (> 4 -> two rounds of node records)."""
+    rng = np.random.default_rng(seed)
+    ang = np.linspace(0, 2 * np.pi, 2 * nquads, endpoint=False)
+    rim = np.stack([np.cos(ang), np.sin(ang), 0.05 * np.sin(3 * ang)], 1) * (1 + 0.1 * rng.uniform(-1, 1, (2 * nquads, 1)))
+    X = np.vstack([[0., 0., 0.02], rim]) @ cases.random_rotation(rng).T
+    conn = np.array([[0, 1 + 2 * i, 1 + (2 * i + 1) % (2 * nquads), 1 + (2 * i + 2) % (2 * nquads)]
+                     for i in range(nquads)], np.int64)
+    nn = X.shape[0]
+    c = dict(kind=kind, x=X.ravel(), conn=conn, props=cases.random_shellprops(rng, 1), ndof=6 * nn,
+             u=1e-4 * rng.normal(size=6 * nn), stress=(1e3, -2e2, 3e2))
+    if kind == "quad4r":
+        c["hg"] = rng.uniform(0.01, 1., (nquads, 5))
+    return c
+
+
+@pytest.mark.parametrize("kind", ["quad4", "quad4r"])
+def test_fused_high_valence_node(kind):
+    case = _fan_case(kind)
+    want = driver.run(case, what=("KC0", "KG", "M0"))
+    _check(case, want)
+
+
+def test_evaluate_assemble_falls_back_for_other_kinds():
+    """Tria3R has no fused kernel: the same call runs evaluation + slab assembly and returns the same outputs."""
+    import scipy.sparse as sp
+    from pyfe3d_b200.batch import AssemblyPlan
+    case, ref = util.load_golden("tria3r_mesh")
+    b = util.batch_from_case(case)
+    n = case["ndof"]
+    plan = AssemblyPlan("KC0", n // 6, [b])
+    coo, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True, mtype=1, indices=True)
+    for name, rk in (("KC0", "KC0"), ("KG", "KG"), ("M", "M1")):
+        r, c, v = ref[rk]
+        assert np.array_equal(coo[name].r.cpu().numpy(), r)
+        assert util.block_relerr(coo[name].v.cpu().numpy(), v, case["conn"].shape[0]) <= util.TOL_VALUES
+        A = plan._sibling(name, 1).to_scipy(csr[name])
+        S = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+        S.sum_duplicates()
+        assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max()
