@@ -30,10 +30,11 @@ namespace {
 #endif
 constexpr double kGpF = 0.5773502691896257645092;
 #ifndef PF3_FUSED_WARPS
-#define PF3_FUSED_WARPS 4   // warps per CTA and CTAs per SM of the fused kernel: 12 warps/SM at 168 registers
-#define PF3_FUSED_CTAS 3    // measured best; the staging shared memory allows at most 15 warps
+#define PF3_FUSED_WARPS 1   // warps per CTA and CTAs per SM of the fused kernel: 12 warps/SM at 168 registers;
+#define PF3_FUSED_CTAS 12   // one-warp CTAs measured best (10.82 ms vs 10.98 for 2x6 and 11.15 for 4x3)
 #endif
 constexpr int kFusedWarps = PF3_FUSED_WARPS;
+
 constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path (NodeRec::gmap)
 constexpr int kRecPlain = 36;               // record doubles without / with rotated A,B,D
 constexpr int kRecRot = 56;
@@ -141,7 +142,14 @@ __global__ void __launch_bounds__(128) quad_record_kernel(const EvalArgs A, doub
 template <int NR, int CNT>
 struct SlabShape {
   static constexpr int kSlab = NR * 4 * CNT;   // doubles per (element, node) COO slab
-  static constexpr int kLd = kSlab + 2;        // padded stride: 146 / 122 / 74 / 38 doubles
+#ifdef PF3_SLAB_PAD2
+  static constexpr int kLd = kSlab + 2;        // older stride 146 / 122 / 74 / 38: 2-way conflicts on the staging stores
+#else
+  // padded stride 152 / 124 / 76 / 44 doubles: even (16-B aligned slabs for the bulk copy) and chosen so that the
+  // staging stores of the 8 incidences of a warp fall into disjoint banks (kLd mod 16 = 8 for the 16-B stores of
+  // KC0 and for KG, 12 for the 8-B stores of M); the +2 stride was 2-way conflicted on every staging store
+  static constexpr int kLd = kSlab + ((CNT == 6 || NR == 3) ? 8 : 4);
+#endif
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -238,19 +246,34 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
 
 // The staging area is reused by the next matrix: before writing it again, wait until the bulk copies issued
 // from it have READ shared memory.  Called as late as possible so the copies drain behind arithmetic.
-__device__ __forceinline__ void stage_reuse_wait() {
+// `pending` = number of most recent bulk groups that may still be reading (they use another staging area).
+__device__ __forceinline__ void stage_reuse_wait(int pending = 0) {
 #if PF3_COO_TMA
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (pending == 0)
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (pending == 1)
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else
+    asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
   __syncwarp();
 #endif
 }
 
-constexpr int kRing = 3;                                   // node-record prefetch ring (records of 2 nodes each)
-constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1168 doubles: the largest matrix (KC0)
-// staged element records: stride rstride + 2 doubles (38 / 58: conflict-free, 16-B aligned), double buffer x 8
-__host__ __device__ constexpr int warp_smem_doubles(int rstride) { return kStageV4 + kRing * 2 * 8 + 2 * 8 * (rstride + 2); }
+constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1216 doubles: the largest matrix (KC0)
+// Optional (PF3_KG_SEP, plain records only): a private staging area for KG, so that staging KG never waits for the
+// bulk copies of the previous round's KC0 slabs.  Measured slower on B200 (less L1 left) - kept for experiments.
+#ifndef PF3_KG_SEP
+#define PF3_KG_SEP 0
+#endif
+constexpr int kStageKG = 8 * SlabShape<3, 3>::kLd;
+__host__ __device__ constexpr bool kg_separate(int rstride) { return PF3_KG_SEP && rstride == kRecPlain; }
+// per warp: slab staging | the two NodeRec of the node pair (128 B) | 8 element records, stride rstride + 2 doubles
+// (38 / 58: conflict-free, 16-B aligned)
+__host__ __device__ constexpr int warp_smem_doubles(int rstride) {
+  return kStageV4 + 2 * 8 + 8 * (rstride + 2) + (kg_separate(rstride) ? kStageKG : 0);
+}
 
-// Stage the element records of the 8 incidences of an item into shared memory with 16-B cp.async; the 4 lanes
+// Stage the element records of the 8 incidences of a node pair into shared memory with 16-B cp.async; the 4 lanes
 // of an incidence split the record's chunks.
 __device__ __forceinline__ void erec_fetch(const double* __restrict__ rec, int rstride, double* buf, int pair0,
                                            int lane) {
@@ -263,17 +286,16 @@ __device__ __forceinline__ void erec_fetch(const double* __restrict__ rec, int r
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// Bring the NodeRec of node pair `np`, round r into ring slot `slot` (8 x 16-B cp.async by lanes 0..7).
-__device__ __forceinline__ void ring_fetch(const FusedArgs& F, NodeRec* ring, int slot, int64_t np, int r,
-                                           int64_t npairs, int lane) {
+// Bring the NodeRec of node pair `np`, round r into shared memory (8 x 16-B cp.async by lanes 0..7).
+__device__ __forceinline__ void noderec_fetch(const FusedArgs& F, NodeRec* dst2, int64_t np, int r, int lane) {
   if (lane < 8) {
     const int hh = lane >> 2, q = lane & 3;
     const int64_t n = 2 * np + hh;
-    char* dst = reinterpret_cast<char*>(ring + slot * 2 + hh) + 16 * q;
-    if (np < npairs && n < F.nown && F.noderec != nullptr) {
+    char* dst = reinterpret_cast<char*>(dst2 + hh) + 16 * q;
+    if (n < F.nown && F.noderec != nullptr) {
       const char* src = reinterpret_cast<const char*>(F.noderec + n * F.rmax + r) + 16 * q;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-    } else if (np < npairs && n < F.nown) {
+    } else if (n < F.nown) {
       // element mode (COO only, no plan): "node" n is element n, its 4 incidences are its own 4 row slabs
       const int p0 = int(n) * 16;
       int4 z = make_int4(-1, -1, -1, -1);
@@ -293,6 +315,10 @@ __device__ __forceinline__ void ring_fetch(const FusedArgs& F, NodeRec* ring, in
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// One warp = one node PAIR (all its rounds), one CTA = kFusedWarps consecutive pairs, and as many CTAs as there is
+// work: the hardware CTA scheduler hands out node pairs in order, so the nodes in flight at any time form a narrow
+// window of the mesh (their COO/CSR destinations are neighbours in DRAM) and a slow warp never holds work back.
+// Measured on B200 at 4 M Quad4: persistent grid-stride warps with a 3-deep prefetch ring 12.4 ms/step, this 10.8.
 template <int KIND>
 __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
                                                                          int rstride) {
@@ -301,47 +327,44 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int eld = rstride + 2;
   double* st = smem + warp * warp_smem_doubles(rstride);
-  NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
-  double* erec = st + kStageV4 + kRing * 2 * 8;
+  NodeRec* nrec = reinterpret_cast<NodeRec*>(st + kStageV4);
+  double* erec = st + kStageV4 + 2 * 8;
+  const bool kgsep = kg_separate(rstride);
+  double* stkg = kgsep ? erec + 8 * eld : st;
+  // bulk groups committed per round (one per active matrix) and how many of the latest may still be reading when a
+  // staging area is written again
+  const bool hasKG = (F.A.what & (PF3_KG | PF3_KG_STRESS)) != 0, hasM = (F.A.what & PF3_M) != 0;
+  const int ngrp = int(hasKG) + int(hasM) + int((F.A.what & PF3_KC0) != 0);
+  const int pendKG = kgsep ? ngrp - 1 : 0;
+  const int pendM = (kgsep && hasKG) ? 1 : 0;
+  const int pendKC0 = hasM ? 0 : pendM;
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
-  const int64_t npairs = (F.nown + 1) >> 1;
+  const int64_t np = int64_t(blockIdx.x) * kFusedWarps + warp;
+  if (2 * np >= F.nown) return;
   const int rmax = F.rmax;
   const double xib = (b == 1 || b == 2) ? 1. : -1., etab = (b >= 2) ? 1. : -1.;
-  const int64_t stride_np = int64_t(gridDim.x) * kFusedWarps;
-  const int64_t np0 = int64_t(blockIdx.x) * kFusedWarps + warp;
-  // flattened work items j = (node pair, round); ring slot j % 3 holds item j
-  auto item_np = [&](int64_t j) { return np0 + (j / rmax) * stride_np; };
-  ring_fetch(F, ring, 0, item_np(0), 0, npairs, lane);
-  ring_fetch(F, ring, 1, item_np(1), int(1 % rmax), npairs, lane);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
-  erec_fetch(rec, rstride, erec, (ring + h)->inc[k], lane);   // element records of item 0
 
-  for (int64_t j = 0;; ++j) {
-    const int64_t np = item_np(j);
-    if (np >= npairs) break;
-    const int r = int(j % rmax);
-    ring_fetch(F, ring, int((j + 2) % kRing), item_np(j + 2), int((j + 2) % rmax), npairs, lane);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j, j+1 and element records j have landed
+  for (int r = 0; r < rmax; ++r) {
+    if (r > 0) stage_reuse_wait(0);   // the node records and element records of the previous round are dead
+    noderec_fetch(F, nrec, np, r, lane);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    const NodeRec* nr = ring + int(j % kRing) * 2 + h;
-    // element records of the next item start flowing now
-    erec_fetch(rec, rstride, erec + int((j + 1) & 1) * 8 * eld, (ring + int((j + 1) % kRing) * 2 + h)->inc[k], lane);
-    const int64_t b0 = nr->b0;
-    const int nb = nr->nb;
+    const NodeRec* nr = nrec + h;
     const int pair0 = nr->inc[k];
     const bool act = pair0 >= 0;
-    if (__ballot_sync(0xffffffffu, act) == 0u) {
-      __syncwarp();
-      continue;
-    }
+    if (__ballot_sync(0xffffffffu, act) == 0u) continue;
+    erec_fetch(rec, rstride, erec, pair0, lane);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const int64_t b0 = nr->b0;
+    const int nb = nr->nb;
     const int64_t e = act ? (pair0 >> 4) : 0;
     const int a = act ? ((pair0 >> 2) & 3) : 0;
     const bool first = (r == 0);
     const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
 
     // ---------------- element record (K1) and property row
-    const double* re = erec + int(j & 1) * 8 * eld + (lane >> 2) * eld;
+    const double* re = erec + (lane >> 2) * eld;
     const double2* re2 = reinterpret_cast<const double2*>(re);
     double rr_[24];
 #pragma unroll
@@ -404,13 +427,13 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
 
     // ---------------- KG : Ge_ab * z z^T on the translations
     if (A.what & (PF3_KG | PF3_KG_STRESS)) {
-      double* sl = st + (lane >> 2) * SlabShape<3, 3>::kLd + b * 3;
-      stage_reuse_wait();
+      double* sl = stkg + (lane >> 2) * SlabShape<3, 3>::kLd + b * 3;
+      stage_reuse_wait(pendKG);
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) sl[i * 12 + jj] = (R.a[i][2] * R.a[jj][2]) * ge;
-      emit_slabs<3, 3>(st, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg, b0 * 9, nb, first,
+      emit_slabs<3, 3>(stkg, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg, b0 * 9, nb, first,
                        lane);
     }
 
@@ -431,7 +454,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       double* coo = A.mv ? A.mv + A.m_k0 : nullptr;
       if (A.mtype != 2) {
         double* sl = st + (lane >> 2) * SlabShape<6, 5>::kLd + b * 5;
-        stage_reuse_wait();
+        stage_reuse_wait(pendM);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           double tt[3], tr[3], rq[3];
@@ -456,7 +479,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
         emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, b0 * 30, nb, first, lane);
       } else {
         double* sl = st + (lane >> 2) * SlabShape<6, 3>::kLd + b * 3;
-        stage_reuse_wait();
+        stage_reuse_wait(pendM);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -539,7 +562,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       rot_block_8(R, -f_pq(cB, cxx, cxy, cyx, cyy), f_pp(cB, cxx, cxy, cyx, cyy), 0.5 * kd * pyab,
                   -f_qq(cB, cxx, cxy, cyx, cyy), f_qp(cB, cxx, cxy, cyx, cyy), -0.5 * kd * pxab, -0.25 * tSa,
                   0.25 * sSa, o2);
-      stage_reuse_wait();
+      stage_reuse_wait(pendKC0);
 #pragma unroll
       for (int i = 0; i < 3; ++i) {   // rows u v w of node a: 6 columns of node b, 24 doubles per COO row
         sl2[i * 12 + 0] = make_double2(o1[i][0], o1[i][1]);
@@ -567,7 +590,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
                        first, lane);
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // the bulk copies read this CTA's shared memory: they must have done so before the CTA retires
+  stage_reuse_wait(0);
 }
 
 }  // namespace
@@ -599,11 +623,11 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   const size_t smem = fused_smem_bytes(stride);
   const int64_t npairs = (F.nown + 1) / 2;
   const int64_t want = (npairs + kFusedWarps - 1) / kFusedWarps;
-  const int64_t cap = 148 * PF3_FUSED_CTAS * 8;
-  const unsigned grid = unsigned(want < cap ? (want < 1 ? 1 : want) : cap);
+  if (want > int64_t(0x7fffffff)) return cudaErrorInvalidConfiguration;
+  const unsigned grid = unsigned(want < 1 ? 1 : want);
   static bool once = false;
   if (!once) {
-    const int maxs = int(fused_smem_bytes(kRecRot));
+    const int maxs = int(fused_smem_bytes(kRecRot) > fused_smem_bytes(kRecPlain) ? fused_smem_bytes(kRecRot) : fused_smem_bytes(kRecPlain));
     cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
     cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
     once = true;
