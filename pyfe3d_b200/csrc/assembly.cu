@@ -652,9 +652,15 @@ __global__ void __launch_bounds__(256) k_assemble_slabs(const NodeRec* __restric
 template <int NR, int CNT>
 int launch_slabs(int nns, const NodeRec* recs, int rmax, int64_t nown, const double* coo, int nn, int size,
                  double* csr, int accumulate, cudaStream_t st) {
-  const int wpc = 8;
+#ifndef PF3_SLAB_WPC
+#define PF3_SLAB_WPC 1   // one-warp CTAs, uncapped grid: the CTA scheduler keeps the nodes in flight a narrow window (as in quad_fused.cu)
+#endif
+#ifndef PF3_SLAB_CAP
+#define PF3_SLAB_CAP 2000000000
+#endif
+  const int wpc = PF3_SLAB_WPC;
   const int64_t npairs = (nown + 1) / 2;
-  const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((npairs + wpc - 1) / wpc, 148 * 16)));
+  const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((npairs + wpc - 1) / wpc, int64_t(PF3_SLAB_CAP))));
   const int vec16 = int((((uintptr_t)coo) & 15) == 0 && (size % 2) == 0);   // 16-B cp.async needs aligned slabs
 #define PF3_SLAB_CASE(N)                                                                                       \
   case N: {                                                                                                    \

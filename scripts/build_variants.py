@@ -19,9 +19,10 @@ def one(arg):
     name, flags = arg.split("=", 1)
     d = os.path.join(VARDIR, name)
     os.makedirs(d, exist_ok=True)
-    obj = os.path.join(d, "quad_fused.o")
-    subprocess.check_call([B._nvcc()] + B.NVCC_FLAGS + flags.split() + ["-c", os.path.join(B.CSRC, "quad_fused.cu"), "-o", obj])
-    objs = [obj if cu == "quad_fused.cu" else os.path.join(B.OBJDIR, cu[:-3] + ".o") for cu in B.CU]
+    src = os.environ.get("VARIANT_SRC", "quad_fused.cu")
+    obj = os.path.join(d, src[:-3] + ".o")
+    subprocess.check_call([B._nvcc()] + B.NVCC_FLAGS + flags.split() + ["-c", os.path.join(B.CSRC, src), "-o", obj])
+    objs = [obj if cu == src else os.path.join(B.OBJDIR, cu[:-3] + ".o") for cu in B.CU]
     subprocess.check_call([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o",
                            os.path.join(d, "libpyfe3d_b200.so")] + objs)
     os.remove(obj)
