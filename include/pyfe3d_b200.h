@@ -229,6 +229,16 @@ int pf3_spmv_csr_masked(pf3_context* ctx, int64_t nrows, const int64_t* indptr, 
 int pf3_csr_diagonal(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
                      const double* vals, int64_t row0, double* diag);
 
+/* y = A x (free_dof == NULL) or y = P A P x (P = diag(free_dof != 0), free_dof[6*nnodes] over GLOBAL dofs) for the
+ * CSR values of a STRUCTURED plan, using the plan's node-block structure instead of per-entry indices (8.2 B per
+ * nonzero instead of 16): the operator the reference scripts hand to cg / eigsh after `KC0[bu, :][:, bu]`
+ * (tests/test_quad4_static_point_load.py:84-104, tests/test_quad4r_linear_buckling_plate.py:135-180).
+ * x[6*nnodes] (global), y[6*nown] (the plan's own rows).  PF3_E_UNSUPPORTED for generic (COO) plans. */
+int pf3_plan_spmv(pf3_context* ctx, const pf3_plan* plan, const double* vals, const unsigned char* free_dof,
+                  const double* x, double* y);
+/* diag[6*nown]: the diagonal of the plan's row block (0 where the pattern has no diagonal entry) */
+int pf3_plan_diagonal(pf3_context* ctx, const pf3_plan* plan, const double* vals, double* diag);
+
 /* ---- host-pointer convenience (numpy callers): copies in, runs, copies out -- */
 int pf3_eval_host(pf3_context* ctx, const pf3_batch* host_batch, int what,
                   const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);

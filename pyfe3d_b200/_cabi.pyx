@@ -63,6 +63,9 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_pattern(pf3_context*, const pf3_plan*, int64_t* indptr, int64_t* indices) nogil
     int pf3_plan_nblocks(const pf3_plan*, int64_t*)
     int pf3_plan_fint(pf3_context*, const pf3_plan*, int group, const pf3_batch*, double* fint) nogil
+    int pf3_plan_spmv(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
+                      const double* x, double* y) nogil
+    int pf3_plan_diagonal(pf3_context*, const pf3_plan*, const double* vals, double* diag) nogil
     int pf3_quad4_update_BL(pf3_context*, int64_t n, const double* xe, double xi, double eta, double* out) nogil
     int pf3_eval_assemble(pf3_context*, const pf3_batch*, const pf3_plan*, int what, const pf3_coo*, const pf3_coo*,
                           const pf3_coo*, double*, double*, double*) nogil
@@ -332,6 +335,19 @@ cdef class Plan:
         cdef int rc
         with nogil:
             rc = pf3_plan_fint(self.owner.ctx, self.plan, group, &b.b, <double*>fint)
+        _check(rc)
+
+    def spmv(self, uintptr_t vals, uintptr_t free_dof, uintptr_t x, uintptr_t y):
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_spmv(self.owner.ctx, self.plan, <const double*>vals, <const unsigned char*>free_dof,
+                               <const double*>x, <double*>y)
+        _check(rc)
+
+    def diagonal(self, uintptr_t vals, uintptr_t diag):
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_diagonal(self.owner.ctx, self.plan, <const double*>vals, <double*>diag)
         _check(rc)
 
     def pattern(self, uintptr_t indptr, uintptr_t indices):

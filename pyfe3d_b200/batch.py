@@ -302,6 +302,24 @@ class AssemblyPlan:
         return sp.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()),
                              shape=(self.nrows, 6 * self.nnodes))
 
+    def spmv(self, vals, x, free=None, out=None):
+        """y = A x (or P A P x with P = diag(free)) for the CSR values ``vals`` of this plan, through the plan's
+        node-block structure (no per-entry indices are read).  ``x``: [6*nnodes] global, ``free``: optional uint8
+        [6*nnodes] DOF mask, result: [nrows] (the plan's own rows)."""
+        if out is None:
+            out = torch.empty(self.nrows, dtype=torch.float64, device=self.device)
+        context(self.device)
+        self._plan.spmv(_ptr(vals), _ptr(free) if free is not None else 0, _ptr(x), _ptr(out))
+        return out
+
+    def diagonal(self, vals, out=None):
+        """Diagonal of the plan's row block (Jacobi scaling)."""
+        if out is None:
+            out = torch.empty(self.nrows, dtype=torch.float64, device=self.device)
+        context(self.device)
+        self._plan.diagonal(_ptr(vals), _ptr(out))
+        return out
+
     def update_fint(self, fint, u=None):
         """fint += internal forces of every batch of the plan (update_fint of the reference), gathered per
         node through the plan's incidence lists: deterministic, no per-call sort, owned rows only."""

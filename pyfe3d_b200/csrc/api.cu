@@ -27,6 +27,9 @@ int spmv_csr_masked(cudaStream_t st, int64_t nrows, const int64_t* indptr, const
                     const unsigned char* free_, const double* x, double* y, int64_t* launches);
 int csr_diagonal(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_t* indices, const double* vals,
                  int64_t row0, double* d, int64_t* launches);
+int plan_spmv(const pf3_plan* pl, cudaStream_t st, const double* vals, const unsigned char* free_, const double* x,
+              double* y, int64_t* launches);
+int plan_diagonal(const pf3_plan* pl, cudaStream_t st, const double* vals, double* diag, int64_t* launches);
 int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64_t* conn, const double* fe,
                 double* fint, int64_t* launches);
 int64_t plan_nnz(const pf3_plan* pl);
@@ -549,6 +552,21 @@ int pf3_csr_diagonal(pf3_context* ctx, int64_t nrows, const int64_t* indptr, con
   if (rc) return rc;
   if (nrows < 0 || !indptr || !diag) return PF3_E_BAD_ARG;
   return pf3::csr_diagonal(ctx->stream, nrows, indptr, indices, vals, row0, diag, &ctx->launches);
+}
+
+int pf3_plan_spmv(pf3_context* ctx, const pf3_plan* plan, const double* vals, const unsigned char* free_dof,
+                  const double* x, double* y) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan || !vals || !x || !y) return PF3_E_BAD_ARG;
+  return pf3::plan_spmv(plan, ctx->stream, vals, free_dof, x, y, &ctx->launches);
+}
+
+int pf3_plan_diagonal(pf3_context* ctx, const pf3_plan* plan, const double* vals, double* diag) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan || !vals || !diag) return PF3_E_BAD_ARG;
+  return pf3::plan_diagonal(plan, ctx->stream, vals, diag, &ctx->launches);
 }
 
 // Host-pointer convenience: every pointer in host_batch / the pf3_coo structs / fint is a HOST pointer.

@@ -882,6 +882,169 @@ int spmv_csr(cudaStream_t st, int64_t nrows, const int64_t* indptr, const int64_
   return int(cudaGetLastError());
 }
 
+// ---- block-structured SpMV on the plan's own layout --------------------------------------------------------
+// The CSR value array of a structured plan is a sequence of node row blocks [dof row d][column block s][masked
+// column r] whose column blocks are listed once per NODE in bcol: y = A x needs 8 B/nonzero of values plus 8 B per
+// 6x6 block of indices (8.2 B/nnz against 16 B/nnz for int64 CSR), and the 6 rows of a node share their x gathers.
+// A half-warp takes one node; lanes stride over the (column block, masked column) positions of a row, rows
+// inner.  free_ (nullable): P A P with P = diag(free), the boundary-condition partition of the reference scripts
+// (tests/test_quad4_static_point_load.py:84-99).  Deterministic (fixed per-lane order + butterfly reduction).
+struct SpmvMask {
+  int8_t cols[6][6];
+  int cnt[6], rowoff[6], mc;
+};
+// CNT > 0: every non-empty row has CNT masked columns per block (0: general); SAME: all non-empty rows share one
+// column set, so the x gather (and its mask byte) is done once per position instead of once per row
+template <int CNT, bool SAME>
+__global__ void __launch_bounds__(128) k_plan_spmv(const SpmvMask M, const int64_t* __restrict__ brow_ptr,
+                                                   const int64_t* __restrict__ bcol, int64_t nown, int64_t node_begin,
+                                                   const double* __restrict__ vals,
+                                                   const unsigned char* __restrict__ free_,
+                                                   const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
+  const int64_t i = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + h;
+  const bool live = i < nown;
+  int64_t b0 = 0;
+  int nb = 0;
+  if (live) {
+    b0 = brow_ptr[i];
+    nb = int(brow_ptr[i + 1] - b0);
+  }
+  const double* v = vals + b0 * M.mc;
+  double acc[6] = {0., 0., 0., 0., 0., 0.};
+  if constexpr (CNT > 0) {
+    const int w = nb * CNT;
+    for (int xx = l16; xx < w; xx += 16) {
+      const int s = xx / CNT, r = xx - s * CNT;
+      const int64_t nc = 6 * bcol[b0 + s];
+      if constexpr (SAME) {
+        int c0 = 0;
+#pragma unroll
+        for (int d = 5; d >= 0; --d)
+          if (M.cnt[d] != 0) c0 = M.cols[d][r];
+        double xv = x[nc + c0];
+        if (free_ != nullptr && !free_[nc + c0]) xv = 0.;
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+          if (M.cnt[d] != 0) acc[d] += v[M.rowoff[d] * nb + xx] * xv;
+      } else {
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+          if (M.cnt[d] == 0) continue;
+          const int64_t col = nc + M.cols[d][r];
+          double xv = x[col];
+          if (free_ != nullptr && !free_[col]) xv = 0.;
+          acc[d] += v[M.rowoff[d] * nb + xx] * xv;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      const int cnt = M.cnt[d];
+      if (cnt == 0) continue;
+      const int w = nb * cnt;
+      for (int xx = l16; xx < w; xx += 16) {
+        const int s = xx / cnt, r = xx - s * cnt;
+        const int64_t col = 6 * bcol[b0 + s] + M.cols[d][r];
+        double xv = x[col];
+        if (free_ != nullptr && !free_[col]) xv = 0.;
+        acc[d] += v[M.rowoff[d] * nb + xx] * xv;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 6; ++d)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+  if (live && l16 < 6) {
+    double out = acc[0];
+#pragma unroll
+    for (int d = 1; d < 6; ++d) out = (l16 == d) ? acc[d] : out;
+    const int64_t row = 6 * i + l16;
+    if (free_ != nullptr && !free_[6 * node_begin + row]) out = 0.;
+    y[row] = out;
+  }
+}
+
+// diag[6 i + d] = A[row, row] (0 when the pattern has no diagonal entry there): Jacobi scaling
+__global__ void k_plan_diag(const SpmvMask M, const int64_t* __restrict__ brow_ptr, const int64_t* __restrict__ bcol,
+                            int64_t nown, int64_t node_begin, const double* __restrict__ vals,
+                            double* __restrict__ diag) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < nown * 6; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t i = t / 6;
+    const int d = int(t - i * 6);
+    const int64_t b0 = brow_ptr[i];
+    const int nb = int(brow_ptr[i + 1] - b0);
+    double out = 0.;
+    int r = -1;
+    for (int q = 0; q < M.cnt[d]; ++q)
+      if (M.cols[d][q] == d) r = q;
+    if (r >= 0)
+      for (int s = 0; s < nb; ++s)
+        if (bcol[b0 + s] == node_begin + i) out = vals[b0 * M.mc + int64_t(M.rowoff[d]) * nb + s * M.cnt[d] + r];
+    diag[t] = out;
+  }
+}
+
+static SpmvMask spmv_mask_of(const pf3_plan* pl) {
+  SpmvMask M;
+  for (int i = 0; i < 6; ++i) {
+    int c = 0;
+    for (int j = 0; j < 6; ++j) {
+      M.cols[i][j] = 0;
+      if (pl->umask[i][j]) M.cols[i][c++] = int8_t(j);
+    }
+    M.cnt[i] = pl->dev.cnt[i];
+    M.rowoff[i] = pl->dev.rowoff[i];
+  }
+  M.mc = pl->dev.mc;
+  return M;
+}
+
+int plan_spmv(const pf3_plan* pl, cudaStream_t st, const double* vals, const unsigned char* free_, const double* x,
+              double* y, int64_t* launches) {
+  if (pl->generic) return PF3_E_UNSUPPORTED;
+  if (pl->nown <= 0) return PF3_OK;
+  const SpmvMask M = spmv_mask_of(pl);
+  int cnt = 0;
+  bool uniform = true;
+  for (int d = 0; d < 6; ++d) {
+    if (M.cnt[d] == 0) continue;
+    if (cnt == 0) cnt = M.cnt[d];
+    if (M.cnt[d] != cnt) uniform = false;
+  }
+  const int wpc = 4;
+  const unsigned grid = unsigned((pl->nown + 2 * wpc - 1) / (2 * wpc));
+  const int64_t nb0 = pl->dev.node_begin;
+  bool same = uniform;
+  for (int d = 0, d0 = -1; d < 6 && same; ++d) {
+    if (M.cnt[d] == 0) continue;
+    if (d0 < 0) d0 = d;
+    for (int r = 0; r < cnt; ++r) same = same && M.cols[d][r] == M.cols[d0][r];
+  }
+#define PF3_SPMV_CASE(C, S) \
+  k_plan_spmv<C, S><<<grid, wpc * 32, 0, st>>>(M, pl->d_brow_ptr, pl->d_bcol, pl->nown, nb0, vals, free_, x, y)
+  if (uniform && cnt == 6 && same) PF3_SPMV_CASE(6, true);
+  else if (uniform && cnt == 3 && same) PF3_SPMV_CASE(3, true);
+  else if (uniform && cnt == 6) PF3_SPMV_CASE(6, false);
+  else if (uniform && cnt == 5) PF3_SPMV_CASE(5, false);
+  else if (uniform && cnt == 3) PF3_SPMV_CASE(3, false);
+  else PF3_SPMV_CASE(0, false);
+#undef PF3_SPMV_CASE
+  ++*launches;
+  return int(cudaGetLastError());
+}
+
+int plan_diagonal(const pf3_plan* pl, cudaStream_t st, const double* vals, double* diag, int64_t* launches) {
+  if (pl->generic) return PF3_E_UNSUPPORTED;
+  if (pl->nown <= 0) return PF3_OK;
+  k_plan_diag<<<grid_for(pl->nown * 6), 256, 0, st>>>(spmv_mask_of(pl), pl->d_brow_ptr, pl->d_bcol, pl->nown,
+                                                      pl->dev.node_begin, vals, diag);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+
 // deterministic fint gather: fint[6*node + d] += sum over incident (element, local node) of fe
 __global__ void k_fint_gather(const uint32_t* __restrict__ sorted_inc, const int64_t* __restrict__ inc_ptr,
                               int64_t nnodes, const double* __restrict__ fe, double* __restrict__ fint) {

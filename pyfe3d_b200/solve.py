@@ -61,3 +61,79 @@ def cg_solve(indptr, indices, vals, b, free=None, rtol=1e-12, maxiter=None, x0=N
         p = z + (rz_new / rz) * p
         rz = rz_new
     return x, -maxiter
+
+
+def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, group=None):
+    """Jacobi-preconditioned CG on the CSR values of a structured ``AssemblyPlan`` through its block SpMV
+    (``pf3_plan_spmv``: no per-entry indices, 8.2 B per nonzero).
+
+    Single GPU: the plan owns every row.  Multi GPU (``group`` = a torch.distributed process group, one rank per
+    GPU): every rank owns the row block of its plan (``node_range``) and holds vectors of its own rows; the search
+    direction is the only vector every rank needs in full, so each iteration does ONE all_gather of the owned
+    slices of p (the halo exchange of SURVEY 8(e)) and two scalar all_reduces.  ``b``/``free``/``x0`` are global
+    [6*nnodes] arrays; returns (x_global, info)."""
+    import torch.distributed as dist
+    dev = vals.device
+    n = 6 * plan.nnodes
+    lo, hi = 6 * plan.node_begin, 6 * plan.node_end
+    multi = group is not None and dist.get_world_size(group) > 1
+    if not multi and (lo != 0 or hi != n):
+        raise ValueError("a row-sharded plan needs the process group of the other shards")
+    if free is None:
+        free = torch.ones(n, dtype=torch.uint8, device=dev)
+    free = _dev(free, torch.uint8, dev)
+    fl = free[lo:hi].to(torch.float64)
+    bl = _dev(b, torch.float64, dev)[lo:hi] * fl
+    d = plan.diagonal(vals)
+    minv = torch.where((fl > 0) & (d != 0), 1.0 / d, torch.zeros_like(d))
+
+    def allsum(t):
+        if multi:
+            dist.all_reduce(t, group=group)
+        return t
+
+    if multi:
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(sizes, torch.tensor([hi - lo], dtype=torch.int64, device=dev), group=group)
+        sizes = [int(t.item()) for t in sizes]
+        same = len(set(sizes)) == 1
+
+    pg = torch.zeros(n, dtype=torch.float64, device=dev)          # global search direction
+
+    def gather(local):
+        if not multi:
+            pg.copy_(local)
+        elif same:
+            dist.all_gather_into_tensor(pg, local.contiguous(), group=group)
+        else:
+            parts = [torch.empty(sz, dtype=torch.float64, device=dev) for sz in sizes]
+            dist.all_gather(parts, local.contiguous(), group=group)
+            torch.cat(parts, out=pg)
+        return pg
+
+    x = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+    if x0 is not None:
+        x = _dev(x0, torch.float64, dev)[lo:hi] * fl
+    r = bl - plan.spmv(vals, gather(x), free=free)
+    z = minv * r
+    p = z.clone()
+    rz = allsum(torch.dot(r, z))
+    bnorm = float(allsum(torch.dot(bl, bl)).sqrt())
+    if bnorm == 0.0:
+        return gather(x).clone(), 0
+    maxiter = maxiter or 10 * n
+    ap = torch.empty_like(x)
+    info = -maxiter
+    for it in range(1, maxiter + 1):
+        plan.spmv(vals, gather(p), free=free, out=ap)
+        alpha = rz / allsum(torch.dot(p, ap))
+        x += alpha * p
+        r -= alpha * ap
+        if it % 8 == 0 and float(allsum(torch.dot(r, r)).sqrt()) <= rtol * bnorm:
+            info = it
+            break
+        z = minv * r
+        rz_new = allsum(torch.dot(r, z))
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return gather(x).clone(), info

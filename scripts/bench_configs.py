@@ -71,7 +71,37 @@ def run(name, case, mats, fused, scale=1.0):
     torch.cuda.empty_cache()
 
 
+def run_spmv(side):
+    """y = KC0 x on the assembled matrix of the north-star mesh, per-entry CSR against the
+    plan's block structure."""
+    from pyfe3d_b200.batch import spmv
+    case = meshes.plate_quad4(side, side)
+    b = util.batch_from_case(case)
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan("KC0", nn, [b])
+    _, csr = plan.evaluate_assemble(KC0=True, write_coo=False)
+    vals = csr["KC0"]
+    x = torch.randn(6 * nn, dtype=torch.float64, device=vals.device)
+    y = torch.empty(6 * nn, dtype=torch.float64, device=vals.device)
+    free = (torch.rand(6 * nn, device=vals.device) > 0.05).to(torch.uint8)
+    nnz, nblk = plan.nnz, plan._plan.nblocks
+    ms_plan = timeit(lambda: plan.spmv(vals, x, out=y), steps=10)
+    ms_mask = timeit(lambda: plan.spmv(vals, x, free=free, out=y), steps=10)
+    alg_plan = nnz * 8 + nblk * 8 + 2 * 6 * nn * 8
+    print(json.dumps({"config": "spmv KC0 %dx%d Quad4 (plan block structure)" % (side, side), "nnz": nnz,
+                      "ms": ms_plan, "ms_masked": ms_mask, "algorithmic_GBps": alg_plan / ms_plan / 1e6,
+                      "frac_of_6538.9": alg_plan / ms_plan / 1e6 / 6538.9}))
+    indptr, indices = plan.pattern()
+    ms_csr = timeit(lambda: spmv(indptr, indices, vals, x, out=y), steps=10)
+    alg_csr = nnz * 16 + 2 * 6 * nn * 8 + 6 * nn * 8
+    print(json.dumps({"config": "spmv KC0 %dx%d Quad4 (int64 CSR)" % (side, side), "nnz": nnz, "ms": ms_csr,
+                      "algorithmic_GBps": alg_csr / ms_csr / 1e6, "frac_of_6538.9": alg_csr / ms_csr / 1e6 / 6538.9}))
+
+
 if __name__ == "__main__":
+    if "--spmv" in sys.argv:
+        run_spmv(200 if "--small" in sys.argv else 2000)
+        sys.exit(0)
     small = "--small" in sys.argv
     f = 0.1 if small else 1.0
     run("config2 BeamC arc 100k, KC0+M", meshes.arc_beamc(int(100001 * f)), ("KC0", "M0"), False)

@@ -1,0 +1,110 @@
+"""GPU: block-structured SpMV / diagonal on the plan's own CSR layout (pf3_plan_spmv, pf3_plan_diagonal) against
+scipy on the same matrix, with and without the boundary-condition mask and on a row shard; plan-based Jacobi-CG on
+config 1."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases, configs, util
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan_and_values(case, matrix, mtype=0, node_range=None):
+    from pyfe3d_b200.batch import AssemblyPlan
+    b = util.batch_from_case(case)
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan(matrix, nn, [b], node_range=node_range, mtype=mtype)
+    if matrix == "KC0":
+        coo = b.update_KC0(update_KC0v_only=1)
+    elif matrix == "KG":
+        coo = b.update_KG(update_KGv_only=1)
+    else:
+        coo = b.update_M(mtype=mtype, indices=False)
+    return plan, plan.assemble(coo.v)
+
+
+@pytest.mark.parametrize("matrix,mtype", [("KC0", 0), ("KG", 0), ("M", 0), ("M", 1), ("M", 2)])
+@pytest.mark.parametrize("shard", [False, True])
+def test_plan_spmv_matches_scipy(matrix, mtype, shard):
+    import torch
+    case = cases.shell_mesh("quad4", 23, 17, seed=11)
+    n = case["ndof"]
+    nn = n // 6
+    rng_ = (nn // 4, nn - 5) if shard else None
+    plan, vals = _plan_and_values(case, matrix, mtype, rng_)
+    A = plan.to_scipy(vals)
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=n)
+    y = plan.spmv(vals, torch.as_tensor(x).cuda()).cpu().numpy()
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
+    free = (rng.random(n) > 0.2).astype(np.uint8)
+    ym = plan.spmv(vals, torch.as_tensor(x).cuda(), free=torch.as_tensor(free).cuda()).cpu().numpy()
+    lo = 6 * plan.node_begin
+    refm = (A @ (x * free)) * free[lo:lo + plan.nrows]
+    assert np.abs(ym - refm).max() <= 1e-13 * np.abs(ref).max()
+    d = plan.diagonal(vals).cpu().numpy()
+    dref = np.asarray(A[:, lo:lo + plan.nrows].diagonal())
+    assert np.array_equal(d, dref)
+
+
+@pytest.mark.parametrize("kind", ["tria3r", "beamc", "truss"])
+def test_plan_spmv_other_kinds(kind):
+    import torch
+    case = cases.shell_mesh("tria3r", 9, 8, seed=2) if kind == "tria3r" else cases.line_chain(kind, 40, seed=4)
+    plan, vals = _plan_and_values(case, "KC0")
+    A = plan.to_scipy(vals)
+    x = np.random.default_rng(5).normal(size=case["ndof"])
+    y = plan.spmv(vals, torch.as_tensor(x).cuda()).cpu().numpy()
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.array_equal(plan.diagonal(vals).cpu().numpy(), A.diagonal())
+
+
+def test_plan_spmv_mixed_groups():
+    """Quad4 skin + BeamC stiffeners in one plan (different masks -> the general row loop)."""
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    cs = configs.build("stiffened_panel")
+    bs = [util.batch_from_case(c) for c in cs]
+    nn = cs[0]["ndof"] // 6
+    for matrix in ("KC0", "M"):
+        plan = AssemblyPlan(matrix, nn, bs)
+        vs = [b.update_KC0(update_KC0v_only=1).v if matrix == "KC0" else b.update_M(indices=False).v for b in bs]
+        vals = plan.assemble(torch.cat(vs))
+        A = plan.to_scipy(vals)
+        x = np.random.default_rng(8).normal(size=6 * nn)
+        y = plan.spmv(vals, torch.as_tensor(x).cuda()).cpu().numpy()
+        ref = A @ x
+        assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_plan_cg_solves_static_config():
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    from pyfe3d_b200.solve import plan_cg_solve
+    gold = json.load(open(os.path.join(util.GOLDEN_DIR, "config_scalars.json")))
+    c = configs.build("quad4_static")[0]
+    b = util.batch_from_case(c)
+    n = c["ndof"]
+    plan = AssemblyPlan("KC0", n // 6, [b])
+    _, csr = plan.evaluate_assemble(KC0=True, write_coo=False)
+    m = c["meta"]
+    X = c["x"].reshape(-1, 3)
+    x, y = X[:, 0], X[:, 1]
+    edge = np.isclose(x, 0.) | np.isclose(x, m["a"]) | np.isclose(y, 0.) | np.isclose(y, m["b"])
+    bk = np.zeros(n, bool)
+    bk[2::6] = edge
+    bk[0::6] = True
+    bk[1::6] = True
+    bk[5::6] = True
+    f = np.zeros(n)
+    f[2::6][np.isclose(x, m["a"] / 2) & np.isclose(y, m["b"] / 2)] = 1.
+    u, info = plan_cg_solve(plan, csr["KC0"], torch.as_tensor(f).cuda(),
+                            free=torch.as_tensor((~bk).astype(np.uint8)).cuda(), rtol=1e-13)
+    assert info > 0
+    want = gold["quad4_static"]["w_max"]
+    assert abs(float(u[2::6].max()) - want) <= 1e-8 * abs(want)
