@@ -61,10 +61,18 @@ extern "C" {
 #define PF3_M 8          /* update_M                e.g. quad4.pyx:3083 */
 #define PF3_FINT 16      /* update_fint             e.g. quad4.pyx:1316 */
 
+/* piston-theory aerodynamic matrices of Quad4 / Quad4R (pf3_eval_aero) */
+#define PF3_KA_BETA 32   /* update_KA_beta   quad4.pyx:9491,  quad4r.pyx:12789 */
+#define PF3_KA_GAMMA 64  /* update_KA_gamma  quad4.pyx:10312, quad4r.pyx:13605 */
+#define PF3_CA 128       /* update_CA        quad4.pyx:11115, quad4r.pyx:14403 */
+
 /* ---- matrix ids for sizes / index fill / assembly plans ----------------- */
 #define PF3_MAT_KC0 0
 #define PF3_MAT_KG 1
 #define PF3_MAT_M 2
+#define PF3_MAT_KA_BETA 3  /* KA_BETA_SPARSE_SIZE / KA_GAMMA_SPARSE_SIZE / CA_SPARSE_SIZE = 144 (quad4.pyx:150-152): */
+#define PF3_MAT_KA_GAMMA 4 /* the translational 12x12 mask of KG                                                    */
+#define PF3_MAT_CA 5
 
 /* ---- property tables ---------------------------------------------------- */
 /* ShellProp scalars read by the elements (shellprop.pxd:38-46): row layout
@@ -163,6 +171,12 @@ int pf3_written_size(int kind, int matrix, int mtype);
  * accumulated (`fint[c+i] += ...`, quad4.pyx:1339) deterministically (node gather). */
 int pf3_eval(pf3_context* ctx, const pf3_batch* batch, int what,
              const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);
+/* Piston-theory aerodynamic matrices of one Quad4 / Quad4R batch: what = PF3_KA_BETA | PF3_KA_GAMMA | PF3_CA, each
+ * filling its own COO arrays (144 entries per element, the KG mask) exactly like
+ * quad.update_KA_beta(KA_betar, KA_betac, KA_betav) etc. (tests/test_quad4r_piston_theory.py:116-118).  Geometry
+ * comes from x (or batch->state); no property table is read.  PF3_E_UNSUPPORTED for other kinds. */
+int pf3_eval_aero(pf3_context* ctx, const pf3_batch* batch, int what, const pf3_coo* ka_beta,
+                  const pf3_coo* ka_gamma, const pf3_coo* ca);
 /* COO row/col indices only (the unrolled `KC0r[k]=..; KC0c[k]=..` blocks) */
 int pf3_fill_indices(pf3_context* ctx, int kind, int matrix, int mtype, int64_t ne,
                      const int64_t* conn, int64_t init_k, int64_t* r, int64_t* c);

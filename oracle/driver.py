@@ -73,6 +73,11 @@ def _run_shell(case, what, state):
         Kl = (S.tria_KG_local(xe, area, pe, m, stress=st) if kind == "tria3r"
               else S.quad_KG_local(xe, pe, m, stress=st))
         out["KGs"] = list(coo.coo_blocks(coo.to_global(Kl, R), conn, "tt", sz["KG"]))
+    if kind != "tria3r" and any(k in what for k in ("KA_beta", "KA_gamma", "CA")):
+        locs = dict(zip(("KA_beta", "KA_gamma", "CA"), S.quad_aero_local(xe, R)))
+        for k in ("KA_beta", "KA_gamma", "CA"):
+            if k in what:
+                out[k] = list(coo.coo_blocks(coo.to_global(locs[k], R), conn, "tt", 144))
     for mt in (0, 1, 2):
         if "M%d" % mt in what:
             Ml = S.tria_M_local(xe, area, pe, mt) if kind == "tria3r" else S.quad_M_local(xe, area, pe, mt)

@@ -91,6 +91,8 @@ def run(case, what=("KC0", "KG", "KGs", "M0", "M1", "M2", "fint"), e0=0, e1=None
              "KGs": getattr(data, "KG_SPARSE_SIZE", 0)}
     for mt in (0, 1, 2):
         sizes["M%d" % mt] = getattr(data, "M_SPARSE_SIZE", 0)
+    for w in ("KA_beta", "KA_gamma", "CA"):
+        sizes[w] = getattr(data, w.upper() + "_SPARSE_SIZE", 0)
     for w in what:
         if w == "fint":
             out["fint"] = np.zeros(case["ndof"])
@@ -158,6 +160,10 @@ def run(case, what=("KC0", "KG", "KGs", "M0", "M1", "M2", "fint"), e0=0, e1=None
                 if mt == 2 and kind not in SHELLS:
                     continue
                 el.update_M(*out[w], prop, mtype=mt)
+        for w in ("KA_beta", "KA_gamma", "CA"):
+            if w in what and w in out:
+                setattr(el, "init_k_" + w, i * sizes[w])
+                getattr(el, "update_" + w)(*out[w])
         if "fint" in what:
             if kind == "spring":
                 el.update_fint(out["fint"])

@@ -352,6 +352,27 @@ def quad_KG_local(xe, pe, m, ue=None, stress=None):
     return _Ge_to_local(Ge, 4)
 
 
+def quad_aero_local(xe, R):
+    """Piston-theory aerodynamic matrices of Quad4 / Quad4R: update_KA_beta (quad4.pyx:9491-10310,
+    quad4r.pyx:12789-13603), update_KA_gamma (quad4.pyx:10312-11113, quad4r.pyx:13605-14401) and update_CA
+    (quad4.pyx:11115-11917, quad4r.pyx:14403-15215).  Like KG they act on w only, 2x2 Gauss, wij = 1:
+        KA_beta [w_a, w_b] = - sum_gp N_a detJ (N_b,x r11 + N_b,y r21)      (quad4.pyx:9687 ff.)
+        KA_gamma[w_a, w_b] =   sum_gp N_a N_b detJ                           (quad4.pyx:10498 ff.)
+        CA      [w_a, w_b] = - sum_gp N_a N_b detJ                           (quad4.pyx:11301 ff.)
+    and the global 3x3 block (a, b) is that scalar times r_{.3} r_{.3}^T.  Returns three local 24x24 matrices."""
+    ne = xe.shape[0]
+    Hb = np.zeros((ne, 4, 4))
+    Hg = np.zeros((ne, 4, 4))
+    r11, r21 = R[:, 0, 0], R[:, 1, 0]
+    for xi in (-GP, GP):
+        for eta in (-GP, GP):
+            N, Nx, Ny, det, _ = quad_shape(xe, xi, eta)
+            flow = Nx * r11[:, None] + Ny * r21[:, None]
+            Hb -= det[:, None, None] * N[None, :, None] * flow[:, None, :]
+            Hg += det[:, None, None] * np.outer(N, N)
+    return _Ge_to_local(Hb, 4), _Ge_to_local(Hg, 4), _Ge_to_local(-Hg, 4)
+
+
 def tria_KG_local(xe, area, pe, m, ue=None, stress=None):
     """Tria3R update_KG (tria3r.pyx:3020-3574) / given stress (:3576-4061); 1 point, w=1/2."""
     ne = xe.shape[0]

@@ -63,6 +63,7 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_pattern(pf3_context*, const pf3_plan*, int64_t* indptr, int64_t* indices) nogil
     int pf3_plan_nblocks(const pf3_plan*, int64_t*)
     int pf3_plan_fint(pf3_context*, const pf3_plan*, int group, const pf3_batch*, double* fint) nogil
+    int pf3_eval_aero(pf3_context*, const pf3_batch*, int what, const pf3_coo*, const pf3_coo*, const pf3_coo*) nogil
     int pf3_plan_spmv(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
                       const double* x, double* y) nogil
     int pf3_plan_diagonal(pf3_context*, const pf3_plan*, const double* vals, double* diag) nogil
@@ -80,7 +81,9 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_memcpy_d2h(pf3_context*, void* dst, const void* src, size_t n) nogil
 
 KC0, KG, KG_STRESS, M, FINT = 1, 2, 4, 8, 16
+KA_BETA, KA_GAMMA, CA = 32, 64, 128
 MAT_KC0, MAT_KG, MAT_M = 0, 1, 2
+MAT_KA_BETA, MAT_KA_GAMMA, MAT_CA = 3, 4, 5
 QUAD4, QUAD4R, TRIA3R, BEAMC, BEAMLR, TRUSS, SPRING = range(7)
 SHELLPROP_STRIDE, BEAMPROP_STRIDE, EPARAM_STRIDE, STATE_STRIDE = 32, 16, 12, 50
 STATE_REFRESH_XE, STATE_REFRESH_UE = 1, 2
@@ -196,6 +199,15 @@ cdef class Context:
                 rc = pf3_eval_host(self.ctx, &b.b, what, p0, p1, p2, <double*>fint)
             else:
                 rc = pf3_eval(self.ctx, &b.b, what, p0, p1, p2, <double*>fint)
+        _check(rc)
+
+    def eval_aero(self, Batch b, int what, Coo ka_beta=None, Coo ka_gamma=None, Coo ca=None):
+        cdef const pf3_coo* p0 = &ka_beta.c if ka_beta is not None else NULL
+        cdef const pf3_coo* p1 = &ka_gamma.c if ka_gamma is not None else NULL
+        cdef const pf3_coo* p2 = &ca.c if ca is not None else NULL
+        cdef int rc
+        with nogil:
+            rc = pf3_eval_aero(self.ctx, &b.b, what, p0, p1, p2)
         _check(rc)
 
     def fill_indices(self, int kind, int matrix, int mtype, int64_t ne, uintptr_t conn, int64_t init_k,

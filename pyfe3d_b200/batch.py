@@ -20,7 +20,9 @@ from . import _cabi
 
 KINDS = {"quad4": _cabi.QUAD4, "quad4r": _cabi.QUAD4R, "tria3r": _cabi.TRIA3R, "beamc": _cabi.BEAMC,
          "beamlr": _cabi.BEAMLR, "truss": _cabi.TRUSS, "spring": _cabi.SPRING}
-MATRICES = {"KC0": _cabi.MAT_KC0, "KG": _cabi.MAT_KG, "M": _cabi.MAT_M}
+MATRICES = {"KC0": _cabi.MAT_KC0, "KG": _cabi.MAT_KG, "M": _cabi.MAT_M,
+            "KA_beta": _cabi.MAT_KA_BETA, "KA_gamma": _cabi.MAT_KA_GAMMA, "CA": _cabi.MAT_CA}
+AERO = {"KA_beta": _cabi.KA_BETA, "KA_gamma": _cabi.KA_GAMMA, "CA": _cabi.CA}
 SHELL_FIELDS = ["A11", "A12", "A16", "A22", "A26", "A66", "B11", "B12", "B16", "B22", "B26", "B66",
                 "D11", "D12", "D16", "D22", "D26", "D66", "E44", "E45", "E55", "scf_k13", "scf_k23", "h",
                 "intrho", "intrhoz", "intrhoz2"]
@@ -203,6 +205,37 @@ class ElementBatch:
         b = self.cabi_batch(mtype, KG_given_stress or (0., 0., 0.), u)
         ctx.eval(b, what, cc("KC0"), cc("KG"), cc("M"), _ptr(fint))
         return coos
+
+    def evaluate_aero(self, KA_beta=False, KA_gamma=False, CA=False, indices=True, out=None):
+        """Piston-theory aerodynamic matrices of every Quad4 / Quad4R element in ONE launch (update_KA_beta,
+        update_KA_gamma, update_CA of the reference: quad4.pyx:9491, 10312, 11115).  Returns {name: Coo}."""
+        if self.kind not in ("quad4", "quad4r"):
+            raise ValueError("the piston-theory matrices exist on Quad4 and Quad4R only")
+        coos = dict(out or {})
+        what = 0
+        for name, on in (("KA_beta", KA_beta), ("KA_gamma", KA_gamma), ("CA", CA)):
+            if on:
+                what |= AERO[name]
+                if name not in coos:
+                    coos[name] = self._alloc(name, indices, None)
+
+        def cc(name):
+            k = coos.get(name)
+            if k is None or not (what & AERO[name]):
+                return None
+            return _cabi.Coo(_ptr(k.r) if indices else 0, _ptr(k.c) if indices else 0, _ptr(k.v), 0, 0)
+
+        context(self.device).eval_aero(self.cabi_batch(), what, cc("KA_beta"), cc("KA_gamma"), cc("CA"))
+        return coos
+
+    def update_KA_beta(self, **kw):
+        return self.evaluate_aero(KA_beta=True, **kw)["KA_beta"]
+
+    def update_KA_gamma(self, **kw):
+        return self.evaluate_aero(KA_gamma=True, **kw)["KA_gamma"]
+
+    def update_CA(self, **kw):
+        return self.evaluate_aero(CA=True, **kw)["CA"]
 
     # -- reference-named conveniences --------------------------------------------------------
     def update_KC0(self, update_KC0v_only=0, **kw):

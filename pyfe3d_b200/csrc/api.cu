@@ -12,6 +12,7 @@ struct pf3_plan;
 namespace pf3 {
 cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st);
 cudaError_t launch_tria(const EvalArgs& A, cudaStream_t st);
+cudaError_t launch_quad_aero(const EvalArgs& A, const AeroOut& O, cudaStream_t st);
 cudaError_t launch_quad4_BL(int64_t n, const double* xe, double xi, double eta, double* out, cudaStream_t st);
 cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st);
 int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnodes, int ngroups,
@@ -421,7 +422,7 @@ int pf3_plan_create(pf3_context* ctx, int matrix, int64_t nnodes, int ngroups, c
                     const int64_t* coo_offsets, int64_t node_begin, int64_t node_end, pf3_plan** plan) {
   int rc = use_device(ctx);
   if (rc) return rc;
-  if (!groups || !plan || matrix < 0 || matrix > 2) return PF3_E_BAD_ARG;
+  if (!groups || !plan || matrix < 0 || matrix > PF3_MAT_CA) return PF3_E_BAD_ARG;
   return pf3::plan_create_structured(ctx->device, ctx->stream, matrix, nnodes, ngroups, groups, coo_offsets,
                                      node_begin, node_end, &ctx->launches, plan);
 }
@@ -552,6 +553,44 @@ int pf3_csr_diagonal(pf3_context* ctx, int64_t nrows, const int64_t* indptr, con
   if (rc) return rc;
   if (nrows < 0 || !indptr || !diag) return PF3_E_BAD_ARG;
   return pf3::csr_diagonal(ctx->stream, nrows, indptr, indices, vals, row0, diag, &ctx->launches);
+}
+
+int pf3_eval_aero(pf3_context* ctx, const pf3_batch* b, int what, const pf3_coo* ka_beta, const pf3_coo* ka_gamma,
+                  const pf3_coo* ca) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!b || b->ne < 0) return PF3_E_BAD_ARG;
+  if (b->kind != PF3_QUAD4 && b->kind != PF3_QUAD4R) return PF3_E_UNSUPPORTED;
+  if (b->ne == 0) return PF3_OK;
+  if (!b->conn || (!b->state && !b->x)) return PF3_E_BAD_ARG;
+  if (b->state && (b->state_flags & PF3_STATE_REFRESH_XE) && !b->x) return PF3_E_BAD_ARG;
+  pf3::EvalArgs A;
+  base_args(b, A);
+  A.u = nullptr;
+  A.evec = nullptr;   // the material axis plays no role in the aerodynamic matrices
+  pf3::AeroOut O;
+  std::memset(&O, 0, sizeof(O));
+  const pf3_coo* dst[3] = {ka_beta, ka_gamma, ca};
+  const int bits[3] = {PF3_KA_BETA, PF3_KA_GAMMA, PF3_CA};
+  bool any = false;
+  for (int w = 0; w < 3; ++w) {
+    if (!(what & bits[w]) || !dst[w]) continue;
+    if (dst[w]->v) {
+      O.v[w] = dst[w]->v;
+      O.k0[w] = dst[w]->init_k;
+      O.acc[w] = dst[w]->accumulate;
+      any = true;
+    }
+    if (dst[w]->r || dst[w]->c) {
+      rc = pf3_fill_indices(ctx, b->kind, PF3_MAT_KA_BETA + w, 0, b->ne, b->conn, dst[w]->init_k, dst[w]->r,
+                            dst[w]->c);
+      if (rc) return rc;
+    }
+  }
+  if (!any) return PF3_OK;
+  cudaError_t e = pf3::launch_quad_aero(A, O, ctx->stream);
+  ++ctx->launches;
+  return int(e);
 }
 
 int pf3_plan_spmv(pf3_context* ctx, const pf3_plan* plan, const double* vals, const unsigned char* free_dof,

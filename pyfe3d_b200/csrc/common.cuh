@@ -44,6 +44,13 @@ struct EvalArgs {
   int acc_kc0, acc_kg, acc_m;
 };
 
+// destinations of the piston-theory matrices (quad_aero_kernel): 0 KA_beta, 1 KA_gamma, 2 CA
+struct AeroOut {
+  double* v[3];
+  int64_t k0[3];
+  int acc[3];
+};
+
 // Per-node work record of the fused kernel, built once per plan (one 64-B load replaces the
 // inc_ptr -> inc_pair0 -> slot pointer chase).  One record per (node, round of 4 incidences).
 struct alignas(16) NodeRec {

@@ -43,7 +43,9 @@ inline int kind_nodes(int kind) {
 inline int kind_sparse_size(int kind, int matrix) {
   static const int T[PF3_NKINDS][3] = {{576, 144, 480}, {576, 144, 480}, {324, 81, 270}, {144, 144, 144},
                                        {144, 36, 144},  {72, 0, 144},    {72, 0, 0}};
-  if (kind < 0 || kind >= PF3_NKINDS || matrix < 0 || matrix > 2) return 0;
+  if (kind < 0 || kind >= PF3_NKINDS || matrix < 0 || matrix > PF3_MAT_CA) return 0;
+  // KA_BETA / KA_GAMMA / CA_SPARSE_SIZE = 144 on the two quads only (quad4.pyx:150-152, quad4r.pyx:116-118)
+  if (matrix > PF3_MAT_M) return (kind == PF3_QUAD4 || kind == PF3_QUAD4R) ? 144 : 0;
   return T[kind][matrix];
 }
 
@@ -55,6 +57,8 @@ inline BlockLayout make_layout(int kind, int matrix, int mtype) {
   const bool shell = kind <= PF3_TRIA3R;
   if (matrix == PF3_MAT_KC0) {
     L.mask = (kind == PF3_TRUSS || kind == PF3_SPRING) ? MASK_D18 : MASK_FULL;
+  } else if (matrix > PF3_MAT_M) {
+    L.mask = MASK_TT;   // piston-theory matrices act on the translations like KG (quad4.pyx:9551 ff.)
   } else if (matrix == PF3_MAT_KG) {
     L.mask = shell ? MASK_TT : (kind == PF3_BEAMLR ? MASK_RR : MASK_FULL);
   } else {

@@ -542,7 +542,76 @@ __global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
   }
 }
 
+// Piston-theory aerodynamic matrices (update_KA_beta quad4.pyx:9491, update_KA_gamma :10312, update_CA :11115;
+// Quad4R: quad4r.pyx:12789, :13605, :14403).  One element per thread.  All three are a 4x4 scalar matrix over the
+// node pairs times z z^T on the translations (z = third column of R), 2x2 Gauss with wij = 1:
+//   KA_beta_ab = - sum_gp N_a detJ (N_b,x r11 + N_b,y r21),  KA_gamma_ab = sum_gp N_a N_b detJ,  CA = -KA_gamma.
+// Same 144-entry block layout as KG, staged per warp and flushed as contiguous runs.
+__global__ void __launch_bounds__(kThreads) quad_aero_kernel(const EvalArgs A, const AeroOut O) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e0 = (int64_t(blockIdx.x) * kWarpsPerCta + warp) * 32;
+  if (e0 >= A.ne) return;
+  const int nvalid = int(min(int64_t(32), A.ne - e0));
+  const int64_t e = e0 + min(lane, nvalid - 1);
+  double* stage = smem + warp * 32 * kStageLd;
+  double* my = stage + lane * kStageLd;
+  ShellGeom<4> g;
+  shell_geom<4>(A, e, g, nullptr);
+  QuadInteg q;
+  quad_integ(g, q);
+  const Mat3& R = g.R;
+  double Hb[4][4], Hg[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      double hb = 0., hg = 0.;
+#pragma unroll
+      for (int gp = 0; gp < 4; ++gp) {
+        hb -= kNgp[gp][a] * (q.Wx[gp][b] * R.a[0][0] + q.Wy[gp][b] * R.a[1][0]);
+        hg += (kNgp[gp][a] * kNgp[gp][b]) * q.dJ[gp];
+      }
+      Hb[a][b] = hb;
+      Hg[a][b] = hg;
+    }
+  double zz[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) zz[i][j] = R.a[i][2] * R.a[j][2];
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    if (O.v[w] == nullptr) continue;
+    double* out = O.v[w] + O.k0[w];
+    const double sgn = (w == 2) ? -1. : 1.;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) my[i * 12 + b * 3 + j] = zz[i][j] * (w == 0 ? Hb[a][b] : sgn * Hg[a][b]);
+      flush_chunk<36>(stage, out, e0, nvalid, 144, a * 36, O.acc[w] != 0, lane);
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_quad_aero(const EvalArgs& A, const AeroOut& O, cudaStream_t st) {
+  if (A.ne <= 0) return cudaSuccess;
+  const int64_t per_cta = 32 * kWarpsPerCta;
+  const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
+  static bool once = false;
+  if (!once) {
+    cudaFuncSetAttribute(quad_aero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    once = true;
+  }
+  quad_aero_kernel<<<grid, kThreads, kStageBytes, st>>>(A, O);
+  return cudaGetLastError();
+}
 
 // Quad4Probe.update_BL (quad4.pyx:273-395): the 11 strain-interpolation rows at one natural point.
 // out[11][24] in the reference's attribute order: BLexx BLeyy BLgxy BLkxx BLkyy BLkxy BLgyz_grad BLgyz_rot

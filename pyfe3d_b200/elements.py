@@ -319,6 +319,40 @@ class _Shell(_Element):
         self._run(_cabi.M, prop, (2, _coo_args(Mr, Mc, Mv, self.init_k_M, size, ("Mr", "Mc", "Mv"))), mtype=int(mtype))
 
 
+class _QuadAero:
+    """update_KA_beta / update_KA_gamma / update_CA of Quad4 and Quad4R (quad4.pyx:9491, 10312, 11115;
+    quad4r.pyx:12789, 13605, 14403): piston-theory aerodynamic matrices, indices always written, values
+    accumulated, from the object's current r11..r33 and probe.xe."""
+
+    def _aero(self, which, r, c, v, init_k, names):
+        import torch
+        ctx = _ctx()
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        r, c, v, init_k, size = _coo_args(r, c, v, init_k, 144, names)
+        b = self._host_batch(None, self._state(), 0, None, None, None)
+        seg = slice(init_k, init_k + size)
+        tv = torch.as_tensor(v[seg]).cuda()
+        outs = [None, None, None]
+        outs[which] = _cabi.Coo(0, 0, tv.data_ptr(), 0, 1)
+        ctx.eval_aero(b, (_cabi.KA_BETA, _cabi.KA_GAMMA, _cabi.CA)[which], outs[0], outs[1], outs[2])
+        v[seg] = tv.cpu().numpy()
+        tr = torch.zeros(size, dtype=torch.int64, device="cuda")
+        tc = torch.zeros(size, dtype=torch.int64, device="cuda")
+        gconn = torch.as_tensor(np.array([cc // 6 for cc in self._cs()], dtype=np.int64)).cuda()
+        ctx.fill_indices(self.KIND, _cabi.MAT_KA_BETA + which, 0, 1, gconn.data_ptr(), 0, tr.data_ptr(), tc.data_ptr())
+        r[seg] = tr.cpu().numpy()
+        c[seg] = tc.cpu().numpy()
+
+    def update_KA_beta(self, KA_betar, KA_betac, KA_betav):
+        self._aero(0, KA_betar, KA_betac, KA_betav, self.init_k_KA_beta, ("KA_betar", "KA_betac", "KA_betav"))
+
+    def update_KA_gamma(self, KA_gammar, KA_gammac, KA_gammav):
+        self._aero(1, KA_gammar, KA_gammac, KA_gammav, self.init_k_KA_gamma, ("KA_gammar", "KA_gammac", "KA_gammav"))
+
+    def update_CA(self, CAr, CAc, CAv):
+        self._aero(2, CAr, CAc, CAv, self.init_k_CA, ("CAr", "CAc", "CAv"))
+
+
 class Quad4Data(_Data):
     KIND = _cabi.QUAD4
 
@@ -354,7 +388,7 @@ class Quad4Probe(_Probe):
             getattr(self, n)[:] = rows[i]
 
 
-class Quad4(_Shell):
+class Quad4(_QuadAero, _Shell):
     KIND = _cabi.QUAD4
 
     def _refresh_KC0ve(self, prop):
@@ -394,7 +428,7 @@ class Quad4RProbe(_Probe):
     KIND = _cabi.QUAD4R
 
 
-class Quad4R(_Shell):
+class Quad4R(_QuadAero, _Shell):
     KIND = _cabi.QUAD4R
 
     def _hg(self, kw):

@@ -35,6 +35,9 @@ def test_sparse_sizes_match_reference_data_classes():
             5: (72, 0, 144), 6: (72, 0, 0)}
     for kind, sizes in want.items():
         assert tuple(lib.pf3_sparse_size(kind, m) for m in range(3)) == sizes
+    # KA_BETA / KA_GAMMA / CA_SPARSE_SIZE (quad4.pyx:150-152): the two quads only
+    for kind in range(7):
+        assert tuple(lib.pf3_sparse_size(kind, m) for m in (3, 4, 5)) == ((144,) * 3 if kind < 2 else (0,) * 3)
     assert lib.pf3_written_size(0, 2, 2) == 288 and lib.pf3_written_size(2, 2, 2) == 162
     assert lib.pf3_written_size(3, 2, 1) == 36 and lib.pf3_written_size(4, 1, 0) == 36
     assert [lib.pf3_num_nodes(k) for k in range(7)] == [4, 4, 3, 2, 2, 2, 2]

@@ -64,3 +64,26 @@ def test_quirk_tria3r_kc0_drops_drilling_couplings():
         np.add.at(Ku, r, v * case["u"][c])
         err = np.abs(Ku - ref["fint"]).max() / np.abs(ref["fint"]).max()
         assert lo <= err <= hi, (kind, err)
+
+
+AERO = ("KA_beta", "KA_gamma", "CA")
+
+
+@pytest.mark.parametrize("name", ["aero_quad4_mesh", "aero_quad4_soup", "aero_quad4r_mesh", "aero_quad4r_soup"])
+def test_oracle_aero_matches_golden(name):
+    """Piston-theory matrices: oracle vs the reference-generated fixtures."""
+    case, ref = util.load_golden(name)
+    got = driver.run(case, what=AERO)
+    checked = util.compare_outputs(got, ref, case["conn"].shape[0], keys=AERO)
+    assert set(checked) == set(AERO)
+    # CA = -KA_gamma in the reference (quad4.pyx:11301 ff. against :10498 ff.)
+    assert np.array_equal(ref["CA"][2], -ref["KA_gamma"][2])
+
+
+@pytest.mark.skipif(not ref_loop.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kind", ["quad4", "quad4r"])
+def test_oracle_aero_matches_live_reference(kind):
+    case = cases.shell_soup(kind, 30, seed=103)
+    ref = ref_loop.run(case, what=AERO)
+    got = driver.run(case, what=AERO)
+    util.compare_outputs(got, ref, case["conn"].shape[0], keys=AERO)

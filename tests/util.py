@@ -16,7 +16,7 @@ TOL_CSR = 1e-11
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith("quad4_probe"))
+                  if not os.path.basename(p).startswith(("quad4_probe", "aero_")))
 
 
 def load_golden(name):
@@ -34,7 +34,7 @@ def load_golden(name):
     for k in z.files:
         if k.startswith("ref_"):
             key = k[4:]
-            if key.endswith(("_r", "_c", "_v")) and key[:-2] in ("KC0", "KG", "KGs", "M0", "M1", "M2"):
+            if key.endswith(("_r", "_c", "_v")) and key[:-2] in ("KC0", "KG", "KGs", "M0", "M1", "M2", "KA_beta", "KA_gamma", "CA"):
                 ref.setdefault(key[:-2], [None, None, None])["rcv".index(key[-1])] = z[k]
             else:
                 ref[key] = z[k]
