@@ -98,7 +98,23 @@ def run_spmv(side):
                       "algorithmic_GBps": alg_csr / ms_csr / 1e6, "frac_of_6538.9": alg_csr / ms_csr / 1e6 / 6538.9}))
 
 
+def run_aero(side):
+    """the three piston-theory matrices of the north-star mesh in one launch (values only)."""
+    case = meshes.plate_quad4(side, side)
+    b = util.batch_from_case(case)
+    coo = b.evaluate_aero(KA_beta=True, KA_gamma=True, CA=True, indices=False)
+    ms = timeit(lambda: b.evaluate_aero(KA_beta=True, KA_gamma=True, CA=True, indices=False, out=coo))
+    ne = case["conn"].shape[0]
+    alg = ne * (3 * 144 * 8 + 32 + 24)
+    print(json.dumps({"config": "aero KA_beta+KA_gamma+CA %dx%d Quad4" % (side, side), "elements": ne, "ms": ms,
+                      "elements_per_s": ne / ms * 1e3, "algorithmic_GBps": alg / ms / 1e6,
+                      "frac_of_6538.9": alg / ms / 1e6 / 6538.9}))
+
+
 if __name__ == "__main__":
+    if "--aero" in sys.argv:
+        run_aero(200 if "--small" in sys.argv else 2000)
+        sys.exit(0)
     if "--spmv" in sys.argv:
         run_spmv(200 if "--small" in sys.argv else 2000)
         sys.exit(0)
