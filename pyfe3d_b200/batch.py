@@ -376,8 +376,8 @@ class AssemblyPlan:
                           coo=None, csr=None, write_coo=True, indices=False):
         """Element matrices -> COO value arrays AND assembled CSR values.
 
-        For the "KC0" plan of a single Quad4/Quad4R batch this is ONE fused kernel that never re-reads the
-        COO arrays; for every other element kind (or when a node couples to more than 16 nodes) it runs the
+        For the "KC0" plan of a single Quad4/Quad4R/Tria3R batch this is ONE fused kernel that never re-reads
+        the COO arrays; for every other element kind (or when a node couples to more than 16 nodes) it runs the
         two-pass path (one evaluation launch + one slab assembly per matrix) with the same outputs.
 
         ``coo`` / ``csr``: optional dicts of preallocated outputs (name -> Coo / tensor).  With
@@ -387,7 +387,7 @@ class AssemblyPlan:
         b = self.batches[0]
         if u is not None:
             u = _dev(u, torch.float64, self.device)
-        if b.kind not in ("quad4", "quad4r") or getattr(self, "_fused_unsupported", False):
+        if b.kind not in ("quad4", "quad4r", "tria3r") or getattr(self, "_fused_unsupported", False):
             return self._evaluate_assemble_two_pass(KC0, KG, KG_given_stress, M, mtype, u, coo, csr, write_coo,
                                                     indices)
         sizes = self.csr_sizes(mtype)

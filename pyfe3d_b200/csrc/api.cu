@@ -42,6 +42,9 @@ int64_t plan_group_ne(const pf3_plan* pl);
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches);
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
 int fused_record_stride(const EvalArgs& A);
+int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
+cudaError_t launch_tria_fused(const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
+int tria_fused_record_stride(const EvalArgs& A);
 int64_t plan_nrows(const pf3_plan* pl);
 }  // namespace pf3
 
@@ -493,7 +496,9 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
   if (b->ne == 0) return PF3_OK;
   pf3::FusedArgs F;
   std::memset(&F, 0, sizeof(F));
-  rc = pf3::plan_fused_args(plan, b->kind, &F, ctx->stream, &ctx->launches);
+  const bool tria = b->kind == PF3_TRIA3R;
+  rc = tria ? pf3::plan_fused_args_tria(plan, &F, ctx->stream, &ctx->launches)
+            : pf3::plan_fused_args(plan, b->kind, &F, ctx->stream, &ctx->launches);
   if (rc) return rc;
   base_args(b, F.A);
   F.A.what = what & (PF3_KC0 | PF3_KG | PF3_KG_STRESS | PF3_M);
@@ -503,9 +508,11 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
   F.csr_kc0 = csr_kc0;
   F.csr_kg = csr_kg;
   F.csr_m = csr_m;
-  rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
+  rc = ensure_scratch(ctx, size_t(b->ne) * (tria ? pf3::tria_fused_record_stride(F.A) : pf3::fused_record_stride(F.A)) *
+                               sizeof(double));
   if (rc) return rc;
-  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
+  cudaError_t e = tria ? pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches)
+                       : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
   if (e != cudaSuccess) return int(e);
   const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
                           (what & PF3_M) ? m : nullptr};

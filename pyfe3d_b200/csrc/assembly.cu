@@ -60,6 +60,7 @@ struct pf3_plan {
   int32_t* d_inc_meta = nullptr;
   int32_t* d_slot = nullptr;
   mutable pf3::NodeRec* d_noderec = nullptr;   // built on first fused use
+  mutable pf3::TriaRec* d_triarec = nullptr;   // ditto, Tria3R
   mutable int rmax = 0;
   mutable std::vector<pf3::NodeRec*> d_grecs;  // per-group records of the slab assembly (built on first use)
   mutable std::vector<int> grmax;
@@ -1132,6 +1133,77 @@ __global__ void k_node_records(const int64_t* __restrict__ brow_ptr, const int64
 }
 }  // namespace
 
+namespace {
+__global__ void k_tria_records(const int64_t* __restrict__ brow_ptr, const int64_t* __restrict__ inc_ptr,
+                               const int64_t* __restrict__ inc_pair0, const int32_t* __restrict__ slot, int64_t nown,
+                               int rmax, TriaRec* __restrict__ out) {
+  const int64_t total = nown * rmax;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t n = t / rmax;
+    const int r = int(t - n * rmax);
+    TriaRec R;
+    R.b0 = brow_ptr[n];
+    R.nb = uint8_t(brow_ptr[n + 1] - R.b0);
+    const int64_t q0 = inc_ptr[n];
+    const int v = int(inc_ptr[n + 1] - q0);
+    for (int s = 0; s < 16; ++s) R.gmap[s] = 0xFFFFFFFFu;
+    int cnt = 0;
+    for (int k = 0; k < 10; ++k) {
+      const int kk = 10 * r + k;
+      R.inc[k] = -1;
+      if (kk < v) {
+        const int64_t p0 = inc_pair0[q0 + kk];
+        R.inc[k] = int32_t(p0);
+        ++cnt;
+        for (int b = 0; b < 3; ++b) {
+          const int s = slot[p0 + b];
+          if (s >= 0 && s < 16) R.gmap[s] = (R.gmap[s] & ~(3u << (2 * k))) | (uint32_t(b) << (2 * k));
+        }
+      }
+    }
+    R.v = uint8_t(cnt);
+    for (int i = 0; i < 14; ++i) R.pad[i] = 0;
+    out[t] = R;
+  }
+}
+}  // namespace
+
+int tria_fused_max_slots();
+int tria_fused_incidences();
+// Triangle twin of plan_fused_args.
+int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches) {
+  if (pl->generic || pl->dev.ngroups != 1 || pl->degenerate) return PF3_E_UNSUPPORTED;
+  const GroupDev& G = pl->dev.g[0];
+  if (G.nn != 3 || G.diag || G.npairs != 9 || G.pairbase != 0) return PF3_E_UNSUPPORTED;
+  if (pl->max_nb > tria_fused_max_slots()) return PF3_E_CAPACITY;
+  if (G.ne * 9 >= (int64_t(1) << 31)) return PF3_E_CAPACITY;
+  if (pl->d_triarec == nullptr) {
+    int* d_mv = nullptr;
+    PF3_CUDA(cudaMalloc((void**)&d_mv, sizeof(int)));
+    PF3_CUDA(cudaMemsetAsync(d_mv, 0, sizeof(int), st));
+    k_max_valence<<<grid_for(pl->nown), 256, 0, st>>>(pl->d_inc_ptr, pl->nown, d_mv);
+    int mv = 0;
+    PF3_CUDA(cudaMemcpyAsync(&mv, d_mv, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PF3_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_mv);
+    const int per = tria_fused_incidences();
+    pl->rmax = mv <= per ? 1 : (mv + per - 1) / per;
+    PF3_CUDA(cudaMalloc((void**)&pl->d_triarec, size_t(pl->nown) * pl->rmax * sizeof(TriaRec)));
+    k_tria_records<<<grid_for(pl->nown * pl->rmax), 256, 0, st>>>(pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_pair0,
+                                                                  pl->d_slot, pl->nown, pl->rmax, pl->d_triarec);
+    *launches += 2;
+    PF3_CUDA(cudaGetLastError());
+  }
+  F->triarec = pl->d_triarec;
+  F->rmax = pl->rmax;
+  F->brow_ptr = pl->d_brow_ptr;
+  F->inc_ptr = pl->d_inc_ptr;
+  F->inc_pair0 = pl->d_inc_pair0;
+  F->slot = pl->d_slot;
+  F->nown = pl->nown;
+  return PF3_OK;
+}
+
 // Fill the plan part of FusedArgs; PF3_E_UNSUPPORTED when the plan cannot drive the fused kernel.
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches) {
   if (pl->generic || pl->dev.ngroups != 1 || pl->degenerate) return PF3_E_UNSUPPORTED;
@@ -1214,7 +1286,7 @@ int64_t plan_nrows(const pf3_plan* pl) { return pl->nrows; }
 extern "C" int pf3_plan_destroy(pf3_plan* pl) {
   if (!pl) return PF3_OK;
   cudaFree(pl->d_brow_ptr); cudaFree(pl->d_bcol); cudaFree(pl->d_inc_ptr); cudaFree(pl->d_inc_src);
-  cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot); cudaFree(pl->d_noderec);
+  cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot); cudaFree(pl->d_noderec); cudaFree(pl->d_triarec);
   for (auto* r : pl->d_grecs) cudaFree(r);
   for (auto* t : pl->d_tabs) cudaFree(t);
   cudaFree(pl->d_indptr); cudaFree(pl->d_indices); cudaFree(pl->d_perm); cudaFree(pl->d_seg);

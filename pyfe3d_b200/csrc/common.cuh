@@ -62,6 +62,16 @@ struct alignas(16) NodeRec {
 };
 static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
 
+// The same for the triangle kernel (tria_fused.cu): one record per (node, round of 10 incidences).
+struct alignas(16) TriaRec {
+  int64_t b0;          // first 6x6 block of the node's CSR row block
+  int32_t inc[10];     // e*9 + a*3 of the incident (element, local node) pairs of this round, -1: none
+  uint32_t gmap[16];   // per column-block slot: 2 bits per incidence k -> local node b feeding it, 3: none
+  uint8_t v, nb;       // incidences in this round, column blocks of the node row
+  uint8_t pad[14];
+};
+static_assert(sizeof(TriaRec) == 128, "TriaRec must be 128 bytes");
+
 // fused evaluate + assemble (quad_fused.cu): element inputs + the plan's block structure
 struct FusedArgs {
   EvalArgs A;
@@ -69,7 +79,8 @@ struct FusedArgs {
   const int64_t* __restrict__ inc_ptr;    // [nown+1] incident (element, local node) pairs per node
   const int64_t* __restrict__ inc_pair0;  // [ninc]   e*16 + a*4
   const int32_t* __restrict__ slot;       // [ne*16]  column-block slot of node pair (e, a, b) in a's row
-  const NodeRec* __restrict__ noderec;    // [nown*rmax]
+  const NodeRec* __restrict__ noderec;    // [nown*rmax]   (quads)
+  const TriaRec* __restrict__ triarec;    // [nown*rmax]   (triangles)
   int rmax;                               // rounds of 4 incidences per node (1 when every valence <= 4)
   int64_t nown;
   double* csr_kc0;

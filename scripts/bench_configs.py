@@ -125,4 +125,5 @@ if __name__ == "__main__":
         ("KC0", "KGs"), True)
     run("config3 (two-pass)", meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)), ("KC0", "KGs"), False)
     run("config4 Tria3R distorted plate 4M, KC0+M(mtype1)", meshes.plate_tria3r(int(1415 * f ** 0.5), int(1415 * f ** 0.5)),
-        ("KC0", "M1"), False)
+        ("KC0", "M1"), True)
+    run("config4 (two-pass)", meshes.plate_tria3r(int(1415 * f ** 0.5), int(1415 * f ** 0.5)), ("KC0", "M1"), False)

@@ -1,5 +1,10 @@
 mkdir -p gpurun_out
-python scripts/bench_configs.py --aero 2>&1 | tee gpurun_out/aero.jsonl | cut -c1-400
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'quad_|k_assemble|k_fill|k_node|k_plan' -c 40 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 5 --warmup 3 --e2e-steps 0 --cpu-side 0 > gpurun_out/launches_bench.log 2>&1
-tail -5 gpurun_out/launches.csv | cut -c1-300
+python -m pytest tests/test_gpu_fused.py -m gpu -x -q 2>&1 | tail -15
+python scripts/bench_configs.py 2>&1 | tee gpurun_out/configs.jsonl | python -c "
+import sys, json
+for ln in sys.stdin:
+    try: d = json.loads(ln)
+    except Exception: print(ln.strip()[:300]); continue
+    if 'kernel_ms' in d: print('   ', d['config'][:28], {k: round(v, 3) for k, v in d['kernel_ms'].items()})
+    else: print('   ', d['config'][:44], d['path'], 'ms %.3f frac %.3f' % (d['ms_per_step'], d['frac_of_6538.9']))
+"

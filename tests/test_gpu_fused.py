@@ -40,21 +40,23 @@ def _check(case, ref, mtype=0, stress=None, node_range=None):
         assert np.abs(A.data - S.data).max() <= util.TOL_CSR * np.abs(S.data).max(), name
 
 
-@pytest.mark.parametrize("name", ["quad4_mesh", "quad4r_mesh", "quad4_soup", "quad4r_soup", "quad4_soup_thick"])
+@pytest.mark.parametrize("name", ["quad4_mesh", "quad4r_mesh", "quad4_soup", "quad4r_soup", "quad4_soup_thick",
+                                  "tria3r_mesh", "tria3r_soup", "tria3r_soup_thick"])
 @pytest.mark.parametrize("mtype", [0, 1, 2])
 def test_fused_matches_reference_golden(name, mtype):
     case, ref = util.load_golden(name)
     _check(case, ref, mtype=mtype)
 
 
-def test_fused_given_stress_and_shard():
-    case, ref = util.load_golden("quad4r_mesh")
+@pytest.mark.parametrize("name", ["quad4r_mesh", "tria3r_mesh"])
+def test_fused_given_stress_and_shard(name):
+    case, ref = util.load_golden(name)
     _check(case, ref, stress=case["stress"])
     nn = case["ndof"] // 6
     _check(case, ref, node_range=(nn // 3, nn - 2))
 
 
-@pytest.mark.parametrize("kind", ["quad4", "quad4r"])
+@pytest.mark.parametrize("kind", ["quad4", "quad4r", "tria3r"])
 def test_fused_large_mesh_matches_oracle_and_twopass(kind):
     import torch
     from pyfe3d_b200.batch import AssemblyPlan
@@ -99,11 +101,30 @@ def test_fused_high_valence_node(kind):
     _check(case, want)
 
 
+def _tria_fan_case(ntri=13, seed=9):
+    """ntri triangles around one centre node: valence 13 > 10 -> two rounds of triangle node records."""
+    rng = np.random.default_rng(seed)
+    ang = np.linspace(0, 2 * np.pi, ntri, endpoint=False)
+    rim = np.stack([np.cos(ang), np.sin(ang), 0.05 * np.sin(3 * ang)], 1) * (1 + 0.1 * rng.uniform(-1, 1, (ntri, 1)))
+    X = np.vstack([[0., 0., 0.02], rim]) @ cases.random_rotation(rng).T
+    conn = np.array([[0, 1 + i, 1 + (i + 1) % ntri] for i in range(ntri)], np.int64)
+    nn = X.shape[0]
+    return dict(kind="tria3r", x=X.ravel(), conn=conn, props=cases.random_shellprops(rng, 1), ndof=6 * nn,
+                u=1e-4 * rng.normal(size=6 * nn), stress=(1e3, -2e2, 3e2))
+
+
+def test_fused_tria_high_valence_node():
+    case = _tria_fan_case()
+    want = driver.run(case, what=("KC0", "KG", "KGs", "M0"))
+    _check(case, want)
+    _check(case, want, stress=case["stress"])
+
+
 def test_evaluate_assemble_falls_back_for_other_kinds():
-    """Tria3R has no fused kernel: the same call runs evaluation + slab assembly and returns the same outputs."""
+    """BeamC has no fused kernel: the same call runs evaluation + slab assembly and returns the same outputs."""
     import scipy.sparse as sp
     from pyfe3d_b200.batch import AssemblyPlan
-    case, ref = util.load_golden("tria3r_mesh")
+    case, ref = util.load_golden("beamc_chain")
     b = util.batch_from_case(case)
     n = case["ndof"]
     plan = AssemblyPlan("KC0", n // 6, [b])
