@@ -218,14 +218,24 @@ __device__ __forceinline__ void tria_emit(const double* st, const TriaRec* nr, d
 }
 
 constexpr int kTStage = kTInc * TSlab<6, 6>::kLd;   // 1140 doubles: the largest matrix (KC0)
-__host__ __device__ constexpr int twarp_smem_doubles(int rstride) { return kTStage + 16 + kTInc * (rstride + 2); }
-
 #ifndef PF3_TFUSED_WARPS
 #define PF3_TFUSED_WARPS 1
-#define PF3_TFUSED_CTAS 12
+#define PF3_TFUSED_CTAS 15   // 14.7 kB of shared memory per one-warp CTA: 15 fit in 227 kB
+#endif
+#ifndef PF3_TFUSED_CHUNK
+#define PF3_TFUSED_CHUNK 4    // consecutive nodes per warp: the records of the next node arrive while this one is computed
 #endif
 constexpr int kTWarps = PF3_TFUSED_WARPS;
+constexpr int kTChunk = PF3_TFUSED_CHUNK;
+constexpr int kTRing = 3;
+// per warp: slab staging | ring of 3 node records (128 B each) | double-buffered element records of 10 incidences
+__host__ __device__ constexpr int twarp_smem_doubles(int rstride) {
+  return kTStage + kTRing * 16 + 2 * kTInc * (rstride + 2);
+}
 
+// One warp = kTChunk consecutive nodes, one CTA = one warp, as many CTAs as there is work (the CTA scheduler keeps
+// the nodes in flight a narrow window of the mesh).  Within a warp the node record of item j+2 and the element
+// records of item j+1 are in flight (cp.async) while item j is evaluated.
 __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kernel(const FusedArgs F,
                                                                                const double* __restrict__ rec,
                                                                                int rstride) {
@@ -234,45 +244,58 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int eld = rstride + 2;
   double* st = smem + warp * twarp_smem_doubles(rstride);
-  TriaRec* nrec = reinterpret_cast<TriaRec*>(st + kTStage);
-  double* erec = st + kTStage + 16;
+  TriaRec* ring = reinterpret_cast<TriaRec*>(st + kTStage);
+  double* erec = st + kTStage + kTRing * 16;
   const int k = lane / 3, b = lane - 3 * k;     // lanes 30, 31: k = 10, never active
-  const int64_t n = int64_t(blockIdx.x) * kTWarps + warp;
-  if (n >= F.nown) return;
+  const int64_t n0 = (int64_t(blockIdx.x) * kTWarps + warp) * kTChunk;
+  if (n0 >= F.nown) return;
   const int rmax = F.rmax;
+  const int nitems = int(min(int64_t(kTChunk), F.nown - n0)) * rmax;   // items j = (node n0 + j / rmax, round j % rmax)
 
-  for (int r = 0; r < rmax; ++r) {
-    if (r > 0) tstage_wait();
-    if (lane < 8) {
-      const char* src = reinterpret_cast<const char*>(F.triarec + n * rmax + r) + 16 * lane;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32t(reinterpret_cast<char*>(nrec) + 16 * lane)),
+  auto rec_fetch = [&](int j) {
+    if (j < nitems && lane < 8) {
+      const char* src = reinterpret_cast<const char*>(F.triarec + (n0 + j / rmax) * rmax + j % rmax) + 16 * lane;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32t(reinterpret_cast<char*>(ring + j % kTRing) + 16 * lane)),
                    "l"(src)
                    : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  };
+  auto erec_fetch = [&](int j) {
+    if (j < nitems && k < kTInc) {
+      const int p0 = (ring + j % kTRing)->inc[k];
+      if (p0 >= 0) {
+        const char* src = reinterpret_cast<const char*>(rec + int64_t(p0 / 9) * rstride);
+        char* dst = reinterpret_cast<char*>(erec + ((j & 1) * kTInc + k) * eld);
+        for (int c = b * 16; c < rstride * 8; c += 48)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32t(dst + c)), "l"(src + c) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  rec_fetch(0);
+  rec_fetch(1);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncwarp();
+  erec_fetch(0);
+
+  for (int j = 0; j < nitems; ++j) {
+    rec_fetch(j + 2);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // node record j+1 and element records j have landed
     __syncwarp();
-    const TriaRec* nr = nrec;
+    erec_fetch(j + 1);
+    const TriaRec* nr = ring + j % kTRing;
     const int pair0 = (k < kTInc) ? nr->inc[k] : -1;
     const bool act = pair0 >= 0;
     if (__ballot_sync(0xffffffffu, act) == 0u) continue;
-    if (act) {
-      const char* src = reinterpret_cast<const char*>(rec + int64_t(pair0 / 9) * rstride);
-      char* dst = reinterpret_cast<char*>(erec + k * eld);
-      for (int c = b * 16; c < rstride * 8; c += 48)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32t(dst + c)), "l"(src + c) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
     const int64_t b0 = nr->b0;
     const int nb = nr->nb, v = nr->v;
     const int64_t e = act ? (pair0 / 9) : 0;
     const int a = act ? ((pair0 - int(e) * 9) / 3) : 0;
-    const bool first = (r == 0);
+    const bool first = (j % rmax == 0);
     const int kk = (k < kTInc) ? k : 0;   // idle lanes compute on slab 0's record but never stage or store
 
-    const double* re = erec + kk * eld;
+    const double* re = erec + ((j & 1) * kTInc + kk) * eld;
     Mat3 R;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -438,7 +461,7 @@ cudaError_t launch_tria_fused(const FusedArgs& F, double* rec, cudaStream_t st, 
   ++*launches;
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) return e1;
-  const int64_t want = (F.nown + kTWarps - 1) / kTWarps;
+  const int64_t want = (F.nown + int64_t(kTWarps) * kTChunk - 1) / (int64_t(kTWarps) * kTChunk);
   if (want > int64_t(0x7fffffff)) return cudaErrorInvalidConfiguration;
   const size_t smem = size_t(kTWarps) * twarp_smem_doubles(stride) * sizeof(double);
   tria_fused_kernel<<<unsigned(want), 32 * kTWarps, smem, st>>>(F, rec, stride);

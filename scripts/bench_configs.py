@@ -120,6 +120,10 @@ if __name__ == "__main__":
         sys.exit(0)
     small = "--small" in sys.argv
     f = 0.1 if small else 1.0
+    if "--config4" in sys.argv:
+        run("config4 Tria3R distorted plate 4M, KC0+M(mtype1)", meshes.plate_tria3r(int(1415 * f ** 0.5), int(1415 * f ** 0.5)),
+            ("KC0", "M1"), True)
+        sys.exit(0)
     run("config2 BeamC arc 100k, KC0+M", meshes.arc_beamc(int(100001 * f)), ("KC0", "M0"), False)
     run("config3 Quad4R cylinder 1M, KC0+KG_given_stress", meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)),
         ("KC0", "KGs"), True)

@@ -3,7 +3,7 @@ cp pyfe3d_b200/lib/libpyfe3d_b200.so /tmp/lib_default.so
 for d in default pyfe3d_b200/lib/variants/*/; do
   if [ "$d" = "default" ]; then name=default; cp /tmp/lib_default.so pyfe3d_b200/lib/libpyfe3d_b200.so; else name=$(basename $d); cp $d/libpyfe3d_b200.so pyfe3d_b200/lib/libpyfe3d_b200.so; fi
   echo "== $name"
-  python scripts/bench_configs.py 2>&1 | python -c "
+  python scripts/bench_configs.py ${CFG_ARGS:-} 2>&1 | python -c "
 import sys, json
 for ln in sys.stdin:
     try: d = json.loads(ln)
