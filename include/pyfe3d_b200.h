@@ -253,6 +253,18 @@ int pf3_plan_spmv(pf3_context* ctx, const pf3_plan* plan, const double* vals, co
 /* diag[6*nown]: the diagonal of the plan's row block (0 where the pattern has no diagonal entry) */
 int pf3_plan_diagonal(pf3_context* ctx, const pf3_plan* plan, const double* vals, double* diag);
 
+/* ---- property tables on the device ---------------------------------------- */
+/* props_out[nrows * PF3_SHELLPROP_STRIDE]: the ShellProp scalars of nrows laminates of nplies plies each, what
+ *   laminated_plate(stack, plyts=..., laminaprops=..., rhos=..., offset=..., calc_scf=...)  (pyfe3d/shellprop_utils.py:96)
+ * returns in A11..D66, E44..E55, scf_k13/k23, h, intrho, intrhoz, intrhoz2 (Lamina.rebuild shellprop.pyx:278,
+ * calc_constitutive_matrix :568, calc_scf :485), one laminate per thread.  Row r reads thetadeg[r*theta_stride + p]
+ * (degrees), plyt[r*plyt_stride + p], lamina[r*lamina_stride + 8*p + {e1,e2,nu12,g12,g13,g23,rho,pad}] and
+ * offset[r*offset_stride] (offset may be NULL = 0); a stride of 0 shares one stack / thickness set / material set /
+ * offset between all rows.  calc_scf == 0 leaves the factors at 5/6. */
+int pf3_laminate_props(pf3_context* ctx, int64_t nrows, int nplies, const double* thetadeg, int64_t theta_stride,
+                       const double* plyt, int64_t plyt_stride, const double* lamina, int64_t lamina_stride,
+                       const double* offset, int64_t offset_stride, int calc_scf, double* props_out);
+
 /* ---- host-pointer convenience (numpy callers): copies in, runs, copies out -- */
 int pf3_eval_host(pf3_context* ctx, const pf3_batch* host_batch, int what,
                   const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);

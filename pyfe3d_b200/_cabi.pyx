@@ -64,6 +64,9 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_nblocks(const pf3_plan*, int64_t*)
     int pf3_plan_fint(pf3_context*, const pf3_plan*, int group, const pf3_batch*, double* fint) nogil
     int pf3_eval_aero(pf3_context*, const pf3_batch*, int what, const pf3_coo*, const pf3_coo*, const pf3_coo*) nogil
+    int pf3_laminate_props(pf3_context*, int64_t nrows, int nplies, const double* thetadeg, int64_t theta_stride,
+                           const double* plyt, int64_t plyt_stride, const double* lamina, int64_t lamina_stride,
+                           const double* offset, int64_t offset_stride, int calc_scf, double* props_out) nogil
     int pf3_plan_spmv(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
                       const double* x, double* y) nogil
     int pf3_plan_diagonal(pf3_context*, const pf3_plan*, const double* vals, double* diag) nogil
@@ -199,6 +202,16 @@ cdef class Context:
                 rc = pf3_eval_host(self.ctx, &b.b, what, p0, p1, p2, <double*>fint)
             else:
                 rc = pf3_eval(self.ctx, &b.b, what, p0, p1, p2, <double*>fint)
+        _check(rc)
+
+    def laminate_props(self, int64_t nrows, int nplies, uintptr_t theta, int64_t theta_stride, uintptr_t plyt,
+                       int64_t plyt_stride, uintptr_t lamina, int64_t lamina_stride, uintptr_t offset,
+                       int64_t offset_stride, int calc_scf, uintptr_t out):
+        cdef int rc
+        with nogil:
+            rc = pf3_laminate_props(self.ctx, nrows, nplies, <const double*>theta, theta_stride, <const double*>plyt,
+                                    plyt_stride, <const double*>lamina, lamina_stride, <const double*>offset,
+                                    offset_stride, calc_scf, <double*>out)
         _check(rc)
 
     def eval_aero(self, Batch b, int what, Coo ka_beta=None, Coo ka_gamma=None, Coo ca=None):

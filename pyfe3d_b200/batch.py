@@ -490,3 +490,53 @@ def spmv(indptr, indices, vals, x, out=None):
         out = torch.empty(nrows, dtype=torch.float64, device=vals.device)
     context(vals.device).spmv_csr(nrows, _ptr(indptr), _ptr(indices), _ptr(vals), _ptr(x), _ptr(out))
     return out
+
+
+def laminate_table(stack, plyts, laminaprops, rhos=0., offset=0., calc_scf=True, device=None, out=None):
+    """Device property table ``[nrows, 32]`` for MANY laminates at once (``pf3_laminate_props``): row r is what the
+    reference's ``laminated_plate(stack[r], plyts=plyts[r], laminaprops=..., rhos=..., offset=offset[r],
+    calc_scf=calc_scf)`` (pyfe3d/shellprop_utils.py:96) stores in its ShellProp, ready to be an ``ElementBatch``'s
+    ``props`` (with ``prop_id = arange(ne)`` for one laminate per element).
+
+    ``stack``: angles in degrees ``[nplies]`` (shared) or ``[nrows, nplies]``; ``plyts``: ``[nplies]`` or
+    ``[nrows, nplies]``; ``laminaprops``: ``(E, nu)``, ``(e1, e2, nu12, g12, g13, g23)`` (shared by all plies), a
+    ``[nplies, 6]`` array or ``[nrows, nplies, 6]``; ``rhos``: scalar, ``[nplies]`` or ``[nrows, nplies]``;
+    ``offset``: scalar or ``[nrows]``.  Arrays may be numpy or CUDA tensors; the number of rows is the largest
+    leading dimension given."""
+    ctx = context(device)
+    dev = torch.device("cuda", ctx.device)
+
+    def t(a):
+        return a.to(dev, torch.float64) if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, float)).to(dev)
+
+    th, tk = t(stack), t(plyts)
+    nplies = th.shape[-1]
+    lp = t(laminaprops)
+    if lp.ndim == 1:
+        if lp.numel() == 2:
+            e, nu = lp[0], lp[1]
+            g = e / (2 * (1 + nu))
+            lp = torch.stack([e, e, nu, g, g, g])
+        lp = lp[:6].expand(nplies, 6)
+    lp = lp[..., :6]
+    rh = t(rhos)
+    rh = rh.expand(lp.shape[:-1]) if rh.ndim <= lp.ndim - 1 else rh
+    if rh.ndim == 2 and lp.ndim == 2:
+        lp = lp.expand(rh.shape[0], nplies, 6)
+    lam = torch.zeros(tuple(lp.shape[:-1]) + (8,), dtype=torch.float64, device=dev)
+    lam[..., :6] = lp
+    lam[..., 6] = rh
+    off = t(offset)
+    nrows = max([a.shape[0] for a, nd in ((th, 2), (tk, 2), (lam, 3), (off, 1)) if a.ndim == nd] + [1])
+    for a, nd, name in ((th, 2, "stack"), (tk, 2, "plyts"), (lam, 3, "laminaprops/rhos"), (off, 1, "offset")):
+        if a.ndim == nd and a.shape[0] != nrows:
+            raise ValueError("%s has %d rows, expected %d" % (name, a.shape[0], nrows))
+    if tk.shape[-1] != nplies or lam.shape[-2] != nplies:
+        raise ValueError("stack, plyts and laminaprops must describe the same number of plies")
+    th, tk, lam, off = th.contiguous(), tk.contiguous(), lam.contiguous(), off.contiguous()
+    if out is None:
+        out = torch.empty((nrows, _cabi.SHELLPROP_STRIDE), dtype=torch.float64, device=dev)
+    ctx.laminate_props(nrows, nplies, _ptr(th), nplies if th.ndim == 2 else 0, _ptr(tk), nplies if tk.ndim == 2 else 0,
+                       _ptr(lam), 8 * nplies if lam.ndim == 3 else 0, _ptr(off), 1 if off.ndim == 1 else 0,
+                       1 if calc_scf else 0, _ptr(out))
+    return out

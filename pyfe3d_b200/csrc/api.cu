@@ -13,6 +13,9 @@ namespace pf3 {
 cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st);
 cudaError_t launch_tria(const EvalArgs& A, cudaStream_t st);
 cudaError_t launch_quad_aero(const EvalArgs& A, const AeroOut& O, cudaStream_t st);
+cudaError_t launch_laminate_props(int64_t nrows, int nplies, const double* theta, int64_t theta_stride,
+                                  const double* plyt, int64_t plyt_stride, const double* lamina, int64_t lamina_stride,
+                                  const double* offset, int64_t offset_stride, int calc_scf, double* out, cudaStream_t st);
 cudaError_t launch_quad4_BL(int64_t n, const double* xe, double xi, double eta, double* out, cudaStream_t st);
 cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st);
 int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnodes, int ngroups,
@@ -596,6 +599,19 @@ int pf3_eval_aero(pf3_context* ctx, const pf3_batch* b, int what, const pf3_coo*
   }
   if (!any) return PF3_OK;
   cudaError_t e = pf3::launch_quad_aero(A, O, ctx->stream);
+  ++ctx->launches;
+  return int(e);
+}
+
+int pf3_laminate_props(pf3_context* ctx, int64_t nrows, int nplies, const double* thetadeg, int64_t theta_stride,
+                       const double* plyt, int64_t plyt_stride, const double* lamina, int64_t lamina_stride,
+                       const double* offset, int64_t offset_stride, int calc_scf, double* props_out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (nrows < 0 || nplies <= 0 || !thetadeg || !plyt || !lamina || !props_out) return PF3_E_BAD_ARG;
+  if (theta_stride < 0 || plyt_stride < 0 || lamina_stride < 0 || offset_stride < 0) return PF3_E_BAD_ARG;
+  cudaError_t e = pf3::launch_laminate_props(nrows, nplies, thetadeg, theta_stride, plyt, plyt_stride, lamina,
+                                             lamina_stride, offset, offset_stride, calc_scf, props_out, ctx->stream);
   ++ctx->launches;
   return int(e);
 }

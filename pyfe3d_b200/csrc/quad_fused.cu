@@ -40,8 +40,11 @@ constexpr int kRecPlain = 36;               // record doubles without / with rot
 constexpr int kRecRot = 56;
 
 // ------------------------------------------------------------------------------------------ K1
+#ifndef PF3_K1_CTAS
+#define PF3_K1_CTAS 3
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128) quad_record_kernel(const EvalArgs A, double* __restrict__ rec, int stride) {
+__global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const EvalArgs A, double* __restrict__ rec, int stride) {
   // records are staged per warp in shared memory (odd leading dimension) and written out as one contiguous
   // run of 32 x stride doubles
   extern __shared__ double k1_smem[];
