@@ -230,6 +230,16 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* batch, const pf3_plan* 
                       const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* csr_kc0,
                       double* csr_kg, double* csr_m);
 
+/* The same step with HOST buffers on a fixed mesh (the optimisation / nonlinear loop of a reference script that
+ * re-runs its element loop and scipy assembly every iteration with new x / u): batch->x and batch->u are HOST
+ * pointers, copied to device staging owned by the context; every other batch pointer (conn, props, prop_id, evec,
+ * eparam) stays device-resident as given to pf3_plan_create; csr_*_host are HOST pointers (pinned memory
+ * recommended) that receive the assembled values; kc0/kg/m are optional DEVICE COO destinations.  Returns after the
+ * copies have completed. */
+int pf3_eval_assemble_host(pf3_context* ctx, const pf3_batch* batch, const pf3_plan* plan, int what,
+                           const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* csr_kc0_host,
+                           double* csr_kg_host, double* csr_m_host);
+
 /* y = A x for a CSR matrix with int64 indptr/indices (downstream cg / eigsh operators) */
 int pf3_spmv_csr(pf3_context* ctx, int64_t nrows, const int64_t* indptr, const int64_t* indices,
                  const double* vals, const double* x, double* y);

@@ -429,6 +429,50 @@ class AssemblyPlan:
                                                     indices)
         return coo, csr
 
+    def evaluate_assemble_host(self, x, u, out, KC0=False, KG=False, KG_given_stress=None, M=False, mtype=0,
+                               coo=None):
+        """One step with HOST buffers through ``pf3_eval_assemble_host``: ``x`` / ``u`` are host arrays (numpy or CPU
+        tensors, pinned for speed) holding this step's coordinates / displacements, ``out`` maps "KC0"/"KG"/"M" to
+        host arrays that receive the assembled CSR values (``csr_sizes()`` gives their lengths).  Connectivity,
+        properties and the plan stay on the device; ``coo`` optionally maps names to DEVICE ``Coo`` value arrays that are
+        filled as well.  Quad4 / Quad4R / Tria3R single-batch KC0 plans only."""
+        if self.matrix != "KC0" or len(self.batches) != 1:
+            raise ValueError("evaluate_assemble_host needs the KC0 plan of a single batch")
+        b = self.batches[0]
+
+        def hptr(a, n, name):
+            if a is None:
+                return 0
+            t = torch.as_tensor(a) if not isinstance(a, torch.Tensor) else a
+            if t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or t.numel() < n:
+                raise ValueError("%s must be a contiguous float64 HOST array with at least %d entries" % (name, n))
+            return t.data_ptr()
+
+        sizes = self.csr_sizes(mtype)
+        what = 0
+        if KC0:
+            what |= _cabi.KC0
+        if KG_given_stress is not None:
+            what |= _cabi.KG_STRESS
+        elif KG:
+            what |= _cabi.KG
+        if M:
+            what |= _cabi.M
+        hb = _cabi.Batch(b.kid, b.ne, b.nnodes, _ptr(b.conn), hptr(x, 3 * b.nnodes, "x"),
+                         hptr(u, 6 * b.nnodes, "u") if u is not None else 0, _ptr(b.props), _ptr(b.prop_id),
+                         0 if b.props is None else b.props.shape[0], _ptr(b.evec), b.evec_stride, _ptr(b.eparam), 0,
+                         mtype, tuple(float(t) for t in (KG_given_stress or (0., 0., 0.))))
+        def cc(name):
+            k = (coo or {}).get(name)
+            return None if k is None else _cabi.Coo(0, 0, _ptr(k.v), 0, 0)
+
+        context(self.device)
+        self._plan.eval_assemble_host(hb, what, cc("KC0"), cc("KG"), cc("M"),
+                                      hptr(out.get("KC0"), sizes["KC0"], "out['KC0']") if KC0 else 0,
+                                      hptr(out.get("KG"), sizes["KG"], "out['KG']") if (KG or KG_given_stress is not None) else 0,
+                                      hptr(out.get("M"), sizes["M"], "out['M']") if M else 0)
+        return out
+
     def _sibling(self, matrix, mtype):
         """Plan of another matrix of the same batches / row shard (cached)."""
         if matrix == self.matrix and mtype == 0:

@@ -59,6 +59,8 @@ struct pf3_context {
   std::map<int, int8_t*> idx_tabs;  // (kind, matrix, mtype) -> device table [4][written]
   double* scratch = nullptr;
   size_t scratch_bytes = 0;
+  double* hostio = nullptr;          // device staging of pf3_eval_assemble_host: x | u | csr_kc0 | csr_kg | csr_m
+  size_t hostio_bytes = 0;
 };
 
 namespace {
@@ -205,6 +207,7 @@ int pf3_destroy(pf3_context* ctx) {
   cudaSetDevice(ctx->device);
   for (auto& kv : ctx->idx_tabs) cudaFree(kv.second);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->hostio) cudaFree(ctx->hostio);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PF3_OK;
@@ -524,6 +527,47 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
       rc = pf3_fill_indices(ctx, b->kind, k, k == 2 ? b->mtype : 0, b->ne, b->conn, cs[k]->init_k, cs[k]->r, cs[k]->c);
       if (rc) return rc;
     }
+  return PF3_OK;
+}
+
+// Host-buffer step on a fixed mesh: x, u come from host memory, the assembled CSR values go back to host memory.
+int pf3_eval_assemble_host(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan, int what, const pf3_coo* kc0,
+                           const pf3_coo* kg, const pf3_coo* m, double* csr_kc0_host, double* csr_kg_host,
+                           double* csr_m_host) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!b || !plan || b->nnodes <= 0) return PF3_E_BAD_ARG;
+  const int64_t nblk = pf3::plan_nblocks(plan);
+  const size_t nx = size_t(b->nnodes) * 3, nu = b->u ? size_t(b->nnodes) * 6 : 0;
+  const size_t n0 = ((what & PF3_KC0) && csr_kc0_host) ? size_t(nblk) * 36 : 0;
+  const size_t n1 = ((what & (PF3_KG | PF3_KG_STRESS)) && csr_kg_host) ? size_t(nblk) * 9 : 0;
+  const size_t n2 = ((what & PF3_M) && csr_m_host) ? size_t(nblk) * (b->mtype == 2 ? 18 : 30) : 0;
+  auto up = [](size_t n) { return (n + 1) & ~size_t(1); };   // keep every piece 16-byte aligned
+  const size_t total = (up(nx) + up(nu) + up(n0) + up(n1) + up(n2)) * sizeof(double);
+  if (total > ctx->hostio_bytes) {
+    if (ctx->hostio) cudaFree(ctx->hostio);
+    ctx->hostio = nullptr;
+    ctx->hostio_bytes = 0;
+    PF3_CUDA(cudaMalloc((void**)&ctx->hostio, total));
+    ctx->hostio_bytes = total;
+  }
+  double* dx = ctx->hostio;
+  double* du = dx + up(nx);
+  double* d0 = du + up(nu);
+  double* d1 = d0 + up(n0);
+  double* d2 = d1 + up(n1);
+  if (!b->x) return PF3_E_BAD_ARG;
+  PF3_CUDA(cudaMemcpyAsync(dx, b->x, nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (nu) PF3_CUDA(cudaMemcpyAsync(du, b->u, nu * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  pf3_batch db = *b;
+  db.x = dx;
+  db.u = nu ? du : nullptr;
+  rc = pf3_eval_assemble(ctx, &db, plan, what, kc0, kg, m, n0 ? d0 : nullptr, n1 ? d1 : nullptr, n2 ? d2 : nullptr);
+  if (rc) return rc;
+  if (n0) PF3_CUDA(cudaMemcpyAsync(csr_kc0_host, d0, n0 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (n1) PF3_CUDA(cudaMemcpyAsync(csr_kg_host, d1, n1 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (n2) PF3_CUDA(cudaMemcpyAsync(csr_m_host, d2, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PF3_CUDA(cudaStreamSynchronize(ctx->stream));
   return PF3_OK;
 }
 

@@ -137,3 +137,29 @@ def test_evaluate_assemble_falls_back_for_other_kinds():
         S = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
         S.sum_duplicates()
         assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max()
+
+
+@pytest.mark.parametrize("kind", ["quad4", "tria3r"])
+def test_host_buffer_step_matches_device_step(kind):
+    """pf3_eval_assemble_host (x, u in and CSR values out through HOST buffers) == the device-resident call."""
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    case = cases.shell_mesh(kind, 17, 13, seed=21)
+    b = util.batch_from_case(case)
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan("KC0", nn, [b])
+    _, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True, mtype=1, write_coo=False)
+    sizes = plan.csr_sizes(1)
+    out = {m: torch.empty(sizes[m], dtype=torch.float64).pin_memory() for m in ("KC0", "KG", "M")}
+    xh = torch.as_tensor(np.ascontiguousarray(case["x"])).pin_memory()
+    uh = torch.as_tensor(np.ascontiguousarray(case["u"])).pin_memory()
+    plan.evaluate_assemble_host(xh, uh, out, KC0=True, KG=True, M=True, mtype=1)
+    for m in ("KC0", "KG", "M"):
+        assert torch.equal(out[m], csr[m].cpu()), m
+    # a new displacement field through the host path changes KG only
+    out2 = {m: np.empty(sizes[m]) for m in ("KC0", "KG")}
+    plan.evaluate_assemble_host(case["x"], 3.0 * case["u"], out2, KC0=True, KG=True)
+    assert np.array_equal(out2["KC0"], csr["KC0"].cpu().numpy())
+    assert np.abs(out2["KG"] - 3.0 * csr["KG"].cpu().numpy()).max() <= 1e-12 * float(csr["KG"].abs().max()) * 3
+    with pytest.raises(ValueError):
+        plan.evaluate_assemble_host(torch.as_tensor(case["x"]).cuda(), uh, out, KC0=True)
