@@ -968,6 +968,54 @@ __global__ void __launch_bounds__(128) k_plan_spmv(const SpmvMask M, const int64
   }
 }
 
+// Full 6x6 blocks (KC0 of shells and beams): 16-byte loads of values and of x, two columns per lane.
+__global__ void __launch_bounds__(128) k_plan_spmv_full(const int64_t* __restrict__ brow_ptr,
+                                                        const int64_t* __restrict__ bcol, int64_t nown, int64_t node_begin,
+                                                        const double* __restrict__ vals,
+                                                        const unsigned char* __restrict__ free_,
+                                                        const double* __restrict__ x, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
+  const int64_t i = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2 + h;
+  const bool live = i < nown;
+  int64_t b0 = 0;
+  int nb = 0;
+  if (live) {
+    b0 = brow_ptr[i];
+    nb = int(brow_ptr[i + 1] - b0);
+  }
+  const double* v = vals + b0 * 36;
+  const int w = nb * 6;
+  double acc[6] = {0., 0., 0., 0., 0., 0.};
+  for (int xx = 2 * l16; xx < w; xx += 32) {
+    const int s = xx / 6, r = xx - s * 6;
+    const int64_t col = 6 * bcol[b0 + s] + r;
+    double2 xv = *reinterpret_cast<const double2*>(x + col);
+    if (free_ != nullptr) {
+      const uchar2 f = *reinterpret_cast<const uchar2*>(free_ + col);
+      if (!f.x) xv.x = 0.;
+      if (!f.y) xv.y = 0.;
+    }
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      const double2 a = *reinterpret_cast<const double2*>(v + d * w + xx);
+      acc[d] += a.x * xv.x;
+      acc[d] += a.y * xv.y;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 6; ++d)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+  if (live && l16 < 6) {
+    double out = acc[0];
+#pragma unroll
+    for (int d = 1; d < 6; ++d) out = (l16 == d) ? acc[d] : out;
+    const int64_t row = 6 * i + l16;
+    if (free_ != nullptr && !free_[6 * node_begin + row]) out = 0.;
+    y[row] = out;
+  }
+}
+
 // diag[6 i + d] = A[row, row] (0 when the pattern has no diagonal entry there): Jacobi scaling
 __global__ void k_plan_diag(const SpmvMask M, const int64_t* __restrict__ brow_ptr, const int64_t* __restrict__ bcol,
                             int64_t nown, int64_t node_begin, const double* __restrict__ vals,
@@ -1026,7 +1074,10 @@ int plan_spmv(const pf3_plan* pl, cudaStream_t st, const double* vals, const uns
   }
 #define PF3_SPMV_CASE(C, S) \
   k_plan_spmv<C, S><<<grid, wpc * 32, 0, st>>>(M, pl->d_brow_ptr, pl->d_bcol, pl->nown, nb0, vals, free_, x, y)
-  if (uniform && cnt == 6 && same) PF3_SPMV_CASE(6, true);
+  const bool al16 = ((((uintptr_t)vals) | ((uintptr_t)x)) & 15) == 0 && (free_ == nullptr || (((uintptr_t)free_) & 1) == 0);
+  if (uniform && cnt == 6 && same && M.mc == 36 && al16)
+    k_plan_spmv_full<<<grid, wpc * 32, 0, st>>>(pl->d_brow_ptr, pl->d_bcol, pl->nown, nb0, vals, free_, x, y);
+  else if (uniform && cnt == 6 && same) PF3_SPMV_CASE(6, true);
   else if (uniform && cnt == 3 && same) PF3_SPMV_CASE(3, true);
   else if (uniform && cnt == 6) PF3_SPMV_CASE(6, false);
   else if (uniform && cnt == 5) PF3_SPMV_CASE(5, false);
