@@ -230,6 +230,19 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* batch, const pf3_plan* 
                       const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* csr_kc0,
                       double* csr_kg, double* csr_m);
 
+/* Mixed meshes (e.g. Quad4 skin + BeamC stiffeners in ONE matrix, BASELINE config 5): fused evaluate + assemble of
+ * group `group` (a Quad4 / Quad4R batch) of a MULTI-group structured plan.  The CSR outputs use the UNION layouts of
+ * KC0 / KG / M over the plan's groups (= the layouts of structured plans of the same groups for those matrices, e.g.
+ * 36 entries per block for KG when a BeamC group is present); positions this group does not have are written as zeros.
+ * kc0/kg/m address the plan-wide COO value arrays (init_k = the group's coo_offset).  Follow with pf3_eval for the
+ * other groups and pf3_plan_assemble_add per matrix. */
+int pf3_eval_assemble_group(pf3_context* ctx, const pf3_batch* batch, const pf3_plan* plan, int group, int what,
+                            const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* csr_kc0, double* csr_kg,
+                            double* csr_m);
+/* csr_v[nnz] += the contributions of every group of the structured plan EXCEPT skip_group, read from the plan-wide
+ * COO value array coo_v; rows of nodes without such contributions are not touched. */
+int pf3_plan_assemble_add(pf3_context* ctx, const pf3_plan* plan, const double* coo_v, double* csr_v, int skip_group);
+
 /* The same step with HOST buffers on a fixed mesh (the optimisation / nonlinear loop of a reference script that
  * re-runs its element loop and scipy assembly every iteration with new x / u): batch->x and batch->u are HOST
  * pointers, copied to device staging owned by the context; every other batch pointer (conn, props, prop_id, evec,

@@ -75,6 +75,9 @@ cdef extern from "pyfe3d_b200.h":
                           const pf3_coo*, double*, double*, double*) nogil
     int pf3_eval_assemble_host(pf3_context*, const pf3_batch*, const pf3_plan*, int what, const pf3_coo*,
                                const pf3_coo*, const pf3_coo*, double*, double*, double*) nogil
+    int pf3_eval_assemble_group(pf3_context*, const pf3_batch*, const pf3_plan*, int group, int what, const pf3_coo*,
+                                const pf3_coo*, const pf3_coo*, double*, double*, double*) nogil
+    int pf3_plan_assemble_add(pf3_context*, const pf3_plan*, const double* coo_v, double* csr_v, int skip_group) nogil
     int pf3_plan_assemble(pf3_context*, const pf3_plan*, const double* coo_v, double* csr_v) nogil
     int pf3_spmv_csr(pf3_context*, int64_t nrows, const int64_t* indptr, const int64_t* indices,
                      const double* vals, const double* x, double* y) nogil
@@ -367,6 +370,23 @@ cdef class Plan:
         with nogil:
             rc = pf3_eval_assemble_host(self.owner.ctx, &b.b, self.plan, what, p0, p1, p2, <double*>csr_kc0,
                                         <double*>csr_kg, <double*>csr_m)
+        _check(rc)
+
+    def eval_assemble_group(self, Batch b, int group, int what, Coo kc0=None, Coo kg=None, Coo m=None,
+                            uintptr_t csr_kc0=0, uintptr_t csr_kg=0, uintptr_t csr_m=0):
+        cdef const pf3_coo* p0 = &kc0.c if kc0 is not None else NULL
+        cdef const pf3_coo* p1 = &kg.c if kg is not None else NULL
+        cdef const pf3_coo* p2 = &m.c if m is not None else NULL
+        cdef int rc
+        with nogil:
+            rc = pf3_eval_assemble_group(self.owner.ctx, &b.b, self.plan, group, what, p0, p1, p2, <double*>csr_kc0,
+                                         <double*>csr_kg, <double*>csr_m)
+        _check(rc)
+
+    def assemble_add(self, uintptr_t coo_v, uintptr_t csr_v, int skip_group):
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_assemble_add(self.owner.ctx, self.plan, <const double*>coo_v, <double*>csr_v, skip_group)
         _check(rc)
 
     def fint(self, int group, Batch b, uintptr_t fint):

@@ -382,8 +382,10 @@ class AssemblyPlan:
 
         ``coo`` / ``csr``: optional dicts of preallocated outputs (name -> Coo / tensor).  With
         ``write_coo=False`` only the CSR values are returned.  Returns (coo, csr) dicts."""
-        if self.matrix != "KC0" or len(self.batches) != 1:
-            raise ValueError("evaluate_assemble needs the KC0 plan of a single batch")
+        if self.matrix != "KC0":
+            raise ValueError("evaluate_assemble needs the KC0 plan")
+        if len(self.batches) != 1:
+            return self._evaluate_assemble_mixed(KC0, KG, KG_given_stress, M, mtype, u, coo, csr, write_coo, indices)
         b = self.batches[0]
         if u is not None:
             u = _dev(u, torch.float64, self.device)
@@ -472,6 +474,59 @@ class AssemblyPlan:
                                       hptr(out.get("KG"), sizes["KG"], "out['KG']") if (KG or KG_given_stress is not None) else 0,
                                       hptr(out.get("M"), sizes["M"], "out['M']") if M else 0)
         return out
+
+    def _evaluate_assemble_mixed(self, KC0, KG, KG_given_stress, M, mtype, u, coo, csr, write_coo, indices):
+        """Several element kinds in ONE matrix (e.g. Quad4 skin + BeamC stiffeners, BASELINE config 5).  When the first
+        batch is Quad4 / Quad4R its share goes through the fused kernel straight into the union CSR layouts
+        (``pf3_eval_assemble_group``); the other batches are evaluated into their slices of the plan-wide COO arrays
+        and added (``pf3_plan_assemble_add``).  Otherwise: evaluation per batch + assembly per matrix.
+        ``coo[name].v`` are plan-wide value arrays (batch g at the sibling plan's ``coo_offsets[g]``)."""
+        if KG_given_stress is not None or indices or not write_coo:
+            raise ValueError("mixed plans: KG_given_stress, index arrays and write_coo=False are not supported here")
+        if u is not None:
+            u = _dev(u, torch.float64, self.device)
+        names = [n for n, on in (("KC0", KC0), ("KG", KG), ("M", M)) if on]
+        plans = {n: self._sibling(n, mtype) for n in names}
+        coo = dict(coo or {})
+        csr = dict(csr or {})
+        for n in names:
+            if n not in coo:
+                coo[n] = Coo(None, None, torch.zeros(plans[n].coo_size, dtype=torch.float64, device=self.device),
+                             6 * self.nnodes)
+            if n not in csr:
+                csr[n] = torch.empty(plans[n].nnz, dtype=torch.float64, device=self.device)
+        kw = dict(KC0=KC0, KG=KG, M=M, mtype=mtype, u=u, indices=False)
+
+        def views(g):
+            b = self.batches[g]
+            return {n: Coo(None, None, coo[n].v[plans[n].coo_offsets[g]:plans[n].coo_offsets[g] + b.ne * b.sizes[n]],
+                           6 * self.nnodes) for n in names}
+
+        b0 = self.batches[0]
+        fused = b0.kind in ("quad4", "quad4r") and not getattr(self, "_fused_unsupported", False)
+        if fused:
+            what = (_cabi.KC0 if KC0 else 0) | (_cabi.KG if KG else 0) | (_cabi.M if M else 0)
+
+            def cc(n):
+                return _cabi.Coo(0, 0, _ptr(coo[n].v), plans[n].coo_offsets[0], 0) if n in names else None
+
+            context(self.device)
+            try:
+                self._plan.eval_assemble_group(b0.cabi_batch(mtype, (0., 0., 0.), u), 0, what, cc("KC0"), cc("KG"),
+                                               cc("M"), _ptr(csr.get("KC0")), _ptr(csr.get("KG")), _ptr(csr.get("M")))
+            except _cabi.Pf3Error as exc:
+                if "capacity" not in str(exc) and "not defined" not in str(exc):
+                    raise
+                self._fused_unsupported = fused = False
+        for g in range(0 if not fused else 1, len(self.batches)):
+            self.batches[g].evaluate(out=views(g), **kw)
+        for n in names:
+            if fused:
+                context(self.device)
+                plans[n]._plan.assemble_add(_ptr(coo[n].v), _ptr(csr[n]), 0)
+            else:
+                plans[n].assemble(coo[n].v, out=csr[n])
+        return coo, csr
 
     def _sibling(self, matrix, mtype):
         """Plan of another matrix of the same batches / row shard (cached)."""

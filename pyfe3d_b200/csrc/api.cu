@@ -46,6 +46,10 @@ int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st,
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
 int fused_record_stride(const EvalArgs& A);
 int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
+int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches);
+int plan_union_map(const pf3_plan* pl, int group, int matrix, int mtype, UnionMap* um);
+int plan_assemble_gather(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int skip_group,
+                         int64_t* launches);
 cudaError_t launch_tria_fused(const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
 int tria_fused_record_stride(const EvalArgs& A);
 int64_t plan_nrows(const pf3_plan* pl);
@@ -528,6 +532,66 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
       if (rc) return rc;
     }
   return PF3_OK;
+}
+
+// Fused evaluate + assemble of ONE Quad4 / Quad4R group of a multi-group plan into the union layouts.
+int pf3_eval_assemble_group(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan, int group, int what,
+                            const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* csr_kc0, double* csr_kg,
+                            double* csr_m) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan) return PF3_E_BAD_ARG;
+  rc = check_batch(b, what);
+  if (rc) return rc;
+  if (b->kind != PF3_QUAD4 && b->kind != PF3_QUAD4R) return PF3_E_UNSUPPORTED;
+  if (b->state || (what & PF3_FINT)) return PF3_E_UNSUPPORTED;
+  if (b->ne != pf3::plan_group_ne_of(plan, group)) return PF3_E_BAD_ARG;
+  if (((what & PF3_KC0) && !csr_kc0) || ((what & (PF3_KG | PF3_KG_STRESS)) && !csr_kg) || ((what & PF3_M) && !csr_m))
+    return PF3_E_BAD_ARG;
+  for (const pf3_coo* c : {kc0, kg, m}) {
+    if (c && c->accumulate) return PF3_E_UNSUPPORTED;
+    if (c && c->v && (((uintptr_t)c->v & 15) != 0 || (c->init_k & 1) != 0)) return PF3_E_UNSUPPORTED;
+  }
+  if ((((uintptr_t)csr_kc0) | ((uintptr_t)csr_kg) | ((uintptr_t)csr_m)) & 15) return PF3_E_UNSUPPORTED;
+  if (b->ne == 0) return PF3_OK;
+  pf3::FusedArgs F;
+  std::memset(&F, 0, sizeof(F));
+  rc = pf3::plan_fused_args_group(plan, group, &F, ctx->stream, &ctx->launches);
+  if (rc) return rc;
+  const int bits[3] = {PF3_KC0, PF3_KG | PF3_KG_STRESS, PF3_M};
+  for (int k = 0; k < 3; ++k) {
+    if (!(what & bits[k])) continue;
+    rc = pf3::plan_union_map(plan, group, k, k == 2 ? b->mtype : 0, &F.um[k]);
+    if (rc) return rc;
+  }
+  F.zero_empty = 1;       // nodes that only other groups touch still get their rows initialised
+  base_args(b, F.A);
+  F.A.what = what & (PF3_KC0 | PF3_KG | PF3_KG_STRESS | PF3_M);
+  if (kc0 && kc0->v) { F.A.kc0v = kc0->v; F.A.kc0_k0 = kc0->init_k; }
+  if (kg && kg->v) { F.A.kgv = kg->v; F.A.kg_k0 = kg->init_k; }
+  if (m && m->v) { F.A.mv = m->v; F.A.m_k0 = m->init_k; }
+  F.csr_kc0 = csr_kc0;
+  F.csr_kg = csr_kg;
+  F.csr_m = csr_m;
+  rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
+  if (rc) return rc;
+  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
+  if (e != cudaSuccess) return int(e);
+  const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
+                          (what & PF3_M) ? m : nullptr};
+  for (int k = 0; k < 3; ++k)
+    if (cs[k] && (cs[k]->r || cs[k]->c)) {
+      rc = pf3_fill_indices(ctx, b->kind, k, k == 2 ? b->mtype : 0, b->ne, b->conn, cs[k]->init_k, cs[k]->r, cs[k]->c);
+      if (rc) return rc;
+    }
+  return PF3_OK;
+}
+
+int pf3_plan_assemble_add(pf3_context* ctx, const pf3_plan* plan, const double* coo_v, double* csr_v, int skip_group) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan || !coo_v || !csr_v || skip_group < 0) return PF3_E_BAD_ARG;
+  return pf3::plan_assemble_gather(plan, ctx->stream, coo_v, csr_v, skip_group, &ctx->launches);
 }
 
 // Host-buffer step on a fixed mesh: x, u come from host memory, the assembled CSR values go back to host memory.

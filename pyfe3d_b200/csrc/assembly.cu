@@ -65,6 +65,9 @@ struct pf3_plan {
   mutable std::vector<pf3::NodeRec*> d_grecs;  // per-group records of the slab assembly (built on first use)
   mutable std::vector<int> grmax;
   std::vector<int> gmask;                      // MaskId of every group
+  std::vector<int> gkind;                      // element kind of every group
+  mutable pf3::NodeRec* d_frecs = nullptr;     // fused-kernel records of ONE group of a multi-group plan
+  mutable int frecs_group = -1, frmax = 0;
   std::vector<uint16_t*> d_tabs;
   // generic
   int64_t n = 0, nnz_coo = 0;
@@ -222,6 +225,8 @@ __global__ void k_pattern(const PlanDev P, const MaskDev M, const int64_t* brow_
 
 // ---- numeric -----------------------------------------------------------------------------
 // One warp per owned node.  acc lives in shared memory (max_nb * mc doubles per warp).
+// skip_group >= 0 (add mode): csr_v += the contributions of every group EXCEPT skip_group; nodes that have none are
+// not touched (the fused kernel has already written group skip_group's share of every row).
 template <bool SAFE>
 __global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t* __restrict__ brow_ptr,
                                                   const int64_t* __restrict__ inc_ptr,
@@ -229,7 +234,8 @@ __global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t
                                                   const int64_t* __restrict__ inc_pair0,
                                                   const int32_t* __restrict__ inc_meta,
                                                   const int32_t* __restrict__ slot, int64_t nown, int acc_stride,
-                                                  const double* __restrict__ coo_v, double* __restrict__ csr_v) {
+                                                  const double* __restrict__ coo_v, double* __restrict__ csr_v,
+                                                  int skip_group) {
   extern __shared__ double sacc[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   double* acc = sacc + size_t(warp) * acc_stride;
@@ -237,11 +243,17 @@ __global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t
     const int64_t b0 = brow_ptr[i];
     const int nb = int(brow_ptr[i + 1] - b0);
     const int nout = nb * P.mc;
+    const int64_t q0 = inc_ptr[i], q1 = inc_ptr[i + 1];
+    if (skip_group >= 0) {
+      bool any = false;
+      for (int64_t q = q0 + lane; q < q1; q += 32) any = any || ((inc_meta[q] & 0xff) != skip_group);
+      if (__ballot_sync(0xffffffffu, any) == 0u) continue;
+    }
     for (int k = lane; k < nout; k += 32) acc[k] = 0.;
     __syncwarp();
-    const int64_t q0 = inc_ptr[i], q1 = inc_ptr[i + 1];
     for (int64_t q = q0; q < q1; ++q) {
       const int meta = inc_meta[q];
+      if ((meta & 0xff) == skip_group) continue;
       const GroupDev& G = P.g[meta & 0xff];
       const int a = meta >> 8;
       const double* src = coo_v + inc_src[q];
@@ -259,7 +271,11 @@ __global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t
       __syncwarp();
     }
     double* out = csr_v + b0 * P.mc;
-    for (int k = lane; k < nout; k += 32) out[k] = acc[k];
+    if (skip_group >= 0) {
+      for (int k = lane; k < nout; k += 32) out[k] += acc[k];
+    } else {
+      for (int k = lane; k < nout; k += 32) out[k] = acc[k];
+    }
     __syncwarp();
   }
 }
@@ -373,6 +389,7 @@ int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnod
     for (int i = 0; i < 6; ++i)
       for (int j = 0; j < 6; ++j) pl->umask[i][j] |= mask_has(L.mask, i, j);
     pl->gmask.push_back(L.mask);
+    pl->gkind.push_back(groups[g].kind);
     GroupDev& G = P.g[g];
     G.conn = groups[g].conn;
     G.ne = groups[g].ne;
@@ -750,6 +767,30 @@ int plan_assemble_slabs(const pf3_plan* pl, cudaStream_t st, const double* coo_v
   return PF3_OK;
 }
 
+// The per-node gather over the union pattern (any mix of masks).  skip_group >= 0: add every other group's share to
+// csr_v (see k_assemble).
+int plan_assemble_gather(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int skip_group,
+                         int64_t* launches) {
+  if (pl->generic) return PF3_E_UNSUPPORTED;
+  const int acc_stride = std::max(1, pl->max_nb * pl->dev.mc);
+  int wpc = 8;
+  while (wpc > 1 && size_t(wpc) * acc_stride * sizeof(double) > 200 * 1024) wpc >>= 1;
+  const size_t smem = size_t(wpc) * acc_stride * sizeof(double);
+  if (smem > 220 * 1024) return PF3_E_CAPACITY;
+  const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((pl->nown + wpc - 1) / wpc, 148 * 64)));
+  if (pl->degenerate) {
+    if (smem > 48 * 1024) PF3_CUDA(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    k_assemble<true><<<grid, wpc * 32, smem, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
+                                                   pl->d_inc_meta, pl->d_slot, pl->nown, acc_stride, coo_v, csr_v, skip_group);
+  } else {
+    if (smem > 48 * 1024) PF3_CUDA(cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    k_assemble<false><<<grid, wpc * 32, smem, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
+                                                    pl->d_inc_meta, pl->d_slot, pl->nown, acc_stride, coo_v, csr_v, skip_group);
+  }
+  ++*launches;
+  return int(cudaGetLastError());
+}
+
 int plan_assemble(const pf3_plan* pl, cudaStream_t st, const double* coo_v, double* csr_v, int64_t* launches) {
   if (!pl->generic) {
     bool done = false;
@@ -761,23 +802,7 @@ int plan_assemble(const pf3_plan* pl, cudaStream_t st, const double* coo_v, doub
     ++*launches;
     return int(cudaGetLastError());
   }
-  const int acc_stride = std::max(1, pl->max_nb * pl->dev.mc);
-  int wpc = 8;
-  while (wpc > 1 && size_t(wpc) * acc_stride * sizeof(double) > 200 * 1024) wpc >>= 1;
-  const size_t smem = size_t(wpc) * acc_stride * sizeof(double);
-  if (smem > 220 * 1024) return PF3_E_CAPACITY;
-  const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((pl->nown + wpc - 1) / wpc, 148 * 64)));
-  if (pl->degenerate) {
-    if (smem > 48 * 1024) PF3_CUDA(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    k_assemble<true><<<grid, wpc * 32, smem, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
-                                                   pl->d_inc_meta, pl->d_slot, pl->nown, acc_stride, coo_v, csr_v);
-  } else {
-    if (smem > 48 * 1024) PF3_CUDA(cudaFuncSetAttribute(k_assemble<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    k_assemble<false><<<grid, wpc * 32, smem, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
-                                                    pl->d_inc_meta, pl->d_slot, pl->nown, acc_stride, coo_v, csr_v);
-  }
-  ++*launches;
-  return int(cudaGetLastError());
+  return plan_assemble_gather(pl, st, coo_v, csr_v, -1, launches);
 }
 
 int plan_create_generic(int device, cudaStream_t st, int64_t n, int64_t nnz_coo, const int64_t* r, const int64_t* c,
@@ -1219,6 +1244,122 @@ __global__ void k_tria_records(const int64_t* __restrict__ brow_ptr, const int64
 }
 }  // namespace
 
+namespace {
+// fused-kernel node records of ONE group of a multi-group plan: incidences filtered by group, pair ids local to the
+// group (e*16 + a*4), slots relative to the union row block
+__global__ void k_node_records_group(const PlanDev P, int gi, const int64_t* __restrict__ brow_ptr,
+                                     const int64_t* __restrict__ inc_ptr, const int64_t* __restrict__ inc_pair0,
+                                     const int32_t* __restrict__ inc_meta, const int32_t* __restrict__ slot,
+                                     int64_t nown, int rmax, NodeRec* __restrict__ out) {
+  const GroupDev& G = P.g[gi];
+  const int64_t total = nown * rmax;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t n = t / rmax;
+    const int r = int(t - n * rmax);
+    NodeRec R;
+    R.b0 = brow_ptr[n];
+    R.nb = uint8_t(brow_ptr[n + 1] - R.b0);
+    for (int s = 0; s < 16; ++s) R.gmap[s] = 0xFFFF;
+    for (int k = 0; k < 4; ++k) R.inc[k] = -1;
+    int seen = 0, cnt = 0;
+    for (int64_t q = inc_ptr[n]; q < inc_ptr[n + 1]; ++q) {
+      if ((inc_meta[q] & 0xff) != gi) continue;
+      const int k = seen - 4 * r;
+      ++seen;
+      if (k < 0 || k >= 4) continue;
+      const int64_t p0 = inc_pair0[q];
+      R.inc[k] = int32_t(p0 - G.pairbase);
+      ++cnt;
+      for (int b = 0; b < 4; ++b) {
+        const int sl = slot[p0 + b];
+        if (sl >= 0 && sl < 16) R.gmap[sl] = uint16_t((R.gmap[sl] & ~(0xF << (4 * k))) | (b << (4 * k)));
+      }
+    }
+    R.v = uint8_t(cnt);
+    for (int i = 0; i < 6; ++i) R.pad[i] = 0;
+    out[t] = R;
+  }
+}
+}  // namespace
+
+// Union layout of `matrix` (with mass type mtype for every group) over the plan's groups, seen from group `group`.
+int plan_union_map(const pf3_plan* pl, int group, int matrix, int mtype, UnionMap* um) {
+  if (pl->generic || group < 0 || group >= pl->dev.ngroups) return PF3_E_BAD_ARG;
+  bool u[6][6], own[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) u[i][j] = own[i][j] = false;
+  for (int g = 0; g < pl->dev.ngroups; ++g) {
+    const BlockLayout L = make_layout(pl->gkind[g], matrix, mtype);
+    if (L.written == 0) return PF3_E_UNSUPPORTED;
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+        u[i][j] = u[i][j] || mask_has(L.mask, i, j);
+        if (g == group) own[i][j] = mask_has(L.mask, i, j);
+      }
+  }
+  bool same = true;
+  int mc = 0, orow = 0;
+  for (int i = 0; i < 6; ++i) {
+    um->rowoff[i] = mc;
+    int c = 0, oc = 0, ownc = 0;
+    for (int j = 0; j < 6; ++j) ownc += own[i][j] ? 1 : 0;
+    for (int j = 0; j < 6; ++j) {
+      um->col[i][j] = -1;
+      if (u[i][j]) {
+        um->col[i][c] = own[i][j] ? int8_t(oc) : int8_t(-1);
+        ++c;
+      }
+      if (own[i][j]) ++oc;
+      same = same && (u[i][j] == own[i][j]);
+    }
+    um->row[i] = ownc > 0 ? int8_t(orow++) : int8_t(-1);
+    um->cnt[i] = c;
+    mc += c;
+    um->colbits[i] = 0;
+    for (int j = 0; j < 6; ++j) um->colbits[i] |= unsigned(um->col[i][j] < 0 ? 0xF : um->col[i][j]) << (4 * j);
+  }
+  um->mc = mc;
+  um->active = same ? 0 : 1;
+  return PF3_OK;
+}
+
+// FusedArgs for group `group` (a Quad4 / Quad4R group) of a multi-group plan.
+int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches) {
+  if (pl->generic || pl->degenerate || group < 0 || group >= pl->dev.ngroups) return PF3_E_UNSUPPORTED;
+  const GroupDev& G = pl->dev.g[group];
+  if (G.nn != 4 || G.diag || G.npairs != 16) return PF3_E_UNSUPPORTED;
+  if (pl->max_nb > fused_max_slots()) return PF3_E_CAPACITY;
+  if (G.ne * 16 >= (int64_t(1) << 31)) return PF3_E_CAPACITY;
+  if (pl->d_frecs == nullptr || pl->frecs_group != group) {
+    cudaFree(pl->d_frecs);
+    pl->d_frecs = nullptr;
+    int* d_mv = nullptr;
+    PF3_CUDA(cudaMalloc((void**)&d_mv, sizeof(int)));
+    PF3_CUDA(cudaMemsetAsync(d_mv, 0, sizeof(int), st));
+    k_group_valence<<<grid_for(pl->nown), 256, 0, st>>>(pl->dev, group, pl->d_inc_ptr, pl->d_inc_meta, pl->nown, d_mv);
+    int mv = 0;
+    PF3_CUDA(cudaMemcpyAsync(&mv, d_mv, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PF3_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_mv);
+    pl->frmax = std::max(1, (mv + 3) / 4);
+    PF3_CUDA(cudaMalloc((void**)&pl->d_frecs, size_t(pl->nown) * pl->frmax * sizeof(NodeRec)));
+    k_node_records_group<<<grid_for(pl->nown * pl->frmax), 256, 0, st>>>(pl->dev, group, pl->d_brow_ptr, pl->d_inc_ptr,
+                                                                        pl->d_inc_pair0, pl->d_inc_meta, pl->d_slot,
+                                                                        pl->nown, pl->frmax, pl->d_frecs);
+    pl->frecs_group = group;
+    *launches += 2;
+    PF3_CUDA(cudaGetLastError());
+  }
+  F->noderec = pl->d_frecs;
+  F->rmax = pl->frmax;
+  F->brow_ptr = pl->d_brow_ptr;
+  F->inc_ptr = pl->d_inc_ptr;
+  F->inc_pair0 = pl->d_inc_pair0;
+  F->slot = pl->d_slot;
+  F->nown = pl->nown;
+  return PF3_OK;
+}
+
 int tria_fused_max_slots();
 int tria_fused_incidences();
 // Triangle twin of plan_fused_args.
@@ -1337,7 +1478,7 @@ int64_t plan_nrows(const pf3_plan* pl) { return pl->nrows; }
 extern "C" int pf3_plan_destroy(pf3_plan* pl) {
   if (!pl) return PF3_OK;
   cudaFree(pl->d_brow_ptr); cudaFree(pl->d_bcol); cudaFree(pl->d_inc_ptr); cudaFree(pl->d_inc_src);
-  cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot); cudaFree(pl->d_noderec); cudaFree(pl->d_triarec);
+  cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot); cudaFree(pl->d_noderec); cudaFree(pl->d_triarec); cudaFree(pl->d_frecs);
   for (auto* r : pl->d_grecs) cudaFree(r);
   for (auto* t : pl->d_tabs) cudaFree(t);
   cudaFree(pl->d_indptr); cudaFree(pl->d_indices); cudaFree(pl->d_perm); cudaFree(pl->d_seg);

@@ -72,6 +72,16 @@ struct alignas(16) TriaRec {
 };
 static_assert(sizeof(TriaRec) == 128, "TriaRec must be 128 bytes");
 
+// Where the fused kernel's own (rows x masked columns) block of one matrix lands inside the UNION row layout of a
+// multi-group plan (e.g. Quad4 skin + BeamC stiffeners: the quad's 3x3 KG entries inside 6x6 union blocks).
+struct UnionMap {
+  int8_t row[6];      // union row d -> own row index (rank among the own non-empty rows), -1: the group has no such row
+  int8_t col[6][6];   // union (row d, column rank ju) -> own masked-column rank in that row, -1: structural zero here
+  int cnt[6], rowoff[6], mc;   // the union layout: columns per block in row d, block-row offset, entries per block
+  unsigned colbits[6];         // col[d][*] packed 4 bits per union column rank (0xF = structural zero)
+  int active;         // 0: the union layout IS the own layout (fast path)
+};
+
 // fused evaluate + assemble (quad_fused.cu): element inputs + the plan's block structure
 struct FusedArgs {
   EvalArgs A;
@@ -86,6 +96,8 @@ struct FusedArgs {
   double* csr_kc0;
   double* csr_kg;
   double* csr_m;
+  UnionMap um[3];                         // KC0, KG, M: only read when um[i].active
+  int zero_empty;                         // multi-group plans: zero the rows of nodes this group does not touch
 };
 
 struct Mat3 {

@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__
 template <int NR, int CNT>
 __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, double* __restrict__ coo,
                                            int64_t slab_base, bool act, double* __restrict__ csr, int64_t csr_base,
-                                           int nb, bool first_round, int lane) {
+                                           int nb, bool first_round, int lane, const UnionMap* um = nullptr) {
   constexpr int kSlab = SlabShape<NR, CNT>::kSlab, kLd = SlabShape<NR, CNT>::kLd;
   const int h = lane >> 4, l16 = lane & 15;
 #if PF3_COO_TMA
@@ -186,7 +186,62 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
       if ((kSlab / 2) % 4 == 0 || 4 * i + (lane & 3) < kSlab / 2) dst[4 * i] = src[4 * i];
   }
 #endif
-  if (nb > 0 && csr != nullptr) {
+  if (nb > 0 && csr != nullptr && um != nullptr) {
+    // multi-group plan: this group's entries land inside the UNION row layout (csr_base = b0 * um->mc); positions
+    // the group does not have are written as zeros so that the other groups can be added afterwards
+    const double* sh = st + h * 4 * kLd;
+    if (um->mc == 36) {
+      // full 6x6 union blocks (shell + beam meshes): positions outer, the 6 union rows inner, column maps as bit fields
+      const int wu = nb * 6;
+      double* out = csr + csr_base;
+#pragma unroll 1
+      for (int x = l16; x < wu; x += 16) {
+        const int s = x / 6, c = x - s * 6;
+        const unsigned gm = nr->gmap[s];
+        int off[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const int nib = (gm >> (4 * k2)) & 0xF;
+          off[k2] = (nib != 0xF) ? (k2 * kLd + nib * CNT) : -1;
+        }
+#pragma unroll
+        for (int du = 0; du < 6; ++du) {
+          const int down = um->row[du];
+          const int j = int((um->colbits[du] >> (4 * c)) & 0xF);
+          double sum = 0.;
+          if (down >= 0 && j != 0xF) {
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2)
+              if (off[k2] >= 0) sum += sh[off[k2] + down * 4 * CNT + j];
+          }
+          double* o = out + du * wu + x;
+          if (first_round) *o = sum; else *o += sum;   // (a 16-byte two-column variant measured 5 % slower)
+        }
+      }
+    } else
+#pragma unroll 1
+    for (int du = 0; du < 6; ++du) {
+      const int cu = um->cnt[du];
+      if (cu == 0) continue;
+      const int wu = nb * cu, down = um->row[du];
+      double* out = csr + csr_base + um->rowoff[du] * nb;
+#pragma unroll 1
+      for (int x = l16; x < wu; x += 16) {
+        const int s = x / cu, ju = x - s * cu;
+        const int j = down >= 0 ? um->col[du][ju] : -1;
+        double sum = 0.;
+        if (j >= 0) {
+          const unsigned gm = nr->gmap[s];
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            const int nib = (gm >> (4 * k2)) & 0xF;
+            if (nib != 0xF) sum += sh[k2 * kLd + down * 4 * CNT + nib * CNT + j];
+          }
+        }
+        if (first_round) out[x] = sum; else out[x] += sum;
+      }
+    }
+  } else if (nb > 0 && csr != nullptr) {
     const int w = nb * CNT;
     const double* sh = st + h * 4 * kLd;
     if (CNT % 2 == 0) {
@@ -342,6 +397,9 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   const int pendM = (kgsep && hasKG) ? 1 : 0;
   const int pendKC0 = hasM ? 0 : pendM;
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
+  const UnionMap* umK = F.um[0].active ? &F.um[0] : nullptr;
+  const UnionMap* umKG = F.um[1].active ? &F.um[1] : nullptr;
+  const UnionMap* umM = F.um[2].active ? &F.um[2] : nullptr;
   const int64_t np = int64_t(blockIdx.x) * kFusedWarps + warp;
   if (2 * np >= F.nown) return;
   const int rmax = F.rmax;
@@ -355,7 +413,26 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     const NodeRec* nr = nrec + h;
     const int pair0 = nr->inc[k];
     const bool act = pair0 >= 0;
-    if (__ballot_sync(0xffffffffu, act) == 0u) continue;
+    if (__ballot_sync(0xffffffffu, act) == 0u) {
+      if (F.zero_empty && r == 0 && nr->nb > 0) {
+        // a node only other groups touch: initialise its rows so that their contributions can be added
+        const int nbz = nr->nb;
+        const int64_t bz = nr->b0;
+        if ((A.what & PF3_KC0) && F.csr_kc0) {
+          const int mc = umK ? umK->mc : 36;
+          for (int x = l16; x < nbz * mc; x += 16) F.csr_kc0[bz * mc + x] = 0.;
+        }
+        if ((A.what & (PF3_KG | PF3_KG_STRESS)) && F.csr_kg) {
+          const int mc = umKG ? umKG->mc : 9;
+          for (int x = l16; x < nbz * mc; x += 16) F.csr_kg[bz * mc + x] = 0.;
+        }
+        if ((A.what & PF3_M) && F.csr_m) {
+          const int mc = umM ? umM->mc : (A.mtype == 2 ? 18 : 30);
+          for (int x = l16; x < nbz * mc; x += 16) F.csr_m[bz * mc + x] = 0.;
+        }
+      }
+      continue;
+    }
     erec_fetch(rec, rstride, erec, pair0, lane);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -436,8 +513,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) sl[i * 12 + jj] = (R.a[i][2] * R.a[jj][2]) * ge;
-      emit_slabs<3, 3>(stkg, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg, b0 * 9, nb, first,
-                       lane);
+      emit_slabs<3, 3>(stkg, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg,
+                       umKG ? b0 * umKG->mc : b0 * 9, nb, first, lane, umKG);
     }
 
     // ---------------- M : H_ab * (T6 m_l T6^T)
@@ -479,7 +556,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
           sl[(3 + i) * 20 + 3] = H * rq[1];
           sl[(3 + i) * 20 + 4] = H * rq[2];
         }
-        emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, b0 * 30, nb, first, lane);
+        emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, umM ? b0 * umM->mc : b0 * 30, nb, first, lane, umM);
       } else {
         double* sl = st + (lane >> 2) * SlabShape<6, 3>::kLd + b * 3;
         stage_reuse_wait(pendM);
@@ -490,7 +567,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
             sl[i * 12 + jj] = H * (r0 * R.a[i][0] * R.a[jj][0] + r0 * R.a[i][1] * R.a[jj][1] + r0 * R.a[i][2] * R.a[jj][2]);
             sl[(3 + i) * 12 + jj] = H * (r2 * R.a[i][0] * R.a[jj][0] + r2 * R.a[i][1] * R.a[jj][1]);
           }
-        emit_slabs<6, 3>(st, nr, coo, e * 480 + a * 72, act, F.csr_m, b0 * 18, nb, first, lane);
+        emit_slabs<6, 3>(st, nr, coo, e * 480 + a * 72, act, F.csr_m, umM ? b0 * umM->mc : b0 * 18, nb, first, lane, umM);
       }
     }
 
@@ -589,8 +666,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
         sl2[(3 + i) * 12 + 1] = make_double2(o1[i][2], o2[i][0]);
         sl2[(3 + i) * 12 + 2] = make_double2(o2[i][1], o2[i][2]);
       }
-      emit_slabs<6, 6>(st, nr, A.kc0v ? A.kc0v + A.kc0_k0 : nullptr, e * 576 + a * 144, act, F.csr_kc0, b0 * 36, nb,
-                       first, lane);
+      emit_slabs<6, 6>(st, nr, A.kc0v ? A.kc0v + A.kc0_k0 : nullptr, e * 576 + a * 144, act, F.csr_kc0,
+                       umK ? b0 * umK->mc : b0 * 36, nb, first, lane, umK);
     }
   }
   // the bulk copies read this CTA's shared memory: they must have done so before the CTA retires

@@ -98,6 +98,64 @@ def run_spmv(side):
                       "algorithmic_GBps": alg_csr / ms_csr / 1e6, "frac_of_6538.9": alg_csr / ms_csr / 1e6 / 6538.9}))
 
 
+def run_mixed(side, nstiff=64):
+    """Config 5 (per-GPU share): Quad4 skin + BeamC stiffeners in ONE matrix per KC0 / KG / M, plus update_fint.
+    The groups have different masks for KG and M, so this is the two-pass path: one evaluation launch per group and
+    the per-node gather assembly over the union pattern."""
+    skin, beams = meshes.stiffened_panel(side, side, nstiff=nstiff)
+    bs = [util.batch_from_case(skin), util.batch_from_case(beams)]
+    nn = skin["ndof"] // 6
+    ne = sum(b.ne for b in bs)
+    names = ("KC0", "KG", "M")
+    plans = {m: AssemblyPlan(m, nn, bs) for m in names}
+    coos = [b.evaluate(KC0=True, KG=True, M=True, indices=False) for b in bs]
+    vals = {m: torch.cat([c[m].v for c in coos]) for m in names}
+    offs = {m: [0, coos[0][m].v.numel()] for m in names}
+    views = [{m: type(coos[g][m])(None, None, vals[m][offs[m][g]:offs[m][g] + coos[g][m].v.numel()], 6 * nn)
+              for m in names} for g in range(2)]
+    csr = {m: torch.empty(plans[m].nnz, dtype=torch.float64, device=bs[0].device) for m in names}
+    fint = torch.zeros(6 * nn, dtype=torch.float64, device=bs[0].device)
+
+    def step():
+        for g, b in enumerate(bs):
+            b.evaluate(KC0=True, KG=True, M=True, indices=False, out=views[g])
+        for m in names:
+            plans[m].assemble(vals[m], out=csr[m])
+        plans["KC0"].update_fint(fint)
+
+    ms = timeit(step)
+    coo_f = {m: type(coos[0][m])(None, None, vals[m], 6 * nn) for m in names}
+
+    def fstep():
+        plans["KC0"].evaluate_assemble(KC0=True, KG=True, M=True, coo=coo_f, csr=csr)
+        plans["KC0"].update_fint(fint)
+
+    ms_f = timeit(fstep)
+    from pyfe3d_b200 import _cabi
+    from pyfe3d_b200.batch import _ptr, context
+    pk = plans["KC0"]
+    what = _cabi.KC0 | _cabi.KG | _cabi.M
+    cc = lambda m: _cabi.Coo(0, 0, _ptr(vals[m]), 0, 0)
+    context(bs[0].device)
+    fparts = {"fused_quad_group": timeit(lambda: pk._plan.eval_assemble_group(bs[0].cabi_batch(), 0, what, cc("KC0"), cc("KG"), cc("M"),
+                                                                             _ptr(csr["KC0"]), _ptr(csr["KG"]), _ptr(csr["M"]))),
+              "beam_eval": timeit(lambda: bs[1].evaluate(KC0=True, KG=True, M=True, indices=False, out=views[1]))}
+    for m in names:
+        fparts["add_" + m] = timeit(lambda m=m: plans[m]._plan.assemble_add(_ptr(vals[m]), _ptr(csr[m]), 0))
+    print(json.dumps({"config": "config5 fused quad share + beams added", "ms_per_step": ms_f,
+                      "elements_per_s": ne / ms_f * 1e3, "kernel_ms": fparts}))
+    parts = {"eval": timeit(lambda: [b.evaluate(KC0=True, KG=True, M=True, indices=False, out=views[g]) for g, b in enumerate(bs)])}
+    for m in names:
+        parts["assemble_" + m] = timeit(lambda m=m: plans[m].assemble(vals[m], out=csr[m]))
+    parts["fint"] = timeit(lambda: plans["KC0"].update_fint(fint))
+    print(json.dumps({"config": "config5 share", "kernel_ms": parts}))
+    alg = sum(sum(b.ne * b.sizes[m] for b in bs) * 8 + plans[m].nnz * 8 for m in names)
+    print(json.dumps({"config": "config5 stiffened panel %dx%d Quad4 + %d BeamC, KC0+KG+M+fint" % (side, side, bs[1].ne),
+                      "kind": "quad4+beamc", "elements": ne, "matrices": list(names), "path": "two-pass", "ms_per_step": ms,
+                      "elements_per_s": ne / ms * 1e3, "algorithmic_GBps": alg / ms / 1e6,
+                      "frac_of_6538.9": alg / ms / 1e6 / 6538.9}))
+
+
 def run_aero(side):
     """the three piston-theory matrices of the north-star mesh in one launch (values only)."""
     case = meshes.plate_quad4(side, side)
@@ -112,6 +170,9 @@ def run_aero(side):
 
 
 if __name__ == "__main__":
+    if "--mixed" in sys.argv:
+        run_mixed(140 if "--small" in sys.argv else 1403)
+        sys.exit(0)
     if "--aero" in sys.argv:
         run_aero(200 if "--small" in sys.argv else 2000)
         sys.exit(0)
@@ -120,6 +181,10 @@ if __name__ == "__main__":
         sys.exit(0)
     small = "--small" in sys.argv
     f = 0.1 if small else 1.0
+    if "--config3" in sys.argv:
+        run("config3 Quad4R cylinder 1M, KC0+KG_given_stress", meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)),
+            ("KC0", "KGs"), True)
+        sys.exit(0)
     if "--config4" in sys.argv:
         run("config4 Tria3R distorted plate 4M, KC0+M(mtype1)", meshes.plate_tria3r(int(1415 * f ** 0.5), int(1415 * f ** 0.5)),
             ("KC0", "M1"), True)

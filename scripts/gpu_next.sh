@@ -1,3 +1,2 @@
-mkdir -p gpurun_out
-python -m pytest tests/test_gpu_spmv.py -m gpu -x -q 2>&1 | tail -4
-python scripts/bench_configs.py --spmv 2>&1 | tee gpurun_out/spmv.jsonl | cut -c1-330
+python -m pytest tests/test_gpu_fused.py -m gpu -x -q -k mixed 2>&1 | tail -3
+python scripts/bench_configs.py --mixed 2>&1 | tail -4 | head -1 | cut -c1-600

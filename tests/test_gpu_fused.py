@@ -163,3 +163,101 @@ def test_host_buffer_step_matches_device_step(kind):
     assert np.abs(out2["KG"] - 3.0 * csr["KG"].cpu().numpy()).max() <= 1e-12 * float(csr["KG"].abs().max()) * 3
     with pytest.raises(ValueError):
         plan.evaluate_assemble_host(torch.as_tensor(case["x"]).cuda(), uh, out, KC0=True)
+
+
+def _mixed_reference(cs, keys):
+    """scipy sum-duplicates of the oracle's triplets of every batch, per matrix."""
+    import scipy.sparse as sp
+    n = cs[0]["ndof"]
+    outs = [driver.run(c, what=keys) for c in cs]
+    mats = {}
+    for k in keys:
+        r = np.concatenate([o[k][0] for o in outs])
+        c = np.concatenate([o[k][1] for o in outs])
+        v = np.concatenate([o[k][2] for o in outs])
+        S = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr()
+        S.sum_duplicates()
+        S.sort_indices()
+        mats[k] = S
+    return outs, mats
+
+
+@pytest.mark.parametrize("kind", ["quad4", "quad4r"])
+def test_fused_mixed_skin_and_stiffeners(kind):
+    """BASELINE config 5 in small: Quad skin + BeamC stiffeners in one KC0 / KG / M each.  The quad share goes through
+    the fused kernel into the union layouts (KG and M have 36 entries per block because of the beams), the beams are
+    added; COO slices and CSR against the oracle + scipy."""
+    import torch
+    from pyfe3d_b200 import meshes
+    from pyfe3d_b200.batch import AssemblyPlan
+    skin, beams = meshes.stiffened_panel(14, 11, nstiff=3)
+    skin["kind"] = kind
+    rng = np.random.default_rng(3)
+    # a beam between two nodes that share no quad (a new block), and one on a node pair of the mesh diagonal
+    nny = 12
+    extra = np.array([[0, 2 * nny + 5], [3 * nny + 3, 4 * nny + 4]], np.int64)
+    beams["conn"] = np.vstack([beams["conn"], extra])
+    beams["vxy"] = np.vstack([beams["vxy"], beams["vxy"][:2]])
+    cs = [skin, beams]
+    bs = [util.batch_from_case(c) for c in cs]
+    nn = skin["ndof"] // 6
+    keys = ("KC0", "KG", "M0")
+    outs, mats = _mixed_reference(cs, keys)
+    plan = AssemblyPlan("KC0", nn, bs)
+    coo, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True)
+    assert not getattr(plan, "_fused_unsupported", False)
+    for name, rk in (("KC0", "KC0"), ("KG", "KG"), ("M", "M0")):
+        p = plan._sibling(name, 0)
+        for g, (c, o) in enumerate(zip(cs, outs)):
+            ne = c["conn"].shape[0]
+            got = coo[name].v[p.coo_offsets[g]:p.coo_offsets[g] + o[rk][2].size].cpu().numpy()
+            assert util.block_relerr(got, o[rk][2], ne) <= util.TOL_VALUES, (name, g)
+        A = p.to_scipy(csr[name])
+        S = mats[rk]
+        # the union-mask layout of a multi-group plan stores explicit zeros where only some kinds have entries
+        # (e.g. the quads' KG inside the beams' 6x6 blocks): same matrix, pattern a superset of scipy's
+        assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max(), name
+        if name == "KC0":
+            assert np.array_equal(A.indptr, S.indptr) and np.array_equal(A.indices, S.indices)
+    # same outputs as the two-pass path of the same plan
+    plan._fused_unsupported = True
+    coo2, csr2 = plan.evaluate_assemble(KC0=True, KG=True, M=True)
+    for name in ("KC0", "KG", "M"):
+        assert float((csr[name] - csr2[name]).abs().max()) <= 1e-12 * float(csr2[name].abs().max()), name
+    # a row shard of the same mesh
+    lo, hi = nn // 3, nn - 7
+    ps = AssemblyPlan("KC0", nn, bs, node_range=(lo, hi))
+    _, csrs = ps.evaluate_assemble(KC0=True, KG=True, M=True)
+    for name, rk in (("KC0", "KC0"), ("KG", "KG"), ("M", "M0")):
+        A = ps._sibling(name, 0).to_scipy(csrs[name])
+        S = mats[rk][6 * lo:6 * hi]
+        assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max()
+
+
+def test_fused_mixed_beam_only_nodes():
+    """Nodes that only the beams touch (a stiffener sticking out of the skin) still get initialised rows."""
+    from pyfe3d_b200 import meshes
+    from pyfe3d_b200.batch import AssemblyPlan
+    skin, beams = meshes.stiffened_panel(6, 5, nstiff=2)
+    nn0 = skin["ndof"] // 6
+    rng = np.random.default_rng(8)
+    xtra = rng.normal(size=(3, 3)) * 0.1 + np.array([1.2, 0.5, 0.1])
+    x = np.concatenate([skin["x"], xtra.ravel()])
+    nn = nn0 + 3
+    u = np.concatenate([skin["u"], 1e-4 * rng.normal(size=18)])
+    for c in (skin, beams):
+        c["x"], c["u"], c["ndof"] = x, u, 6 * nn
+    beams["conn"] = np.vstack([beams["conn"], [[nn0 - 1, nn0], [nn0, nn0 + 1], [nn0 + 1, nn0 + 2]]]).astype(np.int64)
+    beams["vxy"] = np.vstack([beams["vxy"], beams["vxy"][:3]])
+    cs = [skin, beams]
+    bs = [util.batch_from_case(c) for c in cs]
+    keys = ("KC0", "KG", "M0")
+    outs, mats = _mixed_reference(cs, keys)
+    plan = AssemblyPlan("KC0", nn, bs)
+    _, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True)
+    assert not getattr(plan, "_fused_unsupported", False)
+    for name, rk in (("KC0", "KC0"), ("KG", "KG"), ("M", "M0")):
+        A = plan._sibling(name, 0).to_scipy(csr[name])
+        S = mats[rk]
+        assert np.isfinite(A.data).all()
+        assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max(), name
