@@ -318,17 +318,17 @@ __device__ __forceinline__ void stage_reuse_wait(int pending = 0) {
 }
 
 constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1216 doubles: the largest matrix (KC0)
-// Optional (PF3_KG_SEP, plain records only): a private staging area for KG, so that staging KG never waits for the
-// bulk copies of the previous round's KC0 slabs.  Measured slower on B200 (less L1 left) - kept for experiments.
-#ifndef PF3_KG_SEP
-#define PF3_KG_SEP 0
-#endif
-constexpr int kStageKG = 8 * SlabShape<3, 3>::kLd;
-__host__ __device__ constexpr bool kg_separate(int rstride) { return PF3_KG_SEP && rstride == kRecPlain; }
-// per warp: slab staging | the two NodeRec of the node pair (128 B) | 8 element records, stride rstride + 2 doubles
-// (38 / 58: conflict-free, 16-B aligned)
-__host__ __device__ constexpr int warp_smem_doubles(int rstride) {
-  return kStageV4 + 2 * 8 + 8 * (rstride + 2) + (kg_separate(rstride) ? kStageKG : 0);
+// CHUNK = consecutive node pairs per warp.  1: one pair per warp, no prefetch (the store-bound three-matrix call: the
+// CTA scheduler alone orders the work; measured 10.4 ms against 11.0 / 11.5 ms for chunks of 2 / 4, which widen the
+// window of nodes in flight and take L1 away).  4: the next pair's records arrive by cp.async while this one is
+// computed (the latency-bound one- and two-matrix calls: config 3 2.46 -> 2.14 ms).
+constexpr int kFChunkBig = 4;
+__host__ __device__ constexpr int fring(int chunk) { return chunk > 1 ? 3 : 1; }
+__host__ __device__ constexpr int fbufs(int chunk) { return chunk > 1 ? 2 : 1; }
+// per warp: slab staging | ring of node-record pairs (64 B each) | element records of 8 incidences (x2 when
+// prefetching), stride rstride + 2 doubles (38 / 58: conflict-free, 16-B aligned)
+__host__ __device__ constexpr int warp_smem_doubles(int rstride, int chunk) {
+  return kStageV4 + fring(chunk) * 2 * 8 + fbufs(chunk) * 8 * (rstride + 2);
 }
 
 // Stage the element records of the 8 incidences of a node pair into shared memory with 16-B cp.async; the 4 lanes
@@ -373,44 +373,71 @@ __device__ __forceinline__ void noderec_fetch(const FusedArgs& F, NodeRec* dst2,
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// One warp = one node PAIR (all its rounds), one CTA = kFusedWarps consecutive pairs, and as many CTAs as there is
-// work: the hardware CTA scheduler hands out node pairs in order, so the nodes in flight at any time form a narrow
-// window of the mesh (their COO/CSR destinations are neighbours in DRAM) and a slow warp never holds work back.
-// Measured on B200 at 4 M Quad4: persistent grid-stride warps with a 3-deep prefetch ring 12.4 ms/step, this 10.8.
-template <int KIND>
+// One warp = kFChunk consecutive node PAIRS (all their rounds), one CTA = kFusedWarps warps, and as many CTAs as
+// there is work: the hardware CTA scheduler hands out node pairs in order, so the nodes in flight at any time form a
+// narrow window of the mesh (their COO/CSR destinations are neighbours in DRAM) and a slow warp never holds work back.
+// Measured on B200 at 4 M Quad4: persistent grid-stride warps with a 3-deep prefetch ring 12.4 ms/step, this 10.4.
+// Within a warp the node records of item j+2 and the element records of item j+1 are in flight (cp.async) while item j
+// is evaluated (matters for the latency-bound one- and two-matrix calls, e.g. config 3).
+template <int KIND, int CHUNK>
 __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
                                                                          int rstride) {
+  constexpr int kFRing = fring(CHUNK), kFBufs = fbufs(CHUNK);
   extern __shared__ __align__(16) double smem[];
   const EvalArgs& A = F.A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int eld = rstride + 2;
-  double* st = smem + warp * warp_smem_doubles(rstride);
-  NodeRec* nrec = reinterpret_cast<NodeRec*>(st + kStageV4);
-  double* erec = st + kStageV4 + 2 * 8;
-  const bool kgsep = kg_separate(rstride);
-  double* stkg = kgsep ? erec + 8 * eld : st;
-  // bulk groups committed per round (one per active matrix) and how many of the latest may still be reading when a
-  // staging area is written again
-  const bool hasKG = (F.A.what & (PF3_KG | PF3_KG_STRESS)) != 0, hasM = (F.A.what & PF3_M) != 0;
-  const int ngrp = int(hasKG) + int(hasM) + int((F.A.what & PF3_KC0) != 0);
-  const int pendKG = kgsep ? ngrp - 1 : 0;
-  const int pendM = (kgsep && hasKG) ? 1 : 0;
-  const int pendKC0 = hasM ? 0 : pendM;
+  double* st = smem + warp * warp_smem_doubles(rstride, CHUNK);
+  NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
+  double* erec = st + kStageV4 + kFRing * 2 * 8;
+  double* stkg = st;
+  // staging areas are reused matrix after matrix: every staging waits for all earlier bulk reads
+  const int pendKG = 0, pendM = 0, pendKC0 = 0;
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
   const UnionMap* umK = F.um[0].active ? &F.um[0] : nullptr;
   const UnionMap* umKG = F.um[1].active ? &F.um[1] : nullptr;
   const UnionMap* umM = F.um[2].active ? &F.um[2] : nullptr;
-  const int64_t np = int64_t(blockIdx.x) * kFusedWarps + warp;
-  if (2 * np >= F.nown) return;
+  const int64_t npairs = (F.nown + 1) >> 1;
+  const int64_t np0 = (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
+  if (np0 >= npairs) return;
   const int rmax = F.rmax;
+  const int nitems = int(min(int64_t(CHUNK), npairs - np0)) * rmax;   // item j = (pair np0 + j / rmax, round j % rmax)
   const double xib = (b == 1 || b == 2) ? 1. : -1., etab = (b >= 2) ? 1. : -1.;
 
-  for (int r = 0; r < rmax; ++r) {
-    if (r > 0) stage_reuse_wait(0);   // the node records and element records of the previous round are dead
-    noderec_fetch(F, nrec, np, r, lane);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  auto rec_fetch = [&](int j) {
+    if (j < nitems)
+      noderec_fetch(F, ring + (j % kFRing) * 2, np0 + j / rmax, j % rmax, lane);
+    else
+      asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto erec_prefetch = [&](int j) {
+    if (j < nitems)
+      erec_fetch(rec, rstride, erec + (j % kFBufs) * 8 * eld, (ring + (j % kFRing) * 2 + h)->inc[k], lane);
+    else
+      asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if constexpr (CHUNK > 1) {
+    rec_fetch(0);
+    rec_fetch(1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();
-    const NodeRec* nr = nrec + h;
+    erec_prefetch(0);
+  }
+
+  for (int j = 0; j < nitems; ++j) {
+    const int r = j % rmax;
+    if constexpr (CHUNK > 1) {
+      rec_fetch(j + 2);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j+1 and element records j have landed
+      __syncwarp();
+      erec_prefetch(j + 1);
+    } else {
+      if (j > 0) stage_reuse_wait(0);
+      rec_fetch(j);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
+    const NodeRec* nr = ring + (j % kFRing) * 2 + h;
     const int pair0 = nr->inc[k];
     const bool act = pair0 >= 0;
     if (__ballot_sync(0xffffffffu, act) == 0u) {
@@ -433,9 +460,11 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       }
       continue;
     }
-    erec_fetch(rec, rstride, erec, pair0, lane);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    if constexpr (CHUNK == 1) {
+      erec_prefetch(j);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    }
     const int64_t b0 = nr->b0;
     const int nb = nr->nb;
     const int64_t e = act ? (pair0 >> 4) : 0;
@@ -444,7 +473,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
 
     // ---------------- element record (K1) and property row
-    const double* re = erec + (lane >> 2) * eld;
+    const double* re = erec + ((j % kFBufs) * 8 + (lane >> 2)) * eld;
     const double2* re2 = reinterpret_cast<const double2*>(re);
     double rr_[24];
 #pragma unroll
@@ -676,7 +705,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
 
 }  // namespace
 
-size_t fused_smem_bytes(int rstride) { return size_t(kFusedWarps) * warp_smem_doubles(rstride) * sizeof(double); }
+size_t fused_smem_bytes(int rstride, int chunk) { return size_t(kFusedWarps) * warp_smem_doubles(rstride, chunk) * sizeof(double); }
 int fused_max_slots() { return kMaxSlots; }
 int fused_record_stride(const EvalArgs& A) { return A.evec != nullptr ? kRecRot : kRecPlain; }
 
@@ -700,22 +729,33 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   ++*launches;
   cudaError_t e1 = cudaGetLastError();
   if (e1 != cudaSuccess) return e1;
-  const size_t smem = fused_smem_bytes(stride);
+  // doubles written per element (COO + CSR share): the three-matrix north-star call is store-bound, smaller calls are
+  // latency-bound and take the prefetching variant
+  const int w = F.A.what;
+  const int vol = ((w & PF3_KC0) ? 900 : 0) + ((w & (PF3_KG | PF3_KG_STRESS)) ? 225 : 0) + ((w & PF3_M) ? 750 : 0);
+  const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
+  const int chunk = (vol < 1400 && !mapped) ? kFChunkBig : 1;
+  const size_t smem = fused_smem_bytes(stride, chunk);
   const int64_t npairs = (F.nown + 1) / 2;
-  const int64_t want = (npairs + kFusedWarps - 1) / kFusedWarps;
+  const int64_t want = (npairs + int64_t(kFusedWarps) * chunk - 1) / (int64_t(kFusedWarps) * chunk);
   if (want > int64_t(0x7fffffff)) return cudaErrorInvalidConfiguration;
   const unsigned grid = unsigned(want < 1 ? 1 : want);
   static bool once = false;
   if (!once) {
-    const int maxs = int(fused_smem_bytes(kRecRot) > fused_smem_bytes(kRecPlain) ? fused_smem_bytes(kRecRot) : fused_smem_bytes(kRecPlain));
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+    const int m1 = int(fused_smem_bytes(kRecRot, 1)), m4 = int(fused_smem_bytes(kRecRot, kFChunkBig));
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
     once = true;
   }
-  if (kind == PF3_QUAD4)
-    quad_fused_kernel<PF3_QUAD4><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
-  else
-    quad_fused_kernel<PF3_QUAD4R><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
+  if (kind == PF3_QUAD4) {
+    if (chunk == 1) quad_fused_kernel<PF3_QUAD4, 1><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
+    else quad_fused_kernel<PF3_QUAD4, kFChunkBig><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
+  } else {
+    if (chunk == 1) quad_fused_kernel<PF3_QUAD4R, 1><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
+    else quad_fused_kernel<PF3_QUAD4R, kFChunkBig><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
+  }
   ++*launches;
   return cudaGetLastError();
 }
