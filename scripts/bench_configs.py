@@ -156,6 +156,25 @@ def run_mixed(side, nstiff=64):
                       "frac_of_6538.9": alg / ms / 1e6 / 6538.9}))
 
 
+def run_fint(side):
+    """update_fint of every element of the north-star mesh, element kernel + plan gather."""
+    case = meshes.plate_quad4(side, side)
+    for kind in ("quad4", "quad4r"):
+        case["kind"] = kind
+        b = util.batch_from_case(case)
+        nn = case["ndof"] // 6
+        plan = AssemblyPlan("KC0", nn, [b])
+        fint = torch.zeros(6 * nn, dtype=torch.float64, device=b.device)
+        ms = timeit(lambda: plan.update_fint(fint))
+        ms_sort = timeit(lambda: b.update_fint(fint), steps=3, warm=1)
+        ne = case["conn"].shape[0]
+        alg = ne * (32 + 24 + 48 + 2 * 192) + nn * 48 * 2
+        print(json.dumps({"config": "update_fint %s %dx%d" % (kind, side, side), "elements": ne, "ms_plan_gather": ms,
+                          "ms_sort_gather": ms_sort, "elements_per_s": ne / ms * 1e3, "algorithmic_GBps": alg / ms / 1e6,
+                          "frac_of_6538.9": alg / ms / 1e6 / 6538.9}))
+        del plan, b
+
+
 def run_aero(side):
     """the three piston-theory matrices of the north-star mesh in one launch (values only)."""
     case = meshes.plate_quad4(side, side)
@@ -172,6 +191,9 @@ def run_aero(side):
 if __name__ == "__main__":
     if "--mixed" in sys.argv:
         run_mixed(140 if "--small" in sys.argv else 1403)
+        sys.exit(0)
+    if "--fint" in sys.argv:
+        run_fint(200 if "--small" in sys.argv else 2000)
         sys.exit(0)
     if "--aero" in sys.argv:
         run_aero(200 if "--small" in sys.argv else 2000)

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --e2e-steps 0 --cpu-side 0 | python -c "
-import sys, json
-d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('north-star ms', d['ms_per_step'], 'frac', d['roofline']['frac'])"
-python scripts/bench_configs.py --config3 2>&1 | tail -1 | cut -c1-250
-python scripts/bench_configs.py --mixed 2>&1 | tail -4 | head -1 | cut -c1-250
+python scripts/bench_configs.py --fint 2>&1 | tee gpurun_out/fint.jsonl | cut -c1-400
+ncu --set full --clock-control none --import-source on -k regex:'tria_fused|tria_record' -s 8 -c 2 -o gpurun_out/prof_tria \
+    python scripts/bench_configs.py --config4 > gpurun_out/prof_tria.log 2>&1
+ncu --set full --clock-control none -k regex:'quad_eval' -s 2 -c 1 -o gpurun_out/prof_fint \
+    python scripts/bench_configs.py --fint > gpurun_out/prof_fint.log 2>&1
+ls -la gpurun_out/*.ncu-rep
