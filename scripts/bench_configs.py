@@ -156,6 +156,32 @@ def run_mixed(side, nstiff=64):
                       "frac_of_6538.9": alg / ms / 1e6 / 6538.9}))
 
 
+def run_kinds(n):
+    """every element kind, KC0 + KG + M (whatever the kind has) + fint, n elements, values only."""
+    from tests import cases
+    for kind in ("quad4", "quad4r", "tria3r", "beamc", "beamlr", "truss", "spring"):
+        if kind in ("quad4", "quad4r"):
+            side = int(n ** 0.5)
+            case = meshes.plate_quad4(side, side, kind=kind)
+        elif kind == "tria3r":
+            side = int((n / 2) ** 0.5)
+            case = meshes.plate_tria3r(side, side)
+        else:
+            case = cases.line_chain(kind, n, seed=1)
+        b = util.batch_from_case(case)
+        kw = dict(KC0=True, KG=b.sizes["KG"] > 0, M=b.sizes["M"] > 0, indices=False)
+        coo = b.evaluate(**kw)
+        ms = timeit(lambda: b.evaluate(out=coo, **kw))
+        bytes_el = sum(b.sizes[m] for m in ("KC0", "KG", "M")) * 8
+        fint = torch.zeros(case["ndof"], dtype=torch.float64, device=b.device)
+        plan = AssemblyPlan("KC0", case["ndof"] // 6, [b])
+        ms_f = timeit(lambda: plan.update_fint(fint))
+        print(json.dumps({"config": "eval %s, %d elements" % (kind, b.ne), "matrices": [m for m in ("KC0", "KG", "M") if b.sizes[m]],
+                          "ms": ms, "elements_per_s": b.ne / ms * 1e3, "store_GBps": b.ne * bytes_el / ms / 1e6,
+                          "frac_of_6538.9": b.ne * bytes_el / ms / 1e6 / 6538.9, "update_fint_ms": ms_f}))
+        del b, coo, plan
+
+
 def run_fint(side):
     """update_fint of every element of the north-star mesh, element kernel + plan gather."""
     case = meshes.plate_quad4(side, side)
@@ -191,6 +217,9 @@ def run_aero(side):
 if __name__ == "__main__":
     if "--mixed" in sys.argv:
         run_mixed(140 if "--small" in sys.argv else 1403)
+        sys.exit(0)
+    if "--kinds" in sys.argv:
+        run_kinds(20000 if "--small" in sys.argv else 1000000)
         sys.exit(0)
     if "--fint" in sys.argv:
         run_fint(200 if "--small" in sys.argv else 2000)
