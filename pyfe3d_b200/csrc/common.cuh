@@ -165,19 +165,50 @@ __device__ __forceinline__ void flush_chunk(const double* stage, double* __restr
                                             int nvalid, int64_t estride, int off, bool accumulate,
                                             int lane) {
   __syncwarp();
-  const int total = nvalid * LEN;
   double* base = out + e0 * estride + off;
+  // lane walks positions idx = lane, lane + 32, ... of the nvalid x LEN tile; (el, k) follow by carry instead of a
+  // division per store
+  int el = lane / LEN, k = lane - el * LEN;
+  constexpr int kStepEl = 32 / LEN, kStepK = 32 - kStepEl * LEN;
   if (accumulate) {
-    for (int idx = lane; idx < total; idx += 32) {
-      int el = idx / LEN, k = idx - el * LEN;
+    while (el < nvalid) {
       double* p = base + int64_t(el) * estride + k;
       *p += stage[el * kStageLd + k];
+      el += kStepEl;
+      k += kStepK;
+      if (k >= LEN) {
+        k -= LEN;
+        ++el;
+      }
     }
   } else {
-#pragma unroll 4
-    for (int idx = lane; idx < total; idx += 32) {
-      int el = idx / LEN, k = idx - el * LEN;
+    if constexpr (LEN % 2 == 0) {
+      // even runs on 16-byte aligned bases: two doubles per store
+      if (((reinterpret_cast<uintptr_t>(base) & 15) == 0) && (estride & 1) == 0) {
+        constexpr int H = LEN / 2, kStepEl2 = 32 / H, kStepK2 = 32 - kStepEl2 * H;
+        int el2 = lane / H, k2 = lane - el2 * H;
+        while (el2 < nvalid) {
+          const double* s = stage + el2 * kStageLd + 2 * k2;
+          *reinterpret_cast<double2*>(base + int64_t(el2) * estride + 2 * k2) = make_double2(s[0], s[1]);
+          el2 += kStepEl2;
+          k2 += kStepK2;
+          if (k2 >= H) {
+            k2 -= H;
+            ++el2;
+          }
+        }
+        __syncwarp();
+        return;
+      }
+    }
+    while (el < nvalid) {
       base[int64_t(el) * estride + k] = stage[el * kStageLd + k];
+      el += kStepEl;
+      k += kStepK;
+      if (k >= LEN) {
+        k -= LEN;
+        ++el;
+      }
     }
   }
   __syncwarp();
