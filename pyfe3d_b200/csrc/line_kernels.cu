@@ -7,8 +7,11 @@
 //   truss.pyx : update_rotation_matrix :203, update_KC0 :386, update_fint :802, update_M :838
 //   spring.pyx: update_rotation_matrix :147, update_KC0 :295, update_fint :708
 //
-// These elements are tiny (72..144 values each) and purely store-bound; the local 12x12
-// matrix lives in per-thread local memory and is rotated block by block.
+// These elements are tiny (72..144 values each) and purely store-bound.  The closed-form local 12x12 matrices are
+// written once, as lists of `sym(K, i, j, value)` with constant (i, j); they are instantiated per 6x6 NODE-PAIR BLOCK
+// through a sink type (KBlock<A, B>) whose `set` keeps only the entries of its block, so that after inlining only
+// that block's 36 values are computed and they live in registers (the first version kept the whole 12x12 in
+// per-thread local memory: 1152 B of stack, 0.3-0.4 of the store roofline).
 #include "common.cuh"
 
 namespace pf3 {
@@ -19,18 +22,31 @@ struct BeamP {
   double A, E, G, Iyy, Izz, Iyz, J, Ay, Az, r0, ry, rz, ry2, rz2, ryz;
 };
 
-__device__ __forceinline__ void sym(double (*K)[12], int i, int j, double v) {
-  K[i][j] = v;
-  K[j][i] = v;
-}
-__device__ __forceinline__ void zero12(double (*K)[12]) {
-  for (int i = 0; i < 12; ++i)
-    for (int j = 0; j < 12; ++j) K[i][j] = 0.;
+// Sink that keeps rows [6A, 6A+6) x columns [6B, 6B+6) of the local matrix.  Every call site passes literal (i, j):
+// the tests fold at compile time.
+template <int BA, int BB>
+struct KBlock {
+  double v[6][6];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[i][j] = 0.;
+  }
+  __device__ __forceinline__ void set(int i, int j, double x) {
+    if (i / 6 == BA && j / 6 == BB) v[i % 6][j % 6] = x;
+  }
+};
+template <class KS>
+__device__ __forceinline__ void sym(KS& K, int i, int j, double v) {
+  K.set(i, j, v);
+  K.set(j, i, v);
 }
 
 // Timoshenko beam with consistent shape functions (Luo 2008); beamc.pyx:543-624
-__device__ void beamc_Ke(const BeamP& p, double L, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void beamc_Ke(const BeamP& p, double L, KS& K) {
+  K.zero();
   const double L2 = L * L, L3 = L2 * L;
   const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
   const double by = 1 / (1. - ay), bz = 1 / (1. - az);
@@ -67,8 +83,9 @@ __device__ void beamc_Ke(const BeamP& p, double L, double (*K)[12]) {
 }
 
 // beamc.pyx:1889-2179
-__device__ void beamc_KGe(const BeamP& p, double L, const double* ue, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void beamc_KGe(const BeamP& p, double L, const double* ue, KS& K) {
+  K.zero();
   const double L2 = L * L;
   const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
   const double by = 1 / (1. - ay), bz = 1 / (1. - az);
@@ -100,8 +117,9 @@ __device__ void beamc_KGe(const BeamP& p, double L, const double* ue, double (*K
 }
 
 // beamc.pyx:2246-3152; mtype 0 consistent, 1 lumped
-__device__ void beamc_Me(const BeamP& p, double L, int mtype, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void beamc_Me(const BeamP& p, double L, int mtype, KS& K) {
+  K.zero();
   const double L2 = L * L;
   const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
   const double by = 1 / (1. - ay), bz = 1 / (1. - az);
@@ -110,9 +128,10 @@ __device__ void beamc_Me(const BeamP& p, double L, int mtype, double (*K)[12]) {
     const double d[6] = {L * r0 / 2, L * by * by * r0 * (ay - 1) * (ay - 1) / 2, L * bz * bz * r0 * (az - 1) * (az - 1) / 2,
                          L * (ry2 + rz2) / 2, L * bz * bz * rz2 * (az - 1) * (az - 1) / 2,
                          L * by * by * ry2 * (ay - 1) * (ay - 1) / 2};
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
-      K[i][i] = d[i];
-      K[i + 6][i + 6] = d[i];
+      K.set(i, i, d[i]);
+      K.set(i + 6, i + 6, d[i]);
     }
     return;
   }
@@ -154,8 +173,9 @@ __device__ void beamc_Me(const BeamP& p, double L, int mtype, double (*K)[12]) {
 }
 
 // linear Timoshenko beam, one-point reduced integration; beamlr.pyx:460-1186
-__device__ void beamlr_Ke(const BeamP& p, double L, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void beamlr_Ke(const BeamP& p, double L, KS& K) {
+  K.zero();
   const double EA = p.E * p.A / L, EAz = p.E * p.Az / L, EAy = p.E * p.Ay / L;
   const double GA = p.G * p.A, GAy = p.G * p.Ay, GAz = p.G * p.Az, GJ = p.G * p.J / L;
   sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
@@ -179,8 +199,9 @@ __device__ void beamlr_Ke(const BeamP& p, double L, double (*K)[12]) {
 }
 
 // beamlr.pyx:1388-1462 (literal 0.333.. / 0.1666.. constants of the reference kept)
-__device__ void beamlr_KGe(const BeamP& p, double L, const double* ue, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void beamlr_KGe(const BeamP& p, double L, const double* ue, KS& K) {
+  K.zero();
   const double N = p.A * p.E * (-ue[0] + ue[6]) / L;
   const double t = 0.333333333333333 * L * N, s = 0.166666666666667 * L * N;
   sym(K, 4, 4, t); sym(K, 5, 5, t); sym(K, 10, 10, t); sym(K, 11, 11, t);
@@ -190,10 +211,13 @@ __device__ void beamlr_KGe(const BeamP& p, double L, const double* ue, double (*
 }
 
 // beamlr.pyx:1518-2424; truss.pyx:894-1800 (same with the ry/rz inertia removed)
-__device__ void beamlr_Me(const BeamP& p, double L, int mtype, bool truss, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void beamlr_Me(const BeamP& p, double L, int mtype, bool truss, KS& K) {
+  K.zero();
   double mb[6][6];
+#pragma unroll
   for (int i = 0; i < 6; ++i)
+#pragma unroll
     for (int j = 0; j < 6; ++j) mb[i][j] = 0.;
   mb[0][0] = mb[1][1] = mb[2][2] = p.r0;
   mb[0][4] = mb[4][0] = p.rz;
@@ -204,76 +228,148 @@ __device__ void beamlr_Me(const BeamP& p, double L, int mtype, bool truss, doubl
   mb[4][4] = p.rz2;
   mb[5][5] = p.ry2;
   mb[4][5] = mb[5][4] = -p.ryz;
-  if (truss)
+  if (truss) {
+#pragma unroll
     for (int i = 0; i < 6; ++i)
+#pragma unroll
       for (int j = 0; j < 6; ++j)
         if (i >= 4 || j >= 4) mb[i][j] = 0.;
+  }
   if (mtype == 0) {
+#pragma unroll
     for (int a = 0; a < 2; ++a)
+#pragma unroll
       for (int b = 0; b < 2; ++b)
+#pragma unroll
         for (int i = 0; i < 6; ++i)
-          for (int j = 0; j < 6; ++j) K[6 * a + i][6 * b + j] = ((a == b) ? L / 3 : L / 6) * mb[i][j];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) K.set(6 * a + i, 6 * b + j, ((a == b) ? L / 3 : L / 6) * mb[i][j]);
   } else {
+#pragma unroll
     for (int a = 0; a < 2; ++a)
-      for (int i = 0; i < 6; ++i) K[6 * a + i][6 * a + i] = L / 2 * mb[i][i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) K.set(6 * a + i, 6 * a + i, L / 2 * mb[i][i]);
   }
 }
 
-__device__ void truss_Ke(const BeamP& p, double L, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void truss_Ke(const BeamP& p, double L, KS& K) {
+  K.zero();
   const double EA = p.E * p.A / L, GJ = p.G * p.J / L;
   sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
   sym(K, 3, 3, GJ); sym(K, 9, 9, GJ); sym(K, 3, 9, -GJ);
 }
 
-__device__ void spring_Ke(const double* k, double (*K)[12]) {
-  zero12(K);
+template <class KS>
+__device__ __forceinline__ void spring_Ke(const double* k, KS& K) {
+  K.zero();
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
-    K[i][i] = k[i];
-    K[i + 6][i + 6] = k[i];
-    K[i][i + 6] = -k[i];
-    K[i + 6][i] = -k[i];
+    K.set(i, i, k[i]);
+    K.set(i + 6, i + 6, k[i]);
+    K.set(i, i + 6, -k[i]);
+    K.set(i + 6, i, -k[i]);
   }
 }
 
 // mask ids
 constexpr int MK_FULL = 0, MK_D18 = 1, MK_RR = 2;
-__device__ __forceinline__ bool in_mask(int mk, int i, int j) {
-  if (mk == MK_FULL) return true;
-  if (mk == MK_D18) return (i < 3) == (j < 3);
-  return i >= 3 && j >= 3;
+__host__ __device__ constexpr bool in_mask(int mk, int i, int j) {
+  return mk == MK_FULL ? true : (mk == MK_D18 ? ((i < 3) == (j < 3)) : (i >= 3 && j >= 3));
+}
+__host__ __device__ constexpr int mask_rowcnt(int mk, int i) {
+  int c = 0;
+  for (int j = 0; j < 6; ++j) c += in_mask(mk, i, j) ? 1 : 0;
+  return c;
+}
+__host__ __device__ constexpr int mask_colrank(int mk, int i, int j) {
+  int c = 0;
+  for (int q = 0; q < j; ++q) c += in_mask(mk, i, q) ? 1 : 0;
+  return c;
+}
+__host__ __device__ constexpr int mask_rowoff(int mk, int i, int nblocks) {
+  int c = 0;
+  for (int q = 0; q < i; ++q) c += mask_rowcnt(mk, q) * nblocks;
+  return c;
 }
 
-// Rotate the local 12x12 matrix block by block and emit one node-row slab per flush, in the
-// reference's (node_i, dof_i, node_j, dof_j) order restricted to the mask.
-template <int MK, bool DIAG, int SLAB>
-__device__ void emit_line_matrix(const Mat3& R, const double (*K)[12], double* stage, double* my, double* out,
-                                 int64_t e0, int nvalid, int esize, bool acc, int lane) {
-  for (int a = 0; a < 2; ++a) {
-    double Gb[2][6][6];
-    for (int b = 0; b < 2; ++b) {
-      if (DIAG && a != b) continue;
-      for (int s = 0; s < 2; ++s)
-        for (int t = 0; t < 2; ++t) {
-          if (MK == MK_D18 && s != t) continue;
-          if (MK == MK_RR && !(s == 1 && t == 1)) continue;
-          double l[3][3], o[3][3];
-          for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) l[i][j] = K[6 * a + 3 * s + i][6 * b + 3 * t + j];
-          rot_block_full(R, l, o);
-          for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) Gb[b][3 * s + i][3 * t + j] = o[i][j];
+// Which local matrix a block is filled with (one closed form per element kind and matrix)
+enum { FILL_KC0 = 0, FILL_KG = 1, FILL_M = 2 };
+template <int KIND, int WHICH>
+struct LineFill {
+  const BeamP& p;
+  double L;
+  const double* ue;
+  const double* kspr;
+  int mtype;
+  template <class KS>
+  __device__ __forceinline__ void operator()(KS& K) const {
+    if (WHICH == FILL_KC0) {
+      if (KIND == PF3_BEAMC) beamc_Ke(p, L, K);
+      if (KIND == PF3_BEAMLR) beamlr_Ke(p, L, K);
+      if (KIND == PF3_TRUSS) truss_Ke(p, L, K);
+      if (KIND == PF3_SPRING) spring_Ke(kspr, K);
+    } else if (WHICH == FILL_KG) {
+      if (KIND == PF3_BEAMC) beamc_KGe(p, L, ue, K);
+      if (KIND == PF3_BEAMLR) beamlr_KGe(p, L, ue, K);
+    } else {
+      if (KIND == PF3_BEAMC) beamc_Me(p, L, mtype, K);
+      if (KIND == PF3_BEAMLR || KIND == PF3_TRUSS) beamlr_Me(p, L, mtype, KIND == PF3_TRUSS, K);
+    }
+  }
+};
+
+// One 6x6 node-pair block: fill (registers only), rotate its masked 3x3 sub-blocks, drop the entries at their
+// positions of node a's row slab (reference order: dof_i, node_j, dof_j restricted to the mask).
+template <int MK, bool DIAG, int BA, int BB, class Fill>
+__device__ __forceinline__ void stage_line_block(const Mat3& R, const Fill& fill, double* my) {
+  if (DIAG && BA != BB) return;
+  KBlock<BA, BB> K;
+  fill(K);
+  constexpr int nblocks = DIAG ? 1 : 2, bpos = DIAG ? 0 : BB;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (MK == MK_D18 && s != t) continue;
+      if (MK == MK_RR && !(s == 1 && t == 1)) continue;
+      double l[3][3], o[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) l[i][j] = K.v[3 * s + i][3 * t + j];
+      rot_block_full(R, l, o);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int ri = 3 * s + i, cj = 3 * t + j;
+          my[mask_rowoff(MK, ri, nblocks) + bpos * mask_rowcnt(MK, ri) + mask_colrank(MK, ri, cj)] = o[i][j];
         }
     }
-    int cnt = 0;
-    for (int i = 0; i < 6; ++i)
-      for (int b = 0; b < 2; ++b) {
-        if (DIAG && a != b) continue;
-        for (int j = 0; j < 6; ++j)
-          if (in_mask(MK, i, j)) my[cnt++] = Gb[b][i][j];
-      }
-    flush_chunk<SLAB>(stage, out, e0, nvalid, esize, a * SLAB, acc, lane);
-  }
+}
+
+// Emit one node-row slab per flush.
+template <int MK, bool DIAG, int SLAB, class Fill>
+__device__ __forceinline__ void emit_line_matrix(const Mat3& R, const Fill& fill, double* stage, double* my, double* out,
+                                                 int64_t e0, int nvalid, int esize, bool acc, int lane) {
+  stage_line_block<MK, DIAG, 0, 0>(R, fill, my);
+  stage_line_block<MK, DIAG, 0, 1>(R, fill, my);
+  flush_chunk<SLAB>(stage, out, e0, nvalid, esize, 0, acc, lane);
+  stage_line_block<MK, DIAG, 1, 0>(R, fill, my);
+  stage_line_block<MK, DIAG, 1, 1>(R, fill, my);
+  flush_chunk<SLAB>(stage, out, e0, nvalid, esize, SLAB, acc, lane);
+}
+
+// f[6a + i] = sum_b K_ab[i][:] . ue[6b : 6b+6], block by block
+template <int BA, int BB, class Fill>
+__device__ __forceinline__ void line_block_matvec(const Fill& fill, const double* ue, double* f) {
+  KBlock<BA, BB> K;
+  fill(K);
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) f[6 * BA + i] += K.v[i][j] * ue[6 * BB + j];
 }
 
 template <int KIND>
@@ -389,32 +485,32 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
     p.Az = q[8]; p.r0 = q[9]; p.ry = q[10]; p.rz = q[11]; p.ry2 = q[12]; p.rz2 = q[13]; p.ryz = q[14];
   }
 
-  double K[12][12];
   if (A.what & (PF3_KC0 | PF3_FINT)) {
-    if (KIND == PF3_BEAMC) beamc_Ke(p, L, K);
-    if (KIND == PF3_BEAMLR) beamlr_Ke(p, L, K);
-    if (KIND == PF3_TRUSS) truss_Ke(p, L, K);
-    if (KIND == PF3_SPRING) spring_Ke(kspr, K);
+    const LineFill<KIND, FILL_KC0> fill{p, L, ue, kspr, A.mtype};
     if (A.what & PF3_KC0) {
       double* out = A.kc0v + A.kc0_k0;
       if (KIND == PF3_BEAMC || KIND == PF3_BEAMLR)
-        emit_line_matrix<MK_FULL, false, 72>(R, K, stage, my, out, e0, nvalid, 144, A.acc_kc0 != 0, lane);
+        emit_line_matrix<MK_FULL, false, 72>(R, fill, stage, my, out, e0, nvalid, 144, A.acc_kc0 != 0, lane);
       else
-        emit_line_matrix<MK_D18, false, 36>(R, K, stage, my, out, e0, nvalid, 72, A.acc_kc0 != 0, lane);
+        emit_line_matrix<MK_D18, false, 36>(R, fill, stage, my, out, e0, nvalid, 72, A.acc_kc0 != 0, lane);
     }
     if (A.what & PF3_FINT) {
       double f[12];
-      for (int i = 0; i < 12; ++i) {
-        double s = 0.;
-        for (int j = 0; j < 12; ++j) s += K[i][j] * ue[j];
-        f[i] = s;
-      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) f[i] = 0.;
+      line_block_matvec<0, 0>(fill, ue, f);
+      line_block_matvec<0, 1>(fill, ue, f);
+      line_block_matvec<1, 0>(fill, ue, f);
+      line_block_matvec<1, 1>(fill, ue, f);
       if (A.finte != nullptr) {
+#pragma unroll
         for (int i = 0; i < 12; ++i) my[i] = f[i];
         flush_chunk<12>(stage, A.finte, e0, nvalid, 12, 0, false, lane);
       }
       if (A.fe != nullptr) {
+#pragma unroll
         for (int t = 0; t < 4; ++t)
+#pragma unroll
           for (int i = 0; i < 3; ++i)
             my[3 * t + i] = R.a[i][0] * f[3 * t] + R.a[i][1] * f[3 * t + 1] + R.a[i][2] * f[3 * t + 2];
         flush_chunk<12>(stage, A.fe, e0, nvalid, 12, 0, false, lane);
@@ -423,24 +519,19 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
   }
   if ((A.what & PF3_KG) && (KIND == PF3_BEAMC || KIND == PF3_BEAMLR)) {
     double* out = A.kgv + A.kg_k0;
-    if (KIND == PF3_BEAMC) {
-      beamc_KGe(p, L, ue, K);
-      emit_line_matrix<MK_FULL, false, 72>(R, K, stage, my, out, e0, nvalid, 144, A.acc_kg != 0, lane);
-    } else {
-      beamlr_KGe(p, L, ue, K);
-      emit_line_matrix<MK_RR, false, 18>(R, K, stage, my, out, e0, nvalid, 36, A.acc_kg != 0, lane);
-    }
+    const LineFill<KIND, FILL_KG> fill{p, L, ue, kspr, A.mtype};
+    if (KIND == PF3_BEAMC)
+      emit_line_matrix<MK_FULL, false, 72>(R, fill, stage, my, out, e0, nvalid, 144, A.acc_kg != 0, lane);
+    else
+      emit_line_matrix<MK_RR, false, 18>(R, fill, stage, my, out, e0, nvalid, 36, A.acc_kg != 0, lane);
   }
   if ((A.what & PF3_M) && KIND != PF3_SPRING) {
     double* out = A.mv + A.m_k0;
-    if (KIND == PF3_BEAMC)
-      beamc_Me(p, L, A.mtype, K);
-    else
-      beamlr_Me(p, L, A.mtype, KIND == PF3_TRUSS, K);
+    const LineFill<KIND, FILL_M> fill{p, L, ue, kspr, A.mtype};
     if (A.mtype == 0)
-      emit_line_matrix<MK_FULL, false, 72>(R, K, stage, my, out, e0, nvalid, 144, A.acc_m != 0, lane);
+      emit_line_matrix<MK_FULL, false, 72>(R, fill, stage, my, out, e0, nvalid, 144, A.acc_m != 0, lane);
     else  // lumped: two diagonal node blocks only, 36 of 144 entries written (beamc.pyx:2970)
-      emit_line_matrix<MK_D18, true, 18>(R, K, stage, my, out, e0, nvalid, 144, A.acc_m != 0, lane);
+      emit_line_matrix<MK_D18, true, 18>(R, fill, stage, my, out, e0, nvalid, 144, A.acc_m != 0, lane);
   }
 }
 

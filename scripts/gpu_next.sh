@@ -1,12 +1,6 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 python scripts/bench_configs.py --kinds 2>&1 | tee gpurun_out/kinds.jsonl | python -c "
 import sys, json
 for ln in sys.stdin:
     d = json.loads(ln); print(d['config'][:40], 'ms %.3f frac %.3f fint %.3f' % (d['ms'], d['frac_of_6538.9'], d['update_fint_ms']))"
-python scripts/bench_configs.py 2>&1 | grep -v kernel_ms | python -c "
-import sys, json
-for ln in sys.stdin:
-    try: d = json.loads(ln)
-    except Exception: continue
-    print(d['config'][:50], d['path'], 'ms %.3f frac %.3f' % (d['ms_per_step'], d['frac_of_6538.9']))"
