@@ -385,6 +385,21 @@ int pf3_eval(pf3_context* ctx, const pf3_batch* b, int what, const pf3_coo* kc0,
     cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
     return int(e);
   }
+  // Tria3R the same way through the triangle record + node-lane kernels (KG slabs are not 16-byte multiples and go
+  // out as plain stores, so only KC0 and M need the alignment)
+  const bool taligned = (((uintptr_t)A.kc0v | (uintptr_t)A.mv) & 15) == 0 && ((A.kc0_k0 | A.m_k0) & 1) == 0;
+  if (b->kind == PF3_TRIA3R && !(kwhat & PF3_FINT) && !b->state && !A.acc_kc0 && !A.acc_kg && !A.acc_m && taligned &&
+      b->ne * 9 < (int64_t(1) << 31)) {
+    pf3::FusedArgs F;
+    std::memset(&F, 0, sizeof(F));
+    F.A = A;
+    F.nown = (b->ne + 2) / 3;
+    F.rmax = 1;
+    rc = ensure_scratch(ctx, size_t(b->ne) * pf3::tria_fused_record_stride(F.A) * sizeof(double));
+    if (rc) return rc;
+    cudaError_t e = pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches);
+    return int(e);
+  }
   rc = launch_eval(ctx, A, b->kind);
   if (rc) return rc;
   if (kwhat & PF3_FINT) {

@@ -302,17 +302,12 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
   __syncwarp();
 }
 
-// The staging area is reused by the next matrix: before writing it again, wait until the bulk copies issued
-// from it have READ shared memory.  Called as late as possible so the copies drain behind arithmetic.
-// `pending` = number of most recent bulk groups that may still be reading (they use another staging area).
-__device__ __forceinline__ void stage_reuse_wait(int pending = 0) {
+// The staging area is reused by the next matrix: before writing it again, wait until the bulk copies issued from it
+// have READ shared memory.  (A private staging area for KG, so that KG never waits for the previous KC0 copies, was
+// measured slower: the wait is back-pressure from the store path, not a latency to hide.)
+__device__ __forceinline__ void stage_reuse_wait() {
 #if PF3_COO_TMA
-  if (pending == 0)
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  else if (pending == 1)
-    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-  else
-    asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
 #endif
 }
@@ -390,9 +385,6 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   double* st = smem + warp * warp_smem_doubles(rstride, CHUNK);
   NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
   double* erec = st + kStageV4 + kFRing * 2 * 8;
-  double* stkg = st;
-  // staging areas are reused matrix after matrix: every staging waits for all earlier bulk reads
-  const int pendKG = 0, pendM = 0, pendKC0 = 0;
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
   const UnionMap* umK = F.um[0].active ? &F.um[0] : nullptr;
   const UnionMap* umKG = F.um[1].active ? &F.um[1] : nullptr;
@@ -432,7 +424,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       __syncwarp();
       erec_prefetch(j + 1);
     } else {
-      if (j > 0) stage_reuse_wait(0);
+      if (j > 0) stage_reuse_wait();
       rec_fetch(j);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
@@ -536,13 +528,13 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
 
     // ---------------- KG : Ge_ab * z z^T on the translations
     if (A.what & (PF3_KG | PF3_KG_STRESS)) {
-      double* sl = stkg + (lane >> 2) * SlabShape<3, 3>::kLd + b * 3;
-      stage_reuse_wait(pendKG);
+      double* sl = st + (lane >> 2) * SlabShape<3, 3>::kLd + b * 3;
+      stage_reuse_wait();
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) sl[i * 12 + jj] = (R.a[i][2] * R.a[jj][2]) * ge;
-      emit_slabs<3, 3>(stkg, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg,
+      emit_slabs<3, 3>(st, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg,
                        umKG ? b0 * umKG->mc : b0 * 9, nb, first, lane, umKG);
     }
 
@@ -563,7 +555,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       double* coo = A.mv ? A.mv + A.m_k0 : nullptr;
       if (A.mtype != 2) {
         double* sl = st + (lane >> 2) * SlabShape<6, 5>::kLd + b * 5;
-        stage_reuse_wait(pendM);
+        stage_reuse_wait();
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           double tt[3], tr[3], rq[3];
@@ -588,7 +580,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
         emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, umM ? b0 * umM->mc : b0 * 30, nb, first, lane, umM);
       } else {
         double* sl = st + (lane >> 2) * SlabShape<6, 3>::kLd + b * 3;
-        stage_reuse_wait(pendM);
+        stage_reuse_wait();
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -671,7 +663,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       rot_block_8(R, -f_pq(cB, cxx, cxy, cyx, cyy), f_pp(cB, cxx, cxy, cyx, cyy), 0.5 * kd * pyab,
                   -f_qq(cB, cxx, cxy, cyx, cyy), f_qp(cB, cxx, cxy, cyx, cyy), -0.5 * kd * pxab, -0.25 * tSa,
                   0.25 * sSa, o2);
-      stage_reuse_wait(pendKC0);
+      stage_reuse_wait();
 #pragma unroll
       for (int i = 0; i < 3; ++i) {   // rows u v w of node a: 6 columns of node b, 24 doubles per COO row
         sl2[i * 12 + 0] = make_double2(o1[i][0], o1[i][1]);
@@ -700,7 +692,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     }
   }
   // the bulk copies read this CTA's shared memory: they must have done so before the CTA retires
-  stage_reuse_wait(0);
+  stage_reuse_wait();
 }
 
 }  // namespace

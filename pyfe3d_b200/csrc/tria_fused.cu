@@ -253,11 +253,27 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
   const int nitems = int(min(int64_t(kTChunk), F.nown - n0)) * rmax;   // items j = (node n0 + j / rmax, round j % rmax)
 
   auto rec_fetch = [&](int j) {
-    if (j < nitems && lane < 8) {
-      const char* src = reinterpret_cast<const char*>(F.triarec + (n0 + j / rmax) * rmax + j % rmax) + 16 * lane;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32t(reinterpret_cast<char*>(ring + j % kTRing) + 16 * lane)),
-                   "l"(src)
-                   : "memory");
+    if (j < nitems && F.triarec != nullptr) {
+      if (lane < 8) {
+        const char* src = reinterpret_cast<const char*>(F.triarec + (n0 + j / rmax) * rmax + j % rmax) + 16 * lane;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32t(reinterpret_cast<char*>(ring + j % kTRing) + 16 * lane)),
+                     "l"(src)
+                     : "memory");
+      }
+    } else if (j < nitems) {
+      // element mode (COO only, no plan): "node" n stands for elements 3n, 3n+1, 3n+2, its 9 incidences are their
+      // own row slabs; nothing is assembled (nb = 0)
+      TriaRec* t = ring + j % kTRing;
+      const int64_t n = n0 + j;
+      if (lane < kTInc) {
+        const int64_t el = 3 * n + lane / 3;
+        t->inc[lane] = (lane < 9 && el < A.ne) ? int32_t(el * 9 + (lane % 3) * 3) : -1;
+      }
+      if (lane == 10) {
+        t->b0 = 0;
+        t->v = 9;
+        t->nb = 0;
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };

@@ -182,6 +182,19 @@ def run_kinds(n):
         del b, coo, plan
 
 
+def run_indices(side):
+    """First-call cost: the int64 row/col index arrays (the unrolled KC0r[k] = ...; KC0c[k] = ... blocks)."""
+    case = meshes.plate_quad4(side, side)
+    b = util.batch_from_case(case)
+    for m in ("KC0", "KG", "M"):
+        coo = b.fill_indices(m)
+        ms = timeit(lambda m=m, coo=coo: b.fill_indices(m, coo=coo), steps=3, warm=1)
+        n = b.ne * b.sizes[m]
+        print(json.dumps({"config": "fill_indices %s %dx%d Quad4" % (m, side, side), "entries": n, "ms": ms,
+                          "GBps": n * 16 / ms / 1e6, "frac_of_6538.9": n * 16 / ms / 1e6 / 6538.9}))
+        del coo
+
+
 def run_fint(side):
     """update_fint of every element of the north-star mesh, element kernel + plan gather."""
     case = meshes.plate_quad4(side, side)
@@ -220,6 +233,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--kinds" in sys.argv:
         run_kinds(20000 if "--small" in sys.argv else 1000000)
+        sys.exit(0)
+    if "--indices" in sys.argv:
+        run_indices(200 if "--small" in sys.argv else 2000)
         sys.exit(0)
     if "--fint" in sys.argv:
         run_fint(200 if "--small" in sys.argv else 2000)
