@@ -63,9 +63,13 @@ def cg_solve(indptr, indices, vals, b, free=None, rtol=1e-12, maxiter=None, x0=N
     return x, -maxiter
 
 
-def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, group=None):
+def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, group=None, extra=()):
     """Jacobi-preconditioned CG on the CSR values of a structured ``AssemblyPlan`` through its block SpMV
     (``pf3_plan_spmv``: no per-entry indices, 8.2 B per nonzero).
+
+    The operator is ``A = vals + sum(c * v for plan_i, v, c in extra)`` applied as a sum of block SpMVs -- e.g.
+    ``K - sigma M`` with the two matrices kept in their own layouts (``extra=[(plan_M, M, -sigma)]``); every plan
+    must own the same rows.
 
     Single GPU: the plan owns every row.  Multi GPU (``group`` = a torch.distributed process group, one rank per
     GPU): every rank owns the row block of its plan (``node_range``) and holds vectors of its own rows; the search
@@ -85,7 +89,17 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
     fl = free[lo:hi].to(torch.float64)
     bl = _dev(b, torch.float64, dev)[lo:hi] * fl
     d = plan.diagonal(vals)
+    for pe, ve, ce in extra:
+        d = d + ce * pe.diagonal(ve)
     minv = torch.where((fl > 0) & (d != 0), 1.0 / d, torch.zeros_like(d))
+    tmp = torch.empty(hi - lo, dtype=torch.float64, device=dev) if extra else None
+
+    def matvec(xg, out):
+        plan.spmv(vals, xg, free=free, out=out)
+        for pe, ve, ce in extra:
+            pe.spmv(ve, xg, free=free, out=tmp)
+            out.add_(tmp, alpha=ce)
+        return out
 
     def allsum(t):
         if multi:
@@ -114,7 +128,8 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
     x = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
     if x0 is not None:
         x = _dev(x0, torch.float64, dev)[lo:hi] * fl
-    r = bl - plan.spmv(vals, gather(x), free=free)
+    ap = torch.empty_like(x)
+    r = bl - matvec(gather(x), ap)
     z = minv * r
     p = z.clone()
     rz = allsum(torch.dot(r, z))
@@ -122,10 +137,9 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
     if bnorm == 0.0:
         return gather(x).clone(), 0
     maxiter = maxiter or 10 * n
-    ap = torch.empty_like(x)
     info = -maxiter
     for it in range(1, maxiter + 1):
-        plan.spmv(vals, gather(p), free=free, out=ap)
+        matvec(gather(p), ap)
         alpha = rz / allsum(torch.dot(p, ap))
         x += alpha * p
         r -= alpha * ap
@@ -137,3 +151,35 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
         p = z + (rz_new / rz) * p
         rz = rz_new
     return gather(x).clone(), info
+
+
+def shift_invert_operator(plan_a, a_vals, plan_m, m_vals, sigma, free, rtol=1e-13, maxiter=None):
+    """``OPinv`` for ``scipy.sparse.linalg.eigsh(A=Kuu, M=Muu, sigma=sigma, OPinv=...)``: x -> (A - sigma M)^-1 x on
+    the free DOFs, each application one Jacobi-CG on the device with the operator applied as two block SpMVs
+    (the natural-frequency scripts call ``eigsh(A=Kuu, M=Muu, sigma=-1.)``,
+    tests/test_beamc_natural_freq_curved.py:107, tests/test_tria3r_natural_freq_distorted.py:150).
+    ``A - sigma M`` must be positive definite (sigma below the spectrum, e.g. the scripts' -1).  Vectors are indexed
+    like ``K[bu, :][:, bu]``: by the free DOFs in order."""
+    import numpy as np
+    from scipy.sparse.linalg import LinearOperator
+    dev = a_vals.device
+    free_t = _dev(free, torch.uint8, dev)
+    idx = torch.nonzero(free_t).ravel()
+    nfree = int(idx.numel())
+    full = torch.zeros(free_t.numel(), dtype=torch.float64, device=dev)
+    stats = {"solves": 0, "iterations": 0}
+
+    def matvec(v):
+        full.zero_()
+        full[idx] = torch.as_tensor(np.asarray(v, float).ravel()).to(dev)
+        x, info = plan_cg_solve(plan_a, a_vals, full, free=free_t, rtol=rtol, maxiter=maxiter,
+                                extra=[(plan_m, m_vals, -float(sigma))])
+        if info < 0:
+            raise RuntimeError("shift-invert CG did not converge")
+        stats["solves"] += 1
+        stats["iterations"] += info
+        return x[idx].cpu().numpy()
+
+    op = LinearOperator((nfree, nfree), matvec=matvec, dtype=np.float64)
+    op.stats = stats
+    return op
