@@ -288,6 +288,28 @@ int pf3_laminate_props(pf3_context* ctx, int64_t nrows, int nplies, const double
                        const double* plyt, int64_t plyt_stride, const double* lamina, int64_t lamina_stride,
                        const double* offset, int64_t offset_stride, int calc_scf, double* props_out);
 
+/* Lamination-parameter form of the same table and its gradient rows.
+ * props_out[nrows * PF3_SHELLPROP_STRIDE] (may be NULL): what
+ *   shellprop_from_LaminationParameters(thickness, mat, lp)                         (pyfe3d/shellprop.pyx:767-815)
+ * stores in A11..D66, E44..E55 and h; scf_k13 = scf_k23 = 5/6 as that function leaves them.  Row r reads
+ * thickness[r*thickness_stride], the material invariants u1..u7 (MatLamina.rebuild, shellprop.pyx:189-195) at
+ * invariants[r*invariants_stride + 0..6] and xiA1..4, xiB1..4, xiD1..4, xiE1..2 at lp[r*lp_stride + 0..13]; a stride
+ * of 0 shares the value between all rows.  rho (may be NULL) is an extension for homogeneous density: intrho = rho h,
+ * intrhoz = 0, intrhoz2 = rho h^3/12; with NULL the three stay 0 like the reference.
+ * grad_out[nrows * popcount(var_mask) * PF3_SHELLPROP_STRIDE] (may be NULL): for every laminate, one PROPERTY row
+ * per selected variable v (bit v of var_mask; 0 = h, 1..4 = xiA1..4, 5..8 = xiB1..4, 9..12 = xiD1..4, 13..14 =
+ * xiE1..2, in that order) holding d(A, B, D, E, mass integrals)/dv -- the numbers GradABDE.calc_LP_grad
+ * (shellprop.pyx:933-1014) puts in gradAij/gradBij/gradDij/gradEij -- with scf and h repeated, so that update_KC0 /
+ * update_M evaluated with that row are dKC0/dv and dM/dv (the element matrices are linear in these scalars; not
+ * valid for Quad4R's hourglass control, which divides by the inverse of ABD, quad4r.pyx:713-746).
+ * grad_complete == 0 keeps the reference's range(5) loops (shellprop.pyx:968,981,994): d(A66,B66,D66)/d(xi) = 0;
+ * grad_complete != 0 stores the mathematically complete -fac*u3 for xi3. */
+#define PF3_LP_NVARS 15
+int pf3_lamination_parameter_props(pf3_context* ctx, int64_t nrows, const double* thickness, int64_t thickness_stride,
+                                   const double* invariants, int64_t invariants_stride, const double* lp,
+                                   int64_t lp_stride, const double* rho, int64_t rho_stride, int var_mask,
+                                   int grad_complete, double* props_out, double* grad_out);
+
 /* ---- host-pointer convenience (numpy callers): copies in, runs, copies out -- */
 int pf3_eval_host(pf3_context* ctx, const pf3_batch* host_batch, int what,
                   const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);

@@ -67,6 +67,10 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_laminate_props(pf3_context*, int64_t nrows, int nplies, const double* thetadeg, int64_t theta_stride,
                            const double* plyt, int64_t plyt_stride, const double* lamina, int64_t lamina_stride,
                            const double* offset, int64_t offset_stride, int calc_scf, double* props_out) nogil
+    int pf3_lamination_parameter_props(pf3_context*, int64_t nrows, const double* thickness, int64_t thickness_stride,
+                                       const double* invariants, int64_t invariants_stride, const double* lp,
+                                       int64_t lp_stride, const double* rho, int64_t rho_stride, int var_mask,
+                                       int grad_complete, double* props_out, double* grad_out) nogil
     int pf3_plan_spmv(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
                       const double* x, double* y) nogil
     int pf3_plan_diagonal(pf3_context*, const pf3_plan*, const double* vals, double* diag) nogil
@@ -217,6 +221,18 @@ cdef class Context:
             rc = pf3_laminate_props(self.ctx, nrows, nplies, <const double*>theta, theta_stride, <const double*>plyt,
                                     plyt_stride, <const double*>lamina, lamina_stride, <const double*>offset,
                                     offset_stride, calc_scf, <double*>out)
+        _check(rc)
+
+    def lamination_parameter_props(self, int64_t nrows, uintptr_t thickness, int64_t thickness_stride,
+                                   uintptr_t invariants, int64_t invariants_stride, uintptr_t lp, int64_t lp_stride,
+                                   uintptr_t rho, int64_t rho_stride, int var_mask, int grad_complete, uintptr_t out,
+                                   uintptr_t grad):
+        cdef int rc
+        with nogil:
+            rc = pf3_lamination_parameter_props(self.ctx, nrows, <const double*>thickness, thickness_stride,
+                                                <const double*>invariants, invariants_stride, <const double*>lp,
+                                                lp_stride, <const double*>rho, rho_stride, var_mask, grad_complete,
+                                                <double*>out, <double*>grad)
         _check(rc)
 
     def eval_aero(self, Batch b, int what, Coo ka_beta=None, Coo ka_gamma=None, Coo ca=None):

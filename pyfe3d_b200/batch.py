@@ -639,3 +639,49 @@ def laminate_table(stack, plyts, laminaprops, rhos=0., offset=0., calc_scf=True,
                        _ptr(lam), 8 * nplies if lam.ndim == 3 else 0, _ptr(off), 1 if off.ndim == 1 else 0,
                        1 if calc_scf else 0, _ptr(out))
     return out
+
+
+LP_VARIABLES = ("h", "xiA1", "xiA2", "xiA3", "xiA4", "xiB1", "xiB2", "xiB3", "xiB4",
+                "xiD1", "xiD2", "xiD3", "xiD4", "xiE1", "xiE2")
+
+
+def lamination_parameter_table(thickness, invariants, lp, rho=None, grad=(), grad_complete=False, device=None):
+    """Device property table ``[nrows, 32]`` from total thickness, material invariants and lamination parameters
+    (``pf3_lamination_parameter_props``): row r is what the reference's
+    ``shellprop_from_LaminationParameters(thickness[r], mat, lp[r])`` (pyfe3d/shellprop.pyx:767) stores.
+
+    ``thickness``: scalar or ``[nrows]``; ``invariants``: ``(u1..u7)`` (``MatLamina.invariants()``) or ``[nrows, 7]``;
+    ``lp``: the 14 parameters (``LaminationParameters.as_array()``) or ``[nrows, 14]``; ``rho``: optional homogeneous
+    density (scalar or ``[nrows]``) filling the mass integrals, which the reference leaves 0.
+
+    ``grad``: names from ``LP_VARIABLES``; when given, returns ``(table, grad_table)`` with ``grad_table`` of shape
+    ``[nrows, len(grad), 32]`` (rows in ``LP_VARIABLES`` order): property rows holding d(A, B, D, E, mass integrals)/dv
+    -- ``GradABDE.calc_LP_grad`` (shellprop.pyx:933) -- so that an ``ElementBatch`` evaluated with
+    ``props=grad_table[:, j]`` returns dKC0/dv_j and dM/dv_j.  ``grad_complete=False`` keeps the reference's zero
+    d(X66)/d(xi) entries."""
+    ctx = context(device)
+    dev = torch.device("cuda", ctx.device)
+
+    def t(a):
+        return a.to(dev, torch.float64) if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, float)).to(dev)
+
+    hh, uu, xx = t(thickness).contiguous(), t(invariants).contiguous(), t(lp).contiguous()
+    rr = None if rho is None else t(rho).contiguous()
+    if uu.shape[-1] != 7 or xx.shape[-1] != 14:
+        raise ValueError("invariants must have 7 columns (u1..u7) and lp 14 (xiA1..4, xiB1..4, xiD1..4, xiE1..2)")
+    lead = [a.shape[0] for a, nd in ((hh, 1), (uu, 2), (xx, 2)) if a.ndim == nd]
+    if rr is not None and rr.ndim == 1:
+        lead.append(rr.shape[0])
+    nrows = max(lead + [1])
+    if any(n != nrows for n in lead):
+        raise ValueError("thickness, invariants, lp and rho disagree on the number of rows: %s" % lead)
+    mask = 0
+    for name in grad:
+        mask |= 1 << LP_VARIABLES.index(name)
+    out = torch.empty((nrows, _cabi.SHELLPROP_STRIDE), dtype=torch.float64, device=dev)
+    g = torch.empty((nrows, bin(mask).count("1"), _cabi.SHELLPROP_STRIDE), dtype=torch.float64, device=dev) if mask else None
+    ctx.lamination_parameter_props(nrows, _ptr(hh), 1 if hh.ndim == 1 else 0, _ptr(uu), 7 if uu.ndim == 2 else 0,
+                                   _ptr(xx), 14 if xx.ndim == 2 else 0, 0 if rr is None else _ptr(rr),
+                                   1 if rr is not None and rr.ndim == 1 else 0, mask, 1 if grad_complete else 0,
+                                   _ptr(out), 0 if g is None else _ptr(g))
+    return (out, g) if mask else out

@@ -16,6 +16,10 @@ cudaError_t launch_quad_aero(const EvalArgs& A, const AeroOut& O, cudaStream_t s
 cudaError_t launch_laminate_props(int64_t nrows, int nplies, const double* theta, int64_t theta_stride,
                                   const double* plyt, int64_t plyt_stride, const double* lamina, int64_t lamina_stride,
                                   const double* offset, int64_t offset_stride, int calc_scf, double* out, cudaStream_t st);
+cudaError_t launch_lp_props(int64_t nrows, const double* thick, int64_t thick_stride, const double* inv,
+                            int64_t inv_stride, const double* lp, int64_t lp_stride, const double* rho,
+                            int64_t rho_stride, int var_mask, int grad_complete, double* out, double* grad,
+                            cudaStream_t st);
 cudaError_t launch_quad4_BL(int64_t n, const double* xe, double xi, double eta, double* out, cudaStream_t st);
 cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st);
 int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnodes, int ngroups,
@@ -735,6 +739,21 @@ int pf3_laminate_props(pf3_context* ctx, int64_t nrows, int nplies, const double
   if (theta_stride < 0 || plyt_stride < 0 || lamina_stride < 0 || offset_stride < 0) return PF3_E_BAD_ARG;
   cudaError_t e = pf3::launch_laminate_props(nrows, nplies, thetadeg, theta_stride, plyt, plyt_stride, lamina,
                                              lamina_stride, offset, offset_stride, calc_scf, props_out, ctx->stream);
+  ++ctx->launches;
+  return int(e);
+}
+
+int pf3_lamination_parameter_props(pf3_context* ctx, int64_t nrows, const double* thickness, int64_t thickness_stride,
+                                   const double* invariants, int64_t invariants_stride, const double* lp,
+                                   int64_t lp_stride, const double* rho, int64_t rho_stride, int var_mask,
+                                   int grad_complete, double* props_out, double* grad_out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (nrows < 0 || !thickness || !invariants || !lp || (!props_out && !grad_out)) return PF3_E_BAD_ARG;
+  if (thickness_stride < 0 || invariants_stride < 0 || lp_stride < 0 || rho_stride < 0) return PF3_E_BAD_ARG;
+  if (var_mask < 0 || var_mask >= (1 << PF3_LP_NVARS) || (grad_out && !var_mask)) return PF3_E_BAD_ARG;
+  cudaError_t e = pf3::launch_lp_props(nrows, thickness, thickness_stride, invariants, invariants_stride, lp, lp_stride,
+                                       rho, rho_stride, var_mask, grad_complete, props_out, grad_out, ctx->stream);
   ++ctx->launches;
   return int(e);
 }

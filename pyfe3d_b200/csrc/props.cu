@@ -101,6 +101,95 @@ __global__ void __launch_bounds__(128) k_laminate_props(int64_t nrows, int nplie
   for (int i = 27; i < PF3_SHELLPROP_STRIDE; ++i) w[i] = 0.;
 }
 
+
+// Lamination-parameter form (second step): total thickness + the seven material invariants +
+// the 14 lamination parameters -> the same property row, following shellprop_from_LaminationParameters
+// (pyfe3d/shellprop.pyx:767-815), and the rows of GradABDE.calc_LP_grad (:933-1014) laid out as PROPERTY rows, so
+// that -- the element matrices being linear in A, B, D, E and in the mass integrals -- update_KC0 / update_M fed
+// with gradient row v ARE dKC0/dv and dM/dv of the element.  One warp per laminate, one lane per slot of the row:
+// every row leaves as one coalesced 256-byte store.
+//   slot  0..17 : A11 A12 A16 A22 A26 A66, B.., D..  = fac_f * (c_f * K_i + sum_k G_ik xi_f,k)
+//                 fac = h, h^2/4, h^3/12; c = 1, 0, 1; K = (u1, u4, 0, u1, 0, u5); G = "gradinv" of shellprop.pyx:956
+//   slot 18..20 : E44 E45 E55 = h (u6 + u7 xiE1), -h u7 xiE2, h (u6 - u7 xiE1)
+//   slot 21..26 : scf_k13 = scf_k23 = 5/6 (the reference never calls calc_scf on this path), h, and -- only when a
+//                 density is given, an extension: the reference leaves them 0 -- rho h, 0, rho h^3 / 12
+// Variables of the gradient rows: 0 = h, 1..4 = xiA1..4, 5..8 = xiB1..4, 9..12 = xiD1..4, 13..14 = xiE1..2; the rows
+// selected by var_mask are stored consecutively per laminate.  Gradient rows repeat scf and h (the element's
+// thin/thick switch, quad4.pyx:1032, must take the same branch) and carry d(mass integrals)/dh in row 0.
+// grad_complete == 0 reproduces the reference's range(5) loops (:968, :981, :994): d(X66)/d(xi) stays 0.
+__global__ void __launch_bounds__(128) k_lp_props(int64_t nrows, const double* __restrict__ thick, int64_t thick_stride,
+                                                  const double* __restrict__ inv, int64_t inv_stride,
+                                                  const double* __restrict__ lp, int64_t lp_stride,
+                                                  const double* __restrict__ rho, int64_t rho_stride, int var_mask,
+                                                  int grad_complete, double* __restrict__ out,
+                                                  double* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= nrows) return;
+  const double h = thick[row * thick_stride];
+  const double* u = inv + row * inv_stride;
+  const double* xi = lp + row * lp_stride;
+  const double u1 = u[0], u2 = u[1], u3 = u[2], u4 = u[3], u5 = u[4], u6 = u[5], u7 = u[6];
+  const double r = rho ? rho[row * rho_stride] : 0.;
+  const int fam = lane < 18 ? lane / 6 : 3;   // 0 A, 1 B, 2 D, 3 E / tail
+  const int i = lane < 18 ? lane % 6 : lane - 18;
+  double fac = 0., dfac = 0., cst = 0., g[4] = {0., 0., 0., 0.}, x[4] = {0., 0., 0., 0.};
+  if (fam < 3) {
+    fac = fam == 0 ? h : fam == 1 ? h * h / 4. : h * h * h / 12.;
+    dfac = fam == 0 ? 1. : fam == 1 ? h / 2. : h * h / 4.;
+    const double c = fam == 1 ? 0. : 1.;
+    cst = c * (i == 0 || i == 3 ? u1 : i == 1 ? u4 : i == 5 ? u5 : 0.);
+    g[0] = i == 0 ? u2 : i == 3 ? -u2 : 0.;
+    g[1] = (i == 2 || i == 4) ? u2 / 2. : 0.;
+    g[2] = (i == 0 || i == 3) ? u3 : (i == 1 || i == 5) ? -u3 : 0.;
+    g[3] = i == 2 ? u3 : i == 4 ? -u3 : 0.;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = xi[4 * fam + k];
+  } else if (i < 3) {
+    fac = h;
+    dfac = 1.;
+    cst = i == 1 ? 0. : u6;
+    g[0] = i == 0 ? u7 : i == 2 ? -u7 : 0.;
+    g[1] = i == 1 ? -u7 : 0.;
+    x[0] = xi[12];
+    x[1] = xi[13];
+  }
+  const double bracket = cst + g[0] * x[0] + g[1] * x[1] + g[2] * x[2] + g[3] * x[3];
+  const bool stiff = lane < 21;
+  // slots shared by every row: shear correction factors and thickness
+  const double common = (lane == 21 || lane == 22) ? 5. / 6. : lane == 23 ? h : 0.;
+  if (out) {
+    double v = stiff ? fac * bracket : common;
+    if (lane == 24) v = r * h;
+    if (lane == 26) v = r * h * h * h / 12.;
+    out[row * PF3_SHELLPROP_STRIDE + lane] = v;
+  }
+  if (!grad || !var_mask) return;
+  double* w = grad + row * int64_t(__popc(var_mask)) * PF3_SHELLPROP_STRIDE + lane;
+  if (var_mask & 1) {
+    double v = stiff ? dfac * bracket : common;
+    if (lane == 24) v = r;
+    if (lane == 26) v = r * h * h / 4.;
+    *w = v;
+    w += PF3_SHELLPROP_STRIDE;
+  }
+  const bool keep = grad_complete || fam == 3 || i < 5;
+#pragma unroll
+  for (int f = 0; f < 3; ++f)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (var_mask >> (1 + 4 * f + k) & 1) {
+        *w = (fam == f && keep) ? fac * g[k] : common;
+        w += PF3_SHELLPROP_STRIDE;
+      }
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (var_mask >> (13 + k) & 1) {
+      *w = (fam == 3 && i < 3) ? fac * g[k] : common;
+      w += PF3_SHELLPROP_STRIDE;
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_laminate_props(int64_t nrows, int nplies, const double* theta, int64_t theta_stride,
@@ -110,6 +199,16 @@ cudaError_t launch_laminate_props(int64_t nrows, int nplies, const double* theta
   k_laminate_props<<<unsigned((nrows + 127) / 128), 128, 0, st>>>(nrows, nplies, theta, theta_stride, plyt, plyt_stride,
                                                                 lamina, lamina_stride, offset, offset_stride, calc_scf,
                                                                 out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lp_props(int64_t nrows, const double* thick, int64_t thick_stride, const double* inv,
+                            int64_t inv_stride, const double* lp, int64_t lp_stride, const double* rho,
+                            int64_t rho_stride, int var_mask, int grad_complete, double* out, double* grad,
+                            cudaStream_t st) {
+  if (nrows <= 0) return cudaSuccess;
+  k_lp_props<<<unsigned((nrows + 3) / 4), 128, 0, st>>>(nrows, thick, thick_stride, inv, inv_stride, lp, lp_stride, rho,
+                                                        rho_stride, var_mask, grad_complete, out, grad);
   return cudaGetLastError();
 }
 

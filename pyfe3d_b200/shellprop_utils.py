@@ -1,37 +1,55 @@
 """Host-side ShellProp constructors with the reference's names and arguments
-(pyfe3d/shellprop_utils.py:96-206): ``laminated_plate`` and ``isotropic_plate``."""
-from .shellprop import Ply, ShellProp
+(pyfe3d/shellprop_utils.py:13-206): ``read_laminaprop``, ``laminated_plate`` and ``isotropic_plate``."""
+from .shellprop import Lamina, MatLamina, ShellProp
 
 
-def _expand(laminaprop):
-    if len(laminaprop) == 2:      # (E, nu) isotropic
+def read_laminaprop(laminaprop, rho=0):
+    """:class:`MatLamina` from ``(e1, e2, nu12, g12, g13, g23, e3, nu13, nu23)``, its 6-entry
+    plane-stress form or ``(E, nu)`` (pyfe3d/shellprop_utils.py:13-93)."""
+    assert len(laminaprop) in (2, 6, 9), 'Invalid entry for laminaprop: ' + str(laminaprop)
+    if len(laminaprop) == 2:
         e, nu = laminaprop
         g = e / (2 * (1 + nu))
-        return e, e, nu, g, g, g
-    if len(laminaprop) in (6, 9):  # (e1, e2, nu12, g12, g13, g23[, e3, nu13, nu23])
-        return tuple(laminaprop[:6])
-    raise ValueError("laminaprop must be (E, nu) or (e1, e2, nu12, g12, g13, g23[, e3, nu13, nu23])")
+        laminaprop = (e, e, nu, g, g, g, 0, 0, 0)
+    elif len(laminaprop) == 6:
+        laminaprop = tuple(laminaprop) + (0, 0, 0)
+    m = MatLamina()
+    m.e1, m.e2, m.nu12, m.g12, m.g13, m.g23, m.e3, m.nu13, m.nu23 = laminaprop
+    m.nu21 = m.nu12 * m.e2 / m.e1
+    m.nu31 = m.nu13 * m.e3 / m.e1
+    m.nu32 = m.nu23 * m.e3 / m.e2
+    m.rho = rho
+    m.rebuild()
+    return m
 
 
 def laminated_plate(stack, plyt=None, laminaprop=None, rho=0., plyts=None, laminaprops=None, rhos=None,
                     offset=0., calc_scf=True):
-    stack = list(stack)
-    if plyts is None:
-        if plyt is None:
-            raise ValueError("plyt or plyts must be supplied")
-        plyts = [plyt] * len(stack)
-    if laminaprops is None:
-        if laminaprop is None:
-            raise ValueError("laminaprop or laminaprops must be supplied")
-        laminaprops = [laminaprop] * len(stack)
-    if rhos is None:
-        rhos = [rho] * len(stack)
-    if not (len(stack) == len(plyts) == len(laminaprops) == len(rhos)):
-        raise ValueError("stack, plyts, laminaprops and rhos must have the same length")
+    """pyfe3d/shellprop_utils.py:96-179."""
     prop = ShellProp()
     prop.offset = offset
-    prop.stack = stack
-    prop.plies = [Ply(t, th, *_expand(lp), rho=r) for t, lp, th, r in zip(plyts, laminaprops, stack, rhos)]
+    prop.stack = list(stack)
+    if plyts is None:
+        if plyt is None:
+            raise ValueError('plyt or plyts must be supplied')
+        plyts = [plyt for _ in stack]
+    if laminaprops is None:
+        if laminaprop is None:
+            raise ValueError('laminaprop or laminaprops must be supplied')
+        laminaprops = [laminaprop for _ in stack]
+    if rhos is None:
+        rhos = [rho for _ in stack]
+    if not (len(stack) == len(plyts) == len(laminaprops) == len(rhos)):
+        raise ValueError('stack, plyts, laminaprops and rhos must have the same length')
+    plies = []
+    for t, lp, thetadeg, r in zip(plyts, laminaprops, stack, rhos):
+        ply = Lamina()
+        ply.thetadeg = float(thetadeg)
+        ply.h = t
+        ply.matlamina = read_laminaprop(lp, r)
+        ply.rebuild()
+        plies.append(ply)
+    prop.plies = plies
     prop.calc_constitutive_matrix()
     prop.calc_equivalent_properties()
     if calc_scf:
@@ -40,5 +58,6 @@ def laminated_plate(stack, plyt=None, laminaprop=None, rho=0., plyts=None, lamin
 
 
 def isotropic_plate(thickness, E, nu, offset=0., calc_scf=True, rho=0.):
+    """pyfe3d/shellprop_utils.py:182-206."""
     return laminated_plate(plyt=thickness, stack=[0], laminaprop=(E, nu), rho=rho, offset=offset,
                            calc_scf=calc_scf)
