@@ -8,10 +8,6 @@ is the intended switch for existing scripts.
 Importing the package only needs the compiled C-ABI library to be present; any
 compute call needs a CUDA device and raises otherwise (there is no CPU fallback).
 """
-import ctypes as _ct
-
-import numpy as _np
-
 from . import _cabi  # noqa: F401  (fails loudly when the native library was not built)
 from .beamprop import BeamProp
 from .shellprop import ShellProp
@@ -19,7 +15,8 @@ from .elements import (Quad4, Quad4Data, Quad4Probe, Quad4R, Quad4RData, Quad4RP
                        Tria3RProbe, BeamC, BeamCData, BeamCProbe, BeamLR, BeamLRData, BeamLRProbe, Truss,
                        TrussData, TrussProbe, Spring, SpringData, SpringProbe)
 
+from .elements import DOF, DOUBLE, INT
+from . import (beamc, beamlr, beamprop, quad4, quad4r, shellprop, shellprop_utils, spring, tria3r,  # noqa: F401
+               truss)
+
 __version__ = "0.1.0"
-DOF = 6
-INT = _np.int64 if _ct.sizeof(_ct.c_long) == 8 else _np.int32
-DOUBLE = _np.float64

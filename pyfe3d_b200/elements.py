@@ -13,9 +13,16 @@ reference; no arithmetic is done on the host and there is no CPU fallback.  The
 per-call launch latency makes this path a compatibility layer — the fast path is
 :class:`pyfe3d_b200.batch.ElementBatch`.
 """
+import ctypes as _ct
+
 import numpy as np
 
 from . import _cabi
+
+# module-level constants every reference element module defines (e.g. pyfe3d/quad4.pyx:20-24)
+DOF = 6
+INT = np.int64 if _ct.sizeof(_ct.c_long) == 8 else np.int32
+DOUBLE = np.float64
 
 _CTX = [None]
 
