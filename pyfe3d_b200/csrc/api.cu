@@ -1,5 +1,6 @@
 // extern "C" surface of libpyfe3d_b200.so (declared in include/pyfe3d_b200.h).
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -47,7 +48,8 @@ int plan_group_kind_nn(const pf3_plan* pl, int group);
 int64_t plan_group_ne_of(const pf3_plan* pl, int group);
 int64_t plan_group_ne(const pf3_plan* pl);
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches);
-cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
+cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches,
+                              int phases = 3);
 int fused_record_stride(const EvalArgs& A);
 int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches);
@@ -59,6 +61,8 @@ int tria_fused_record_stride(const EvalArgs& A);
 int64_t plan_nrows(const pf3_plan* pl);
 }  // namespace pf3
 
+#define PF3_HOST_CHUNKS 8   // row ranges of the pipelined host-buffer step
+
 struct pf3_context {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -69,6 +73,8 @@ struct pf3_context {
   size_t scratch_bytes = 0;
   double* hostio = nullptr;          // device staging of pf3_eval_assemble_host: x | u | csr_kc0 | csr_kg | csr_m
   size_t hostio_bytes = 0;
+  cudaStream_t copy_stream = nullptr;   // pf3_eval_assemble_host: device->host copies of finished row ranges
+  cudaEvent_t chunk_done[PF3_HOST_CHUNKS] = {};
 };
 
 namespace {
@@ -216,6 +222,9 @@ int pf3_destroy(pf3_context* ctx) {
   for (auto& kv : ctx->idx_tabs) cudaFree(kv.second);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->hostio) cudaFree(ctx->hostio);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (cudaEvent_t ev : ctx->chunk_done)
+    if (ev) cudaEventDestroy(ev);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return PF3_OK;
@@ -505,8 +514,51 @@ int pf3_plan_nblocks(const pf3_plan* plan, int64_t* nblk) {
   return PF3_OK;
 }
 
-int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan, int what, const pf3_coo* kc0,
-                      const pf3_coo* kg, const pf3_coo* m, double* csr_kc0, double* csr_kg, double* csr_m) {
+namespace {
+
+// Quad4 / Quad4R host-buffer step as a pipeline: K1 once, then K2 over PF3_HOST_CHUNKS ranges of node pairs; a node's
+// CSR rows are complete when its CTA retires and a range's rows are contiguous in every value array, so each range
+// goes back to the host on a second stream while the next one is being evaluated.
+int fused_pipelined(pf3_context* ctx, int kind, pf3::FusedArgs& F, double* const dev_out[3], double* const host_out[3],
+                    const int per_block[3]) {
+  if (!ctx->copy_stream) PF3_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t& ev : ctx->chunk_done)
+    if (!ev) PF3_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  const int64_t npairs = (F.nown + 1) / 2;
+  int64_t pair_at[PF3_HOST_CHUNKS + 1], block_at[PF3_HOST_CHUNKS + 1];
+  for (int c = 0; c <= PF3_HOST_CHUNKS; ++c) {
+    pair_at[c] = npairs * c / PF3_HOST_CHUNKS;
+    const int64_t node = std::min<int64_t>(2 * pair_at[c], F.nown);
+    PF3_CUDA(cudaMemcpyAsync(&block_at[c], F.brow_ptr + node, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PF3_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaError_t e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 1);
+  if (e != cudaSuccess) return int(e);
+  for (int c = 0; c < PF3_HOST_CHUNKS; ++c) {
+    F.pair_first = pair_at[c];
+    F.pair_count = pair_at[c + 1] - pair_at[c];
+    if (F.pair_count <= 0) continue;
+    e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 2);
+    if (e != cudaSuccess) return int(e);
+    PF3_CUDA(cudaEventRecord(ctx->chunk_done[c], ctx->stream));
+    PF3_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done[c], 0));
+    for (int k = 0; k < 3; ++k) {
+      if (!host_out[k] || !dev_out[k]) continue;
+      const int64_t lo = block_at[c] * per_block[k], hi = block_at[c + 1] * per_block[k];
+      if (hi > lo)
+        PF3_CUDA(cudaMemcpyAsync(host_out[k] + lo, dev_out[k] + lo, size_t(hi - lo) * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+  }
+  F.pair_first = F.pair_count = 0;
+  PF3_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  return PF3_OK;
+}
+
+// host_out (nullable): host destinations of the three CSR value arrays; *copied reports whether they were filled here.
+int eval_assemble_impl(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan, int what, const pf3_coo* kc0,
+                       const pf3_coo* kg, const pf3_coo* m, double* csr_kc0, double* csr_kg, double* csr_m,
+                       double* const host_out[3], bool* copied) {
   int rc = use_device(ctx);
   if (rc) return rc;
   if (!plan) return PF3_E_BAD_ARG;
@@ -540,9 +592,18 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
   rc = ensure_scratch(ctx, size_t(b->ne) * (tria ? pf3::tria_fused_record_stride(F.A) : pf3::fused_record_stride(F.A)) *
                                sizeof(double));
   if (rc) return rc;
-  cudaError_t e = tria ? pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches)
-                       : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
-  if (e != cudaSuccess) return int(e);
+  // the pipeline pays off when the device->host copies dominate: enough node pairs for PF3_HOST_CHUNKS full waves
+  if (host_out && !tria && F.nown >= int64_t(PF3_HOST_CHUNKS) * 16384) {
+    double* const dev_out[3] = {csr_kc0, csr_kg, csr_m};
+    const int per_block[3] = {36, 9, b->mtype == 2 ? 18 : 30};
+    rc = fused_pipelined(ctx, b->kind, F, dev_out, host_out, per_block);
+    if (rc) return rc;
+    *copied = true;
+  } else {
+    cudaError_t e = tria ? pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches)
+                         : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
+    if (e != cudaSuccess) return int(e);
+  }
   const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
                           (what & PF3_M) ? m : nullptr};
   for (int k = 0; k < 3; ++k)
@@ -551,6 +612,13 @@ int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan
       if (rc) return rc;
     }
   return PF3_OK;
+}
+
+}  // namespace
+
+int pf3_eval_assemble(pf3_context* ctx, const pf3_batch* b, const pf3_plan* plan, int what, const pf3_coo* kc0,
+                      const pf3_coo* kg, const pf3_coo* m, double* csr_kc0, double* csr_kg, double* csr_m) {
+  return eval_assemble_impl(ctx, b, plan, what, kc0, kg, m, csr_kc0, csr_kg, csr_m, nullptr, nullptr);
 }
 
 // Fused evaluate + assemble of ONE Quad4 / Quad4R group of a multi-group plan into the union layouts.
@@ -645,11 +713,16 @@ int pf3_eval_assemble_host(pf3_context* ctx, const pf3_batch* b, const pf3_plan*
   pf3_batch db = *b;
   db.x = dx;
   db.u = nu ? du : nullptr;
-  rc = pf3_eval_assemble(ctx, &db, plan, what, kc0, kg, m, n0 ? d0 : nullptr, n1 ? d1 : nullptr, n2 ? d2 : nullptr);
+  double* const host_out[3] = {n0 ? csr_kc0_host : nullptr, n1 ? csr_kg_host : nullptr, n2 ? csr_m_host : nullptr};
+  bool copied = false;
+  rc = eval_assemble_impl(ctx, &db, plan, what, kc0, kg, m, n0 ? d0 : nullptr, n1 ? d1 : nullptr, n2 ? d2 : nullptr,
+                          host_out, &copied);
   if (rc) return rc;
-  if (n0) PF3_CUDA(cudaMemcpyAsync(csr_kc0_host, d0, n0 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (n1) PF3_CUDA(cudaMemcpyAsync(csr_kg_host, d1, n1 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (n2) PF3_CUDA(cudaMemcpyAsync(csr_m_host, d2, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!copied) {
+    if (n0) PF3_CUDA(cudaMemcpyAsync(csr_kc0_host, d0, n0 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n1) PF3_CUDA(cudaMemcpyAsync(csr_kg_host, d1, n1 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n2) PF3_CUDA(cudaMemcpyAsync(csr_m_host, d2, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   PF3_CUDA(cudaStreamSynchronize(ctx->stream));
   return PF3_OK;
 }

@@ -6,12 +6,25 @@
 // contiguous >=256 B run of the caller's COO value array (an element's block is
 // contiguous: 576 / 144 / 480 doubles).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "../../include/pyfe3d_b200.h"
 
 namespace pf3 {
+
+// Function attributes (cudaFuncSetAttribute) are per DEVICE: a call site's first() is true once per device, so a
+// process that drives several GPUs (tests, a multi-context host) raises the shared-memory limit on each of them.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> seen{0ull};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    return (seen.fetch_or(bit) & bit) == 0ull;
+  }
+};
 
 constexpr int kWarpsPerCta = 4;
 constexpr int kThreads = 32 * kWarpsPerCta;
@@ -98,6 +111,8 @@ struct FusedArgs {
   double* csr_m;
   UnionMap um[3];                         // KC0, KG, M: only read when um[i].active
   int zero_empty;                         // multi-group plans: zero the rows of nodes this group does not touch
+  int64_t pair_first;                     // quads: this launch covers node pairs [pair_first, pair_first + pair_count)
+  int64_t pair_count;                     //        (pair_count == 0: all pairs) -- pf3_eval_assemble_host's pipeline
 };
 
 struct Mat3 {

@@ -541,13 +541,12 @@ cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st) {
   if (A.ne <= 0) return cudaSuccess;
   const int64_t per_cta = 32 * kWarpsPerCta;
   const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
-  static bool once = false;
-  if (!once) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(line_eval_kernel<PF3_BEAMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
     cudaFuncSetAttribute(line_eval_kernel<PF3_BEAMLR>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
     cudaFuncSetAttribute(line_eval_kernel<PF3_TRUSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
     cudaFuncSetAttribute(line_eval_kernel<PF3_SPRING>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-    once = true;
   }
   switch (kind) {
     case PF3_BEAMC: line_eval_kernel<PF3_BEAMC><<<grid, kThreads, kStageBytes, st>>>(A); break;

@@ -389,8 +389,8 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   const UnionMap* umK = F.um[0].active ? &F.um[0] : nullptr;
   const UnionMap* umKG = F.um[1].active ? &F.um[1] : nullptr;
   const UnionMap* umM = F.um[2].active ? &F.um[2] : nullptr;
-  const int64_t npairs = (F.nown + 1) >> 1;
-  const int64_t np0 = (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
+  const int64_t npairs = F.pair_count ? F.pair_first + F.pair_count : (F.nown + 1) >> 1;   // end of this launch's range
+  const int64_t np0 = F.pair_first + (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
   if (np0 >= npairs) return;
   const int rmax = F.rmax;
   const int nitems = int(min(int64_t(CHUNK), npairs - np0)) * rmax;   // item j = (pair np0 + j / rmax, round j % rmax)
@@ -701,26 +701,29 @@ size_t fused_smem_bytes(int rstride, int chunk) { return size_t(kFusedWarps) * w
 int fused_max_slots() { return kMaxSlots; }
 int fused_record_stride(const EvalArgs& A) { return A.evec != nullptr ? kRecRot : kRecPlain; }
 
-// rec: device scratch of ne * fused_record_stride doubles
-cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches) {
+// rec: device scratch of ne * fused_record_stride doubles.  phases: bit 0 = K1 (records of ALL elements), bit 1 = K2 for
+// the node pairs [F.pair_first, F.pair_first + F.pair_count) (all pairs when pair_count == 0).
+cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases) {
   if (F.nown <= 0 || F.A.ne <= 0) return cudaSuccess;
   const int stride = fused_record_stride(F.A);
-  const unsigned g1 = unsigned((F.A.ne + 127) / 128);
-  const size_t smem1 = size_t(4) * 32 * (stride + 1) * sizeof(double);
-  static bool once1 = false;
-  if (!once1) {
-    const int maxs = int(size_t(4) * 32 * (kRecRot + 1) * sizeof(double));
-    cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
-    cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
-    once1 = true;
+  if (phases & 1) {
+    const unsigned g1 = unsigned((F.A.ne + 127) / 128);
+    const size_t smem1 = size_t(4) * 32 * (stride + 1) * sizeof(double);
+    static PerDeviceOnce once1;
+    if (once1.first()) {
+      const int maxs = int(size_t(4) * 32 * (kRecRot + 1) * sizeof(double));
+      cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+      cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+    }
+    if (kind == PF3_QUAD4)
+      quad_record_kernel<PF3_QUAD4><<<g1, 128, smem1, st>>>(F.A, rec, stride);
+    else
+      quad_record_kernel<PF3_QUAD4R><<<g1, 128, smem1, st>>>(F.A, rec, stride);
+    ++*launches;
+    cudaError_t e1 = cudaGetLastError();
+    if (e1 != cudaSuccess) return e1;
   }
-  if (kind == PF3_QUAD4)
-    quad_record_kernel<PF3_QUAD4><<<g1, 128, smem1, st>>>(F.A, rec, stride);
-  else
-    quad_record_kernel<PF3_QUAD4R><<<g1, 128, smem1, st>>>(F.A, rec, stride);
-  ++*launches;
-  cudaError_t e1 = cudaGetLastError();
-  if (e1 != cudaSuccess) return e1;
+  if (!(phases & 2)) return cudaSuccess;
   // doubles written per element (COO + CSR share): the three-matrix north-star call is store-bound, smaller calls are
   // latency-bound and take the prefetching variant
   const int w = F.A.what;
@@ -728,18 +731,17 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
   const int chunk = (vol < 1400 && !mapped) ? kFChunkBig : 1;
   const size_t smem = fused_smem_bytes(stride, chunk);
-  const int64_t npairs = (F.nown + 1) / 2;
+  const int64_t npairs = F.pair_count ? F.pair_count : (F.nown + 1) / 2;
   const int64_t want = (npairs + int64_t(kFusedWarps) * chunk - 1) / (int64_t(kFusedWarps) * chunk);
   if (want > int64_t(0x7fffffff)) return cudaErrorInvalidConfiguration;
   const unsigned grid = unsigned(want < 1 ? 1 : want);
-  static bool once = false;
-  if (!once) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     const int m1 = int(fused_smem_bytes(kRecRot, 1)), m4 = int(fused_smem_bytes(kRecRot, kFChunkBig));
     cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
     cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
     cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
     cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
-    once = true;
   }
   if (kind == PF3_QUAD4) {
     if (chunk == 1) quad_fused_kernel<PF3_QUAD4, 1><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);

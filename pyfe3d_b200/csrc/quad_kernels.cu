@@ -604,10 +604,9 @@ cudaError_t launch_quad_aero(const EvalArgs& A, const AeroOut& O, cudaStream_t s
   if (A.ne <= 0) return cudaSuccess;
   const int64_t per_cta = 32 * kWarpsPerCta;
   const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
-  static bool once = false;
-  if (!once) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(quad_aero_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-    once = true;
   }
   quad_aero_kernel<<<grid, kThreads, kStageBytes, st>>>(A, O);
   return cudaGetLastError();
@@ -658,19 +657,17 @@ cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st) {
   const int64_t per_cta = 32 * kWarpsPerCta;
   const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
   if (kind == PF3_QUAD4) {
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once;
+    if (once.first()) {
       cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
       cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-      once = true;
     }
     quad_eval_kernel<PF3_QUAD4><<<grid, kThreads, kStageBytes, st>>>(A);
   } else {
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once;
+    if (once.first()) {
       cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
       cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-      once = true;
     }
     quad_eval_kernel<PF3_QUAD4R><<<grid, kThreads, kStageBytes, st>>>(A);
   }

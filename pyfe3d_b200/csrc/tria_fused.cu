@@ -465,13 +465,12 @@ cudaError_t launch_tria_fused(const FusedArgs& F, double* rec, cudaStream_t st, 
   const int stride = tria_fused_record_stride(F.A);
   const unsigned g1 = unsigned((F.A.ne + 127) / 128);
   const size_t smem1 = size_t(4) * 32 * (stride + 1) * sizeof(double);
-  static bool once = false;
-  if (!once) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(tria_record_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(size_t(4) * 32 * (kTRecRot + 1) * sizeof(double)));
     cudaFuncSetAttribute(tria_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(size_t(kTWarps) * twarp_smem_doubles(kTRecRot) * sizeof(double)));
-    once = true;
   }
   tria_record_kernel<<<g1, 128, smem1, st>>>(F.A, rec, stride);
   ++*launches;

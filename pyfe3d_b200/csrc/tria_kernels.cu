@@ -299,10 +299,9 @@ cudaError_t launch_tria(const EvalArgs& A, cudaStream_t st) {
   if (A.ne <= 0) return cudaSuccess;
   const int64_t per_cta = 32 * kWarpsPerCta;
   const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
-  static bool once = false;
-  if (!once) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     cudaFuncSetAttribute(tria_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-    once = true;
   }
   tria_eval_kernel<<<grid, kThreads, kStageBytes, st>>>(A);
   return cudaGetLastError();

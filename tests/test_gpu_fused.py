@@ -165,6 +165,37 @@ def test_host_buffer_step_matches_device_step(kind):
         plan.evaluate_assemble_host(torch.as_tensor(case["x"]).cuda(), uh, out, KC0=True)
 
 
+@pytest.mark.parametrize("kind,mtype", [("quad4", 0), ("quad4r", 2)])
+def test_host_buffer_step_pipelined_ranges(kind, mtype):
+    """pf3_eval_assemble_host on a mesh large enough (>= 131 072 nodes) for the pipelined path: K1 once, K2 over 8 ranges
+    of node pairs, every range's CSR rows copied back on a second stream while the next range is evaluated.  The host
+    arrays must equal the device-resident fused result bit for bit (same kernels, same order of operations), with an
+    odd node count (a half pair at the end) and the COO arrays still written on the device."""
+    import torch
+    from pyfe3d_b200 import meshes
+    from pyfe3d_b200.batch import AssemblyPlan
+    case = meshes.plate_quad4(402, 326, kind=kind)          # 403 x 327 = 131 781 nodes (odd)
+    nn = case["ndof"] // 6
+    assert nn >= 131072 and nn % 2 == 1
+    b = util.batch_from_case(case)
+    plan = AssemblyPlan("KC0", nn, [b])
+    coo, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True, mtype=mtype)
+    sizes = plan.csr_sizes(mtype)
+    out = {m: torch.full((sizes[m],), float("nan"), dtype=torch.float64).pin_memory() for m in ("KC0", "KG", "M")}
+    xh = torch.as_tensor(np.ascontiguousarray(case["x"])).pin_memory()
+    uh = torch.as_tensor(np.ascontiguousarray(case["u"])).pin_memory()
+    coo2 = {m: b._alloc(m, False, None) for m in ("KC0", "KG", "M")}
+    plan.evaluate_assemble_host(xh, uh, out, KC0=True, KG=True, M=True, mtype=mtype, coo=coo2)
+    for m in ("KC0", "KG", "M"):
+        assert torch.equal(out[m], csr[m].cpu()), m
+        assert torch.equal(coo2[m].v, coo[m].v), m
+    # a second call reuses the stream / events, only KG changes with u
+    out2 = {m: torch.empty(sizes[m], dtype=torch.float64).pin_memory() for m in ("KC0", "KG")}
+    plan.evaluate_assemble_host(xh, 2.0 * uh, out2, KC0=True, KG=True)
+    assert torch.equal(out2["KC0"], csr["KC0"].cpu())
+    assert (out2["KG"] - 2.0 * csr["KG"].cpu()).abs().max() <= 1e-12 * 2 * float(csr["KG"].abs().max())
+
+
 def _mixed_reference(cs, keys):
     """scipy sum-duplicates of the oracle's triplets of every batch, per matrix."""
     import scipy.sparse as sp
