@@ -203,9 +203,14 @@ def run_ours(args):
     e2e = None
     if args.e2e_steps > 0:
         try:
-            xh = torch.as_tensor(case["x"]).pin_memory()
-            uh = torch.as_tensor(case["u"]).pin_memory()
-            outh = {m: torch.empty(plans[m].nnz, dtype=torch.float64).pin_memory() for m in mats}
+            # pinned buffers are first-touched by a thread running on the GPU's own NUMA node, so that with several
+            # ranks the device->host copies do not all land in (or cross) one socket's memory
+            with numa_local(local) as numa:
+                xh = torch.as_tensor(case["x"]).pin_memory()
+                uh = torch.as_tensor(case["u"]).pin_memory()
+                outh = {m: torch.empty(plans[m].nnz, dtype=torch.float64).pin_memory() for m in mats}
+                for o in outh.values():
+                    o.zero_()
             h2d = xh.numel() * 8 + uh.numel() * 8
             d2h = sum(o.numel() * 8 for o in outh.values())
 
@@ -231,7 +236,7 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             e2e = {"value": ne_unique_total * args.e2e_steps / float(dt.item()), "unit": UNIT,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "numa": numa,
                    "what": "one pf3_eval_assemble_host call per step (C ABI, host buffers): H2D of x,u from pinned host "
                            "memory -> record + fused kernels -> D2H of the KC0/KG/M CSR value arrays into pinned host "
                            "memory (pattern is static; the COO value arrays are written on the device as in the timed steps)"}
@@ -304,6 +309,42 @@ def run_ours(args):
         dist.destroy_process_group()
     return 0
 
+
+
+class numa_local:
+    """Context manager: run the enclosed host allocations on the CPUs of the NUMA node the GPU hangs off
+    (/sys/bus/pci/devices/<bus id>/numa_node), then restore the affinity.  Best effort: a no-op where /sys does not
+    say (single-socket hosts, restricted containers).  Enters as a dict describing what was done."""
+
+    def __init__(self, local):
+        self.local, self.saved, self.info = local, None, {"node": None}
+
+    def __enter__(self):
+        try:
+            import torch
+            p = torch.cuda.get_device_properties(self.local)
+            bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+            if node < 0:
+                return self.info
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = os.sched_getaffinity(0)
+            use = cpus & allowed
+            if use:
+                self.saved = allowed
+                os.sched_setaffinity(0, use)
+                self.info.update(node=node, cpus=len(use), gpu=bdf)
+        except Exception as exc:   # noqa: BLE001 - diagnostics only
+            self.info["note"] = str(exc)[:80]
+        return self.info
+
+    def __exit__(self, *a):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
 
 def main():
     ap = argparse.ArgumentParser()
