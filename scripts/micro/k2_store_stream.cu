@@ -1,0 +1,104 @@
+// Micro-benchmark: the STORE STREAM of the fused quad kernel without its arithmetic.  One-warp CTAs, one node pair
+// each, hardware CTA scheduling -- exactly K2's launch shape -- writing, for a structured (n+1) x (n+1)-node mesh, the
+// 8 (element, node) COO slabs of KC0 (1152 B), M (960 B) and KG (288 B) by TMA bulk copies from shared memory and the two
+// nodes' CSR row blocks (9 blocks x 36 / 30 / 9 doubles) by 16-byte stores.  If this runs well above K2's 6.18 TB/s the
+// kernel is bound by latency inside the CTA (12 one-warp CTAs per SM), not by the address pattern of its stores.
+//   mode 0: as K2 (TMA slabs + STG CSR)      mode 1: CSR only      mode 2: COO slabs only      mode 3: all by STG.128
+//   ctas:   resident CTAs per SM are limited with dynamic shared memory (12 = K2, 16, 24, 32)
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o k2_store_stream k2_store_stream.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+template <int MODE>
+__global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, double* c0, double* cg, double* cm, int n,
+                                        int64_t npairs) {
+  extern __shared__ __align__(128) double st[];   // 8 slabs x 152 doubles (K2's KC0 staging)
+  const int lane = threadIdx.x;
+  const int64_t p = blockIdx.x;
+  if (p >= npairs) return;
+  for (int i = lane; i < 8 * 152; i += 32) st[i] = double(i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const int nn1 = n + 1;
+  const int h = lane >> 4, l16 = lane & 15, kq = l16 >> 2;
+  const int64_t node = 2 * p + h;
+  const int64_t nnodes = int64_t(nn1) * nn1;
+  const bool valid = node < nnodes;
+  const int i = int(node / nn1), j = int(node - int64_t(i) * nn1);
+  // incidence kq of node (i, j): element (i - 1 + (kq & 1), j - 1 + (kq >> 1)), local node a
+  const int ei = i - 1 + (kq & 1), ej = j - 1 + (kq >> 1);
+  const bool act = valid && ei >= 0 && ei < n && ej >= 0 && ej < n;
+  const int64_t e = int64_t(ei) * n + ej;
+  const int a = (kq == 0) ? 2 : (kq == 1) ? 3 : (kq == 2) ? 1 : 0;
+  if (MODE == 0 || MODE == 2) {
+    if (act && (lane & 3) == 0) {
+      const uint32_t src = smem_u32(st + (lane >> 2) * 152);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kg + e * 144 + a * 36), "r"(src), "r"(288) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(m + e * 480 + a * 120), "r"(src), "r"(960) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kc0 + e * 576 + a * 144), "r"(src), "r"(1152) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  if (MODE == 3 && act) {
+    const double2 v = make_double2(1., 2.);
+    const int q = lane & 3;
+    double2* d0 = reinterpret_cast<double2*>(kg + e * 144 + a * 36);
+    for (int t = q; t < 18; t += 4) d0[t] = v;
+    double2* d1 = reinterpret_cast<double2*>(m + e * 480 + a * 120);
+    for (int t = q; t < 60; t += 4) d1[t] = v;
+    double2* d2 = reinterpret_cast<double2*>(kc0 + e * 576 + a * 144);
+    for (int t = q; t < 72; t += 4) d2[t] = v;
+  }
+  if ((MODE == 0 || MODE == 1 || MODE == 3) && valid) {
+    const double2 v = make_double2(3., 4.);
+    double2* o0 = reinterpret_cast<double2*>(c0 + node * 324);
+    for (int t = l16; t < 162; t += 16) o0[t] = v;
+    double2* o1 = reinterpret_cast<double2*>(cm + node * 270);
+    for (int t = l16; t < 135; t += 16) o1[t] = v;
+    double* o2 = cg + node * 81;
+    for (int t = l16; t < 81; t += 16) o2[t] = 5.;
+  }
+  if (MODE == 0 || MODE == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+template <int MODE>
+float run(double** b, int n, int64_t npairs, size_t smem) {
+  cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaEvent_t s, e;
+  cudaEventCreate(&s); cudaEventCreate(&e);
+  float best = 1e9f;
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(s);
+    k<MODE><<<unsigned(npairs), 32, smem>>>(b[0], b[1], b[2], b[3], b[4], b[5], n, npairs);
+    cudaEventRecord(e);
+    cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, s, e);
+    if (r > 0 && ms < best) best = ms;
+  }
+  return best;
+}
+int main() {
+  const int n = 2000;
+  const int64_t ne = int64_t(n) * n, nnodes = int64_t(n + 1) * (n + 1), npairs = (nnodes + 1) / 2;
+  const size_t sizes[6] = {size_t(ne) * 576, size_t(ne) * 144, size_t(ne) * 480, size_t(nnodes) * 324 + 16, size_t(nnodes) * 81 + 16,
+                           size_t(nnodes) * 270 + 16};
+  double* b[6];
+  for (int i = 0; i < 6; ++i) { cudaMalloc(&b[i], sizes[i] * 8); cudaMemset(b[i], 0, sizes[i] * 8); }
+  const double coo = double(ne) * (576 + 144 + 480) * 8, csr = double(nnodes) * (324 + 81 + 270) * 8;
+  const char* names[] = {"TMA slabs + STG CSR (K2)", "CSR rows only", "COO slabs only (TMA)", "everything by STG.128"};
+  for (int ctas : {12, 16, 24, 32})
+    for (int mode = 0; mode < 4; ++mode) {
+      const size_t smem = (size_t(227) * 1024 / ctas - 1024) & ~size_t(127);
+      float ms = 0;
+      switch (mode) {
+        case 0: ms = run<0>(b, n, npairs, smem); break;
+        case 1: ms = run<1>(b, n, npairs, smem); break;
+        case 2: ms = run<2>(b, n, npairs, smem); break;
+        case 3: ms = run<3>(b, n, npairs, smem); break;
+      }
+      const double bytes = (mode == 1) ? csr : (mode == 2) ? coo : coo + csr;
+      printf("{\"ctas_per_sm\": %d, \"mode\": \"%s\", \"ms\": %.3f, \"GBps\": %.1f, \"err\": %d}\n", ctas, names[mode], ms,
+             bytes / ms / 1e6, int(cudaGetLastError()));
+    }
+  return 0;
+}
