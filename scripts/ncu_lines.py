@@ -2,7 +2,8 @@
 """Per-source-line stall samples / executed instructions of one kernel from an ncu report captured with
 --import-source on.  ncu's csv source page is SASS-only, so the SASS stream is aligned (instruction by instruction) with
 `nvdisasm --print-line-info` of the same kernel in the in-tree library.
-usage: python scripts/ncu_lines.py <report.ncu-rep> <kernel name substring in ncu> <mangled substring in the cubin> [cu file] [top]"""
+usage: python scripts/ncu_lines.py <report.ncu-rep> <kernel name substring in ncu> <mangled substring in the cubin> [cu file] [top]
+env NCU_LINES_CUBIN=<file.cubin>: align against this cubin instead of the in-tree library."""
 import csv
 import io
 import os
@@ -30,8 +31,12 @@ hdr, data = blk["rows"][0], blk["rows"][1:]
 ia, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "pyfe3d_b200", "lib", "libpyfe3d_b200.so")], cwd=tmp,
-               capture_output=True)
+if os.environ.get("NCU_LINES_CUBIN"):     # a cubin of the profiled version of the source (when the tree has moved on)
+    import shutil
+    shutil.copy(os.environ["NCU_LINES_CUBIN"], tmp)
+else:
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "pyfe3d_b200", "lib", "libpyfe3d_b200.so")], cwd=tmp,
+                   capture_output=True)
 seq = None
 for f in sorted(os.listdir(tmp)):
     txt = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, f)], capture_output=True, text=True).stdout
