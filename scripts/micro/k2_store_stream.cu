@@ -4,7 +4,9 @@
 // nodes' CSR row blocks (9 blocks x 36 / 30 / 9 doubles) by 16-byte stores.  If this runs well above K2's 6.18 TB/s the
 // kernel is bound by latency inside the CTA (12 one-warp CTAs per SM), not by the address pattern of its stores.
 //   mode 0: as K2 (TMA slabs + STG CSR)      mode 1: CSR only      mode 2: COO slabs only      mode 3: all by STG.128
-//   ctas:   resident CTAs per SM are limited with dynamic shared memory (12 = K2, 16, 24, 32)
+//   ctas:   resident CTAs per SM are limited with dynamic shared memory (12 = K2, 16)
+//   chunk:  consecutive node pairs per CTA (1 = K2; 2 and 4 = the prefetching variant's shape: does a wider front of
+//           addresses in flight cost DRAM write efficiency, as the persistent shape does?)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o k2_store_stream k2_store_stream.cu
 #include <cstdio>
 #include <cstdint>
@@ -12,14 +14,15 @@
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 template <int MODE>
 __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, double* c0, double* cg, double* cm, int n,
-                                        int64_t npairs) {
+                                        int64_t npairs, int chunk) {
   extern __shared__ __align__(128) double st[];   // 8 slabs x 152 doubles (K2's KC0 staging)
   const int lane = threadIdx.x;
-  const int64_t p = blockIdx.x;
-  if (p >= npairs) return;
   for (int i = lane; i < 8 * 152; i += 32) st[i] = double(i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
+  for (int cc = 0; cc < chunk; ++cc) {
+  const int64_t p = int64_t(blockIdx.x) * chunk + cc;
+  if (p >= npairs) break;
   const int nn1 = n + 1;
   const int h = lane >> 4, l16 = lane & 15, kq = l16 >> 2;
   const int64_t node = 2 * p + h;
@@ -60,16 +63,17 @@ __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, doub
     for (int t = l16; t < 81; t += 16) o2[t] = 5.;
   }
   if (MODE == 0 || MODE == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 }
 template <int MODE>
-float run(double** b, int n, int64_t npairs, size_t smem) {
+float run(double** b, int n, int64_t npairs, size_t smem, int chunk) {
   cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   cudaEvent_t s, e;
   cudaEventCreate(&s); cudaEventCreate(&e);
   float best = 1e9f;
   for (int r = 0; r < 4; ++r) {
     cudaEventRecord(s);
-    k<MODE><<<unsigned(npairs), 32, smem>>>(b[0], b[1], b[2], b[3], b[4], b[5], n, npairs);
+    k<MODE><<<unsigned((npairs + chunk - 1) / chunk), 32, smem>>>(b[0], b[1], b[2], b[3], b[4], b[5], n, npairs, chunk);
     cudaEventRecord(e);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, s, e);
@@ -86,19 +90,19 @@ int main() {
   for (int i = 0; i < 6; ++i) { cudaMalloc(&b[i], sizes[i] * 8); cudaMemset(b[i], 0, sizes[i] * 8); }
   const double coo = double(ne) * (576 + 144 + 480) * 8, csr = double(nnodes) * (324 + 81 + 270) * 8;
   const char* names[] = {"TMA slabs + STG CSR (K2)", "CSR rows only", "COO slabs only (TMA)", "everything by STG.128"};
-  for (int ctas : {12, 16, 24, 32})
-    for (int mode = 0; mode < 4; ++mode) {
-      const size_t smem = (size_t(227) * 1024 / ctas - 1024) & ~size_t(127);
-      float ms = 0;
-      switch (mode) {
-        case 0: ms = run<0>(b, n, npairs, smem); break;
-        case 1: ms = run<1>(b, n, npairs, smem); break;
-        case 2: ms = run<2>(b, n, npairs, smem); break;
-        case 3: ms = run<3>(b, n, npairs, smem); break;
+  for (int ctas : {12, 16})
+    for (int chunk : {1, 2, 4, 8})
+      for (int mode : {0, 3}) {
+        const size_t smem = (size_t(227) * 1024 / ctas - 1024) & ~size_t(127);
+        const float ms = mode == 0 ? run<0>(b, n, npairs, smem, chunk) : run<3>(b, n, npairs, smem, chunk);
+        printf("{\"ctas_per_sm\": %d, \"pairs_per_cta\": %d, \"mode\": \"%s\", \"ms\": %.3f, \"GBps\": %.1f, \"err\": %d}\n", ctas,
+               chunk, names[mode], ms, (coo + csr) / ms / 1e6, int(cudaGetLastError()));
       }
-      const double bytes = (mode == 1) ? csr : (mode == 2) ? coo : coo + csr;
-      printf("{\"ctas_per_sm\": %d, \"mode\": \"%s\", \"ms\": %.3f, \"GBps\": %.1f, \"err\": %d}\n", ctas, names[mode], ms,
-             bytes / ms / 1e6, int(cudaGetLastError()));
-    }
+  for (int mode : {1, 2}) {
+    const size_t smem = (size_t(227) * 1024 / 12 - 1024) & ~size_t(127);
+    const float ms = mode == 1 ? run<1>(b, n, npairs, smem, 1) : run<2>(b, n, npairs, smem, 1);
+    printf("{\"ctas_per_sm\": 12, \"pairs_per_cta\": 1, \"mode\": \"%s\", \"ms\": %.3f, \"GBps\": %.1f, \"err\": %d}\n", names[mode], ms,
+           (mode == 1 ? csr : coo) / ms / 1e6, int(cudaGetLastError()));
+  }
   return 0;
 }

@@ -3,7 +3,8 @@
 --import-source on.  ncu's csv source page is SASS-only, so the SASS stream is aligned (instruction by instruction) with
 `nvdisasm --print-line-info` of the same kernel in the in-tree library.
 usage: python scripts/ncu_lines.py <report.ncu-rep> <kernel name substring in ncu> <mangled substring in the cubin> [cu file] [top]
-env NCU_LINES_CUBIN=<file.cubin>: align against this cubin instead of the in-tree library."""
+env NCU_LINES_CUBIN=<file.cubin>: align against this cubin instead of the in-tree library.
+env NCU_LINES_SHARED=1: rank the lines by shared-memory wavefronts (actual / ideal / excess = bank conflicts) instead."""
 import csv
 import io
 import os
@@ -66,6 +67,18 @@ def opcode(t):
 
 mism = sum(opcode(t) != opcode(r[ia].strip()) for (_, t), r in zip(seq, data))
 print("# %s: %d SASS instructions in the report, %d in the library, %d opcode mismatches" % (blk["name"][:60], len(data), len(seq), mism))
+if os.environ.get("NCU_LINES_SHARED"):
+    iw, ii, ix = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Ideal"), hdr.index("L1 Wavefronts Shared Excessive")
+    agg = defaultdict(lambda: [0, 0, 0, 0])
+    for (w, t), r in zip(seq, data):
+        if int(r[iw] or 0):
+            a = agg[(w, t.split()[1] if t.startswith("@") else t.split()[0])]
+            a[0] += int(r[iw] or 0); a[1] += int(r[ii] or 0); a[2] += int(r[ix] or 0); a[3] += int(r[iex])
+    tot = sum(a[0] for a in agg.values()) or 1
+    print("# shared-memory wavefronts: %d, of which %d excess (bank conflicts)" % (tot, sum(a[2] for a in agg.values())))
+    for (w, op), a in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
+        print("%-26s %-12s wavefronts %10d %5.1f%%  ideal %10d  excess %10d  executed %9d" % ("%s:%d" % w if w else "?", op, a[0], 100 * a[0] / tot, a[1], a[2], a[3]))
+    sys.exit(0)
 bys, bye = defaultdict(int), defaultdict(int)
 for (w, _), r in zip(seq, data):
     bys[w] += int(r[isamp])
