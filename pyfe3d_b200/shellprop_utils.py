@@ -23,33 +23,41 @@ def read_laminaprop(laminaprop, rho=0):
     return m
 
 
+def _per_ply(single, many, nplies, what):
+    """One value per ply from either the shared value or the explicit list (the reference's plyt/plyts,
+    laminaprop/laminaprops, rho/rhos argument pairs)."""
+    if many is not None:
+        return list(many)
+    if single is None:
+        raise ValueError('%s or %ss must be supplied' % (what, what))
+    return [single] * nplies
+
+
+def _ply(thickness, laminaprop, thetadeg, rho):
+    ply = Lamina()
+    ply.thetadeg = float(thetadeg)
+    ply.h = thickness
+    ply.matlamina = read_laminaprop(laminaprop, rho)
+    ply.rebuild()
+    return ply
+
+
 def laminated_plate(stack, plyt=None, laminaprop=None, rho=0., plyts=None, laminaprops=None, rhos=None,
                     offset=0., calc_scf=True):
-    """pyfe3d/shellprop_utils.py:96-179."""
+    """ShellProp of a stacking sequence (angles in degrees), same arguments, defaults and errors as
+    pyfe3d/shellprop_utils.py:96-179: per-ply lists override the shared plyt / laminaprop / rho; the ABD(E) matrix and
+    the equivalent moduli are always computed, the shear correction factors when ``calc_scf``."""
+    angles = list(stack)
+    n = len(angles)
+    thicknesses = _per_ply(plyt, plyts, n, 'plyt')
+    materials = _per_ply(laminaprop, laminaprops, n, 'laminaprop')
+    densities = _per_ply(rho, rhos, n, 'rho')
+    if not (n == len(thicknesses) == len(materials) == len(densities)):
+        raise ValueError('stack, plyts, laminaprops and rhos must have the same length')
     prop = ShellProp()
     prop.offset = offset
-    prop.stack = list(stack)
-    if plyts is None:
-        if plyt is None:
-            raise ValueError('plyt or plyts must be supplied')
-        plyts = [plyt for _ in stack]
-    if laminaprops is None:
-        if laminaprop is None:
-            raise ValueError('laminaprop or laminaprops must be supplied')
-        laminaprops = [laminaprop for _ in stack]
-    if rhos is None:
-        rhos = [rho for _ in stack]
-    if not (len(stack) == len(plyts) == len(laminaprops) == len(rhos)):
-        raise ValueError('stack, plyts, laminaprops and rhos must have the same length')
-    plies = []
-    for t, lp, thetadeg, r in zip(plyts, laminaprops, stack, rhos):
-        ply = Lamina()
-        ply.thetadeg = float(thetadeg)
-        ply.h = t
-        ply.matlamina = read_laminaprop(lp, r)
-        ply.rebuild()
-        plies.append(ply)
-    prop.plies = plies
+    prop.stack = angles
+    prop.plies = [_ply(*args) for args in zip(thicknesses, materials, angles, densities)]
     prop.calc_constitutive_matrix()
     prop.calc_equivalent_properties()
     if calc_scf:
