@@ -311,8 +311,20 @@ int pf3_lamination_parameter_props(pf3_context* ctx, int64_t nrows, const double
                                    int grad_complete, double* props_out, double* grad_out);
 
 /* ---- host-pointer convenience (numpy callers): copies in, runs, copies out -- */
+/* Every pointer in host_batch / the pf3_coo structs / fint is a HOST pointer.  Calls whose arrays fit the
+ * context's 1 MiB staging buffer (the per-element methods of pyfe3d_b200/elements.py: X.update_KC0(KC0r, KC0c,
+ * KC0v, prop) etc., quad4.pyx:1204) cost one packed copy in each direction and one stream synchronisation. */
 int pf3_eval_host(pf3_context* ctx, const pf3_batch* host_batch, int what,
                   const pf3_coo* kc0, const pf3_coo* kg, const pf3_coo* m, double* fint);
+/* Host-pointer forms of pf3_eval_state / pf3_eval_finte / pf3_eval_aero / pf3_quad4_update_BL for small batches
+ * (update_rotation_matrix / update_probe_xe / update_probe_ue quad4.pyx:491,682,627; update_probe_finte :1174;
+ * update_KA_beta :9491; Quad4Probe.update_BL :273).  PF3_E_CAPACITY when the arrays exceed the staging buffer:
+ * use the device-pointer entry points for large batches. */
+int pf3_eval_state_host(pf3_context* ctx, const pf3_batch* host_batch, double* state_out);
+int pf3_eval_finte_host(pf3_context* ctx, const pf3_batch* host_batch, double* finte_out);
+int pf3_eval_aero_host(pf3_context* ctx, const pf3_batch* host_batch, int what, const pf3_coo* ka_beta,
+                       const pf3_coo* ka_gamma, const pf3_coo* ca);
+int pf3_quad4_update_BL_host(pf3_context* ctx, int64_t n, const double* xe, double xi, double eta, double* out);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

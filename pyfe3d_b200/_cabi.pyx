@@ -53,6 +53,10 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_fill_indices(pf3_context*, int kind, int matrix, int mtype, int64_t ne, const int64_t* conn,
                          int64_t init_k, int64_t* r, int64_t* c) nogil
     int pf3_eval_state(pf3_context*, const pf3_batch*, double* out) nogil
+    int pf3_eval_state_host(pf3_context*, const pf3_batch*, double* out) nogil
+    int pf3_eval_finte_host(pf3_context*, const pf3_batch*, double* out) nogil
+    int pf3_eval_aero_host(pf3_context*, const pf3_batch*, int what, const pf3_coo*, const pf3_coo*, const pf3_coo*) nogil
+    int pf3_quad4_update_BL_host(pf3_context*, int64_t n, const double* xe, double xi, double eta, double* out) nogil
     int pf3_eval_finte(pf3_context*, const pf3_batch*, double* out) nogil
     int pf3_plan_create(pf3_context*, int matrix, int64_t nnodes, int ngroups, const pf3_batch* groups,
                         const int64_t* coo_offsets, int64_t node_begin, int64_t node_end, pf3_plan** plan) nogil
@@ -235,13 +239,16 @@ cdef class Context:
                                                 <double*>out, <double*>grad)
         _check(rc)
 
-    def eval_aero(self, Batch b, int what, Coo ka_beta=None, Coo ka_gamma=None, Coo ca=None):
+    def eval_aero(self, Batch b, int what, Coo ka_beta=None, Coo ka_gamma=None, Coo ca=None, bint host=False):
         cdef const pf3_coo* p0 = &ka_beta.c if ka_beta is not None else NULL
         cdef const pf3_coo* p1 = &ka_gamma.c if ka_gamma is not None else NULL
         cdef const pf3_coo* p2 = &ca.c if ca is not None else NULL
         cdef int rc
         with nogil:
-            rc = pf3_eval_aero(self.ctx, &b.b, what, p0, p1, p2)
+            if host:
+                rc = pf3_eval_aero_host(self.ctx, &b.b, what, p0, p1, p2)
+            else:
+                rc = pf3_eval_aero(self.ctx, &b.b, what, p0, p1, p2)
         _check(rc)
 
     def fill_indices(self, int kind, int matrix, int mtype, int64_t ne, uintptr_t conn, int64_t init_k,
@@ -252,22 +259,31 @@ cdef class Context:
                                   <int64_t*>r, <int64_t*>c)
         _check(rc)
 
-    def eval_state(self, Batch b, uintptr_t out):
+    def eval_state(self, Batch b, uintptr_t out, bint host=False):
         cdef int rc
         with nogil:
-            rc = pf3_eval_state(self.ctx, &b.b, <double*>out)
+            if host:
+                rc = pf3_eval_state_host(self.ctx, &b.b, <double*>out)
+            else:
+                rc = pf3_eval_state(self.ctx, &b.b, <double*>out)
         _check(rc)
 
-    def quad4_update_BL(self, int64_t n, uintptr_t xe, double xi, double eta, uintptr_t out):
+    def quad4_update_BL(self, int64_t n, uintptr_t xe, double xi, double eta, uintptr_t out, bint host=False):
         cdef int rc
         with nogil:
-            rc = pf3_quad4_update_BL(self.ctx, n, <const double*>xe, xi, eta, <double*>out)
+            if host:
+                rc = pf3_quad4_update_BL_host(self.ctx, n, <const double*>xe, xi, eta, <double*>out)
+            else:
+                rc = pf3_quad4_update_BL(self.ctx, n, <const double*>xe, xi, eta, <double*>out)
         _check(rc)
 
-    def eval_finte(self, Batch b, uintptr_t out):
+    def eval_finte(self, Batch b, uintptr_t out, bint host=False):
         cdef int rc
         with nogil:
-            rc = pf3_eval_finte(self.ctx, &b.b, <double*>out)
+            if host:
+                rc = pf3_eval_finte_host(self.ctx, &b.b, <double*>out)
+            else:
+                rc = pf3_eval_finte(self.ctx, &b.b, <double*>out)
         _check(rc)
 
     def spmv_csr(self, int64_t nrows, uintptr_t indptr, uintptr_t indices, uintptr_t vals, uintptr_t x, uintptr_t y):

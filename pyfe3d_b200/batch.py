@@ -202,7 +202,7 @@ class ElementBatch:
             return _cabi.Coo(_ptr(k.r) if indices else 0, _ptr(k.c) if indices else 0, _ptr(k.v), 0,
                              1 if accumulate else 0)
 
-        b = self.cabi_batch(mtype, KG_given_stress or (0., 0., 0.), u)
+        b = self.cabi_batch(mtype, (0., 0., 0.) if KG_given_stress is None else KG_given_stress, u)
         ctx.eval(b, what, cc("KC0"), cc("KG"), cc("M"), _ptr(fint))
         return coos
 
@@ -420,7 +420,7 @@ class AssemblyPlan:
 
         context(self.device)
         try:
-            self._plan.eval_assemble(b.cabi_batch(mtype, KG_given_stress or (0., 0., 0.), u), what, cc("KC0"),
+            self._plan.eval_assemble(b.cabi_batch(mtype, (0., 0., 0.) if KG_given_stress is None else KG_given_stress, u), what, cc("KC0"),
                                      cc("KG"), cc("M"), _ptr(csr.get("KC0")), _ptr(csr.get("KG")),
                                      _ptr(csr.get("M")))
         except _cabi.Pf3Error as exc:
@@ -463,7 +463,7 @@ class AssemblyPlan:
         hb = _cabi.Batch(b.kid, b.ne, b.nnodes, _ptr(b.conn), hptr(x, 3 * b.nnodes, "x"),
                          hptr(u, 6 * b.nnodes, "u") if u is not None else 0, _ptr(b.props), _ptr(b.prop_id),
                          0 if b.props is None else b.props.shape[0], _ptr(b.evec), b.evec_stride, _ptr(b.eparam), 0,
-                         mtype, tuple(float(t) for t in (KG_given_stress or (0., 0., 0.))))
+                         mtype, tuple(float(t) for t in ((0., 0., 0.) if KG_given_stress is None else KG_given_stress)))
         def cc(name):
             k = (coo or {}).get(name)
             return None if k is None else _cabi.Coo(0, 0, _ptr(k.v), 0, 0)
@@ -495,8 +495,6 @@ class AssemblyPlan:
                              6 * self.nnodes)
             if n not in csr:
                 csr[n] = torch.empty(plans[n].nnz, dtype=torch.float64, device=self.device)
-        kw = dict(KC0=KC0, KG=KG, M=M, mtype=mtype, u=u, indices=False)
-
         def views(g):
             b = self.batches[g]
             return {n: Coo(None, None, coo[n].v[plans[n].coo_offsets[g]:plans[n].coo_offsets[g] + b.ne * b.sizes[n]],
@@ -504,24 +502,38 @@ class AssemblyPlan:
 
         b0 = self.batches[0]
         fused = b0.kind in ("quad4", "quad4r") and not getattr(self, "_fused_unsupported", False)
-        if fused:
-            what = (_cabi.KC0 if KC0 else 0) | (_cabi.KG if KG else 0) | (_cabi.M if M else 0)
+        # the fused kernel walks THIS (KC0) plan's node blocks for every matrix it writes: a matrix whose own plan has
+        # a different block structure (lumped beam / truss mass: diagonal node pairs only, pattern.hpp diag_pairs) must
+        # take the two-pass path, otherwise its CSR array would be written at the KC0 plan's offsets
+        fnames = [n for n in names if fused and plans[n]._plan.nblocks == self._plan.nblocks]
+        if fnames:
+            what = ((_cabi.KC0 if "KC0" in fnames else 0) | (_cabi.KG if "KG" in fnames else 0)
+                    | (_cabi.M if "M" in fnames else 0))
 
             def cc(n):
-                return _cabi.Coo(0, 0, _ptr(coo[n].v), plans[n].coo_offsets[0], 0) if n in names else None
+                return _cabi.Coo(0, 0, _ptr(coo[n].v), plans[n].coo_offsets[0], 0) if n in fnames else None
 
             context(self.device)
             try:
                 self._plan.eval_assemble_group(b0.cabi_batch(mtype, (0., 0., 0.), u), 0, what, cc("KC0"), cc("KG"),
-                                               cc("M"), _ptr(csr.get("KC0")), _ptr(csr.get("KG")), _ptr(csr.get("M")))
+                                               cc("M"), _ptr(csr.get("KC0")) if "KC0" in fnames else 0,
+                                               _ptr(csr.get("KG")) if "KG" in fnames else 0,
+                                               _ptr(csr.get("M")) if "M" in fnames else 0)
             except _cabi.Pf3Error as exc:
                 if "capacity" not in str(exc) and "not defined" not in str(exc):
                     raise
-                self._fused_unsupported = fused = False
-        for g in range(0 if not fused else 1, len(self.batches)):
-            self.batches[g].evaluate(out=views(g), **kw)
+                self._fused_unsupported = True
+                fnames = []
+        rest = [n for n in names if n not in fnames]
+        for g in range(len(self.batches)):
+            todo = rest if g == 0 else names
+            if not todo:
+                continue
+            v = views(g)
+            self.batches[g].evaluate(KC0="KC0" in todo, KG="KG" in todo, M="M" in todo, mtype=mtype, u=u,
+                                     indices=False, out={n: v[n] for n in todo})
         for n in names:
-            if fused:
+            if n in fnames:
                 context(self.device)
                 plans[n]._plan.assemble_add(_ptr(coo[n].v), _ptr(csr[n]), 0)
             else:

@@ -1,5 +1,6 @@
 // extern "C" surface of libpyfe3d_b200.so (declared in include/pyfe3d_b200.h).
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -49,7 +50,7 @@ int64_t plan_group_ne_of(const pf3_plan* pl, int group);
 int64_t plan_group_ne(const pf3_plan* pl);
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches);
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches,
-                              int phases = 3);
+                              int phases, unsigned long long* work);
 int fused_record_stride(const EvalArgs& A);
 int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches);
@@ -75,7 +76,11 @@ struct pf3_context {
   size_t hostio_bytes = 0;
   cudaStream_t copy_stream = nullptr;   // pf3_eval_assemble_host: device->host copies of finished row ranges
   cudaEvent_t chunk_done[PF3_HOST_CHUNKS] = {};
+  unsigned long long* work = nullptr;   // in-order work counter of the persistent fused kernel
+  char* stage_host = nullptr;           // pinned + device staging of the small host-pointer calls (per-element drop-in)
+  char* stage_dev = nullptr;
 };
+#define PF3_STAGE_BYTES (size_t(1) << 20)
 
 namespace {
 
@@ -88,6 +93,13 @@ namespace {
 int use_device(pf3_context* ctx) {
   if (!ctx) return PF3_E_BAD_ARG;
   PF3_CUDA(cudaSetDevice(ctx->device));
+  // The runtime keeps ONE last-error slot per host thread, shared with every other CUDA user in the process (torch,
+  // cub, ...): a non-sticky error left there by someone else's call must not surface as the status of this call, whose
+  // launches are checked with cudaGetLastError().  Sticky (fatal) errors are returned again by the next call anyway.
+  const cudaError_t stale = cudaGetLastError();
+  if (stale != cudaSuccess && std::getenv("PF3_DEBUG"))
+    std::fprintf(stderr, "pyfe3d_b200: cleared a stale CUDA error left by an earlier call: %d (%s)\n", int(stale),
+                 cudaGetErrorString(stale));
   return PF3_OK;
 }
 
@@ -241,6 +253,12 @@ int pf3_create(int device, pf3_context** out) {
     return int(e);
   }
   ctx->own_stream = true;
+  e = cudaMalloc((void**)&ctx->work, 64);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return int(e);
+  }
   *out = ctx;
   return PF3_OK;
 }
@@ -251,6 +269,9 @@ int pf3_destroy(pf3_context* ctx) {
   for (auto& kv : ctx->idx_tabs) cudaFree(kv.second);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->hostio) cudaFree(ctx->hostio);
+  if (ctx->work) cudaFree(ctx->work);
+  if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  if (ctx->stage_dev) cudaFree(ctx->stage_dev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (cudaEvent_t ev : ctx->chunk_done)
     if (ev) cudaEventDestroy(ev);
@@ -431,7 +452,7 @@ int pf3_eval(pf3_context* ctx, const pf3_batch* b, int what, const pf3_coo* kc0,
     F.rmax = 1;
     rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
     if (rc) return rc;
-    cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
+    cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3, ctx->work);
     return int(e);
   }
   // Tria3R the same way through the triangle record + node-lane kernels (KG slabs are not 16-byte multiples and go
@@ -568,13 +589,13 @@ int fused_pipelined(pf3_context* ctx, int kind, pf3::FusedArgs& F, double* const
     PF3_CUDA(cudaMemcpyAsync(&block_at[c], F.brow_ptr + node, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
   PF3_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaError_t e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 1);
+  cudaError_t e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 1, ctx->work);
   if (e != cudaSuccess) return int(e);
   for (int c = 0; c < PF3_HOST_CHUNKS; ++c) {
     F.pair_first = pair_at[c];
     F.pair_count = pair_at[c + 1] - pair_at[c];
     if (F.pair_count <= 0) continue;
-    e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 2);
+    e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 2, ctx->work);
     if (e != cudaSuccess) return int(e);
     PF3_CUDA(cudaEventRecord(ctx->chunk_done[c], ctx->stream));
     PF3_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done[c], 0));
@@ -637,7 +658,7 @@ int eval_assemble_impl(pf3_context* ctx, const pf3_batch* b, const pf3_plan* pla
     *copied = true;
   } else {
     cudaError_t e = tria ? pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches)
-                         : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
+                         : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3, ctx->work);
     if (e != cudaSuccess) return int(e);
   }
   const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
@@ -698,7 +719,7 @@ int pf3_eval_assemble_group(pf3_context* ctx, const pf3_batch* b, const pf3_plan
   F.csr_m = csr_m;
   rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
   if (rc) return rc;
-  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches);
+  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3, ctx->work);
   if (e != cudaSuccess) return int(e);
   const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
                           (what & PF3_M) ? m : nullptr};
@@ -733,6 +754,9 @@ int pf3_eval_assemble_host(pf3_context* ctx, const pf3_batch* b, const pf3_plan*
   const size_t total = (up(nx) + up(nu) + up(n0) + up(n1) + up(n2)) * sizeof(double);
   if (total > ctx->hostio_bytes) {
     if (ctx->hostio) cudaFree(ctx->hostio);
+  if (ctx->work) cudaFree(ctx->work);
+  if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
+  if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     ctx->hostio = nullptr;
     ctx->hostio_bytes = 0;
     PF3_CUDA(cudaMalloc((void**)&ctx->hostio, total));
@@ -882,6 +906,233 @@ int pf3_plan_diagonal(pf3_context* ctx, const pf3_plan* plan, const double* vals
   return pf3::plan_diagonal(plan, ctx->stream, vals, diag, &ctx->launches);
 }
 
+}  // extern "C"
+
+namespace {
+
+// Small host-pointer calls (the per-element drop-in classes make one per method call): every input is packed into ONE
+// pinned staging buffer and goes to the device in one copy, the kernels run on the device image, and one copy brings
+// the image back; only the `out` pieces are written to the caller's arrays.  Two PCIe transfers and one stream
+// synchronisation per call instead of one cudaMalloc + copy per array.
+struct Stager {
+  pf3_context* ctx;
+  size_t off = 0;
+  bool overflow = false;
+  struct Seg { void* host; size_t bytes, off; };
+  Seg outs[16];
+  int nouts = 0;
+  explicit Stager(pf3_context* c) : ctx(c) {}
+  int init() {
+    if (!ctx->stage_host) {
+      PF3_CUDA(cudaHostAlloc((void**)&ctx->stage_host, PF3_STAGE_BYTES, cudaHostAllocDefault));
+      PF3_CUDA(cudaMalloc((void**)&ctx->stage_dev, PF3_STAGE_BYTES));
+    }
+    return PF3_OK;
+  }
+  template <class T>
+  T* add(const T* host, size_t count, bool in, bool out) {
+    if (!host || count == 0) return nullptr;
+    const size_t bytes = count * sizeof(T);
+    off = (off + 15) & ~size_t(15);
+    if (off + bytes > PF3_STAGE_BYTES || (out && nouts == 16)) {
+      overflow = true;
+      return nullptr;
+    }
+    if (in) std::memcpy(ctx->stage_host + off, host, bytes);
+    if (out) outs[nouts++] = Seg{(void*)host, bytes, off};
+    T* d = reinterpret_cast<T*>(ctx->stage_dev + off);
+    off += bytes;
+    return d;
+  }
+  int upload() {
+    if (off) PF3_CUDA(cudaMemcpyAsync(ctx->stage_dev, ctx->stage_host, off, cudaMemcpyHostToDevice, ctx->stream));
+    return PF3_OK;
+  }
+  int download() {
+    if (off) PF3_CUDA(cudaMemcpyAsync(ctx->stage_host, ctx->stage_dev, off, cudaMemcpyDeviceToHost, ctx->stream));
+    PF3_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nouts; ++i) std::memcpy(outs[i].host, ctx->stage_host + outs[i].off, outs[i].bytes);
+    return PF3_OK;
+  }
+};
+
+size_t batch_host_bytes(const pf3_batch* hb) {
+  const int nn = pf3::kind_nodes(hb->kind);
+  const int pstride = (hb->kind <= PF3_TRIA3R) ? PF3_SHELLPROP_STRIDE : PF3_BEAMPROP_STRIDE;
+  size_t n = size_t(hb->ne) * nn * 8 + 256;
+  if (hb->x) n += size_t(hb->nnodes) * 24;
+  if (hb->u) n += size_t(hb->nnodes) * 48;
+  if (hb->props) n += size_t(hb->nprop) * pstride * 8;
+  if (hb->prop_id) n += size_t(hb->ne) * 4;
+  if (hb->evec) n += (hb->evec_stride ? size_t(hb->ne) * hb->evec_stride : 0) * 8 + 64;
+  if (hb->eparam) n += size_t(hb->ne) * PF3_EPARAM_STRIDE * 8;
+  if (hb->state) n += size_t(hb->ne) * PF3_STATE_STRIDE * 8;
+  return n;
+}
+
+// device image of a host batch inside the stager
+void stage_batch(Stager& S, const pf3_batch* hb, pf3_batch* db) {
+  const int nn = pf3::kind_nodes(hb->kind);
+  const int pstride = (hb->kind <= PF3_TRIA3R) ? PF3_SHELLPROP_STRIDE : PF3_BEAMPROP_STRIDE;
+  *db = *hb;
+  db->conn = S.add(hb->conn, size_t(hb->ne) * nn, true, false);
+  db->x = S.add(hb->x, size_t(hb->nnodes) * 3, true, false);
+  db->u = S.add(hb->u, size_t(hb->nnodes) * 6, true, false);
+  db->props = S.add(hb->props, size_t(hb->nprop) * pstride, true, false);
+  db->prop_id = S.add(hb->prop_id, size_t(hb->ne), true, false);
+  if (hb->evec) {
+    const int width = (hb->kind == PF3_SPRING) ? 6 : 3;
+    const size_t cnt = hb->evec_stride ? size_t(hb->ne - 1) * hb->evec_stride + width : width;
+    db->evec = S.add(hb->evec, cnt, true, false);
+  }
+  db->eparam = S.add(hb->eparam, size_t(hb->ne) * PF3_EPARAM_STRIDE, true, false);
+  db->state = S.add(hb->state, size_t(hb->ne) * PF3_STATE_STRIDE, true, false);
+}
+
+// pf3_eval on a staged image; *handled = false when the call does not fit the staging buffer
+int eval_host_staged(pf3_context* ctx, const pf3_batch* hb, int what, const pf3_coo* kc0, const pf3_coo* kg,
+                     const pf3_coo* m, double* fint, bool* handled) {
+  *handled = false;
+  const pf3_coo* hs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
+                          (what & PF3_M) ? m : nullptr};
+  size_t need = batch_host_bytes(hb);
+  for (int k = 0; k < 3; ++k)
+    if (hs[k]) need += size_t(hb->ne) * pf3::kind_sparse_size(hb->kind, k) * 24 + 64;
+  if ((what & PF3_FINT) && fint) need += size_t(hb->nnodes) * 48 + 16;
+  if (need > PF3_STAGE_BYTES) return PF3_OK;
+  Stager S(ctx);
+  int rc = S.init();
+  if (rc) return rc;
+  pf3_batch b;
+  stage_batch(S, hb, &b);
+  pf3_coo dc[3];
+  for (int k = 0; k < 3; ++k) {
+    std::memset(&dc[k], 0, sizeof(pf3_coo));
+    const size_t n = size_t(hb->ne) * pf3::kind_sparse_size(hb->kind, k);
+    if (!hs[k] || n == 0) {
+      hs[k] = nullptr;
+      continue;
+    }
+    dc[k].accumulate = hs[k]->accumulate;
+    // existing values / indices are needed for `+=` and for the unwritten lumped-mass tail: every piece goes both ways
+    if (hs[k]->v) dc[k].v = S.add(hs[k]->v + hs[k]->init_k, n, true, true);
+    if (hs[k]->r) dc[k].r = S.add(hs[k]->r + hs[k]->init_k, n, true, true);
+    if (hs[k]->c) dc[k].c = S.add(hs[k]->c + hs[k]->init_k, n, true, true);
+  }
+  double* dfint = ((what & PF3_FINT) && fint) ? S.add(fint, size_t(hb->nnodes) * 6, true, true) : nullptr;
+  if (S.overflow) return PF3_OK;
+  rc = S.upload();
+  if (rc) return rc;
+  rc = pf3_eval(ctx, &b, what, hs[0] ? &dc[0] : nullptr, hs[1] ? &dc[1] : nullptr, hs[2] ? &dc[2] : nullptr, dfint);
+  if (rc) return rc;
+  rc = S.download();
+  if (rc) return rc;
+  *handled = true;
+  return PF3_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- small host-pointer calls of the per-element drop-in classes (pyfe3d_b200/elements.py) ---------------------
+int pf3_eval_state_host(pf3_context* ctx, const pf3_batch* hb, double* state_out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  rc = check_batch(hb, 0);
+  if (rc) return rc;
+  if (!state_out) return PF3_E_BAD_ARG;
+  if (hb->ne == 0) return PF3_OK;
+  if (batch_host_bytes(hb) + size_t(hb->ne) * PF3_STATE_STRIDE * 8 > PF3_STAGE_BYTES) return PF3_E_CAPACITY;
+  Stager S(ctx);
+  rc = S.init();
+  if (rc) return rc;
+  pf3_batch b;
+  stage_batch(S, hb, &b);
+  double* dout = S.add(state_out, size_t(hb->ne) * PF3_STATE_STRIDE, false, true);
+  if (S.overflow) return PF3_E_CAPACITY;
+  rc = S.upload();
+  if (rc) return rc;
+  rc = pf3_eval_state(ctx, &b, dout);
+  if (rc) return rc;
+  return S.download();
+}
+
+int pf3_eval_finte_host(pf3_context* ctx, const pf3_batch* hb, double* finte_out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  rc = check_batch(hb, PF3_FINT);
+  if (rc) return rc;
+  if (!finte_out) return PF3_E_BAD_ARG;
+  if (hb->ne == 0) return PF3_OK;
+  const int nn = pf3::kind_nodes(hb->kind);
+  if (batch_host_bytes(hb) + size_t(hb->ne) * 6 * nn * 8 > PF3_STAGE_BYTES) return PF3_E_CAPACITY;
+  Stager S(ctx);
+  rc = S.init();
+  if (rc) return rc;
+  pf3_batch b;
+  stage_batch(S, hb, &b);
+  double* dout = S.add(finte_out, size_t(hb->ne) * 6 * nn, false, true);
+  if (S.overflow) return PF3_E_CAPACITY;
+  rc = S.upload();
+  if (rc) return rc;
+  rc = pf3_eval_finte(ctx, &b, dout);
+  if (rc) return rc;
+  return S.download();
+}
+
+int pf3_eval_aero_host(pf3_context* ctx, const pf3_batch* hb, int what, const pf3_coo* ka_beta,
+                       const pf3_coo* ka_gamma, const pf3_coo* ca) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!hb || hb->ne < 0) return PF3_E_BAD_ARG;
+  if (hb->kind != PF3_QUAD4 && hb->kind != PF3_QUAD4R) return PF3_E_UNSUPPORTED;
+  if (hb->ne == 0) return PF3_OK;
+  if (batch_host_bytes(hb) + size_t(hb->ne) * 144 * 24 * 3 > PF3_STAGE_BYTES) return PF3_E_CAPACITY;
+  Stager S(ctx);
+  rc = S.init();
+  if (rc) return rc;
+  pf3_batch b;
+  stage_batch(S, hb, &b);
+  const pf3_coo* hs[3] = {ka_beta, ka_gamma, ca};
+  const int bits[3] = {PF3_KA_BETA, PF3_KA_GAMMA, PF3_CA};
+  pf3_coo dc[3];
+  const size_t n = size_t(hb->ne) * 144;
+  for (int k = 0; k < 3; ++k) {
+    std::memset(&dc[k], 0, sizeof(pf3_coo));
+    if (!(what & bits[k])) hs[k] = nullptr;
+    if (!hs[k]) continue;
+    dc[k].accumulate = hs[k]->accumulate;
+    if (hs[k]->v) dc[k].v = S.add(hs[k]->v + hs[k]->init_k, n, true, true);
+    if (hs[k]->r) dc[k].r = S.add(hs[k]->r + hs[k]->init_k, n, true, true);
+    if (hs[k]->c) dc[k].c = S.add(hs[k]->c + hs[k]->init_k, n, true, true);
+  }
+  if (S.overflow) return PF3_E_CAPACITY;
+  rc = S.upload();
+  if (rc) return rc;
+  rc = pf3_eval_aero(ctx, &b, what, hs[0] ? &dc[0] : nullptr, hs[1] ? &dc[1] : nullptr, hs[2] ? &dc[2] : nullptr);
+  if (rc) return rc;
+  return S.download();
+}
+
+int pf3_quad4_update_BL_host(pf3_context* ctx, int64_t n, const double* xe, double xi, double eta, double* out) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!xe || !out))) return PF3_E_BAD_ARG;
+  if (n == 0) return PF3_OK;
+  if (size_t(n) * (12 + 264) * 8 + 64 > PF3_STAGE_BYTES) return PF3_E_CAPACITY;
+  Stager S(ctx);
+  rc = S.init();
+  if (rc) return rc;
+  const double* dxe = S.add(xe, size_t(n) * 12, true, false);
+  double* dout = S.add(out, size_t(n) * 264, false, true);
+  rc = S.upload();
+  if (rc) return rc;
+  rc = pf3_quad4_update_BL(ctx, n, dxe, xi, eta, dout);
+  if (rc) return rc;
+  return S.download();
+}
+
 // Host-pointer convenience: every pointer in host_batch / the pf3_coo structs / fint is a HOST pointer.
 int pf3_eval_host(pf3_context* ctx, const pf3_batch* hb, int what, const pf3_coo* kc0, const pf3_coo* kg,
                   const pf3_coo* m, double* fint) {
@@ -890,6 +1141,11 @@ int pf3_eval_host(pf3_context* ctx, const pf3_batch* hb, int what, const pf3_coo
   rc = check_batch(hb, what);
   if (rc) return rc;
   if (hb->ne == 0) return PF3_OK;
+  {
+    bool handled = false;   // small calls: one packed copy each way (see Stager)
+    rc = eval_host_staged(ctx, hb, what, kc0, kg, m, fint, &handled);
+    if (rc || handled) return rc;
+  }
   const int nn = pf3::kind_nodes(hb->kind);
   const int pstride = (hb->kind <= PF3_TRIA3R) ? PF3_SHELLPROP_STRIDE : PF3_BEAMPROP_STRIDE;
   std::vector<void*> owned;

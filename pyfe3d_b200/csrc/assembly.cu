@@ -110,7 +110,7 @@ __global__ void k_pair_keys(const PlanDev P, int gi, int64_t* keys, uint32_t* va
     const int q = int(t - e * G.npairs);
     const int a = G.diag ? q : q / G.nn, b = G.diag ? q : q % G.nn;
     const int64_t na = G.conn[e * G.nn + a], nb = G.conn[e * G.nn + b];
-    const bool own = na >= P.node_begin && na < P.node_end;
+    const bool own = na >= P.node_begin && na < P.node_end && nb >= 0 && nb < P.nnodes;   // bad ids: rejected below
     keys[G.pairbase + t] = own ? na * P.nnodes + nb : P.nnodes * P.nnodes;
     vals[G.pairbase + t] = uint32_t(G.pairbase + t);
   }
@@ -123,6 +123,7 @@ __global__ void k_inc_keys(const PlanDev P, int gi, int64_t* keys, uint32_t* val
     const int64_t e = t / G.nn;
     const int a = int(t - e * G.nn);
     const int64_t na = G.conn[t];
+    if (na < 0 || na >= P.nnodes) degenerate[1] = 1;   // node id outside [0, nnodes): would alias keys na*nnodes+nb
     for (int b = 0; b < a; ++b)
       if (G.conn[e * G.nn + b] == na) *degenerate = 1;
     const bool own = na >= P.node_begin && na < P.node_end;
@@ -227,7 +228,9 @@ __global__ void k_pattern(const PlanDev P, const MaskDev M, const int64_t* brow_
 // One warp per owned node.  acc lives in shared memory (max_nb * mc doubles per warp).
 // skip_group >= 0 (add mode): csr_v += the contributions of every group EXCEPT skip_group; nodes that have none are
 // not touched (the fused kernel has already written group skip_group's share of every row).
-template <bool SAFE>
+// GLOBAL: the accumulator is the node's CSR row block itself (hub nodes coupled to hundreds of nodes, e.g. spider / RBE
+// style springs, whose row block does not fit shared memory): slower read-modify-write of global memory, same order.
+template <bool SAFE, bool GLOBAL = false>
 __global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t* __restrict__ brow_ptr,
                                                   const int64_t* __restrict__ inc_ptr,
                                                   const int64_t* __restrict__ inc_src,
@@ -243,13 +246,15 @@ __global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t
     const int64_t b0 = brow_ptr[i];
     const int nb = int(brow_ptr[i + 1] - b0);
     const int nout = nb * P.mc;
+    if (GLOBAL) acc = csr_v + b0 * P.mc;
     const int64_t q0 = inc_ptr[i], q1 = inc_ptr[i + 1];
     if (skip_group >= 0) {
       bool any = false;
       for (int64_t q = q0 + lane; q < q1; q += 32) any = any || ((inc_meta[q] & 0xff) != skip_group);
       if (__ballot_sync(0xffffffffu, any) == 0u) continue;
     }
-    for (int k = lane; k < nout; k += 32) acc[k] = 0.;
+    if (!(GLOBAL && skip_group >= 0))
+      for (int k = lane; k < nout; k += 32) acc[k] = 0.;
     __syncwarp();
     for (int64_t q = q0; q < q1; ++q) {
       const int meta = inc_meta[q];
@@ -270,11 +275,13 @@ __global__ void __launch_bounds__(256) k_assemble(const PlanDev P, const int64_t
       }
       __syncwarp();
     }
-    double* out = csr_v + b0 * P.mc;
-    if (skip_group >= 0) {
-      for (int k = lane; k < nout; k += 32) out[k] += acc[k];
-    } else {
-      for (int k = lane; k < nout; k += 32) out[k] = acc[k];
+    if (!GLOBAL) {
+      double* out = csr_v + b0 * P.mc;
+      if (skip_group >= 0) {
+        for (int k = lane; k < nout; k += 32) out[k] += acc[k];
+      } else {
+        for (int k = lane; k < nout; k += 32) out[k] = acc[k];
+      }
     }
     __syncwarp();
   }
@@ -406,7 +413,7 @@ int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnod
   }
   pl->npair = pairbase;
   pl->ninc = incbase;
-  if (pairbase >= (int64_t(1) << 32) || incbase >= (int64_t(1) << 32)) {
+  if (pairbase >= (int64_t(1) << 31) || incbase >= (int64_t(1) << 31)) {   // int32 scans of head flags, uint32 ids
     delete pl;
     return PF3_E_CAPACITY;
   }
@@ -458,8 +465,8 @@ int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnod
   PF3_TRY(dalloc(&vals2, NMAX));
   PF3_TRY(dalloc(&flags, NMAX));
   PF3_TRY(dalloc(&incl, NMAX));
-  PF3_TRY(dalloc(&d_flagsmall, 2));
-  PF3_TRY(int(cudaMemsetAsync(d_flagsmall, 0, 2 * sizeof(int), st)));
+  PF3_TRY(dalloc(&d_flagsmall, 3));
+  PF3_TRY(int(cudaMemsetAsync(d_flagsmall, 0, 3 * sizeof(int), st)));
 
   // ---- node-pair blocks
   for (int g = 0; g < ngroups; ++g) {
@@ -497,11 +504,12 @@ int plan_create_structured(int device, cudaStream_t st, int matrix, int64_t nnod
   int64_t h_first = 0, h_last = 0;
   PF3_TRY(int(cudaMemcpyAsync(&h_first, pl->d_inc_ptr, sizeof(int64_t), cudaMemcpyDeviceToHost, st)));
   PF3_TRY(int(cudaMemcpyAsync(&h_last, pl->d_inc_ptr + pl->nown, sizeof(int64_t), cudaMemcpyDeviceToHost, st)));
-  int h_small[2] = {0, 0};
-  PF3_TRY(int(cudaMemcpyAsync(h_small, d_flagsmall, 2 * sizeof(int), cudaMemcpyDeviceToHost, st)));
+  int h_small[3] = {0, 0, 0};
+  PF3_TRY(int(cudaMemcpyAsync(h_small, d_flagsmall, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)));
   cudaStreamSynchronize(st);
   pl->max_nb = h_small[0];
   pl->degenerate = h_small[1];
+  if (h_small[2]) PF3_TRY(PF3_E_BAD_ARG);   // connectivity refers to a node outside [0, nnodes)
   const int64_t nvalid = h_last;  // sorted keys < nnodes come first; owned range may start after 0
   PF3_TRY(dalloc(&pl->d_inc_src, nvalid));
   PF3_TRY(dalloc(&pl->d_inc_pair0, nvalid));
@@ -776,7 +784,18 @@ int plan_assemble_gather(const pf3_plan* pl, cudaStream_t st, const double* coo_
   int wpc = 8;
   while (wpc > 1 && size_t(wpc) * acc_stride * sizeof(double) > 200 * 1024) wpc >>= 1;
   const size_t smem = size_t(wpc) * acc_stride * sizeof(double);
-  if (smem > 220 * 1024) return PF3_E_CAPACITY;
+  if (smem > 200 * 1024) {
+    // a hub node's row block exceeds shared memory: accumulate in the CSR array itself
+    const unsigned gridg = unsigned(std::max<int64_t>(1, std::min<int64_t>((pl->nown + 7) / 8, 148 * 64)));
+    if (pl->degenerate)
+      k_assemble<true, true><<<gridg, 256, 0, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
+                                                     pl->d_inc_meta, pl->d_slot, pl->nown, 0, coo_v, csr_v, skip_group);
+    else
+      k_assemble<false, true><<<gridg, 256, 0, st>>>(pl->dev, pl->d_brow_ptr, pl->d_inc_ptr, pl->d_inc_src, pl->d_inc_pair0,
+                                                      pl->d_inc_meta, pl->d_slot, pl->nown, 0, coo_v, csr_v, skip_group);
+    ++*launches;
+    return int(cudaGetLastError());
+  }
   const unsigned grid = unsigned(std::max<int64_t>(1, std::min<int64_t>((pl->nown + wpc - 1) / wpc, 148 * 64)));
   if (pl->degenerate) {
     if (smem > 48 * 1024) PF3_CUDA(cudaFuncSetAttribute(k_assemble<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1291,6 +1310,9 @@ int plan_union_map(const pf3_plan* pl, int group, int matrix, int mtype, UnionMa
   for (int g = 0; g < pl->dev.ngroups; ++g) {
     const BlockLayout L = make_layout(pl->gkind[g], matrix, mtype);
     if (L.written == 0) return PF3_E_UNSUPPORTED;
+    // a group that contributes only diagonal node pairs to this matrix (lumped beam / truss mass) gives the matrix a
+    // block structure that may differ from this plan's: the fused kernel, which walks this plan's blocks, cannot write it
+    if (L.diag_pairs && !pl->dev.g[g].diag) return PF3_E_UNSUPPORTED;
     for (int i = 0; i < 6; ++i)
       for (int j = 0; j < 6; ++j) {
         u[i][j] = u[i][j] || mask_has(L.mask, i, j);

@@ -19,6 +19,8 @@
 //     node-pair blocks = 16 lanes, each lane evaluating ONE 6x6 block (a, b) of ONE element with the same
 //     instruction stream (no divergence).  Blocks are staged in shared memory, streamed out as contiguous
 //     COO slabs (1152 B each) and summed per CSR slot in a fixed order (deterministic, no atomics).
+#include <algorithm>
+
 #include "shell.cuh"
 
 namespace pf3 {
@@ -262,9 +264,13 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2)
             if (off[k2] >= 0) {
+#ifdef PF3_ABL_NORED
+              sum.x += double(off[k2]);
+#else
               const double2 t = *reinterpret_cast<const double2*>(sh + d * 4 * CNT + off[k2]);
               sum.x += t.x;
               sum.y += t.y;
+#endif
             }
           double2* o = reinterpret_cast<double2*>(out + d * w + x);
           if (!first_round) {
@@ -292,7 +298,11 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
           double sum = 0.;
 #pragma unroll
           for (int k2 = 0; k2 < 4; ++k2)
+#ifdef PF3_ABL_NORED
+            if (off[k2] >= 0) sum += double(off[k2]);
+#else
             if (off[k2] >= 0) sum += sh[d * 4 * CNT + off[k2]];
+#endif
           double* o = out + d * w + x;
           if (first_round) *o = sum; else *o += sum;
         }
@@ -374,15 +384,16 @@ __device__ __forceinline__ void noderec_fetch(const FusedArgs& F, NodeRec* dst2,
 // Measured on B200 at 4 M Quad4: persistent grid-stride warps with a 3-deep prefetch ring 12.4 ms/step, this 10.4.
 // Within a warp the node records of item j+2 and the element records of item j+1 are in flight (cp.async) while item j
 // is evaluated (matters for the latency-bound one- and two-matrix calls, e.g. config 3).
-template <int KIND, int CHUNK>
+template <int KIND, int CHUNK, bool DYN>
 __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
-                                                                         int rstride) {
-  constexpr int kFRing = fring(CHUNK), kFBufs = fbufs(CHUNK);
+                                                                         int rstride, unsigned long long* __restrict__ work) {
+  constexpr bool PRE = CHUNK > 1 || DYN;   // records of the next items arrive by cp.async while this one is evaluated
+  constexpr int kFRing = PRE ? 3 : 1, kFBufs = PRE ? 2 : 1;
   extern __shared__ __align__(16) double smem[];
   const EvalArgs& A = F.A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int eld = rstride + 2;
-  double* st = smem + warp * warp_smem_doubles(rstride, CHUNK);
+  double* st = smem + warp * warp_smem_doubles(rstride, PRE ? kFChunkBig : 1);
   NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
   double* erec = st + kStageV4 + kFRing * 2 * 8;
   const int h = lane >> 4, l16 = lane & 15, k = l16 >> 2, b = l16 & 3;
@@ -390,44 +401,86 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   const UnionMap* umKG = F.um[1].active ? &F.um[1] : nullptr;
   const UnionMap* umM = F.um[2].active ? &F.um[2] : nullptr;
   const int64_t npairs = F.pair_count ? F.pair_first + F.pair_count : (F.nown + 1) >> 1;   // end of this launch's range
-  const int64_t np0 = F.pair_first + (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
-  if (np0 >= npairs) return;
   const int rmax = F.rmax;
-  const int nitems = int(min(int64_t(CHUNK), npairs - np0)) * rmax;   // item j = (pair np0 + j / rmax, round j % rmax)
   const double xib = (b == 1 || b == 2) ? 1. : -1., etab = (b >= 2) ? 1. : -1.;
+  // static schedule: this warp owns CHUNK consecutive pairs.  DYN: persistent warps claim pairs one at a time, IN ORDER,
+  // from a global counter (rmax == 1 only), three claims ahead of the pair being evaluated: the record loads of the
+  // claimed pairs are in flight while the front of pairs being STORED stays as narrow as with one pair per CTA.
+  int64_t np0 = 0, pq0 = -1, pq1 = -1, pq2 = -1;   // DYN: pairs of items j, j+1, j+2
+  unsigned long long raw = 0ull;                   // DYN: lane 0's pending claim (item j+3)
+  int nitems = 0;
+  if constexpr (DYN) {
+    const unsigned long long total = (unsigned long long)(npairs - F.pair_first);
+    if (lane == 0) raw = atomicAdd(work, 3ull);
+    const unsigned long long q = __shfl_sync(0xffffffffu, raw, 0);
+    if (q >= total) return;
+    pq0 = F.pair_first + int64_t(q);
+    pq1 = (q + 1 < total) ? pq0 + 1 : -1;
+    pq2 = (q + 2 < total) ? pq0 + 2 : -1;
+    if (lane == 0) raw = atomicAdd(work, 1ull);
+  } else {
+    np0 = F.pair_first + (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
+    if (np0 >= npairs) return;
+    nitems = int(min(int64_t(CHUNK), npairs - np0)) * rmax;   // item j = (pair np0 + j / rmax, round j % rmax)
+  }
 
-  auto rec_fetch = [&](int j) {
-    if (j < nitems)
-      noderec_fetch(F, ring + (j % kFRing) * 2, np0 + j / rmax, j % rmax, lane);
+  auto rec_fetch_pair = [&](int slot3, int64_t pair, int r) {
+    if (pair >= 0)
+      noderec_fetch(F, ring + slot3 * 2, pair, r, lane);
     else
       asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto erec_prefetch = [&](int j) {
-    if (j < nitems)
+  auto rec_fetch = [&](int j) { rec_fetch_pair(j % kFRing, j < nitems ? np0 + j / rmax : int64_t(-1), j % rmax); };
+  auto erec_prefetch = [&](int j, bool valid) {
+    if (valid)
       erec_fetch(rec, rstride, erec + (j % kFBufs) * 8 * eld, (ring + (j % kFRing) * 2 + h)->inc[k], lane);
     else
       asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if constexpr (CHUNK > 1) {
+  if constexpr (DYN) {
+    rec_fetch_pair(0, pq0, 0);
+    rec_fetch_pair(1, pq1, 0);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    erec_prefetch(0, true);
+  } else if constexpr (CHUNK > 1) {
     rec_fetch(0);
     rec_fetch(1);
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();
-    erec_prefetch(0);
+    erec_prefetch(0, 0 < nitems);
   }
 
-  for (int j = 0; j < nitems; ++j) {
-    const int r = j % rmax;
-    if constexpr (CHUNK > 1) {
-      rec_fetch(j + 2);
+  for (int j = 0;; ++j) {
+    int r = 0;
+    if constexpr (DYN) {
+      if (j > 0) {   // rotate: item j-1 is done
+        pq0 = pq1;
+        pq1 = pq2;
+        const unsigned long long total = (unsigned long long)(npairs - F.pair_first);
+        const unsigned long long q = __shfl_sync(0xffffffffu, raw, 0);   // claimed one item ago
+        pq2 = (q < total) ? F.pair_first + int64_t(q) : -1;
+        if (lane == 0 && q < total) raw = atomicAdd(work, 1ull);
+      }
+      if (pq0 < 0) break;
+      rec_fetch_pair((j + 2) % 3, pq2, 0);
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j+1 and element records j have landed
       __syncwarp();
-      erec_prefetch(j + 1);
+      erec_prefetch(j + 1, pq1 >= 0);
     } else {
-      if (j > 0) stage_reuse_wait();
-      rec_fetch(j);
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
+      if (j >= nitems) break;
+      r = j % rmax;
+      if constexpr (CHUNK > 1) {
+        rec_fetch(j + 2);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j+1 and element records j have landed
+        __syncwarp();
+        erec_prefetch(j + 1, j + 1 < nitems);
+      } else {
+        if (j > 0) stage_reuse_wait();
+        rec_fetch(j);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+      }
     }
     const NodeRec* nr = ring + (j % kFRing) * 2 + h;
     const int pair0 = nr->inc[k];
@@ -452,10 +505,12 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       }
       continue;
     }
-    if constexpr (CHUNK == 1) {
-      erec_prefetch(j);
+    if constexpr (!PRE) {
+#ifndef PF3_ABL_NOEREC
+      erec_prefetch(j, true);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
+#endif
     }
     const int64_t b0 = nr->b0;
     const int nb = nr->nb;
@@ -702,8 +757,13 @@ int fused_max_slots() { return kMaxSlots; }
 int fused_record_stride(const EvalArgs& A) { return A.evec != nullptr ? kRecRot : kRecPlain; }
 
 // rec: device scratch of ne * fused_record_stride doubles.  phases: bit 0 = K1 (records of ALL elements), bit 1 = K2 for
-// the node pairs [F.pair_first, F.pair_first + F.pair_count) (all pairs when pair_count == 0).
-cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases) {
+// the node pairs [F.pair_first, F.pair_first + F.pair_count) (all pairs when pair_count == 0).  work: an 8-byte device
+// counter owned by the caller's context (the in-order work queue of the persistent variant).
+#ifndef PF3_DYN
+#define PF3_DYN 0   // 1: three-matrix calls on single-round plans run the persistent, dynamically scheduled variant
+#endif
+cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases,
+                              unsigned long long* work) {
   if (F.nown <= 0 || F.A.ne <= 0) return cudaSuccess;
   const int stride = fused_record_stride(F.A);
   if (phases & 1) {
@@ -730,25 +790,39 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   const int vol = ((w & PF3_KC0) ? 900 : 0) + ((w & (PF3_KG | PF3_KG_STRESS)) ? 225 : 0) + ((w & PF3_M) ? 750 : 0);
   const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
   const int chunk = (vol < 1400 && !mapped) ? kFChunkBig : 1;
-  const size_t smem = fused_smem_bytes(stride, chunk);
+  const bool dyn = PF3_DYN && chunk == 1 && !mapped && !F.zero_empty && F.rmax == 1 && work != nullptr;
+  const size_t smem = fused_smem_bytes(stride, dyn ? kFChunkBig : chunk);
   const int64_t npairs = F.pair_count ? F.pair_count : (F.nown + 1) / 2;
-  const int64_t want = (npairs + int64_t(kFusedWarps) * chunk - 1) / (int64_t(kFusedWarps) * chunk);
+  int64_t want = (npairs + int64_t(kFusedWarps) * chunk - 1) / (int64_t(kFusedWarps) * chunk);
+  if (dyn) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    want = std::min<int64_t>(want, int64_t(sms) * PF3_FUSED_CTAS);
+    cudaError_t em = cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
+    if (em != cudaSuccess) return em;
+  }
   if (want > int64_t(0x7fffffff)) return cudaErrorInvalidConfiguration;
   const unsigned grid = unsigned(want < 1 ? 1 : want);
   static PerDeviceOnce once;
   if (once.first()) {
     const int m1 = int(fused_smem_bytes(kRecRot, 1)), m4 = int(fused_smem_bytes(kRecRot, kFChunkBig));
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, kFChunkBig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, kFChunkBig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
   }
+  const unsigned nt = 32 * kFusedWarps;
   if (kind == PF3_QUAD4) {
-    if (chunk == 1) quad_fused_kernel<PF3_QUAD4, 1><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
-    else quad_fused_kernel<PF3_QUAD4, kFChunkBig><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
+    if (dyn) quad_fused_kernel<PF3_QUAD4, 1, true><<<grid, nt, smem, st>>>(F, rec, stride, work);
+    else if (chunk == 1) quad_fused_kernel<PF3_QUAD4, 1, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
+    else quad_fused_kernel<PF3_QUAD4, kFChunkBig, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
   } else {
-    if (chunk == 1) quad_fused_kernel<PF3_QUAD4R, 1><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
-    else quad_fused_kernel<PF3_QUAD4R, kFChunkBig><<<grid, 32 * kFusedWarps, smem, st>>>(F, rec, stride);
+    if (dyn) quad_fused_kernel<PF3_QUAD4R, 1, true><<<grid, nt, smem, st>>>(F, rec, stride, work);
+    else if (chunk == 1) quad_fused_kernel<PF3_QUAD4R, 1, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
+    else quad_fused_kernel<PF3_QUAD4R, kFChunkBig, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
   }
   ++*launches;
   return cudaGetLastError();

@@ -6,12 +6,17 @@ tria3r.pyx:128-292, beamc.pyx:23-156, beamlr.pyx:23-158, truss.pyx:29-148,
 spring.pyx:21-145), so existing element-loop scripts run unchanged after
 ``import pyfe3d_b200 as pyfe3d``.
 
-Every method is a batch-of-one call into the same CUDA kernels through the C ABI
-(``pf3_eval_host`` / ``pf3_eval_state`` / ``pf3_eval_finte``): the host objects only
+Every method is a batch-of-one call into the same CUDA kernels through the host-pointer
+entry points of the C ABI (``pf3_eval_host`` / ``pf3_eval_state_host`` /
+``pf3_eval_finte_host`` / ``pf3_eval_aero_host``): the caller's numpy arrays are packed
+into one pinned staging buffer, copied to the device once, evaluated, and copied back
+once (two PCIe transfers + one stream synchronisation per method call, on the context's
+own stream; the call returns when the arrays hold the result).  The host objects only
 hold state (r11..r33, m11..m22, area/length, probe.xe/ue/finte) exactly like the
-reference; no arithmetic is done on the host and there is no CPU fallback.  The
-per-call launch latency makes this path a compatibility layer — the fast path is
-:class:`pyfe3d_b200.batch.ElementBatch`.
+reference; no arithmetic is done on the host and there is no CPU fallback.  The per-call
+latency (tens of microseconds) makes this path a compatibility layer — the fast path is
+:class:`pyfe3d_b200.batch.ElementBatch` (``pyfe3d_b200.elements.CALLS`` counts the
+per-element calls made so far; a one-time ``UserWarning`` points there after 50 000 calls).
 """
 import ctypes as _ct
 
@@ -25,13 +30,21 @@ INT = np.int64 if _ct.sizeof(_ct.c_long) == 8 else np.int32
 DOUBLE = np.float64
 
 _CTX = [None]
+CALLS = [0]          # per-element C-ABI calls made by this process (see the module docstring)
+_HINT_AT = 50000
 
 
 def _ctx():
     if _CTX[0] is None:
         if _cabi.device_count() <= 0:
             raise RuntimeError("pyfe3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        _CTX[0] = _cabi.Context(0)
+        _CTX[0] = _cabi.Context(0)   # its own stream; every per-element call is synchronous on it
+    CALLS[0] += 1
+    if CALLS[0] == _HINT_AT:
+        import warnings
+        warnings.warn("pyfe3d_b200: %d per-element calls so far, each a separate device round trip; "
+                      "pyfe3d_b200.batch.ElementBatch evaluates all elements of one kind in one launch" % _HINT_AT,
+                      UserWarning, stacklevel=3)
     return _CTX[0]
 
 
@@ -169,12 +182,9 @@ class _Element:
         self._take_state(out, ue=True)
 
     def _eval_state(self, batch):
-        import torch
-        tout = torch.zeros(_cabi.STATE_STRIDE, dtype=torch.float64, device="cuda")
-        ctx = _ctx()
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        ctx.eval_state(batch, tout.data_ptr())
-        return tout.cpu().numpy()
+        out = np.zeros(_cabi.STATE_STRIDE)
+        _ctx().eval_state(batch, out.ctypes.data, host=True)
+        return out
 
     def update_probe_xe(self, x):
         """probe.xe = R^T x and area/length (e.g. quad4.pyx:682)."""
@@ -183,66 +193,51 @@ class _Element:
         out = self._eval_state(self._host_batch(None, self._state(), _cabi.STATE_REFRESH_XE, xl, None, None))
         self._take_state(out, xe=True)
 
-    def _host_batch(self, prop, state, flags, x, u, ep, evec=None, mtype=0, stress=(0., 0., 0.)):
-        """Device copies of the tiny per-element inputs, kept alive on self."""
-        import torch  # device buffers only
-        dev = {}
-        for k, a in (("prop", prop), ("state", state), ("x", x), ("u", u), ("ep", ep), ("evec", evec)):
-            dev[k] = None if a is None else torch.as_tensor(np.ascontiguousarray(a)).cuda()
-        conn = torch.arange(self._nn, dtype=torch.int64, device="cuda")
-        if dev["prop"] is None and self.KIND != _cabi.SPRING:
-            dev["prop"] = torch.zeros(_cabi.SHELLPROP_STRIDE, dtype=torch.float64, device="cuda")
-        self._keep = (dev, conn)
-        g = lambda t: 0 if t is None else t.data_ptr()
-        return _cabi.Batch(self.KIND, 1, self._nn, conn.data_ptr(), g(dev["x"]), g(dev["u"]), g(dev["prop"]), 0,
-                           1, g(dev["evec"]), 0, g(dev["ep"]), g(dev["state"]), mtype, stress, flags)
+    def _host_batch(self, prop, state, flags, x, u, ep, evec=None, mtype=0, stress=(0., 0., 0.), conn=None):
+        """pf3_batch of ONE element over HOST arrays (kept alive on self until the call returns)."""
+        if prop is None and self.KIND != _cabi.SPRING:
+            prop = np.zeros(_cabi.SHELLPROP_STRIDE)
+        if conn is None:
+            conn = self._conn                      # local node numbers 0..nn-1: x / u hold this element's nodes only
+        hold = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (prop, state, x, u, ep, evec)]
+        self._keep = (hold, conn)
+        prop, state, x, u, ep, evec = hold
+        return _cabi.Batch(self.KIND, 1, self._nn, conn.ctypes.data, _p(x), _p(u), _p(prop), 0, 1, _p(evec), 0,
+                           _p(ep), _p(state), mtype, stress, flags)
 
-    def _run(self, what, prop, coo, mtype=0, stress=(0., 0., 0.), hg=None, values_only=False, fint=None):
-        """One batch-of-one evaluation from the object's current state."""
-        import torch
+    def _run(self, what, prop, coo, mtype=0, stress=(0., 0., 0.), hg=None, values_only=False, fint=None, state=None):
+        """One batch-of-one evaluation from the object's current state: ONE pf3_eval_host call."""
         ctx = _ctx()
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        b = self._host_batch(self._props_row(prop) if prop is not None else None, self._state(), 0, None, None,
-                             self._eparam(hg), mtype=mtype, stress=stress)
+        gconn = None
+        if coo is not None:
+            # the element's own global node positions, so that the COO indices come out global (x / u are not read
+            # when a state is given)
+            gconn = np.array([c // 6 for c in self._cs()], dtype=np.int64)
+        b = self._host_batch(self._props_row(prop) if prop is not None else None,
+                             self._state() if state is None else state, 0, None, None, self._eparam(hg), mtype=mtype,
+                             stress=stress, conn=gconn)
         outs = [None, None, None]
-        tens = {}
         if coo is not None:
             which, (r, c, v, init_k, size) = coo
-            seg = slice(init_k, init_k + size)
-            tv = torch.as_tensor(v[seg]).cuda()
-            tr = tc = None
-            if not values_only:
-                tr = torch.as_tensor(r[seg]).cuda()
-                tc = torch.as_tensor(c[seg]).cuda()
-                # global DOF positions: the kernels see local node numbers 0..nn-1
-            tens = dict(v=tv, r=tr, c=tc)
-            outs[which] = _cabi.Coo(0, 0, tv.data_ptr(), 0, 1)
-        tf = None
+            if init_k < 0 or init_k + size > v.shape[0] or (not values_only and
+                                                            (init_k + size > r.shape[0] or init_k + size > c.shape[0])):
+                raise ValueError("COO arrays too short for init_k + SPARSE_SIZE")
+            outs[which] = _cabi.Coo(0 if values_only else r.ctypes.data, 0 if values_only else c.ctypes.data,
+                                    v.ctypes.data, init_k, 1)
+        fl = None
         if fint is not None:
-            tf = torch.zeros(6 * self._nn, dtype=torch.float64, device="cuda")
-        ctx.eval(b, what, outs[0], outs[1], outs[2], 0 if tf is None else tf.data_ptr())
-        if coo is not None:
-            v[seg] = tens["v"].cpu().numpy()
-            if not values_only:
-                mat = (_cabi.MAT_KC0, _cabi.MAT_KG, _cabi.MAT_M)[which]
-                gconn = torch.as_tensor(np.array([c // 6 for c in self._cs()], dtype=np.int64)).cuda()
-                ctx.fill_indices(self.KIND, mat, mtype, 1, gconn.data_ptr(), 0, tens["r"].data_ptr(),
-                                 tens["c"].data_ptr())
-                r[seg] = tens["r"].cpu().numpy()
-                c[seg] = tens["c"].cpu().numpy()
+            fl = np.zeros(6 * self._nn)
+        ctx.eval(b, what, outs[0], outs[1], outs[2], 0 if fl is None else fl.ctypes.data, host=True)
         if fint is not None:
-            fl = tf.cpu().numpy()
             for a, cpos in enumerate(self._cs()):
                 fint[cpos:cpos + 6] += fl[6 * a:6 * a + 6]
 
     def _finte(self, prop, hg=None):
-        import torch
-        ctx = _ctx()
         b = self._host_batch(self._props_row(prop) if prop is not None else None, self._state(), 0, None, None,
                              self._eparam(hg))
-        out = torch.zeros(6 * self._nn, dtype=torch.float64, device="cuda")
-        ctx.eval_finte(b, out.data_ptr())
-        self.probe.finte[:] = out.cpu().numpy()
+        out = np.zeros(6 * self._nn)
+        _ctx().eval_finte(b, out.ctypes.data, host=True)
+        self.probe.finte[:] = out
 
 
 def _coo_args(KCr, KCc, KCv, init_k, size, names):
@@ -271,42 +266,29 @@ class _Shell(_Element):
         ep = self._eparam()
         ep[7] = 1.
         ep[8:12] = [self.m11, self.m12, self.m21, self.m22]
-        out = np.zeros(_cabi.STATE_STRIDE)
-        import torch
         b = self._host_batch(None, None, 0, xl, None, ep, evec=np.array([xmati, xmatj, xmatk], float))
-        tout = torch.zeros(_cabi.STATE_STRIDE, dtype=torch.float64, device="cuda")
-        _ctx().eval_state(b, tout.data_ptr())
-        self._take_state(tout.cpu().numpy(), rot=True)
+        self._take_state(self._eval_state(b), rot=True)
 
     def update_area(self):
         # area is refreshed together with xe (update_probe_xe calls update_area, quad4.pyx:730);
         # calling it alone re-derives it from the probe's current xe with R = I
-        save = (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33)
-        xe = self.probe.xe.copy()
-        (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = (1., 0., 0., 0., 1., 0., 0., 0., 1.)
         st = self._state()
-        import torch
-        tout = torch.zeros(_cabi.STATE_STRIDE, dtype=torch.float64, device="cuda")
-        _ctx().eval_state(self._host_batch(None, st, _cabi.STATE_REFRESH_XE, xe, None, None), tout.data_ptr())
-        (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = save
-        self.area = float(tout.cpu().numpy()[13])
+        st[0:9] = [1., 0., 0., 0., 1., 0., 0., 0., 1.]
+        out = self._eval_state(self._host_batch(None, st, _cabi.STATE_REFRESH_XE, self.probe.xe.copy(), None, None))
+        self.area = float(out[13])
 
-    def update_probe_finte(self, prop, **hg):
-        self._finte(prop, self._hg(hg))
+    def update_probe_finte(self, prop):
+        self._finte(prop)
 
-    def _hg(self, kw):
-        return None
-
-    def update_KC0(self, KC0r, KC0c, KC0v, prop, update_KC0v_only=0, **hg):
+    def update_KC0(self, KC0r, KC0c, KC0v, prop, update_KC0v_only=0):
         size = _cabi.sparse_size(self.KIND, _cabi.MAT_KC0)
         self._run(_cabi.KC0, prop, (0, _coo_args(KC0r, KC0c, KC0v, self.init_k_KC0, size, ("KC0r", "KC0c", "KC0v"))),
-                  hg=self._hg(hg), values_only=bool(update_KC0v_only))
+                  values_only=bool(update_KC0v_only))
 
-    def update_fint(self, fint, prop, **hg):
+    def update_fint(self, fint, prop):
         _check_array(fint, np.float64, "fint")
-        h = self._hg(hg)
-        self._finte(prop, h)
-        self._run(_cabi.FINT, prop, None, hg=h, fint=fint)
+        self._finte(prop)
+        self._run(_cabi.FINT, prop, None, fint=fint)
 
     def _kg_values_only(self, flag):
         return bool(flag)
@@ -332,23 +314,15 @@ class _QuadAero:
     accumulated, from the object's current r11..r33 and probe.xe."""
 
     def _aero(self, which, r, c, v, init_k, names):
-        import torch
         ctx = _ctx()
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         r, c, v, init_k, size = _coo_args(r, c, v, init_k, 144, names)
-        b = self._host_batch(None, self._state(), 0, None, None, None)
-        seg = slice(init_k, init_k + size)
-        tv = torch.as_tensor(v[seg]).cuda()
+        if init_k < 0 or init_k + size > min(r.shape[0], c.shape[0], v.shape[0]):
+            raise ValueError("COO arrays too short for init_k + SPARSE_SIZE")
+        gconn = np.array([cc // 6 for cc in self._cs()], dtype=np.int64)
+        b = self._host_batch(None, self._state(), 0, None, None, None, conn=gconn)
         outs = [None, None, None]
-        outs[which] = _cabi.Coo(0, 0, tv.data_ptr(), 0, 1)
-        ctx.eval_aero(b, (_cabi.KA_BETA, _cabi.KA_GAMMA, _cabi.CA)[which], outs[0], outs[1], outs[2])
-        v[seg] = tv.cpu().numpy()
-        tr = torch.zeros(size, dtype=torch.int64, device="cuda")
-        tc = torch.zeros(size, dtype=torch.int64, device="cuda")
-        gconn = torch.as_tensor(np.array([cc // 6 for cc in self._cs()], dtype=np.int64)).cuda()
-        ctx.fill_indices(self.KIND, _cabi.MAT_KA_BETA + which, 0, 1, gconn.data_ptr(), 0, tr.data_ptr(), tc.data_ptr())
-        r[seg] = tr.cpu().numpy()
-        c[seg] = tc.cpu().numpy()
+        outs[which] = _cabi.Coo(r.ctypes.data, c.ctypes.data, v.ctypes.data, init_k, 1)
+        ctx.eval_aero(b, (_cabi.KA_BETA, _cabi.KA_GAMMA, _cabi.CA)[which], outs[0], outs[1], outs[2], host=True)
 
     def update_KA_beta(self, KA_betar, KA_betac, KA_betav):
         self._aero(0, KA_betar, KA_betac, KA_betav, self.init_k_KA_beta, ("KA_betar", "KA_betac", "KA_betav"))
@@ -379,18 +353,32 @@ class Quad4Probe(_Probe):
 
     def __init__(self):
         super().__init__()
-        self.KC0ve = np.zeros(576)
+        self._KC0ve = np.zeros(576)
+        self._KC0ve_pending = None
         for n in self._BL:
             setattr(self, n, np.zeros(24))
 
+    @property
+    def KC0ve(self):
+        """Local 24x24 stiffness of the element last passed through update_KC0 / update_probe_finte
+        (quad4.pyx:755, :1196).  The reference fills it as a by-product of those calls; here the inputs of that
+        call are remembered and the block is evaluated (the same kernel with R = I) when it is first read."""
+        if self._KC0ve_pending is not None:
+            elem, state, prop_row, ep = self._KC0ve_pending
+            self._KC0ve_pending = None
+            st = state.copy()
+            st[0:9] = [1., 0., 0., 0., 1., 0., 0., 0., 1.]
+            v = np.zeros(576)
+            b = elem._host_batch(prop_row, st, 0, None, None, ep)
+            _ctx().eval(b, _cabi.KC0, _cabi.Coo(0, 0, v.ctypes.data, 0, 0), None, None, 0, host=True)
+            self._KC0ve[:] = v
+        return self._KC0ve
+
     def update_BL(self, xi, eta):
-        import torch
-        ctx = _ctx()
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        xe = torch.as_tensor(np.ascontiguousarray(self.xe)).cuda()
-        out = torch.zeros(264, dtype=torch.float64, device="cuda")
-        ctx.quad4_update_BL(1, xe.data_ptr(), float(xi), float(eta), out.data_ptr())
-        rows = out.cpu().numpy().reshape(11, 24)
+        out = np.zeros(264)
+        xe = np.ascontiguousarray(self.xe, dtype=np.float64)
+        _ctx().quad4_update_BL(1, xe.ctypes.data, float(xi), float(eta), out.ctypes.data, host=True)
+        rows = out.reshape(11, 24)
         for i, n in enumerate(self._BL):
             getattr(self, n)[:] = rows[i]
 
@@ -398,25 +386,16 @@ class Quad4Probe(_Probe):
 class Quad4(_QuadAero, _Shell):
     KIND = _cabi.QUAD4
 
-    def _refresh_KC0ve(self, prop):
-        """probe.KC0ve = the local 24x24 stiffness (quad4.pyx:755): the same kernel evaluated with R = I."""
-        save = (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33)
-        (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = (1., 0., 0., 0., 1., 0., 0., 0., 1.)
-        try:
-            r = np.zeros(576, np.int64)
-            v = np.zeros(576)
-            self._run(_cabi.KC0, prop, (0, (r, r.copy(), v, 0, 576)), values_only=True)
-            self.probe.KC0ve[:] = v
-        finally:
-            (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = save
+    def _remember_KC0ve(self, prop):
+        self.probe._KC0ve_pending = (self, self._state(), self._props_row(prop), self._eparam())
 
     def update_KC0(self, KC0r, KC0c, KC0v, prop, update_KC0v_only=0):
         super().update_KC0(KC0r, KC0c, KC0v, prop, update_KC0v_only)
-        self._refresh_KC0ve(prop)
+        self._remember_KC0ve(prop)
 
     def _finte(self, prop, hg=None):   # update_probe_finte recomputes KC0ve in the reference (quad4.pyx:1196)
         super()._finte(prop, hg)
-        self._refresh_KC0ve(prop)
+        self._remember_KC0ve(prop)
 
     # Quad4.update_KG / update_KG_given_stress take no update_KGv_only (quad4.pyx:1365, 2259):
     # indices are always written
@@ -436,14 +415,25 @@ class Quad4RProbe(_Probe):
 
 
 class Quad4R(_QuadAero, _Shell):
+    """hgfactor_u .. hgfactor_ry are ordinary positional-or-keyword parameters with default 1., as in
+    quad4r.pyx:549-556 (update_probe_finte), :1145-1156 (update_KC0), :4620-4627 (update_fint)."""
     KIND = _cabi.QUAD4R
 
-    def _hg(self, kw):
-        names = ("hgfactor_u", "hgfactor_v", "hgfactor_w", "hgfactor_rx", "hgfactor_ry")
-        bad = set(kw) - set(names)
-        if bad:
-            raise TypeError("unexpected keyword argument(s) %s" % sorted(bad))
-        return np.array([float(kw.get(n, 1.)) for n in names])
+    def update_probe_finte(self, prop, hgfactor_u=1., hgfactor_v=1., hgfactor_w=1., hgfactor_rx=1., hgfactor_ry=1.):
+        self._finte(prop, np.array([hgfactor_u, hgfactor_v, hgfactor_w, hgfactor_rx, hgfactor_ry], float))
+
+    def update_KC0(self, KC0r, KC0c, KC0v, prop, update_KC0v_only=0, hgfactor_u=1., hgfactor_v=1., hgfactor_w=1.,
+                   hgfactor_rx=1., hgfactor_ry=1.):
+        size = _cabi.sparse_size(self.KIND, _cabi.MAT_KC0)
+        self._run(_cabi.KC0, prop, (0, _coo_args(KC0r, KC0c, KC0v, self.init_k_KC0, size, ("KC0r", "KC0c", "KC0v"))),
+                  hg=np.array([hgfactor_u, hgfactor_v, hgfactor_w, hgfactor_rx, hgfactor_ry], float),
+                  values_only=bool(update_KC0v_only))
+
+    def update_fint(self, fint, prop, hgfactor_u=1., hgfactor_v=1., hgfactor_w=1., hgfactor_rx=1., hgfactor_ry=1.):
+        _check_array(fint, np.float64, "fint")
+        h = np.array([hgfactor_u, hgfactor_v, hgfactor_w, hgfactor_rx, hgfactor_ry], float)
+        self._finte(prop, h)
+        self._run(_cabi.FINT, prop, None, hg=h, fint=fint)
 
 
 class Tria3RData(_Data):
@@ -471,26 +461,19 @@ class _Line(_Element):
         self.vxyi = self.vxyj = self.vxyk = 0.
 
     def update_length(self):
-        save = (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33)
-        xe = self.probe.xe.copy()
-        (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = (1., 0., 0., 0., 1., 0., 0., 0., 1.)
         st = self._state()
-        import torch
-        tout = torch.zeros(_cabi.STATE_STRIDE, dtype=torch.float64, device="cuda")
-        _ctx().eval_state(self._host_batch(self._dummy_prop(), st, _cabi.STATE_REFRESH_XE, xe, None, None), tout.data_ptr())
-        (self.r11, self.r12, self.r13, self.r21, self.r22, self.r23, self.r31, self.r32, self.r33) = save
-        self.length = float(tout.cpu().numpy()[13])
+        st[0:9] = [1., 0., 0., 0., 1., 0., 0., 0., 1.]
+        out = self._eval_state(self._host_batch(self._dummy_prop(), st, _cabi.STATE_REFRESH_XE, self.probe.xe.copy(),
+                                                None, None))
+        self.length = float(out[13])
 
     def _dummy_prop(self):
         return np.zeros(_cabi.BEAMPROP_STRIDE)
 
     def _rot(self, x, vxy):
-        import torch
         xl = self._local(x, 3, 2)
         b = self._host_batch(self._dummy_prop(), None, 0, xl, None, None, evec=vxy)
-        tout = torch.zeros(_cabi.STATE_STRIDE, dtype=torch.float64, device="cuda")
-        _ctx().eval_state(b, tout.data_ptr())
-        self._take_state(tout.cpu().numpy(), rot=True)
+        self._take_state(self._eval_state(b), rot=True)
 
     def update_probe_finte(self, prop):
         self._finte(prop)
@@ -589,13 +572,10 @@ class Spring(_Element):
         self.r11 = self.r22 = self.r33 = 1.   # default R = I (spring.pyx:138-144)
 
     def update_rotation_matrix(self, xi, xj, xk, vxyi, vxyj, vxyk):
-        import torch
         self.vxyi, self.vxyj, self.vxyk = float(vxyi), float(vxyj), float(vxyk)
         b = self._host_batch(None, None, 0, None, None, self._eparam(),
                              evec=np.array([xi, xj, xk, vxyi, vxyj, vxyk], float))
-        tout = torch.zeros(_cabi.STATE_STRIDE, dtype=torch.float64, device="cuda")
-        _ctx().eval_state(b, tout.data_ptr())
-        self._take_state(tout.cpu().numpy(), rot=True)
+        self._take_state(self._eval_state(b), rot=True)
 
     def update_probe_finte(self):
         self._finte(None)

@@ -167,6 +167,57 @@ def line_chain(kind, n, seed):
     return _finish(case, n, rng)
 
 
+def shell_degenerate_xmat(kind, seed):
+    """The guards of update_rotation_matrix (quad4.pyx:588-598, tria3r.pyx:388-398; the situation of
+    tests/test_quad4r_static_point_load_mat_coord_error.py:74 in the reference): material direction EXACTLY parallel
+    to the element normal (flat elements in the global xy plane: z = (0,0,1) without rounding), parallel up to
+    rounding (xmat = the computed normal of a rotated element, and the exact normal plus a perturbation far below
+    tol = |z|/1e10), antiparallel, null, and -- as controls -- in-plane and generic directions.  In every degenerate
+    row the reference leaves m at its previous value, which is the identity for a fresh element."""
+    rng = np.random.default_rng(seed)
+    nn = 3 if kind == "tria3r" else 4
+    base = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], float)[:nn]
+    if nn == 3:
+        base = np.array([[0, 0, 0], [1, 0, 0], [0.3, 0.9, 0]], float)
+    ne = 14
+    X = np.zeros((ne * nn, 3))
+    xm = np.zeros((ne, 3))
+    for e in range(ne):
+        s = 10 ** rng.uniform(-1.5, 0.)
+        pts = s * (base + 0.15 * rng.uniform(-1, 1, (nn, 3)) * [1, 1, 0]) + s * rng.normal(size=3) * [1, 1, 0]
+        if e < 8:
+            X[e * nn:(e + 1) * nn] = pts                      # flat, unrotated: normal = +z exactly
+        else:
+            X[e * nn:(e + 1) * nn] = pts @ random_rotation(rng).T
+    conn = np.arange(ne * nn, dtype=np.int64).reshape(ne, nn)
+    P = X.reshape(ne, nn, 3)
+    if nn == 4:
+        nrm = np.cross(P[:, 1] - P[:, 3], P[:, 2] - P[:, 0])
+    else:
+        nrm = np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
+    unit = nrm / np.linalg.norm(nrm, axis=1)[:, None]
+    xm[0] = [0., 0., 1.]
+    xm[1] = [0., 0., 2.5]
+    xm[2] = [0., 0., -3.]
+    xm[3] = [0., 0., 0.]
+    xm[4] = [1e-13, -2e-13, 1.]          # |z x xmat| ~ 2e-13 < tol
+    xm[5] = [1., 0., 0.]                 # in plane: m = identity through the regular branch
+    xm[6] = [0.3, 0.7, 0.]
+    xm[7] = [0.3, 0.7, 5.]
+    xm[8] = unit[8]                      # computed normals of rotated elements: parallel up to rounding
+    xm[9] = -4. * unit[9]
+    xm[10] = nrm[10]                     # unnormalised
+    xm[11] = unit[11] + 1e-14 * rng.normal(size=3)
+    xm[12] = rng.normal(size=3)          # generic controls
+    xm[13] = rng.normal(size=3)
+    props = random_shellprops(rng, 2)
+    case = dict(kind=kind, x=X.ravel(), conn=conn, props=props, prop_id=rng.integers(0, 2, ne).astype(np.int32),
+                stress=(0.9e3, 0.2e3, -0.5e3), xmat=xm)
+    if kind == "quad4r":
+        case["hg"] = rng.uniform(0.001, 2.0, (ne, 5))
+    return _finish(case, ne * nn, rng)
+
+
 SHELL_KINDS = ("quad4", "quad4r", "tria3r")
 LINE_KINDS = ("beamc", "beamlr", "truss", "spring")
 
@@ -178,6 +229,7 @@ def golden_cases():
         out[k + "_soup"] = shell_soup(k, 24, seed=11)
         out[k + "_soup_thick"] = shell_soup(k, 8, seed=12, size_range=(-3., -2.5), thick=True)
         out[k + "_mesh"] = shell_mesh(k, 5, 4, seed=13)
+        out[k + "_xmat_degenerate"] = shell_degenerate_xmat(k, seed=14)
     for k in LINE_KINDS:
         out[k + "_soup"] = line_soup(k, 24, seed=21)
         out[k + "_chain"] = line_chain(k, 9, seed=22)

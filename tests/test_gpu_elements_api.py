@@ -143,6 +143,69 @@ def test_sticky_material_axis_and_accumulate():
     assert util.block_relerr(v1, want, 1) <= util.TOL_VALUES
 
 
+@pytest.mark.parametrize("kind", ["quad4", "quad4r", "tria3r"])
+def test_degenerate_material_axis_keeps_state(kind):
+    """xmat parallel to the element normal / null after a regular one: m11..m22 stay what the regular call left
+    (quad4.pyx:588-598; the situation of tests/test_quad4r_static_point_load_mat_coord_error.py:74), and batch state of
+    the degenerate golden rows is the identity.  Reference sequence: tests/golden/sticky_xmat.npz."""
+    import os
+    z = np.load(os.path.join(util.GOLDEN_DIR, "sticky_xmat.npz"))
+    case, ref = util.load_golden(kind + "_xmat_degenerate")
+    m_ref = ref["m"].reshape(-1, 4)
+    for e in (0, 1, 2, 3, 4, 8, 9, 10, 11):
+        assert np.array_equal(m_ref[e], [1., 0., 0., 1.])      # the fixture really exercises the guards
+    e = 6
+    x = np.ascontiguousarray(case["x"], float)
+    el = getattr(pf, CLS[kind])(getattr(pf, CLS[kind] + "Probe")())
+    for a in range(case["conn"].shape[1]):
+        setattr(el, "c%d" % (a + 1), int(6 * case["conn"][e, a]))
+    for step, xm in enumerate((case["xmat"][e], (0., 0., 2.5), (0., 0., 0.), (0., 0., -1.))):
+        el.update_rotation_matrix(x, float(xm[0]), float(xm[1]), float(xm[2]))
+        got = np.array([el.m11, el.m12, el.m21, el.m22])
+        assert np.abs(got - z[kind + "_m"][step]).max() <= 1e-12, (step, got)
+        if step > 0:
+            assert np.array_equal(got, first)                  # untouched, not recomputed
+        else:
+            first = got
+            assert abs(got[1]) > 0.1
+    el.update_probe_xe(x)
+    prop = _props(kind, case["props"])[int(case["prop_id"][e])]
+    n = getattr(pf, CLS[kind] + "Data")().KC0_SPARSE_SIZE
+    r, c, v = np.zeros(n, pf.INT), np.zeros(n, pf.INT), np.zeros(n)
+    el.update_KC0(r, c, v, prop)
+    assert util.block_relerr(v, z[kind + "_KC0v"], 1) <= util.TOL_VALUES
+    # the batched state of the same fixture: degenerate rows come out as the identity
+    st = util.batch_from_case(case).state().cpu().numpy()
+    assert np.abs(st[:, 9:13] - m_ref).max() <= 1e-12
+
+
+def test_quad4r_hgfactors_positional():
+    """hgfactor_u..ry are positional parameters of Quad4R.update_KC0 / update_fint / update_probe_finte
+    (quad4r.pyx:1145-1156, 4620-4627, 549-556)."""
+    case, ref = util.load_golden("quad4r_soup")
+    x = np.ascontiguousarray(case["x"], float)
+    u = np.ascontiguousarray(case["u"], float)
+    e = 2
+    el = pf.Quad4R(pf.Quad4RProbe())
+    for a in range(4):
+        setattr(el, "c%d" % (a + 1), int(6 * case["conn"][e, a]))
+    el.K6ROT = float(case["K6ROT"][e])
+    el.update_rotation_matrix(x, *[float(t) for t in case["xmat"][e]])
+    el.update_probe_xe(x)
+    el.update_probe_ue(u)
+    prop = _props("quad4r", case["props"])[int(case["prop_id"][e])]
+    hg = [float(t) for t in case["hg"][e]]
+    r, c, v = np.zeros(576, pf.INT), np.zeros(576, pf.INT), np.zeros(576)
+    el.update_KC0(r, c, v, prop, 0, *hg)
+    assert util.block_relerr(v, ref["KC0"][2][576 * e:576 * (e + 1)], 1) <= util.TOL_VALUES
+    fint = np.zeros(case["ndof"])
+    el.update_fint(fint, prop, *hg)
+    el.update_probe_finte(prop, *hg)
+    nodes = case["conn"][e]
+    sel = np.concatenate([np.arange(6 * n, 6 * n + 6) for n in nodes])
+    assert util.vec_relerr(fint[sel], ref["fint"][sel]) <= util.TOL_VALUES
+
+
 def test_array_contract():
     probe = pf.Quad4Probe()
     el = pf.Quad4(probe)

@@ -17,9 +17,12 @@ SIDE = 2000
 
 @pytest.fixture(scope="module")
 def big():
+    import gc
     import torch
     from pyfe3d_b200 import meshes
     from pyfe3d_b200.batch import AssemblyPlan, ElementBatch
+    gc.collect()
+    torch.cuda.empty_cache()     # the C ABI's own cudaMalloc calls cannot use blocks torch still caches
     case = meshes.plate_quad4(SIDE, SIDE)
     b = ElementBatch("quad4", case["conn"], case["x"], case["props"], u=case["u"])
     nn = case["ndof"] // 6

@@ -41,7 +41,8 @@ def _check(case, ref, mtype=0, stress=None, node_range=None):
 
 
 @pytest.mark.parametrize("name", ["quad4_mesh", "quad4r_mesh", "quad4_soup", "quad4r_soup", "quad4_soup_thick",
-                                  "tria3r_mesh", "tria3r_soup", "tria3r_soup_thick"])
+                                  "tria3r_mesh", "tria3r_soup", "tria3r_soup_thick", "quad4_xmat_degenerate",
+                                  "quad4r_xmat_degenerate", "tria3r_xmat_degenerate"])
 @pytest.mark.parametrize("mtype", [0, 1, 2])
 def test_fused_matches_reference_golden(name, mtype):
     case, ref = util.load_golden(name)
@@ -292,3 +293,63 @@ def test_fused_mixed_beam_only_nodes():
         S = mats[rk]
         assert np.isfinite(A.data).all()
         assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max(), name
+
+
+def test_fused_mixed_lumped_beam_mass_takes_two_pass_for_M():
+    """mtype = 1 on a skin + stiffener plan: the BeamC group contributes only DIAGONAL node pairs to M
+    (lumped beam mass, beamc.pyx:2969), so the M plan has fewer node blocks than the KC0 plan wherever a beam joins two
+    nodes that share no quad.  The fused kernel walks the KC0 plan's blocks and must not write such an M: KC0 and KG go
+    through the fused group path, M through evaluation + its own plan; all three against the oracle + scipy."""
+    from pyfe3d_b200 import _cabi, meshes
+    from pyfe3d_b200.batch import AssemblyPlan
+    skin, beams = meshes.stiffened_panel(9, 7, nstiff=2)
+    nny = 8
+    extra = np.array([[0, 2 * nny + 5], [3 * nny + 3, 5 * nny + 1]], np.int64)      # node pairs that share no quad
+    beams["conn"] = np.vstack([beams["conn"], extra])
+    beams["vxy"] = np.vstack([beams["vxy"], beams["vxy"][:2]])
+    cs = [skin, beams]
+    bs = [util.batch_from_case(c) for c in cs]
+    nn = skin["ndof"] // 6
+    outs, mats = _mixed_reference(cs, ("KC0", "KG", "M1"))
+    plan = AssemblyPlan("KC0", nn, bs)
+    pm = plan._sibling("M", 1)
+    assert pm._plan.nblocks < plan._plan.nblocks                    # the hazard is real on this mesh
+    coo, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True, mtype=1)
+    assert not getattr(plan, "_fused_unsupported", False)           # KC0 / KG still took the fused path
+    assert csr["M"].numel() == pm.nnz
+    for name, rk, mt in (("KC0", "KC0", 0), ("KG", "KG", 0), ("M", "M1", 1)):
+        p = plan._sibling(name, mt)
+        for g, (c, o) in enumerate(zip(cs, outs)):
+            got = coo[name].v[p.coo_offsets[g]:p.coo_offsets[g] + o[rk][2].size].cpu().numpy()
+            assert util.block_relerr(got, o[rk][2], c["conn"].shape[0]) <= util.TOL_VALUES, (name, g)
+        A = p.to_scipy(csr[name])
+        assert abs(A - mats[rk]).max() <= util.TOL_CSR * np.abs(mats[rk].data).max(), name
+    # the C ABI refuses the hazardous combination outright
+    with pytest.raises(_cabi.Pf3Error):
+        plan._plan.eval_assemble_group(bs[0].cabi_batch(1, (0., 0., 0.), None), 0, _cabi.M, None, None,
+                                       _cabi.Coo(0, 0, coo["M"].v.data_ptr(), 0, 0), 0, 0, csr["M"].data_ptr())
+
+
+def test_plan_rejects_out_of_range_connectivity_and_handles_hub_rows():
+    """node ids outside [0, nnodes) are rejected at plan creation; a hub node coupled to 1600 nodes (spider of
+    springs) exceeds the shared-memory accumulator of the per-node gather and takes the global-memory variant."""
+    import scipy.sparse as sp
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan, ElementBatch
+    rng = np.random.default_rng(5)
+    conn = np.array([[0, 1], [1, 7]], np.int64)
+    b = ElementBatch("spring", conn, k=np.ones((2, 6)), axes=np.tile([1., 0, 0, 0, 1., 0], (2, 1)), nnodes=5)
+    with pytest.raises(ValueError):
+        AssemblyPlan("KC0", 5, [b])
+    nsp = 1600          # 1601 blocks x 18 entries x 8 B = 230 kB > the 200 kB shared-memory budget of one warp
+    conn = np.stack([np.zeros(nsp, np.int64), np.arange(1, nsp + 1)], 1)
+    case = dict(kind="spring", conn=conn, k=10 ** rng.uniform(3, 6, (nsp, 6)),
+                axes=np.concatenate([rng.normal(size=(nsp, 3)), rng.normal(size=(nsp, 3))], 1), props=None,
+                ndof=6 * (nsp + 1), u=np.zeros(6 * (nsp + 1)), x=np.zeros(3 * (nsp + 1)))
+    bb = util.batch_from_case(case)
+    coo = bb.update_KC0()
+    plan = AssemblyPlan("KC0", nsp + 1, [bb])
+    A = plan.to_scipy(plan.assemble(coo.v))
+    want = driver.run(case, what=("KC0",))["KC0"]
+    S = sp.coo_matrix((want[2], (want[0], want[1])), shape=(case["ndof"],) * 2).tocsr()
+    assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max()

@@ -16,7 +16,7 @@ TOL_CSR = 1e-11
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not os.path.basename(p).startswith(("quad4_probe", "aero_", "laminates", "lamination")))
+                  if not os.path.basename(p).startswith(("quad4_probe", "aero_", "laminates", "lamination", "sticky_")))
 
 
 def load_golden(name):
