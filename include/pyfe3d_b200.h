@@ -276,6 +276,50 @@ int pf3_plan_spmv(pf3_context* ctx, const pf3_plan* plan, const double* vals, co
 /* diag[6*nown]: the diagonal of the plan's row block (0 where the pattern has no diagonal entry) */
 int pf3_plan_diagonal(pf3_context* ctx, const pf3_plan* plan, const double* vals, double* diag);
 
+/* ---- device solves on the assembled matrix ------------------------------------------ */
+/* Jacobi-preconditioned conjugate gradient for (P A P) x = P b, everything on the device:
+ *   A = sum_i coefs[i] * (CSR values vals[i] of STRUCTURED plan plans[i])   -- e.g. K, or K - sigma M with the two
+ *       matrices kept in their own layouts; every plan must own all rows (single device; a row-sharded solve exchanges
+ *       the search direction between ranks, pyfe3d_b200/solve.py);
+ *   P = diag(free_dof != 0) (NULL: no constraints): the partition K[bu,:][:,bu] of
+ *       tests/test_quad4_static_point_load.py:84-99, applied inside the SpMV;
+ *   b, x: float64[6*nnodes] over ALL dofs; x is zero on constrained dofs on return; use_x0 != 0 starts from x.
+ * One iteration = the plans' block SpMV (8.2 B per nonzero) + three fused vector kernels (dot; x/r update with both
+ * reductions; direction update), reductions in a fixed order (bit-reproducible), convergence decided on the device and
+ * looked at by the host every (flags >> 8) iterations (0: 16).  This is the reference scripts' diagonally scaled solve
+ *   D = diag(Kuu)^-1/2;  cg(D Kuu D, D fu, atol=...);  uu = D uu_scaled   (tests/test_quad4r_linear_buckling_plate.py:135-146)
+ * written as preconditioned CG on the unscaled system (identical iterates).  Stops when the residual norm
+ * <= max(rtol * |b|, atol); PF3_CG_SCALED_NORM measures both in the scaled norm (r.D^2.r) that scipy's cg sees on the
+ * scaled system.  maxiter <= 0: 10 * ndof. */
+#define PF3_CG_SCALED_NORM 1
+typedef struct pf3_cg_info {
+  int32_t iterations;
+  int32_t status;   /* 0 converged, 1 maxiter reached, 2 breakdown (p.Ap <= 0: matrix not positive definite on bu) */
+  double residual;  /* the norm the criterion used */
+  double bnorm;
+} pf3_cg_info;
+int pf3_plan_cg(pf3_context* ctx, int nops, const pf3_plan* const* plans, const double* const* vals,
+                const double* coefs, const unsigned char* free_dof, const double* b, double* x, int use_x0,
+                double rtol, double atol, int maxiter, int flags, pf3_cg_info* info);
+/* y = S P A P S x with S = diag(scale[6*nnodes]): the scaled operators KC0uu_scaled / KGuu_scaled the reference hands to
+ * eigsh (tests/test_quad4r_linear_buckling_plate.py:172-180).  Plan owning all rows only. */
+int pf3_plan_spmv_scaled(pf3_context* ctx, const pf3_plan* plan, const double* vals, const unsigned char* free_dof,
+                         const double* scale, const double* x, double* y);
+
+/* K[bu, :][:, bu] as an explicit CSR matrix (tests/test_quad4_static_point_load.py:84-99) from a device CSR matrix whose
+ * rows are the global rows [row0, row0 + nrows) (row0 = 6*node_begin of a row-sharded plan, else 0) and whose column
+ * indices are global in [0, ncols): rows / columns with free_dof[.] != 0 are kept and renumbered by their rank among
+ * the free dofs (columns: global rank; rows: rank within this row block).
+ *  symbolic: colmap[ncols + 1] <- exclusive scan of the free flags (scratch the fill step needs again),
+ *            out_indptr[<= nrows + 1] <- row pointers of the compacted block; *nkeep rows, *nnz entries (host).
+ *  fill:     out_indices[nnz] (may be NULL: values-only refresh for a fixed pattern), out_vals[nnz] (may be NULL). */
+int pf3_csr_compact_symbolic(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
+                             const int64_t* indices, const unsigned char* free_dof, int64_t row0, int64_t* colmap,
+                             int64_t* out_indptr, int64_t* nkeep, int64_t* nnz);
+int pf3_csr_compact_fill(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
+                         const int64_t* indices, const double* vals, const unsigned char* free_dof, int64_t row0,
+                         const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices, double* out_vals);
+
 /* ---- property tables on the device ---------------------------------------- */
 /* props_out[nrows * PF3_SHELLPROP_STRIDE]: the ShellProp scalars of nrows laminates of nplies plies each, what
  *   laminated_plate(stack, plyts=..., laminaprops=..., rhos=..., offset=..., calc_scf=...)  (pyfe3d/shellprop_utils.py:96)

@@ -78,6 +78,23 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_spmv(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
                       const double* x, double* y) nogil
     int pf3_plan_diagonal(pf3_context*, const pf3_plan*, const double* vals, double* diag) nogil
+    ctypedef struct pf3_cg_info:
+        int32_t iterations
+        int32_t status
+        double residual
+        double bnorm
+    int pf3_plan_cg(pf3_context*, int nops, const pf3_plan* const* plans, const double* const* vals,
+                    const double* coefs, const unsigned char* free_dof, const double* b, double* x, int use_x0,
+                    double rtol, double atol, int maxiter, int flags, pf3_cg_info* info) nogil
+    int pf3_plan_spmv_scaled(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
+                             const double* scale, const double* x, double* y) nogil
+    int pf3_csr_compact_symbolic(pf3_context*, int64_t nrows, int64_t ncols, const int64_t* indptr,
+                                 const int64_t* indices, const unsigned char* free_dof, int64_t row0, int64_t* colmap,
+                                 int64_t* out_indptr, int64_t* nkeep, int64_t* nnz) nogil
+    int pf3_csr_compact_fill(pf3_context*, int64_t nrows, int64_t ncols, const int64_t* indptr,
+                             const int64_t* indices, const double* vals, const unsigned char* free_dof, int64_t row0,
+                             const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices,
+                             double* out_vals) nogil
     int pf3_quad4_update_BL(pf3_context*, int64_t n, const double* xe, double xi, double eta, double* out) nogil
     int pf3_eval_assemble(pf3_context*, const pf3_batch*, const pf3_plan*, int what, const pf3_coo*, const pf3_coo*,
                           const pf3_coo*, double*, double*, double*) nogil
@@ -309,6 +326,50 @@ cdef class Context:
                                   <const double*>vals, row0, <double*>diag)
         _check(rc)
 
+    def csr_compact_symbolic(self, int64_t nrows, int64_t ncols, uintptr_t indptr, uintptr_t indices,
+                             uintptr_t free_dof, int64_t row0, uintptr_t colmap, uintptr_t out_indptr):
+        cdef int rc
+        cdef int64_t nkeep = 0, nnz = 0
+        with nogil:
+            rc = pf3_csr_compact_symbolic(self.ctx, nrows, ncols, <const int64_t*>indptr, <const int64_t*>indices,
+                                          <const unsigned char*>free_dof, row0, <int64_t*>colmap,
+                                          <int64_t*>out_indptr, &nkeep, &nnz)
+        _check(rc)
+        return nkeep, nnz
+
+    def csr_compact_fill(self, int64_t nrows, int64_t ncols, uintptr_t indptr, uintptr_t indices, uintptr_t vals,
+                         uintptr_t free_dof, int64_t row0, uintptr_t colmap, uintptr_t out_indptr,
+                         uintptr_t out_indices, uintptr_t out_vals):
+        cdef int rc
+        with nogil:
+            rc = pf3_csr_compact_fill(self.ctx, nrows, ncols, <const int64_t*>indptr, <const int64_t*>indices,
+                                      <const double*>vals, <const unsigned char*>free_dof, row0,
+                                      <const int64_t*>colmap, <const int64_t*>out_indptr, <int64_t*>out_indices,
+                                      <double*>out_vals)
+        _check(rc)
+
+    def plan_cg(self, list plans, list vals, list coefs, uintptr_t free_dof, uintptr_t b, uintptr_t x, bint use_x0,
+                double rtol, double atol, int maxiter, int flags):
+        """pf3_plan_cg: returns (iterations, status, residual norm, |b|)."""
+        cdef int n = len(plans)
+        if n < 1 or n > 8 or len(vals) != n or len(coefs) != n:
+            raise ValueError("1..8 (plan, values, coefficient) triples")
+        cdef const pf3_plan* pp[8]
+        cdef const double* vv[8]
+        cdef double cc[8]
+        cdef int i
+        for i in range(n):
+            pp[i] = (<Plan>plans[i]).plan
+            vv[i] = <const double*><uintptr_t>vals[i]
+            cc[i] = coefs[i]
+        cdef pf3_cg_info info
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_cg(self.ctx, n, pp, vv, cc, <const unsigned char*>free_dof, <const double*>b, <double*>x,
+                             use_x0, rtol, atol, maxiter, flags, &info)
+        _check(rc)
+        return info.iterations, info.status, info.residual, info.bnorm
+
     def memcpy_h2d(self, uintptr_t dst, uintptr_t src, size_t n):
         cdef int rc
         with nogil:
@@ -438,6 +499,13 @@ cdef class Plan:
         cdef int rc
         with nogil:
             rc = pf3_plan_diagonal(self.owner.ctx, self.plan, <const double*>vals, <double*>diag)
+        _check(rc)
+
+    def spmv_scaled(self, uintptr_t vals, uintptr_t free_dof, uintptr_t scale, uintptr_t x, uintptr_t y):
+        cdef int rc
+        with nogil:
+            rc = pf3_plan_spmv_scaled(self.owner.ctx, self.plan, <const double*>vals, <const unsigned char*>free_dof,
+                                      <const double*>scale, <const double*>x, <double*>y)
         _check(rc)
 
     def pattern(self, uintptr_t indptr, uintptr_t indices):

@@ -345,6 +345,15 @@ class AssemblyPlan:
         self._plan.spmv(_ptr(vals), _ptr(free) if free is not None else 0, _ptr(x), _ptr(out))
         return out
 
+    def spmv_scaled(self, vals, scale, x, free=None, out=None):
+        """y = S P A P S x with S = diag(scale): the diagonally scaled operators (``D_inv_sqrt @ KC0uu @ D_inv_sqrt``)
+        the reference scripts hand to eigsh, tests/test_quad4r_linear_buckling_plate.py:172-180."""
+        if out is None:
+            out = torch.empty(self.nrows, dtype=torch.float64, device=self.device)
+        context(self.device)
+        self._plan.spmv_scaled(_ptr(vals), _ptr(free) if free is not None else 0, _ptr(scale), _ptr(x), _ptr(out))
+        return out
+
     def diagonal(self, vals, out=None):
         """Diagonal of the plan's row block (Jacobi scaling)."""
         if out is None:

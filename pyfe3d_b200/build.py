@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(LIBDIR, "libpyfe3d_b200.so")
-CU = ["quad_kernels.cu", "quad_fused.cu", "tria_kernels.cu", "tria_fused.cu", "props.cu", "line_kernels.cu", "assembly.cu", "api.cu"]
+CU = ["quad_kernels.cu", "quad_fused.cu", "tria_kernels.cu", "tria_fused.cu", "props.cu", "line_kernels.cu", "assembly.cu", "solve.cu", "api.cu"]
 HDRS = ["common.cuh", "shell.cuh", "pattern.hpp", os.path.join(ROOT, "include", "pyfe3d_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

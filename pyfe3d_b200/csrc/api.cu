@@ -50,7 +50,7 @@ int64_t plan_group_ne_of(const pf3_plan* pl, int group);
 int64_t plan_group_ne(const pf3_plan* pl);
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches);
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches,
-                              int phases, unsigned long long* work);
+                              int phases);
 int fused_record_stride(const EvalArgs& A);
 int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches);
@@ -60,6 +60,23 @@ int plan_assemble_gather(const pf3_plan* pl, cudaStream_t st, const double* coo_
 cudaError_t launch_tria_fused(const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches);
 int tria_fused_record_stride(const EvalArgs& A);
 int64_t plan_nrows(const pf3_plan* pl);
+struct CgOp {
+  const pf3_plan* plan;
+  const double* vals;
+  double coef;
+};
+size_t cg_work_bytes(int64_t n);
+int plan_cg(cudaStream_t st, int nops, const CgOp* ops, int64_t n, const unsigned char* free_, const double* b,
+            double* x, int use_x0, double rtol, double atol, int maxiter, int flags, void* work, int* iters,
+            int* status, double* resid, double* bnorm, int64_t* launches);
+int plan_spmv_scaled(const pf3_plan* pl, cudaStream_t st, const double* vals, const unsigned char* free_,
+                     const double* scale, const double* x, double* y, double* tmp, int64_t n, int64_t* launches);
+int csr_compact_symbolic(cudaStream_t st, int64_t nrows, int64_t ncols, const int64_t* indptr, const int64_t* indices,
+                         const unsigned char* free_, int64_t row0, int64_t* colmap, int64_t* out_ptr, int64_t* nkeep,
+                         int64_t* nnz, int64_t* launches);
+int csr_compact_fill(cudaStream_t st, int64_t nrows, int64_t ncols, const int64_t* indptr, const int64_t* indices,
+                     const double* vals, const unsigned char* free_, int64_t row0, const int64_t* colmap,
+                     const int64_t* out_ptr, int64_t* out_idx, double* out_val, int64_t* launches);
 }  // namespace pf3
 
 #define PF3_HOST_CHUNKS 8   // row ranges of the pipelined host-buffer step
@@ -76,9 +93,10 @@ struct pf3_context {
   size_t hostio_bytes = 0;
   cudaStream_t copy_stream = nullptr;   // pf3_eval_assemble_host: device->host copies of finished row ranges
   cudaEvent_t chunk_done[PF3_HOST_CHUNKS] = {};
-  unsigned long long* work = nullptr;   // in-order work counter of the persistent fused kernel
   char* stage_host = nullptr;           // pinned + device staging of the small host-pointer calls (per-element drop-in)
   char* stage_dev = nullptr;
+  void* solve_work = nullptr;           // vectors + scalars of pf3_plan_cg / pf3_plan_spmv_scaled
+  size_t solve_work_bytes = 0;
 };
 #define PF3_STAGE_BYTES (size_t(1) << 20)
 
@@ -253,12 +271,6 @@ int pf3_create(int device, pf3_context** out) {
     return int(e);
   }
   ctx->own_stream = true;
-  e = cudaMalloc((void**)&ctx->work, 64);
-  if (e != cudaSuccess) {
-    cudaStreamDestroy(ctx->stream);
-    delete ctx;
-    return int(e);
-  }
   *out = ctx;
   return PF3_OK;
 }
@@ -269,9 +281,9 @@ int pf3_destroy(pf3_context* ctx) {
   for (auto& kv : ctx->idx_tabs) cudaFree(kv.second);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->hostio) cudaFree(ctx->hostio);
-  if (ctx->work) cudaFree(ctx->work);
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+  if (ctx->solve_work) cudaFree(ctx->solve_work);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (cudaEvent_t ev : ctx->chunk_done)
     if (ev) cudaEventDestroy(ev);
@@ -452,7 +464,7 @@ int pf3_eval(pf3_context* ctx, const pf3_batch* b, int what, const pf3_coo* kc0,
     F.rmax = 1;
     rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
     if (rc) return rc;
-    cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3, ctx->work);
+    cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3);
     return int(e);
   }
   // Tria3R the same way through the triangle record + node-lane kernels (KG slabs are not 16-byte multiples and go
@@ -589,13 +601,13 @@ int fused_pipelined(pf3_context* ctx, int kind, pf3::FusedArgs& F, double* const
     PF3_CUDA(cudaMemcpyAsync(&block_at[c], F.brow_ptr + node, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   }
   PF3_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaError_t e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 1, ctx->work);
+  cudaError_t e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 1);
   if (e != cudaSuccess) return int(e);
   for (int c = 0; c < PF3_HOST_CHUNKS; ++c) {
     F.pair_first = pair_at[c];
     F.pair_count = pair_at[c + 1] - pair_at[c];
     if (F.pair_count <= 0) continue;
-    e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 2, ctx->work);
+    e = pf3::launch_quad_fused(kind, F, ctx->scratch, ctx->stream, &ctx->launches, 2);
     if (e != cudaSuccess) return int(e);
     PF3_CUDA(cudaEventRecord(ctx->chunk_done[c], ctx->stream));
     PF3_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done[c], 0));
@@ -658,7 +670,7 @@ int eval_assemble_impl(pf3_context* ctx, const pf3_batch* b, const pf3_plan* pla
     *copied = true;
   } else {
     cudaError_t e = tria ? pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches)
-                         : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3, ctx->work);
+                         : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3);
     if (e != cudaSuccess) return int(e);
   }
   const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
@@ -719,7 +731,7 @@ int pf3_eval_assemble_group(pf3_context* ctx, const pf3_batch* b, const pf3_plan
   F.csr_m = csr_m;
   rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
   if (rc) return rc;
-  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3, ctx->work);
+  cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3);
   if (e != cudaSuccess) return int(e);
   const pf3_coo* cs[3] = {(what & PF3_KC0) ? kc0 : nullptr, (what & (PF3_KG | PF3_KG_STRESS)) ? kg : nullptr,
                           (what & PF3_M) ? m : nullptr};
@@ -754,9 +766,6 @@ int pf3_eval_assemble_host(pf3_context* ctx, const pf3_batch* b, const pf3_plan*
   const size_t total = (up(nx) + up(nu) + up(n0) + up(n1) + up(n2)) * sizeof(double);
   if (total > ctx->hostio_bytes) {
     if (ctx->hostio) cudaFree(ctx->hostio);
-  if (ctx->work) cudaFree(ctx->work);
-  if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
-  if (ctx->stage_dev) cudaFree(ctx->stage_dev);
     ctx->hostio = nullptr;
     ctx->hostio_bytes = 0;
     PF3_CUDA(cudaMalloc((void**)&ctx->hostio, total));
@@ -904,6 +913,79 @@ int pf3_plan_diagonal(pf3_context* ctx, const pf3_plan* plan, const double* vals
   if (rc) return rc;
   if (!plan || !vals || !diag) return PF3_E_BAD_ARG;
   return pf3::plan_diagonal(plan, ctx->stream, vals, diag, &ctx->launches);
+}
+
+int pf3_plan_cg(pf3_context* ctx, int nops, const pf3_plan* const* plans, const double* const* vals,
+                const double* coefs, const unsigned char* free_dof, const double* b, double* x, int use_x0,
+                double rtol, double atol, int maxiter, int flags, pf3_cg_info* info) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (nops < 1 || nops > 8 || !plans || !vals || !b || !x) return PF3_E_BAD_ARG;
+  pf3::CgOp ops[8];
+  for (int i = 0; i < nops; ++i) {
+    if (!plans[i] || !vals[i]) return PF3_E_BAD_ARG;
+    ops[i] = {plans[i], vals[i], coefs ? coefs[i] : 1.};
+  }
+  const int64_t n = pf3::plan_nrows(plans[0]);
+  if (n <= 0) return PF3_E_BAD_ARG;
+  const size_t need = pf3::cg_work_bytes(n);
+  if (need > ctx->solve_work_bytes) {
+    if (ctx->solve_work) cudaFree(ctx->solve_work);
+    ctx->solve_work = nullptr;
+    ctx->solve_work_bytes = 0;
+    PF3_CUDA(cudaMalloc(&ctx->solve_work, need));
+    ctx->solve_work_bytes = need;
+  }
+  int iters = 0, status = 0;
+  double resid = 0., bnorm = 0.;
+  rc = pf3::plan_cg(ctx->stream, nops, ops, n, free_dof, b, x, use_x0, rtol, atol, maxiter, flags, ctx->solve_work,
+                    &iters, &status, &resid, &bnorm, &ctx->launches);
+  if (info) {
+    info->iterations = iters;
+    info->status = status;
+    info->residual = resid;
+    info->bnorm = bnorm;
+  }
+  return rc;
+}
+
+int pf3_plan_spmv_scaled(pf3_context* ctx, const pf3_plan* plan, const double* vals, const unsigned char* free_dof,
+                         const double* scale, const double* x, double* y) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!plan || !vals || !scale || !x || !y) return PF3_E_BAD_ARG;
+  const int64_t n = pf3::plan_nrows(plan);
+  if (n <= 0) return PF3_E_BAD_ARG;
+  const size_t need = pf3::cg_work_bytes(n);
+  if (need > ctx->solve_work_bytes) {
+    if (ctx->solve_work) cudaFree(ctx->solve_work);
+    ctx->solve_work = nullptr;
+    ctx->solve_work_bytes = 0;
+    PF3_CUDA(cudaMalloc(&ctx->solve_work, need));
+    ctx->solve_work_bytes = need;
+  }
+  return pf3::plan_spmv_scaled(plan, ctx->stream, vals, free_dof, scale, x, y, static_cast<double*>(ctx->solve_work),
+                               n, &ctx->launches);
+}
+
+int pf3_csr_compact_symbolic(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
+                             const int64_t* indices, const unsigned char* free_dof, int64_t row0, int64_t* colmap,
+                             int64_t* out_indptr, int64_t* nkeep, int64_t* nnz) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!indptr || !indices || !free_dof || !colmap || !out_indptr) return PF3_E_BAD_ARG;
+  return pf3::csr_compact_symbolic(ctx->stream, nrows, ncols, indptr, indices, free_dof, row0, colmap, out_indptr,
+                                   nkeep, nnz, &ctx->launches);
+}
+
+int pf3_csr_compact_fill(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
+                         const int64_t* indices, const double* vals, const unsigned char* free_dof, int64_t row0,
+                         const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices, double* out_vals) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (!indptr || !indices || !free_dof || !colmap || !out_indptr || (out_vals && !vals)) return PF3_E_BAD_ARG;
+  return pf3::csr_compact_fill(ctx->stream, nrows, ncols, indptr, indices, vals, free_dof, row0, colmap, out_indptr,
+                               out_indices, out_vals, &ctx->launches);
 }
 
 }  // extern "C"

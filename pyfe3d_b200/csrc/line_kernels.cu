@@ -446,8 +446,14 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
       xe[3 * a + 1] = yh[0] * P[0] + yh[1] * P[1] + yh[2] * P[2];
       xe[3 * a + 2] = zh[0] * P[0] + zh[1] * P[1] + zh[2] * P[2];
     }
-    const double dx = xe[3] - xe[0], dy = xe[4] - xe[1], dz = xe[5] - xe[2];
-    L = sqrt(dx * dx + dy * dy + dz * dz);  // update_length, beamc.pyx:336-349
+    // update_length (beamc.pyx:336-349) with the difference formed in global coordinates BEFORE the rotation: the
+    // reference subtracts the rotated absolute positions and loses |x| / L * eps (6e-12 on the 100 k-element arc of
+    // config 2); see ShellGeom in shell.cuh
+    const double q[3] = {P1[0] - P0[0], P1[1] - P0[1], P1[2] - P0[2]};
+    const double dx = xh[0] * q[0] + xh[1] * q[1] + xh[2] * q[2];
+    const double dy = yh[0] * q[0] + yh[1] * q[1] + yh[2] * q[2];
+    const double dz = zh[0] * q[0] + zh[1] * q[1] + zh[2] * q[2];
+    L = sqrt(dx * dx + dy * dy + dz * dz);
   }
   if (need_u) {
     for (int a = 0; a < 2; ++a)

@@ -38,8 +38,19 @@ constexpr double kGpF = 0.5773502691896257645092;
 constexpr int kFusedWarps = PF3_FUSED_WARPS;
 
 constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path (NodeRec::gmap)
-constexpr int kRecPlain = 36;               // record doubles without / with rotated A,B,D
-constexpr int kRecRot = 56;
+// Element record (doubles): 0..5 the element x and y axes (R columns 0 and 1, row-major 3 x 2; z = x X y is recomputed
+// by the consumer) | 6..13 the eight local edge differences | 14..17 1/detJ at the 2x2 Gauss points | 18 1/detJ at the
+// centre | 19 area | [KG from u: 12 membrane force resultants Nxx, Nyy, Nxy at the 4 Gauss points] | [material axes: the
+// rotated A, B, D, 18 doubles].  20 / 32 / 38 / 50 doubles = 160 / 256 / 304 / 400 B: the three-matrix north-star call
+// reads 256-byte records that never straddle a third 128-byte line.
+constexpr int kRecBase = 20;
+constexpr int kRecN = 12;
+constexpr int kRecABD = 18;
+constexpr int kRecMax = kRecBase + kRecN + kRecABD;
+__host__ __device__ constexpr int rec_stride(bool kg_u, bool rot) { return kRecBase + (kg_u ? kRecN : 0) + (rot ? kRecABD : 0); }
+// shared-memory stride of a staged record: even (16-byte aligned) and = 2 mod 4, so that the 16-byte loads of the 8
+// incidences of a warp fall into disjoint banks
+__host__ __device__ constexpr int rec_ld(int stride) { return stride + ((stride & 3) == 2 ? 0 : 2); }
 
 // ------------------------------------------------------------------------------------------ K1
 #ifndef PF3_K1_CTAS
@@ -62,15 +73,16 @@ __global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const Eva
   ShellGeom<4> g;
   shell_geom<4>(A, e, g, kg_u ? ue : nullptr);
   double* r = stage + lane * ld;
-  for (int i = 23; i < stride; ++i) r[i] = 0.;
+  const bool rot = A.evec != nullptr;
 #pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) r[3 * i + j] = g.R.a[i][j];
+  for (int i = 0; i < 3; ++i) {
+    r[2 * i] = g.R.a[i][0];
+    r[2 * i + 1] = g.R.a[i][1];
+  }
   const double d[8] = {g.X[1] - g.X[0], g.X[2] - g.X[3], g.X[3] - g.X[0], g.X[2] - g.X[1],
                        g.Y[1] - g.Y[0], g.Y[2] - g.Y[3], g.Y[3] - g.Y[0], g.Y[2] - g.Y[1]};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r[9 + i] = d[i];
+  for (int i = 0; i < 8; ++i) r[6 + i] = d[i];
   double J11e[2], J12e[2], J21x[2], J22x[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -84,25 +96,23 @@ __global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const Eva
 #pragma unroll
   for (int gp = 0; gp < 4; ++gp) {
     idJ[gp] = 1. / (J11e[gp & 1] * J22x[gp >> 1] - J12e[gp & 1] * J21x[gp >> 1]);
-    r[17 + gp] = idJ[gp];
+    r[14 + gp] = idJ[gp];
   }
   const double J11c = 0.25 * (d[0] + d[1]), J12c = 0.25 * (d[4] + d[5]);
   const double J21c = 0.25 * (d[2] + d[3]), J22c = 0.25 * (d[6] + d[7]);
-  r[21] = 1. / (J11c * J22c - J12c * J21c);
-  r[22] = g.area;
-  r[23] = 0.;
-  if (kg_u || stride == kRecRot) {
+  r[18] = 1. / (J11c * J22c - J12c * J21c);
+  r[19] = g.area;
+  if (kg_u || rot) {
     ShellCoef c;
     shell_coef<4>(A, e, g, c);
-    if (stride == kRecRot) {
+    if (rot) {
+      double* ra = r + kRecBase + (kg_u ? kRecN : 0);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        r[36 + i] = c.A[i];
-        r[42 + i] = c.B[i];
-        r[48 + i] = c.D[i];
+        ra[i] = c.A[i];
+        ra[6 + i] = c.B[i];
+        ra[12 + i] = c.D[i];
       }
-      r[54] = 0.;
-      r[55] = 0.;
     }
     if (kg_u) {
       // membrane force resultants per Gauss point (quad4.pyx:1965-1967)
@@ -124,17 +134,18 @@ __global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const Eva
           kyy -= ny * ue[6 * cn + 3];
           kxy += ny * ue[6 * cn + 4] - nx * ue[6 * cn + 3];
         }
-        r[24 + gp] = c.A[0] * exx + c.A[1] * eyy + c.A[2] * gxy + c.B[0] * kxx + c.B[1] * kyy + c.B[2] * kxy;
-        r[28 + gp] = c.A[1] * exx + c.A[3] * eyy + c.A[4] * gxy + c.B[1] * kxx + c.B[3] * kyy + c.B[4] * kxy;
-        r[32 + gp] = c.A[2] * exx + c.A[4] * eyy + c.A[5] * gxy + c.B[2] * kxx + c.B[4] * kyy + c.B[5] * kxy;
+        r[20 + gp] = c.A[0] * exx + c.A[1] * eyy + c.A[2] * gxy + c.B[0] * kxx + c.B[1] * kyy + c.B[2] * kxy;
+        r[24 + gp] = c.A[1] * exx + c.A[3] * eyy + c.A[4] * gxy + c.B[1] * kxx + c.B[3] * kyy + c.B[4] * kxy;
+        r[28 + gp] = c.A[2] * exx + c.A[4] * eyy + c.A[5] * gxy + c.B[2] * kxx + c.B[4] * kyy + c.B[5] * kxy;
       }
     }
   }
   __syncwarp();
   double* out = rec + e0 * stride;
   const int total = nvalid * stride;
-  if (stride == kRecPlain) {
-    for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / kRecPlain) * ld + idx % kRecPlain];
+  if (stride == rec_stride(true, false)) {   // the north-star call: division by a constant
+    constexpr int kS = rec_stride(true, false);
+    for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / kS) * ld + idx % kS];
   } else {
     for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / stride) * ld + idx % stride];
   }
@@ -331,18 +342,38 @@ constexpr int kFChunkBig = 4;
 __host__ __device__ constexpr int fring(int chunk) { return chunk > 1 ? 3 : 1; }
 __host__ __device__ constexpr int fbufs(int chunk) { return chunk > 1 ? 2 : 1; }
 // per warp: slab staging | ring of node-record pairs (64 B each) | element records of 8 incidences (x2 when
-// prefetching), stride rstride + 2 doubles (38 / 58: conflict-free, 16-B aligned)
+// prefetching), stride rec_ld(rstride) doubles (conflict-free, 16-B aligned)
 __host__ __device__ constexpr int warp_smem_doubles(int rstride, int chunk) {
-  return kStageV4 + fring(chunk) * 2 * 8 + fbufs(chunk) * 8 * (rstride + 2);
+  return kStageV4 + fring(chunk) * 2 * 8 + fbufs(chunk) * 8 * rec_ld(rstride);
+}
+
+// Which of the warp's 8 incidence slots holds the record of this lane's element: the two nodes of a pair usually share
+// two of their elements (and in element mode all four "incidences" are the same element), so a record is fetched once
+// per warp, by the lowest incidence that names it, and read by all of them.
+#ifndef PF3_EREC_DEDUP
+#define PF3_EREC_DEDUP 1
+#endif
+__device__ __forceinline__ int erec_owner(int pair0, int lane) {
+#if PF3_EREC_DEDUP
+  const unsigned same = __match_any_sync(0xffffffffu, pair0 >= 0 ? (pair0 >> 4) : (-1 - lane));
+  return (__ffs(same) - 1) >> 2;
+#else
+  return lane >> 2;
+#endif
 }
 
 // Stage the element records of the 8 incidences of a node pair into shared memory with 16-B cp.async; the 4 lanes
 // of an incidence split the record's chunks.
 __device__ __forceinline__ void erec_fetch(const double* __restrict__ rec, int rstride, double* buf, int pair0,
                                            int lane) {
-  if (pair0 >= 0) {
+  const int owner = erec_owner(pair0, lane);
+  if (pair0 >= 0 && owner == (lane >> 2)) {
+#ifdef PF3_ABL_ERECSAME
+    const char* src = reinterpret_cast<const char*>(rec + int64_t(lane >> 2) * rstride);
+#else
     const char* src = reinterpret_cast<const char*>(rec + int64_t(pair0 >> 4) * rstride);
-    char* dst = reinterpret_cast<char*>(buf + (lane >> 2) * (rstride + 2));
+#endif
+    char* dst = reinterpret_cast<char*>(buf + (lane >> 2) * rec_ld(rstride));
     for (int c = (lane & 3) * 16; c < rstride * 8; c += 64)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
   }
@@ -384,15 +415,15 @@ __device__ __forceinline__ void noderec_fetch(const FusedArgs& F, NodeRec* dst2,
 // Measured on B200 at 4 M Quad4: persistent grid-stride warps with a 3-deep prefetch ring 12.4 ms/step, this 10.4.
 // Within a warp the node records of item j+2 and the element records of item j+1 are in flight (cp.async) while item j
 // is evaluated (matters for the latency-bound one- and two-matrix calls, e.g. config 3).
-template <int KIND, int CHUNK, bool DYN>
+template <int KIND, int CHUNK>
 __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_kernel(const FusedArgs F, const double* __restrict__ rec,
-                                                                         int rstride, unsigned long long* __restrict__ work) {
-  constexpr bool PRE = CHUNK > 1 || DYN;   // records of the next items arrive by cp.async while this one is evaluated
+                                                                         int rstride) {
+  constexpr bool PRE = CHUNK > 1;   // records of the next items arrive by cp.async while this one is evaluated
   constexpr int kFRing = PRE ? 3 : 1, kFBufs = PRE ? 2 : 1;
   extern __shared__ __align__(16) double smem[];
   const EvalArgs& A = F.A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int eld = rstride + 2;
+  const int eld = rec_ld(rstride);
   double* st = smem + warp * warp_smem_doubles(rstride, PRE ? kFChunkBig : 1);
   NodeRec* ring = reinterpret_cast<NodeRec*>(st + kStageV4);
   double* erec = st + kStageV4 + kFRing * 2 * 8;
@@ -403,26 +434,10 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   const int64_t npairs = F.pair_count ? F.pair_first + F.pair_count : (F.nown + 1) >> 1;   // end of this launch's range
   const int rmax = F.rmax;
   const double xib = (b == 1 || b == 2) ? 1. : -1., etab = (b >= 2) ? 1. : -1.;
-  // static schedule: this warp owns CHUNK consecutive pairs.  DYN: persistent warps claim pairs one at a time, IN ORDER,
-  // from a global counter (rmax == 1 only), three claims ahead of the pair being evaluated: the record loads of the
-  // claimed pairs are in flight while the front of pairs being STORED stays as narrow as with one pair per CTA.
-  int64_t np0 = 0, pq0 = -1, pq1 = -1, pq2 = -1;   // DYN: pairs of items j, j+1, j+2
-  unsigned long long raw = 0ull;                   // DYN: lane 0's pending claim (item j+3)
-  int nitems = 0;
-  if constexpr (DYN) {
-    const unsigned long long total = (unsigned long long)(npairs - F.pair_first);
-    if (lane == 0) raw = atomicAdd(work, 3ull);
-    const unsigned long long q = __shfl_sync(0xffffffffu, raw, 0);
-    if (q >= total) return;
-    pq0 = F.pair_first + int64_t(q);
-    pq1 = (q + 1 < total) ? pq0 + 1 : -1;
-    pq2 = (q + 2 < total) ? pq0 + 2 : -1;
-    if (lane == 0) raw = atomicAdd(work, 1ull);
-  } else {
-    np0 = F.pair_first + (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
-    if (np0 >= npairs) return;
-    nitems = int(min(int64_t(CHUNK), npairs - np0)) * rmax;   // item j = (pair np0 + j / rmax, round j % rmax)
-  }
+  // static schedule: this warp owns CHUNK consecutive pairs
+  const int64_t np0 = F.pair_first + (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
+  if (np0 >= npairs) return;
+  const int nitems = int(min(int64_t(CHUNK), npairs - np0)) * rmax;   // item j = (pair np0 + j / rmax, round j % rmax)
 
   auto rec_fetch_pair = [&](int slot3, int64_t pair, int r) {
     if (pair >= 0)
@@ -437,13 +452,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     else
       asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if constexpr (DYN) {
-    rec_fetch_pair(0, pq0, 0);
-    rec_fetch_pair(1, pq1, 0);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    erec_prefetch(0, true);
-  } else if constexpr (CHUNK > 1) {
+  if constexpr (CHUNK > 1) {
     rec_fetch(0);
     rec_fetch(1);
     asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -452,35 +461,18 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   }
 
   for (int j = 0;; ++j) {
-    int r = 0;
-    if constexpr (DYN) {
-      if (j > 0) {   // rotate: item j-1 is done
-        pq0 = pq1;
-        pq1 = pq2;
-        const unsigned long long total = (unsigned long long)(npairs - F.pair_first);
-        const unsigned long long q = __shfl_sync(0xffffffffu, raw, 0);   // claimed one item ago
-        pq2 = (q < total) ? F.pair_first + int64_t(q) : -1;
-        if (lane == 0 && q < total) raw = atomicAdd(work, 1ull);
-      }
-      if (pq0 < 0) break;
-      rec_fetch_pair((j + 2) % 3, pq2, 0);
+    if (j >= nitems) break;
+    const int r = j % rmax;
+    if constexpr (CHUNK > 1) {
+      rec_fetch(j + 2);
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j+1 and element records j have landed
       __syncwarp();
-      erec_prefetch(j + 1, pq1 >= 0);
+      erec_prefetch(j + 1, j + 1 < nitems);
     } else {
-      if (j >= nitems) break;
-      r = j % rmax;
-      if constexpr (CHUNK > 1) {
-        rec_fetch(j + 2);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j+1 and element records j have landed
-        __syncwarp();
-        erec_prefetch(j + 1, j + 1 < nitems);
-      } else {
-        if (j > 0) stage_reuse_wait();
-        rec_fetch(j);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-      }
+      if (j > 0) stage_reuse_wait();
+      rec_fetch(j);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
     }
     const NodeRec* nr = ring + (j % kFRing) * 2 + h;
     const int pair0 = nr->inc[k];
@@ -520,26 +512,31 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     const double xia = (a == 1 || a == 2) ? 1. : -1., etaa = (a >= 2) ? 1. : -1.;
 
     // ---------------- element record (K1) and property row
-    const double* re = erec + ((j % kFBufs) * 8 + (lane >> 2)) * eld;
+    const double* re = erec + ((j % kFBufs) * 8 + erec_owner(pair0, lane)) * eld;
     const double2* re2 = reinterpret_cast<const double2*>(re);
-    double rr_[24];
+    double rr_[kRecBase];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < kRecBase / 2; ++i) {
       const double2 t = re2[i];
       rr_[2 * i] = t.x;
       rr_[2 * i + 1] = t.y;
     }
     Mat3 R;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int jj = 0; jj < 3; ++jj) R.a[i][jj] = rr_[3 * i + jj];
-    const double dX10 = rr_[9], dX23 = rr_[10], dX30 = rr_[11], dX21 = rr_[12];
-    const double dY10 = rr_[13], dY23 = rr_[14], dY30 = rr_[15], dY21 = rr_[16];
-    const double idJ[4] = {rr_[17], rr_[18], rr_[19], rr_[20]};
-    const double idJ0 = rr_[21], area = rr_[22];
+    for (int i = 0; i < 3; ++i) {
+      R.a[i][0] = rr_[2 * i];
+      R.a[i][1] = rr_[2 * i + 1];
+    }
+    R.a[0][2] = R.a[1][0] * R.a[2][1] - R.a[2][0] * R.a[1][1];   // z = x X y
+    R.a[1][2] = R.a[2][0] * R.a[0][1] - R.a[0][0] * R.a[2][1];
+    R.a[2][2] = R.a[0][0] * R.a[1][1] - R.a[1][0] * R.a[0][1];
+    const double dX10 = rr_[6], dX23 = rr_[7], dX30 = rr_[8], dX21 = rr_[9];
+    const double dY10 = rr_[10], dY23 = rr_[11], dY30 = rr_[12], dY21 = rr_[13];
+    const double idJ[4] = {rr_[14], rr_[15], rr_[16], rr_[17]};
+    const double idJ0 = rr_[18], area = rr_[19];
+    const bool kg_u = (A.what & PF3_KG) != 0;
     const double* prow = A.props + int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE;
-    const double* abd = (rstride == kRecRot) ? re + 36 : prow;
+    const double* abd = (A.evec != nullptr) ? re + kRecBase + (kg_u ? kRecN : 0) : prow;
 
     // Jacobian rows: J11,J12 depend on eta only, J21,J22 on xi only (index 0: -p, 1: +p)
     double J11e[2], J12e[2], J21x[2], J22x[2];
@@ -551,7 +548,6 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       J21x[i] = 0.25 * ((1. - t) * dX30 + (1. + t) * dX21);
       J22x[i] = 0.25 * ((1. - t) * dY30 + (1. + t) * dY21);
     }
-    const bool kg_u = (A.what & PF3_KG) != 0;
 
     // gradient Gram of the pair over the 2x2 Gauss points, the mixed N / N,x sums, and Ge_ab
     double gxx = 0., gxy = 0., gyx = 0., gyy = 0., pyab = 0., pxab = 0., pyba = 0., pxba = 0., hab = 0., ge = 0.;
@@ -575,7 +571,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       pxba += wxb * na;
       hab += (na * nbv) * (J11e[ie] * J22x[ix] - J12e[ie] * J21x[ix]);
       if (kg_u) {
-        const double nxx = re[24 + gp], nyy = re[28 + gp], nxy = re[32 + gp];
+        const double nxx = re[20 + gp], nyy = re[24 + gp], nxy = re[28 + gp];
         ge += wxb * (vax * nxx + vay * nxy) + wyb * (vax * nxy + vay * nyy);
       }
     }
@@ -754,16 +750,11 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
 
 size_t fused_smem_bytes(int rstride, int chunk) { return size_t(kFusedWarps) * warp_smem_doubles(rstride, chunk) * sizeof(double); }
 int fused_max_slots() { return kMaxSlots; }
-int fused_record_stride(const EvalArgs& A) { return A.evec != nullptr ? kRecRot : kRecPlain; }
+int fused_record_stride(const EvalArgs& A) { return rec_stride((A.what & PF3_KG) != 0, A.evec != nullptr); }
 
 // rec: device scratch of ne * fused_record_stride doubles.  phases: bit 0 = K1 (records of ALL elements), bit 1 = K2 for
-// the node pairs [F.pair_first, F.pair_first + F.pair_count) (all pairs when pair_count == 0).  work: an 8-byte device
-// counter owned by the caller's context (the in-order work queue of the persistent variant).
-#ifndef PF3_DYN
-#define PF3_DYN 0   // 1: three-matrix calls on single-round plans run the persistent, dynamically scheduled variant
-#endif
-cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases,
-                              unsigned long long* work) {
+// the node pairs [F.pair_first, F.pair_first + F.pair_count) (all pairs when pair_count == 0).
+cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases) {
   if (F.nown <= 0 || F.A.ne <= 0) return cudaSuccess;
   const int stride = fused_record_stride(F.A);
   if (phases & 1) {
@@ -771,7 +762,7 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
     const size_t smem1 = size_t(4) * 32 * (stride + 1) * sizeof(double);
     static PerDeviceOnce once1;
     if (once1.first()) {
-      const int maxs = int(size_t(4) * 32 * (kRecRot + 1) * sizeof(double));
+      const int maxs = int(size_t(4) * 32 * (kRecMax + 1) * sizeof(double));
       cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
       cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
     }
@@ -790,39 +781,26 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   const int vol = ((w & PF3_KC0) ? 900 : 0) + ((w & (PF3_KG | PF3_KG_STRESS)) ? 225 : 0) + ((w & PF3_M) ? 750 : 0);
   const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
   const int chunk = (vol < 1400 && !mapped) ? kFChunkBig : 1;
-  const bool dyn = PF3_DYN && chunk == 1 && !mapped && !F.zero_empty && F.rmax == 1 && work != nullptr;
-  const size_t smem = fused_smem_bytes(stride, dyn ? kFChunkBig : chunk);
+  const size_t smem = fused_smem_bytes(stride, chunk);
   const int64_t npairs = F.pair_count ? F.pair_count : (F.nown + 1) / 2;
-  int64_t want = (npairs + int64_t(kFusedWarps) * chunk - 1) / (int64_t(kFusedWarps) * chunk);
-  if (dyn) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    want = std::min<int64_t>(want, int64_t(sms) * PF3_FUSED_CTAS);
-    cudaError_t em = cudaMemsetAsync(work, 0, sizeof(unsigned long long), st);
-    if (em != cudaSuccess) return em;
-  }
+  const int64_t want = (npairs + int64_t(kFusedWarps) * chunk - 1) / (int64_t(kFusedWarps) * chunk);
   if (want > int64_t(0x7fffffff)) return cudaErrorInvalidConfiguration;
   const unsigned grid = unsigned(want < 1 ? 1 : want);
   static PerDeviceOnce once;
   if (once.first()) {
-    const int m1 = int(fused_smem_bytes(kRecRot, 1)), m4 = int(fused_smem_bytes(kRecRot, kFChunkBig));
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, kFChunkBig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, kFChunkBig, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
-    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
+    const int m1 = int(fused_smem_bytes(kRecMax, 1)), m4 = int(fused_smem_bytes(kRecMax, kFChunkBig));
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m1);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
+    cudaFuncSetAttribute(quad_fused_kernel<PF3_QUAD4R, kFChunkBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, m4);
   }
   const unsigned nt = 32 * kFusedWarps;
   if (kind == PF3_QUAD4) {
-    if (dyn) quad_fused_kernel<PF3_QUAD4, 1, true><<<grid, nt, smem, st>>>(F, rec, stride, work);
-    else if (chunk == 1) quad_fused_kernel<PF3_QUAD4, 1, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
-    else quad_fused_kernel<PF3_QUAD4, kFChunkBig, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
+    if (chunk == 1) quad_fused_kernel<PF3_QUAD4, 1><<<grid, nt, smem, st>>>(F, rec, stride);
+    else quad_fused_kernel<PF3_QUAD4, kFChunkBig><<<grid, nt, smem, st>>>(F, rec, stride);
   } else {
-    if (dyn) quad_fused_kernel<PF3_QUAD4R, 1, true><<<grid, nt, smem, st>>>(F, rec, stride, work);
-    else if (chunk == 1) quad_fused_kernel<PF3_QUAD4R, 1, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
-    else quad_fused_kernel<PF3_QUAD4R, kFChunkBig, false><<<grid, nt, smem, st>>>(F, rec, stride, work);
+    if (chunk == 1) quad_fused_kernel<PF3_QUAD4R, 1><<<grid, nt, smem, st>>>(F, rec, stride);
+    else quad_fused_kernel<PF3_QUAD4R, kFChunkBig><<<grid, nt, smem, st>>>(F, rec, stride);
   }
   ++*launches;
   return cudaGetLastError();

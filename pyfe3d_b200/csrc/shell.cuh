@@ -22,7 +22,13 @@ template <int NN>
 struct ShellGeom {
   Mat3 R;                  // columns = element x,y,z axes in global coordinates
   double m11, m12, m21, m22;
+  // local coordinates RELATIVE TO NODE 0 (every matrix is translation-invariant); O = R^T x_0 is the absolute local
+  // position of node 0, only needed for probe.xe.  The differences are formed in GLOBAL coordinates first and then
+  // rotated, so that elements far from the origin (|x| / h ~ 1e3 on the 2000 x 2000 benchmark plate) keep full
+  // precision; the reference rotates absolute positions and subtracts afterwards (quad4.pyx:724-728, :939-942) and
+  // loses |x| / h * eps there -- its results move by ~1e-12 under a rigid translation, ours do not.
   double X[NN], Y[NN], Z[NN];
+  double O[3];
   double area;
 };
 
@@ -110,11 +116,14 @@ __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGe
     g.m21 = s[11];
     g.m22 = s[12];
     g.area = s[13];
+    g.O[0] = s[14];
+    g.O[1] = s[15];
+    g.O[2] = s[16];
 #pragma unroll
     for (int a = 0; a < NN; ++a) {
-      g.X[a] = s[14 + 3 * a];
-      g.Y[a] = s[15 + 3 * a];
-      g.Z[a] = s[16 + 3 * a];
+      g.X[a] = s[14 + 3 * a] - g.O[0];
+      g.Y[a] = s[15 + 3 * a] - g.O[1];
+      g.Z[a] = s[16 + 3 * a] - g.O[2];
     }
     if (ue != nullptr)
 #pragma unroll
@@ -166,11 +175,16 @@ __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGe
     material_axes<NN>(g, xm, znorm, mprev);
   }
   if (need_x) {
+    g.O[0] = xh[0] * P[0][0] + xh[1] * P[0][1] + xh[2] * P[0][2];
+    g.O[1] = yh[0] * P[0][0] + yh[1] * P[0][1] + yh[2] * P[0][2];
+    g.O[2] = zh[0] * P[0][0] + zh[1] * P[0][1] + zh[2] * P[0][2];
+    g.X[0] = g.Y[0] = g.Z[0] = 0.;
 #pragma unroll
-    for (int a = 0; a < NN; ++a) {
-      g.X[a] = xh[0] * P[a][0] + xh[1] * P[a][1] + xh[2] * P[a][2];
-      g.Y[a] = yh[0] * P[a][0] + yh[1] * P[a][1] + yh[2] * P[a][2];
-      g.Z[a] = zh[0] * P[a][0] + zh[1] * P[a][1] + zh[2] * P[a][2];
+    for (int a = 1; a < NN; ++a) {
+      const double q[3] = {P[a][0] - P[0][0], P[a][1] - P[0][1], P[a][2] - P[0][2]};
+      g.X[a] = xh[0] * q[0] + xh[1] * q[1] + xh[2] * q[2];
+      g.Y[a] = yh[0] * q[0] + yh[1] * q[1] + yh[2] * q[2];
+      g.Z[a] = zh[0] * q[0] + zh[1] * q[1] + zh[2] * q[2];
     }
     if (NN == 4) {
       g.area = 0.5 * fabs((g.X[0] * g.Y[1] + g.X[1] * g.Y[2] + g.X[2] * g.Y[NN - 1] + g.X[NN - 1] * g.Y[0]) -
@@ -209,9 +223,9 @@ __device__ __forceinline__ void store_state(const EvalArgs& A, int64_t e, const 
   s[13] = g.area;
 #pragma unroll
   for (int a = 0; a < NN; ++a) {
-    s[14 + 3 * a] = g.X[a];
-    s[15 + 3 * a] = g.Y[a];
-    s[16 + 3 * a] = g.Z[a];
+    s[14 + 3 * a] = g.O[0] + g.X[a];
+    s[15 + 3 * a] = g.O[1] + g.Y[a];
+    s[16 + 3 * a] = g.O[2] + g.Z[a];
   }
   for (int i = 0; i < 6 * NN; ++i) s[26 + i] = ue ? ue[i] : 0.;
   for (int i = 26 + 6 * NN; i < PF3_STATE_STRIDE; ++i) s[i] = 0.;

@@ -5,8 +5,11 @@ leaves the GPU.  What it replaces in a reference script (tests/test_quad4_static
     KC0uu = KC0[bu, :][:, bu]                 ->  u = cg_solve(indptr, indices, vals, fext, free=bu)
     uu, info = cg(KC0uu, fext[bu], atol=1e-9)
 
-The SpMV and the diagonal extraction are C-ABI kernels; vector updates and dot products use torch tensors
-(device plumbing)."""
+Single device: ``plan_cg_solve`` runs ``pf3_plan_cg`` -- the whole iteration in native kernels (block SpMV + three fused
+vector kernels, deterministic reductions, convergence flag on the device).  Row-sharded over several GPUs it keeps the
+loop here, because the search direction is exchanged between ranks every iteration (NCCL all_gather).
+``compact_csr`` / ``plan_compact`` return ``K[bu, :][:, bu]`` itself as a CSR matrix for callers that hand Kuu to scipy's
+``spsolve`` / ``eigsh``."""
 import torch
 
 from .batch import _dev, _ptr, context
@@ -49,15 +52,21 @@ def cg_solve(indptr, indices, vals, b, free=None, rtol=1e-12, maxiter=None, x0=N
         return x, 0
     maxiter = maxiter or 10 * n
     ap = torch.empty_like(x)
+    tol = rtol * float(bnorm)
+    if float(torch.linalg.vector_norm(r)) <= tol or float(rz) == 0.0:
+        return x, 0
     for it in range(1, maxiter + 1):
         masked_spmv(indptr, indices, vals, free, p, out=ap)
-        alpha = rz / torch.dot(p, ap)
+        pap = torch.dot(p, ap)
+        if it % 8 == 1 and not float(pap) > 0.0:           # breakdown: not positive definite on the free dofs
+            return x, -it
+        alpha = rz / pap
         x += alpha * p
         r -= alpha * ap
-        if it % 8 == 0 and float(torch.linalg.vector_norm(r)) <= rtol * float(bnorm):
-            return x, it
         z = minv * r
         rz_new = torch.dot(r, z)
+        if (it % 8 == 0 or it == maxiter) and (float(torch.linalg.vector_norm(r)) <= tol or float(rz_new) == 0.0):
+            return x, it
         p = z + (rz_new / rz) * p
         rz = rz_new
     return x, -maxiter
@@ -86,6 +95,9 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
     if free is None:
         free = torch.ones(n, dtype=torch.uint8, device=dev)
     free = _dev(free, torch.uint8, dev)
+    if not multi:
+        x, it, status, _, _ = plan_cg_native(plan, vals, b, free=free, rtol=rtol, maxiter=maxiter, x0=x0, extra=extra)
+        return x, (it if status == 0 else -max(it, 1))
     fl = free[lo:hi].to(torch.float64)
     bl = _dev(b, torch.float64, dev)[lo:hi] * fl
     d = plan.diagonal(vals)
@@ -138,19 +150,83 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
         return gather(x).clone(), 0
     maxiter = maxiter or 10 * n
     info = -maxiter
+    if float(allsum(torch.dot(r, r)).sqrt()) <= rtol * bnorm or float(rz) == 0.0:
+        return gather(x).clone(), 0
     for it in range(1, maxiter + 1):
         matvec(gather(p), ap)
-        alpha = rz / allsum(torch.dot(p, ap))
+        pap = allsum(torch.dot(p, ap))
+        if it % 8 == 1 and not float(pap) > 0.0:           # breakdown: not positive definite on the free dofs
+            info = -it
+            break
+        alpha = rz / pap
         x += alpha * p
         r -= alpha * ap
-        if it % 8 == 0 and float(allsum(torch.dot(r, r)).sqrt()) <= rtol * bnorm:
-            info = it
-            break
         z = minv * r
         rz_new = allsum(torch.dot(r, z))
+        if (it % 8 == 0 or it == maxiter) and (float(allsum(torch.dot(r, r)).sqrt()) <= rtol * bnorm
+                                               or float(rz_new) == 0.0):
+            info = it
+            break
         p = z + (rz_new / rz) * p
         rz = rz_new
     return gather(x).clone(), info
+
+
+def plan_cg_native(plan, vals, b, free=None, rtol=1e-12, atol=0.0, maxiter=None, x0=None, extra=(),
+                   scaled_norm=False, check_every=16):
+    """``pf3_plan_cg``: Jacobi-preconditioned CG for ``(P A P) x = P b`` entirely in native kernels on ONE device,
+    ``A = vals + sum(c * v for plan_i, v, c in extra)``.  ``scaled_norm=True`` applies the stopping test
+    ``|r| <= max(rtol |b|, atol)`` in the diagonally scaled norm, i.e. exactly what the reference's
+    ``cg(D Kuu D, D fu, atol=...)`` measures (tests/test_quad4r_linear_buckling_plate.py:135-146).
+    Returns (x[6*nnodes], iterations, status, residual norm, |b|); status 0 = converged, 1 = maxiter, 2 = breakdown."""
+    dev = vals.device
+    n = 6 * plan.nnodes
+    if plan.nrows != n:
+        raise ValueError("pf3_plan_cg needs a plan that owns every row")
+    ctx = context(dev)
+    free_t = None if free is None else _dev(free, torch.uint8, dev)
+    bt = _dev(b, torch.float64, dev).reshape(-1)
+    if bt.numel() != n:
+        raise ValueError("b must have 6*nnodes entries")
+    x = torch.zeros(n, dtype=torch.float64, device=dev) if x0 is None else _dev(x0, torch.float64, dev).clone()
+    plans = [plan._plan] + [pe._plan for pe, _, _ in extra]
+    vlist = [_ptr(vals)] + [_ptr(ve) for _, ve, _ in extra]
+    coefs = [1.0] + [float(ce) for _, _, ce in extra]
+    flags = (1 if scaled_norm else 0) | (int(check_every) << 8)
+    it, status, res, bn = ctx.plan_cg(plans, vlist, coefs, _ptr(free_t) if free_t is not None else 0, _ptr(bt),
+                                      _ptr(x), x0 is not None, float(rtol), float(atol), int(maxiter or 0), flags)
+    return x, it, status, res, bn
+
+
+def compact_csr(indptr, indices, vals, free, row0=0, pattern=None):
+    """``K[bu, :][:, bu]`` (tests/test_quad4_static_point_load.py:84-99) as device CSR arrays from a device CSR matrix:
+    rows / columns whose ``free`` flag is set are kept and renumbered by their rank among the free dofs.  ``row0``: the
+    global index of the matrix' first row (row-sharded plans).  Returns ((indptr_uu, indices_uu, vals_uu), pattern);
+    hand ``pattern`` back in to refresh only the values of a fixed pattern."""
+    dev = indptr.device
+    ctx = context(dev)
+    nrows = indptr.numel() - 1
+    free = _dev(free, torch.uint8, dev)
+    ncols = free.numel()
+    if pattern is None:
+        colmap = torch.empty(ncols + 1, dtype=torch.int64, device=dev)
+        optr = torch.empty(nrows + 1, dtype=torch.int64, device=dev)
+        nkeep, nnz = ctx.csr_compact_symbolic(nrows, ncols, _ptr(indptr), _ptr(indices), _ptr(free), row0, _ptr(colmap),
+                                              _ptr(optr))
+        optr = optr[:nkeep + 1]
+        oidx = torch.empty(nnz, dtype=torch.int64, device=dev)
+        pattern = (colmap, optr, oidx, nnz, False)
+    colmap, optr, oidx, nnz, filled = pattern
+    oval = torch.empty(nnz, dtype=torch.float64, device=dev) if vals is not None else None
+    ctx.csr_compact_fill(nrows, ncols, _ptr(indptr), _ptr(indices), _ptr(vals) if vals is not None else 0, _ptr(free),
+                         row0, _ptr(colmap), _ptr(optr), 0 if filled else _ptr(oidx), _ptr(oval) if oval is not None else 0)
+    return (optr, oidx, oval), (colmap, optr, oidx, nnz, True)
+
+
+def plan_compact(plan, vals, free, pattern=None):
+    """``compact_csr`` on the CSR values of an ``AssemblyPlan`` (its own row block when row-sharded)."""
+    indptr, indices = plan.pattern()
+    return compact_csr(indptr, indices, vals, free, row0=6 * plan.node_begin, pattern=pattern)
 
 
 def shift_invert_operator(plan_a, a_vals, plan_m, m_vals, sigma, free, rtol=1e-13, maxiter=None):

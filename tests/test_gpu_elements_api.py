@@ -152,8 +152,11 @@ def test_degenerate_material_axis_keeps_state(kind):
     z = np.load(os.path.join(util.GOLDEN_DIR, "sticky_xmat.npz"))
     case, ref = util.load_golden(kind + "_xmat_degenerate")
     m_ref = ref["m"].reshape(-1, 4)
-    for e in (0, 1, 2, 3, 4, 8, 9, 10, 11):
-        assert np.array_equal(m_ref[e], [1., 0., 0., 1.])      # the fixture really exercises the guards
+    # the fixture really exercises the guards.  Row 4 (|z x xmat| ~ 2e-13 against tol = |z| / 1e10) sits ON the guard:
+    # which branch the reference takes there depends on the element's size (the small triangle of this seed has
+    # tol < 2e-13 and takes the regular branch), so it is compared with the reference below, not with the identity
+    for e in (0, 1, 2, 3, 8, 9, 10, 11):
+        assert np.array_equal(m_ref[e], [1., 0., 0., 1.])
     e = 6
     x = np.ascontiguousarray(case["x"], float)
     el = getattr(pf, CLS[kind])(getattr(pf, CLS[kind] + "Probe")())

@@ -1,0 +1,184 @@
+"""GPU: the native device solve (pf3_plan_cg), the scaled operator (pf3_plan_spmv_scaled) and the explicit
+boundary-condition partition K[bu,:][:,bu] (pf3_csr_compact_*) -- SURVEY 8(f) ranks 1-2 -- against scipy on the same
+matrices, in the forms the reference scripts use them (tests/test_quad4_static_point_load.py:84-104,
+tests/test_quad4r_linear_buckling_plate.py:135-146,172-180)."""
+import numpy as np
+import pytest
+
+from tests import cases, util
+
+pytestmark = pytest.mark.gpu
+
+
+def _plate(kind="quad4", nx=19, ny=15, seed=3):
+    """A connected distorted shell mesh, its KC0 / M plans and values, and a clamped-edge dof mask."""
+    import torch  # noqa: F401
+    from pyfe3d_b200.batch import AssemblyPlan
+    case = cases.shell_mesh(kind, nx, ny, seed=seed)
+    b = util.batch_from_case(case)
+    n = case["ndof"]
+    pk = AssemblyPlan("KC0", n // 6, [b])
+    pm = AssemblyPlan("M", n // 6, [b])
+    K = pk.assemble(b.update_KC0(update_KC0v_only=1).v)
+    M = pm.assemble(b.update_M(mtype=0, indices=False).v)
+    conn = np.asarray(case["conn"])
+    # constrain every dof of the nodes of the first 2*ny elements' first nodes (a clamped strip), and drilling nowhere
+    fixed_nodes = np.unique(conn[: 2 * ny])
+    free = np.ones(n, np.uint8)
+    for d in range(6):
+        free[6 * fixed_nodes + d] = 0
+    return case, pk, K, pm, M, free
+
+
+def test_native_cg_matches_spsolve():
+    import torch
+    from scipy.sparse.linalg import spsolve
+    from pyfe3d_b200.solve import plan_cg_native
+    case, pk, K, pm, M, free = _plate()
+    n = case["ndof"]
+    rng = np.random.default_rng(1)
+    f = rng.normal(size=n)
+    bu = free.astype(bool)
+    A = pk.to_scipy(K).tocsc()
+    want = np.zeros(n)
+    want[bu] = spsolve(A[bu, :][:, bu], f[bu])
+    x, it, status, res, bn = plan_cg_native(pk, K, torch.as_tensor(f).cuda(), free=torch.as_tensor(free).cuda(),
+                                            rtol=1e-14, check_every=8)
+    assert status == 0 and it > 0
+    assert res <= 1e-14 * bn
+    got = x.cpu().numpy()
+    assert np.all(got[~bu] == 0.)
+    assert np.abs(got - want).max() <= 1e-8 * np.abs(want).max()
+    # bit-reproducible: fixed-order reductions
+    x2, it2, *_ = plan_cg_native(pk, K, torch.as_tensor(f).cuda(), free=torch.as_tensor(free).cuda(), rtol=1e-14,
+                                 check_every=8)
+    assert it2 == it and torch.equal(x, x2)
+    # warm start from the solution converges at once
+    x3, it3, st3, *_ = plan_cg_native(pk, K, torch.as_tensor(f).cuda(), free=torch.as_tensor(free).cuda(), rtol=1e-10,
+                                      x0=x)
+    assert st3 == 0 and it3 <= 2
+    assert np.abs(x3.cpu().numpy() - want).max() <= 1e-8 * np.abs(want).max()
+
+
+def test_native_cg_is_the_reference_scaled_cg():
+    """D = diag(Kuu)^-1/2; cg(D Kuu D, D fu, atol) of tests/test_quad4r_linear_buckling_plate.py:135-146: same stopping
+    test (scaled norm, atol), same solution."""
+    import scipy.sparse as sp
+    import torch
+    from scipy.sparse.linalg import cg
+    from pyfe3d_b200.solve import plan_cg_native
+    case, pk, K, pm, M, free = _plate("quad4r", 17, 13, seed=5)
+    n = case["ndof"]
+    bu = free.astype(bool)
+    f = np.zeros(n)
+    f[2::6] = 1.0
+    Kuu = pk.to_scipy(K).tocsc()[bu, :][:, bu]
+    dis = 1.0 / np.sqrt(np.maximum(Kuu.diagonal(), 1e-30))
+    D = sp.diags(dis)
+    fs = D @ f[bu]
+    atol = 1e-9 * np.linalg.norm(fs)
+    us, out = cg(D @ Kuu @ D, fs, atol=atol, rtol=0., maxiter=20000)
+    assert out == 0
+    want = np.zeros(n)
+    want[bu] = D @ us
+    x, it, status, res, bn = plan_cg_native(pk, K, torch.as_tensor(f).cuda(), free=torch.as_tensor(free).cuda(),
+                                            rtol=0., atol=atol, scaled_norm=True)
+    assert status == 0
+    assert res <= atol and abs(bn - np.linalg.norm(fs)) <= 1e-12 * bn
+    assert np.abs(x.cpu().numpy() - want).max() <= 1e-6 * np.abs(want).max()
+
+
+def test_native_cg_sum_of_operators_and_failure_modes():
+    import torch
+    from scipy.sparse.linalg import spsolve
+    from pyfe3d_b200.solve import plan_cg_native
+    case, pk, K, pm, M, free = _plate()
+    n = case["ndof"]
+    bu = free.astype(bool)
+    f = np.random.default_rng(2).normal(size=n)
+    sigma = -3.0e3
+    A = (pk.to_scipy(K) - sigma * pm.to_scipy(M)).tocsc()
+    want = np.zeros(n)
+    want[bu] = spsolve(A[bu, :][:, bu], f[bu])
+    ft, fr = torch.as_tensor(f).cuda(), torch.as_tensor(free).cuda()
+    x, it, status, *_ = plan_cg_native(pk, K, ft, free=fr, rtol=1e-14, extra=[(pm, M, -sigma)])
+    assert status == 0
+    assert np.abs(x.cpu().numpy() - want).max() <= 1e-8 * np.abs(want).max()
+    # maxiter reached is reported, not an exception; x is finite
+    x, it, status, *_ = plan_cg_native(pk, K, ft, free=fr, rtol=1e-14, maxiter=3)
+    assert status == 1 and it == 3 and bool(torch.isfinite(x).all())
+    # an indefinite operator (-K) breaks down cleanly
+    x, it, status, *_ = plan_cg_native(pk, -K, ft, free=fr, rtol=1e-14)
+    assert status == 2 and bool(torch.isfinite(x).all())
+    # zero right-hand side: converged at iteration 0
+    x, it, status, *_ = plan_cg_native(pk, K, torch.zeros_like(ft), free=fr)
+    assert status == 0 and it == 0 and float(x.abs().max()) == 0.
+
+
+def test_scaled_operator_matches_scipy():
+    import scipy.sparse as sp
+    import torch
+    case, pk, K, pm, M, free = _plate()
+    n = case["ndof"]
+    A = pk.to_scipy(K)
+    d = pk.diagonal(K).cpu().numpy()
+    s = 1.0 / np.sqrt(np.maximum(d, 1e-30))
+    x = np.random.default_rng(4).normal(size=n)
+    P = sp.diags(free.astype(float))
+    S = sp.diags(s)
+    ref = S @ (P @ (A @ (P @ (S @ x))))
+    y = pk.spmv_scaled(K, torch.as_tensor(s).cuda(), torch.as_tensor(x).cuda(), free=torch.as_tensor(free).cuda())
+    assert np.abs(y.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("matrix", ["KC0", "M"])
+@pytest.mark.parametrize("shard", [False, True])
+def test_compact_csr_is_scipy_extraction(matrix, shard):
+    """K[bu,:][:,bu] (tests/test_quad4_static_point_load.py:84-99): pattern bit-exact, values bit-exact (a pure copy)."""
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    from pyfe3d_b200.solve import plan_compact
+    case = cases.shell_mesh("quad4", 14, 11, seed=9)
+    b = util.batch_from_case(case)
+    n = case["ndof"]
+    nn = n // 6
+    rng_ = (nn // 3, nn - 7) if shard else None
+    plan = AssemblyPlan(matrix, nn, [b], node_range=rng_)
+    coo = b.update_KC0(update_KC0v_only=1) if matrix == "KC0" else b.update_M(indices=False)
+    vals = plan.assemble(coo.v)
+    rng = np.random.default_rng(12)
+    free = (rng.random(n) > 0.3).astype(np.uint8)
+    free[2::6] = 1
+    bu = free.astype(bool)
+    lo = 6 * plan.node_begin
+    A = plan.to_scipy(vals).tocsr()
+    want = A[bu[lo:lo + plan.nrows], :][:, bu].tocsr()
+    want.sort_indices()
+    (ip, ix, v), pat = plan_compact(plan, vals, torch.as_tensor(free).cuda())
+    assert np.array_equal(ip.cpu().numpy(), want.indptr)
+    assert np.array_equal(ix.cpu().numpy(), want.indices)
+    assert np.array_equal(v.cpu().numpy(), want.data)
+    # values-only refresh through the cached pattern
+    (ip2, ix2, v2), _ = plan_compact(plan, 2.0 * vals, torch.as_tensor(free).cuda(), pattern=pat)
+    assert ip2 is ip and ix2 is ix
+    assert np.array_equal(v2.cpu().numpy(), 2.0 * want.data)
+
+
+def test_compact_csr_edge_masks():
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    from pyfe3d_b200.solve import plan_compact
+    case = cases.shell_mesh("quad4", 5, 4, seed=1)
+    b = util.batch_from_case(case)
+    n = case["ndof"]
+    plan = AssemblyPlan("KC0", n // 6, [b])
+    vals = plan.assemble(b.update_KC0(update_KC0v_only=1).v)
+    A = plan.to_scipy(vals).tocsr()
+    A.sort_indices()
+    # everything free: the matrix itself
+    (ip, ix, v), _ = plan_compact(plan, vals, torch.ones(n, dtype=torch.uint8).cuda())
+    assert np.array_equal(ip.cpu().numpy(), A.indptr) and np.array_equal(ix.cpu().numpy(), A.indices)
+    assert np.array_equal(v.cpu().numpy(), A.data)
+    # nothing free: an empty 0 x 0 matrix
+    (ip, ix, v), _ = plan_compact(plan, vals, torch.zeros(n, dtype=torch.uint8).cuda())
+    assert ip.numel() == 1 and int(ip[0]) == 0 and ix.numel() == 0 and v.numel() == 0
