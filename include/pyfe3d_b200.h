@@ -292,6 +292,8 @@ int pf3_plan_diagonal(pf3_context* ctx, const pf3_plan* plan, const double* vals
  * <= max(rtol * |b|, atol); PF3_CG_SCALED_NORM measures both in the scaled norm (r.D^2.r) that scipy's cg sees on the
  * scaled system.  maxiter <= 0: 10 * ndof. */
 #define PF3_CG_SCALED_NORM 1
+#define PF3_CG_GRAPH 2 /* replay each batch of iterations as ONE CUDA graph (launch-bound small systems); needs a
+                          capturable stream -- on the legacy default stream the call falls back to plain launches */
 typedef struct pf3_cg_info {
   int32_t iterations;
   int32_t status;   /* 0 converged, 1 maxiter reached, 2 breakdown (p.Ap <= 0: matrix not positive definite on bu) */
@@ -310,15 +312,20 @@ int pf3_plan_spmv_scaled(pf3_context* ctx, const pf3_plan* plan, const double* v
  * rows are the global rows [row0, row0 + nrows) (row0 = 6*node_begin of a row-sharded plan, else 0) and whose column
  * indices are global in [0, ncols): rows / columns with free_dof[.] != 0 are kept and renumbered by their rank among
  * the free dofs (columns: global rank; rows: rank within this row block).
+ * free_dof == NULL keeps every row and column.  flags & PF3_COMPACT_UPPER additionally keeps only entries with
+ * col >= row (scipy.sparse.triu): KC0, KG and M are symmetric, so a host consumer that accepts one triangle needs 5/9
+ * of the values moved over PCIe.
  *  symbolic: colmap[ncols + 1] <- exclusive scan of the free flags (scratch the fill step needs again),
  *            out_indptr[<= nrows + 1] <- row pointers of the compacted block; *nkeep rows, *nnz entries (host).
  *  fill:     out_indices[nnz] (may be NULL: values-only refresh for a fixed pattern), out_vals[nnz] (may be NULL). */
+#define PF3_COMPACT_UPPER 1
 int pf3_csr_compact_symbolic(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
-                             const int64_t* indices, const unsigned char* free_dof, int64_t row0, int64_t* colmap,
-                             int64_t* out_indptr, int64_t* nkeep, int64_t* nnz);
+                             const int64_t* indices, const unsigned char* free_dof, int flags, int64_t row0,
+                             int64_t* colmap, int64_t* out_indptr, int64_t* nkeep, int64_t* nnz);
 int pf3_csr_compact_fill(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
-                         const int64_t* indices, const double* vals, const unsigned char* free_dof, int64_t row0,
-                         const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices, double* out_vals);
+                         const int64_t* indices, const double* vals, const unsigned char* free_dof, int flags,
+                         int64_t row0, const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices,
+                         double* out_vals);
 
 /* ---- property tables on the device ---------------------------------------- */
 /* props_out[nrows * PF3_SHELLPROP_STRIDE]: the ShellProp scalars of nrows laminates of nplies plies each, what

@@ -65,3 +65,33 @@ class ReferenceBench:
         return ("%dx%d-element sub-plate of the workload mesh (%d Quad4), reference Cython loop "
                 "rot+xe+ue+KC0+KG+M(mtype0) with indices, then scipy coo->csr per slice; %d processes"
                 % (self.side, self.side, self.ne, self.nproc))
+
+
+def reference_static_solve(side, rtol=1e-9):
+    """Reference arm of the static solve on the host: Cython element loop (KC0) -> coo_matrix.tocsc ->
+    K[bu,:][:,bu] -> diagonally scaled scipy cg.  Returns (seconds, iterations, max normal displacement)."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import cg
+    from oracle import ref_loop
+    ref_loop.load()
+    from pyfe3d_b200 import meshes
+    case, free, f, normal = meshes.static_case(side)
+    n = case["ndof"]
+    t0 = time.perf_counter()
+    out = ref_loop.run(case, what=("KC0",))
+    r, c, v = out["KC0"]
+    K = sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsc()
+    Kuu = K[free, :][:, free]
+    dis = 1.0 / np.sqrt(np.maximum(Kuu.diagonal(), 1e-30))
+    D = sp.diags(dis)
+    fs = D @ f[free]
+    its = [0]
+
+    def cb(_):
+        its[0] += 1
+    us, info = cg(D @ Kuu @ D, fs, rtol=0., atol=rtol * np.linalg.norm(fs), maxiter=200000, callback=cb)
+    u = np.zeros(n)
+    u[free] = D @ us
+    dt = time.perf_counter() - t0
+    w = u[0::6] * normal[0] + u[1::6] * normal[1] + u[2::6] * normal[2]
+    return dt, its[0], float(np.abs(w).max()), info

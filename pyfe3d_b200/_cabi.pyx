@@ -89,11 +89,11 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_spmv_scaled(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
                              const double* scale, const double* x, double* y) nogil
     int pf3_csr_compact_symbolic(pf3_context*, int64_t nrows, int64_t ncols, const int64_t* indptr,
-                                 const int64_t* indices, const unsigned char* free_dof, int64_t row0, int64_t* colmap,
-                                 int64_t* out_indptr, int64_t* nkeep, int64_t* nnz) nogil
+                                 const int64_t* indices, const unsigned char* free_dof, int flags, int64_t row0,
+                                 int64_t* colmap, int64_t* out_indptr, int64_t* nkeep, int64_t* nnz) nogil
     int pf3_csr_compact_fill(pf3_context*, int64_t nrows, int64_t ncols, const int64_t* indptr,
-                             const int64_t* indices, const double* vals, const unsigned char* free_dof, int64_t row0,
-                             const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices,
+                             const int64_t* indices, const double* vals, const unsigned char* free_dof, int flags,
+                             int64_t row0, const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices,
                              double* out_vals) nogil
     int pf3_quad4_update_BL(pf3_context*, int64_t n, const double* xe, double xi, double eta, double* out) nogil
     int pf3_eval_assemble(pf3_context*, const pf3_batch*, const pf3_plan*, int what, const pf3_coo*, const pf3_coo*,
@@ -327,23 +327,23 @@ cdef class Context:
         _check(rc)
 
     def csr_compact_symbolic(self, int64_t nrows, int64_t ncols, uintptr_t indptr, uintptr_t indices,
-                             uintptr_t free_dof, int64_t row0, uintptr_t colmap, uintptr_t out_indptr):
+                             uintptr_t free_dof, int flags, int64_t row0, uintptr_t colmap, uintptr_t out_indptr):
         cdef int rc
         cdef int64_t nkeep = 0, nnz = 0
         with nogil:
             rc = pf3_csr_compact_symbolic(self.ctx, nrows, ncols, <const int64_t*>indptr, <const int64_t*>indices,
-                                          <const unsigned char*>free_dof, row0, <int64_t*>colmap,
+                                          <const unsigned char*>free_dof, flags, row0, <int64_t*>colmap,
                                           <int64_t*>out_indptr, &nkeep, &nnz)
         _check(rc)
         return nkeep, nnz
 
     def csr_compact_fill(self, int64_t nrows, int64_t ncols, uintptr_t indptr, uintptr_t indices, uintptr_t vals,
-                         uintptr_t free_dof, int64_t row0, uintptr_t colmap, uintptr_t out_indptr,
+                         uintptr_t free_dof, int flags, int64_t row0, uintptr_t colmap, uintptr_t out_indptr,
                          uintptr_t out_indices, uintptr_t out_vals):
         cdef int rc
         with nogil:
             rc = pf3_csr_compact_fill(self.ctx, nrows, ncols, <const int64_t*>indptr, <const int64_t*>indices,
-                                      <const double*>vals, <const unsigned char*>free_dof, row0,
+                                      <const double*>vals, <const unsigned char*>free_dof, flags, row0,
                                       <const int64_t*>colmap, <const int64_t*>out_indptr, <int64_t*>out_indices,
                                       <double*>out_vals)
         _check(rc)

@@ -56,10 +56,12 @@ def build_lib(force=False, verbose=True):
     with ThreadPoolExecutor(len(CU)) as ex:
         objs = list(ex.map(one, CU))
     if force or _newer(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        # link next to the target and rename: a reader (e.g. a gpurun snapshot) never sees a half-written library
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB + ".tmp"] + objs
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        os.replace(LIB + ".tmp", LIB)
     return LIB
 
 
@@ -74,11 +76,12 @@ def build_cabi(force=False, verbose=True):
     subprocess.check_call([sys.executable, "-m", "cython", "-3", pyx, "-o", c])
     import numpy
     cmd = ["gcc", "-O2", "-fPIC", "-shared", "-w", "-I", sysconfig.get_paths()["include"],
-           "-I", numpy.get_include(), "-I", os.path.join(ROOT, "include"), c, "-o", so,
+           "-I", numpy.get_include(), "-I", os.path.join(ROOT, "include"), c, "-o", so + ".tmp",
            "-L", LIBDIR, "-lpyfe3d_b200", "-Wl,-rpath,$ORIGIN/lib"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    os.replace(so + ".tmp", so)
     return so
 
 

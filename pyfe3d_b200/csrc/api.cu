@@ -52,6 +52,9 @@ int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st,
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches,
                               int phases);
 int fused_record_stride(const EvalArgs& A);
+bool fused_split_applies(const FusedArgs& F);
+cudaError_t launch_quad_fused_split(int kind, FusedArgs& F, double* rec, cudaStream_t st, cudaStream_t aux,
+                                    cudaEvent_t* ev, FusedSplit* S, int64_t* launches);
 int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_union_map(const pf3_plan* pl, int group, int matrix, int mtype, UnionMap* um);
@@ -72,10 +75,10 @@ int plan_cg(cudaStream_t st, int nops, const CgOp* ops, int64_t n, const unsigne
 int plan_spmv_scaled(const pf3_plan* pl, cudaStream_t st, const double* vals, const unsigned char* free_,
                      const double* scale, const double* x, double* y, double* tmp, int64_t n, int64_t* launches);
 int csr_compact_symbolic(cudaStream_t st, int64_t nrows, int64_t ncols, const int64_t* indptr, const int64_t* indices,
-                         const unsigned char* free_, int64_t row0, int64_t* colmap, int64_t* out_ptr, int64_t* nkeep,
-                         int64_t* nnz, int64_t* launches);
+                         const unsigned char* free_, int upper, int64_t row0, int64_t* colmap, int64_t* out_ptr,
+                         int64_t* nkeep, int64_t* nnz, int64_t* launches);
 int csr_compact_fill(cudaStream_t st, int64_t nrows, int64_t ncols, const int64_t* indptr, const int64_t* indices,
-                     const double* vals, const unsigned char* free_, int64_t row0, const int64_t* colmap,
+                     const double* vals, const unsigned char* free_, int upper, int64_t row0, const int64_t* colmap,
                      const int64_t* out_ptr, int64_t* out_idx, double* out_val, int64_t* launches);
 }  // namespace pf3
 
@@ -95,6 +98,9 @@ struct pf3_context {
   cudaEvent_t chunk_done[PF3_HOST_CHUNKS] = {};
   char* stage_host = nullptr;           // pinned + device staging of the small host-pointer calls (per-element drop-in)
   char* stage_dev = nullptr;
+  cudaStream_t k1_stream = nullptr;     // high-priority side stream of the split fused launch (records of later ranges)
+  cudaEvent_t k1_done[pf3::kFusedMaxSplit] = {};
+  pf3::FusedSplit split;                // cached cut points of the last plan
   void* solve_work = nullptr;           // vectors + scalars of pf3_plan_cg / pf3_plan_spmv_scaled
   size_t solve_work_bytes = 0;
 };
@@ -284,6 +290,9 @@ int pf3_destroy(pf3_context* ctx) {
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->stage_dev) cudaFree(ctx->stage_dev);
   if (ctx->solve_work) cudaFree(ctx->solve_work);
+  if (ctx->k1_stream) cudaStreamDestroy(ctx->k1_stream);
+  for (cudaEvent_t ev : ctx->k1_done)
+    if (ev) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (cudaEvent_t ev : ctx->chunk_done)
     if (ev) cudaEventDestroy(ev);
@@ -668,6 +677,17 @@ int eval_assemble_impl(pf3_context* ctx, const pf3_batch* b, const pf3_plan* pla
     rc = fused_pipelined(ctx, b->kind, F, dev_out, host_out, per_block);
     if (rc) return rc;
     *copied = true;
+  } else if (!tria && pf3::fused_split_applies(F)) {
+    // K1 of the later node-pair ranges runs on a side stream behind K2 of the earlier ones
+    if (!ctx->k1_stream) {
+      int lo = 0, hi = 0;
+      PF3_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      PF3_CUDA(cudaStreamCreateWithPriority(&ctx->k1_stream, cudaStreamNonBlocking, hi));
+      for (cudaEvent_t& ev : ctx->k1_done) PF3_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    cudaError_t e = pf3::launch_quad_fused_split(b->kind, F, ctx->scratch, ctx->stream, ctx->k1_stream, ctx->k1_done,
+                                                 &ctx->split, &ctx->launches);
+    if (e != cudaSuccess) return int(e);
   } else {
     cudaError_t e = tria ? pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches)
                          : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3);
@@ -969,23 +989,24 @@ int pf3_plan_spmv_scaled(pf3_context* ctx, const pf3_plan* plan, const double* v
 }
 
 int pf3_csr_compact_symbolic(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
-                             const int64_t* indices, const unsigned char* free_dof, int64_t row0, int64_t* colmap,
-                             int64_t* out_indptr, int64_t* nkeep, int64_t* nnz) {
+                             const int64_t* indices, const unsigned char* free_dof, int flags, int64_t row0,
+                             int64_t* colmap, int64_t* out_indptr, int64_t* nkeep, int64_t* nnz) {
   int rc = use_device(ctx);
   if (rc) return rc;
-  if (!indptr || !indices || !free_dof || !colmap || !out_indptr) return PF3_E_BAD_ARG;
-  return pf3::csr_compact_symbolic(ctx->stream, nrows, ncols, indptr, indices, free_dof, row0, colmap, out_indptr,
-                                   nkeep, nnz, &ctx->launches);
+  if (!indptr || !indices || !colmap || !out_indptr) return PF3_E_BAD_ARG;
+  return pf3::csr_compact_symbolic(ctx->stream, nrows, ncols, indptr, indices, free_dof, flags & PF3_COMPACT_UPPER, row0,
+                                   colmap, out_indptr, nkeep, nnz, &ctx->launches);
 }
 
 int pf3_csr_compact_fill(pf3_context* ctx, int64_t nrows, int64_t ncols, const int64_t* indptr,
-                         const int64_t* indices, const double* vals, const unsigned char* free_dof, int64_t row0,
-                         const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices, double* out_vals) {
+                         const int64_t* indices, const double* vals, const unsigned char* free_dof, int flags,
+                         int64_t row0, const int64_t* colmap, const int64_t* out_indptr, int64_t* out_indices,
+                         double* out_vals) {
   int rc = use_device(ctx);
   if (rc) return rc;
-  if (!indptr || !indices || !free_dof || !colmap || !out_indptr || (out_vals && !vals)) return PF3_E_BAD_ARG;
-  return pf3::csr_compact_fill(ctx->stream, nrows, ncols, indptr, indices, vals, free_dof, row0, colmap, out_indptr,
-                               out_indices, out_vals, &ctx->launches);
+  if (!indptr || !indices || !colmap || !out_indptr || (out_vals && !vals)) return PF3_E_BAD_ARG;
+  return pf3::csr_compact_fill(ctx->stream, nrows, ncols, indptr, indices, vals, free_dof, flags & PF3_COMPACT_UPPER,
+                               row0, colmap, out_indptr, out_indices, out_vals, &ctx->launches);
 }
 
 }  // extern "C"

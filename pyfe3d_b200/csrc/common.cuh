@@ -115,6 +115,16 @@ struct FusedArgs {
   int64_t pair_count;                     //        (pair_count == 0: all pairs) -- pf3_eval_assemble_host's pipeline
 };
 
+// cut points of the split launch of the fused quad kernels (quad_fused.cu: launch_quad_fused_split)
+constexpr int kFusedMaxSplit = 8;
+struct FusedSplit {
+  const void* key = nullptr;          // the plan's node records these cuts were computed for
+  int64_t nown = 0, ne = 0;
+  int n = 0;
+  int64_t pair_at[kFusedMaxSplit + 1];   // K2 of range r: node pairs [pair_at[r], pair_at[r+1])
+  int64_t elem_to[kFusedMaxSplit];       // K1 of range r: elements [elem_to[r-1], elem_to[r])
+};
+
 struct Mat3 {
   double a[3][3];
 };

@@ -376,7 +376,7 @@ template <int KIND>
 __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t e0 = (int64_t(blockIdx.x) * kWarpsPerCta + warp) * 32;
+  const int64_t e0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;   // CTAs of 1 or kWarpsPerCta warps
   if (e0 >= A.ne) return;
   const int nvalid = int(min(int64_t(32), A.ne - e0));
   const int64_t e = e0 + min(lane, nvalid - 1);
@@ -545,8 +545,13 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
 
 cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st) {
   if (A.ne <= 0) return cudaSuccess;
-  const int64_t per_cta = 32 * kWarpsPerCta;
+  // small batches (BASELINE config 2: 100 k beams = 3 125 warps for 148 SMs) are latency-bound: one-warp CTAs spread
+  // them over every SM instead of filling a fifth of the machine with 4-warp CTAs
+  const int warps = A.ne < int64_t(148) * 8 * 32 * kWarpsPerCta ? 1 : kWarpsPerCta;
+  const int64_t per_cta = 32 * warps;
   const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
+  const unsigned nthreads = unsigned(32 * warps);
+  const size_t smem = kStageBytes / kWarpsPerCta * warps;
   static PerDeviceOnce once;
   if (once.first()) {
     cudaFuncSetAttribute(line_eval_kernel<PF3_BEAMC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
@@ -555,10 +560,10 @@ cudaError_t launch_line(int kind, const EvalArgs& A, cudaStream_t st) {
     cudaFuncSetAttribute(line_eval_kernel<PF3_SPRING>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
   }
   switch (kind) {
-    case PF3_BEAMC: line_eval_kernel<PF3_BEAMC><<<grid, kThreads, kStageBytes, st>>>(A); break;
-    case PF3_BEAMLR: line_eval_kernel<PF3_BEAMLR><<<grid, kThreads, kStageBytes, st>>>(A); break;
-    case PF3_TRUSS: line_eval_kernel<PF3_TRUSS><<<grid, kThreads, kStageBytes, st>>>(A); break;
-    case PF3_SPRING: line_eval_kernel<PF3_SPRING><<<grid, kThreads, kStageBytes, st>>>(A); break;
+    case PF3_BEAMC: line_eval_kernel<PF3_BEAMC><<<grid, nthreads, smem, st>>>(A); break;
+    case PF3_BEAMLR: line_eval_kernel<PF3_BEAMLR><<<grid, nthreads, smem, st>>>(A); break;
+    case PF3_TRUSS: line_eval_kernel<PF3_TRUSS><<<grid, nthreads, smem, st>>>(A); break;
+    case PF3_SPRING: line_eval_kernel<PF3_SPRING><<<grid, nthreads, smem, st>>>(A); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

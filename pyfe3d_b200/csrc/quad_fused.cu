@@ -37,6 +37,9 @@ constexpr double kGpF = 0.5773502691896257645092;
 #endif
 constexpr int kFusedWarps = PF3_FUSED_WARPS;
 
+#ifndef PF3_K1_SPLIT
+#define PF3_K1_SPLIT 4   // node-pair ranges of the split launch (1: K1 then K2, no overlap)
+#endif
 constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path (NodeRec::gmap)
 // Element record (doubles): 0..5 the element x and y axes (R columns 0 and 1, row-major 3 x 2; z = x X y is recomputed
 // by the consumer) | 6..13 the eight local edge differences | 14..17 1/detJ at the 2x2 Gauss points | 18 1/detJ at the
@@ -57,14 +60,16 @@ __host__ __device__ constexpr int rec_ld(int stride) { return stride + ((stride 
 #define PF3_K1_CTAS 3
 #endif
 template <int KIND>
-__global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const EvalArgs A, double* __restrict__ rec, int stride) {
+__global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const EvalArgs A, double* __restrict__ rec, int stride,
+                                                                       int64_t e_begin, int64_t e_end) {
   // records are staged per warp in shared memory (odd leading dimension) and written out as one contiguous
   // run of 32 x stride doubles
   extern __shared__ double k1_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t e0 = (int64_t(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
-  if (e0 >= A.ne) return;
-  const int nvalid = int(min(int64_t(32), A.ne - e0));
+  // this launch covers elements [e_begin, e_end)
+  const int64_t e0 = e_begin + (int64_t(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+  if (e0 >= e_end) return;
+  const int nvalid = int(min(int64_t(32), e_end - e0));
   const int64_t e = e0 + min(lane, nvalid - 1);
   const int ld = stride + 1;
   double* stage = k1_smem + warp * 32 * ld;
@@ -752,26 +757,58 @@ size_t fused_smem_bytes(int rstride, int chunk) { return size_t(kFusedWarps) * w
 int fused_max_slots() { return kMaxSlots; }
 int fused_record_stride(const EvalArgs& A) { return rec_stride((A.what & PF3_KG) != 0, A.evec != nullptr); }
 
+namespace {
+
+cudaError_t launch_k1(int kind, const EvalArgs& A, double* rec, int stride, int64_t e_begin, int64_t e_end, int warps,
+                      cudaStream_t st, int64_t* launches) {
+  if (e_end <= e_begin) return cudaSuccess;
+  static PerDeviceOnce once1;
+  if (once1.first()) {
+    const int maxs = int(size_t(4) * 32 * (kRecMax + 1) * sizeof(double));
+    cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+    cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
+  }
+  const int64_t per = int64_t(warps) * 32;
+  const unsigned g1 = unsigned((e_end - e_begin + per - 1) / per);
+  const size_t smem1 = size_t(warps) * 32 * (stride + 1) * sizeof(double);
+  if (kind == PF3_QUAD4)
+    quad_record_kernel<PF3_QUAD4><<<g1, 32 * warps, smem1, st>>>(A, rec, stride, e_begin, e_end);
+  else
+    quad_record_kernel<PF3_QUAD4R><<<g1, 32 * warps, smem1, st>>>(A, rec, stride, e_begin, e_end);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+// largest element index the node records of each pair range refer to
+struct PairCuts {
+  int n;
+  int64_t at[kFusedMaxSplit + 1];
+};
+__global__ void k_range_emax(const NodeRec* __restrict__ rec, int64_t nown, int rmax, PairCuts C, int* __restrict__ out) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < nown * rmax; t += int64_t(gridDim.x) * blockDim.x) {
+    const NodeRec& r = rec[t];
+    int m = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (r.inc[k] >= 0) m = max(m, r.inc[k] >> 4);
+    if (m < 0) continue;
+    const int64_t pair = (t / rmax) >> 1;
+    int g = 0;
+    for (int q = 1; q < C.n; ++q)
+      if (pair >= C.at[q]) g = q;
+    if (m > out[g]) atomicMax(out + g, m);
+  }
+}
+
+}  // namespace
+
 // rec: device scratch of ne * fused_record_stride doubles.  phases: bit 0 = K1 (records of ALL elements), bit 1 = K2 for
 // the node pairs [F.pair_first, F.pair_first + F.pair_count) (all pairs when pair_count == 0).
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases) {
   if (F.nown <= 0 || F.A.ne <= 0) return cudaSuccess;
   const int stride = fused_record_stride(F.A);
   if (phases & 1) {
-    const unsigned g1 = unsigned((F.A.ne + 127) / 128);
-    const size_t smem1 = size_t(4) * 32 * (stride + 1) * sizeof(double);
-    static PerDeviceOnce once1;
-    if (once1.first()) {
-      const int maxs = int(size_t(4) * 32 * (kRecMax + 1) * sizeof(double));
-      cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
-      cudaFuncSetAttribute(quad_record_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs);
-    }
-    if (kind == PF3_QUAD4)
-      quad_record_kernel<PF3_QUAD4><<<g1, 128, smem1, st>>>(F.A, rec, stride);
-    else
-      quad_record_kernel<PF3_QUAD4R><<<g1, 128, smem1, st>>>(F.A, rec, stride);
-    ++*launches;
-    cudaError_t e1 = cudaGetLastError();
+    cudaError_t e1 = launch_k1(kind, F.A, rec, stride, 0, F.A.ne, 4, st, launches);
     if (e1 != cudaSuccess) return e1;
   }
   if (!(phases & 2)) return cudaSuccess;
@@ -804,6 +841,80 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   }
   ++*launches;
   return cudaGetLastError();
+}
+
+// The store-bound three-matrix call with K1 hidden behind K2: the node pairs are cut into S->n ranges; K1 runs on `st`
+// only for the elements the FIRST range needs, the records of the later ranges are produced on the high-priority side
+// stream `aux` by one-warp CTAs (the footprint of a K2 CTA, so they slot into the SMs as K2 CTAs retire) while K2 of
+// the earlier ranges is running; K2 of range r waits for its records through ev[r].  K1 is latency-bound on its gathers
+//  and K2 leaves issue slots and DRAM bandwidth unused, so the two overlap almost for free.
+// S caches the element cut points of a plan (they depend on the node records only).
+bool fused_split_applies(const FusedArgs& F) {
+  const int w = F.A.what;
+  const int vol = ((w & PF3_KC0) ? 900 : 0) + ((w & (PF3_KG | PF3_KG_STRESS)) ? 225 : 0) + ((w & PF3_M) ? 750 : 0);
+  const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
+  return PF3_K1_SPLIT > 1 && vol >= 1400 && !mapped && F.noderec != nullptr && F.pair_count == 0 &&
+         F.nown >= int64_t(PF3_K1_SPLIT) * 65536;
+}
+
+cudaError_t launch_quad_fused_split(int kind, FusedArgs& F, double* rec, cudaStream_t st, cudaStream_t aux,
+                                    cudaEvent_t* ev, FusedSplit* S, int64_t* launches) {
+  const int n = PF3_K1_SPLIT;
+  const int64_t npairs = (F.nown + 1) / 2;
+  if (S->key != F.noderec || S->nown != F.nown || S->ne != F.A.ne || S->n != n) {
+    PairCuts C;
+    C.n = n;
+    for (int r = 0; r <= n; ++r) C.at[r] = npairs * r / n;
+    int* d_out = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_out, sizeof(int) * kFusedMaxSplit);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(d_out, 0xff, sizeof(int) * kFusedMaxSplit, st);   // -1
+    k_range_emax<<<148 * 8, 256, 0, st>>>(F.noderec, F.nown, F.rmax, C, d_out);
+    ++*launches;
+    int h[kFusedMaxSplit];
+    e = cudaMemcpyAsync(h, d_out, sizeof(int) * kFusedMaxSplit, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return e;
+    int64_t upto = 0;
+    for (int r = 0; r < n; ++r) {
+      upto = std::max<int64_t>(upto, int64_t(h[r]) + 1);
+      S->pair_at[r] = C.at[r];
+      S->elem_to[r] = (r == n - 1) ? F.A.ne : std::min<int64_t>(upto, F.A.ne);
+    }
+    S->pair_at[n] = npairs;
+    S->key = F.noderec;
+    S->nown = F.nown;
+    S->ne = F.A.ne;
+    S->n = n;
+  }
+  const int stride = fused_record_stride(F.A);
+  cudaError_t e = cudaEventRecord(ev[0], st);   // the inputs (x, u, ...) and the previous call's K2 are ordered before this
+  if (e != cudaSuccess) return e;
+  e = cudaStreamWaitEvent(aux, ev[0], 0);
+  if (e != cudaSuccess) return e;
+  e = launch_k1(kind, F.A, rec, stride, 0, S->elem_to[0], 4, st, launches);
+  if (e != cudaSuccess) return e;
+  for (int r = 1; r < n; ++r) {
+    e = launch_k1(kind, F.A, rec, stride, S->elem_to[r - 1], S->elem_to[r], 1, aux, launches);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(ev[r], aux);
+    if (e != cudaSuccess) return e;
+  }
+  for (int r = 0; r < n; ++r) {
+    if (r > 0) {
+      e = cudaStreamWaitEvent(st, ev[r], 0);
+      if (e != cudaSuccess) return e;
+    }
+    F.pair_first = S->pair_at[r];
+    F.pair_count = S->pair_at[r + 1] - S->pair_at[r];
+    if (F.pair_count > 0) {
+      e = launch_quad_fused(kind, F, rec, st, launches, 2);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  F.pair_first = F.pair_count = 0;
+  return cudaSuccess;
 }
 
 }  // namespace pf3

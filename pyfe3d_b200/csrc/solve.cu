@@ -40,8 +40,8 @@ constexpr int kCgMaxBlocks = 148 * 8;
 // device scalars of one solve
 struct CgScal {
   double rz, rzn, pap, rr, bb, tol2;   // r.z, new r.z, p.Ap, the norm the criterion uses (squared), |b|^2, threshold^2
-  int done;                            // 0 running, 1 converged, 2 breakdown (p.Ap <= 0 or not finite)
-  int iters;
+  int done;                            // 0 running, 1 converged, 2 breakdown (p.Ap <= 0 or not finite), 3 maxiter
+  int iters, maxiter;
   unsigned ticket[3];
   int scaled;                          // criterion in the Jacobi-scaled norm r.D^-1.r (what cg on D K D measures)
 };
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_start(int64_t n, const unsign
                                                          const double* __restrict__ b, double* __restrict__ minv,
                                                          double* __restrict__ x, double* __restrict__ r,
                                                          double* __restrict__ p, const double* __restrict__ ax,
-                                                         int use_x0, double rtol, double atol, double* partial,
-                                                         CgScal* S) {
+                                                         int use_x0, double rtol, double atol, int maxiter,
+                                                         double* partial, CgScal* S) {
   double acc[3] = {0., 0., 0.};
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const bool fr = free_ == nullptr || free_[i] != 0;
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_start(int64_t n, const unsign
     const double tol = fmax(rtol * sqrt(t[1]), atol);
     S->tol2 = tol * tol;
     S->iters = 0;
+    S->maxiter = maxiter;
     S->done = (t[2] <= tol * tol || t[0] == 0.) ? 1 : 0;
   });
 }
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_update(int64_t n, const doubl
     S->rr = S->scaled ? t[0] : t[1];
     S->iters += 1;
     if (S->rr <= S->tol2 || t[0] == 0.) S->done = 1;
+    else if (S->iters >= S->maxiter) S->done = 3;
   });
 }
 
@@ -264,18 +266,21 @@ int plan_cg(cudaStream_t st, int nops, const CgOp* ops, int64_t n, const unsigne
     int rc = matvec(x, ap);   // the SpMV masks constrained columns and rows itself
     if (rc) return rc;
   }
-  k_cg_start<<<grid, kCgThreads, 0, st>>>(n, free_, b, minv, x, r, p, ap, use_x0, rtol, atol, partial, S);
+  if (maxiter <= 0) maxiter = int(std::min<int64_t>(10 * n, 2000000000));
+  k_cg_start<<<grid, kCgThreads, 0, st>>>(n, free_, b, minv, x, r, p, ap, use_x0, rtol, atol, maxiter, partial, S);
   ++*launches;
   PF3_CUDA(cudaGetLastError());
-  if (maxiter <= 0) maxiter = int(std::min<int64_t>(10 * n, 2000000000));
   const int every = (flags >> 8) > 0 ? (flags >> 8) : 16;   // iterations between two looks at the device flag
   CgScal h;
   PF3_CUDA(cudaMemcpyAsync(&h, S, sizeof(CgScal), cudaMemcpyDeviceToHost, st));
   PF3_CUDA(cudaStreamSynchronize(st));
-  int it = 0;
-  while (!h.done && it < maxiter) {
-    const int batch = std::min(every, maxiter - it);
-    for (int k = 0; k < batch; ++k) {
+  // one batch = `every` iterations; every kernel returns at once when the device flag is set (converged, breakdown
+  // or maxiter), so a batch may be enqueued blindly.  With PF3_CG_GRAPH the batch is captured once into a CUDA graph
+  // and replayed: small systems are launch-bound (4 launches of a few microseconds per iteration).
+  int64_t per_batch = 0;
+  auto enqueue = [&]() -> int {
+    const int64_t l0 = *launches;
+    for (int k = 0; k < every; ++k) {
       int rc = matvec(p, ap);
       if (rc) return rc;
       k_cg_dot<<<grid, kCgThreads, 0, st>>>(n, p, ap, partial, S);
@@ -283,13 +288,36 @@ int plan_cg(cudaStream_t st, int nops, const CgOp* ops, int64_t n, const unsigne
       k_cg_dir<<<grid, kCgThreads, 0, st>>>(n, r, minv, p, S);
       *launches += 3;
     }
-    PF3_CUDA(cudaGetLastError());
-    it += batch;
+    per_batch = *launches - l0;
+    return int(cudaGetLastError());
+  };
+  cudaGraphExec_t gexec = nullptr;
+  if ((flags & 2) && !h.done) {
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      const int rc = enqueue();
+      const cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (rc == 0 && ce == cudaSuccess && g != nullptr && cudaGraphInstantiate(&gexec, g, 0) != cudaSuccess) gexec = nullptr;
+      if (g) cudaGraphDestroy(g);
+      *launches -= per_batch;   // captured, not yet run
+    }
+    cudaGetLastError();         // a refused capture (e.g. the legacy default stream) falls back to plain launches
+  }
+  int64_t guard = (int64_t(maxiter) + every - 1) / every + 1;
+  while (!h.done && guard-- > 0) {
+    if (gexec) {
+      PF3_CUDA(cudaGraphLaunch(gexec, st));
+      *launches += per_batch;
+    } else {
+      int rc = enqueue();
+      if (rc) return rc;
+    }
     PF3_CUDA(cudaMemcpyAsync(&h, S, sizeof(CgScal), cudaMemcpyDeviceToHost, st));
     PF3_CUDA(cudaStreamSynchronize(st));
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
   if (iters) *iters = h.iters;
-  if (status) *status = h.done == 1 ? 0 : (h.done == 2 ? 2 : 1);
+  if (status) *status = h.done == 1 ? 0 : (h.done == 2 ? 2 : 1);   // 0 converged, 1 maxiter, 2 breakdown
   if (resid) *resid = sqrt(h.rr);
   if (bnorm) *bnorm = sqrt(h.bb);
   return PF3_OK;
@@ -310,25 +338,33 @@ int plan_spmv_scaled(const pf3_plan* pl, cudaStream_t st, const double* vals, co
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K[bu, :][:, bu] as CSR (tests/test_quad4_static_point_load.py:84-99): rows with free_rows[row0 + i] != 0 are kept and
-// renumbered in order; columns with free_cols[c] != 0 are kept and renumbered by their rank among the free columns.
+// K[bu, :][:, bu] as CSR (tests/test_quad4_static_point_load.py:84-99): rows with free_[row0 + i] != 0 are kept and
+// renumbered in order; columns with free_[c] != 0 are kept and renumbered by their rank among the free columns
+// (free_ == NULL: everything is kept).  upper: additionally only entries with col >= row (scipy.sparse.triu): KC0, KG
+// and M are symmetric, so a host consumer that accepts a triangle (CHOLMOD, PARDISO, eigsh on a symmetric operator)
+// needs 5/9 of the bytes moved over PCIe.
 namespace {
 
 __global__ void k_flag_i64(int64_t n, const unsigned char* __restrict__ f, int64_t* __restrict__ out) {
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
-    out[i] = f[i] != 0 ? 1 : 0;
+    out[i] = (f == nullptr || f[i] != 0) ? 1 : 0;
+}
+// keep entry (row, col)?  free_ == NULL: no constraints; upper: the upper triangle col >= row only (symmetric matrices:
+// half the values to move)
+__device__ __forceinline__ bool keep_entry(const unsigned char* free_, bool upper, int64_t grow, int64_t col) {
+  return (free_ == nullptr || free_[col] != 0) && (!upper || col >= grow);
 }
 
 // one warp per source row: number of kept entries -> cnt[rank of the row] (kept rows only)
 __global__ void k_compact_count(int64_t nrows, const int64_t* __restrict__ indptr, const int64_t* __restrict__ indices,
-                                const unsigned char* __restrict__ free_, int64_t row0,
+                                const unsigned char* __restrict__ free_, int upper, int64_t row0,
                                 const int64_t* __restrict__ colmap, int64_t* __restrict__ cnt) {
   const int lane = threadIdx.x & 31;
   for (int64_t row = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5; row < nrows;
        row += (int64_t(gridDim.x) * blockDim.x) >> 5) {
-    if (!free_[row0 + row]) continue;
+    if (free_ != nullptr && !free_[row0 + row]) continue;
     int64_t c = 0;
-    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) c += free_[indices[k]] != 0;
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) c += keep_entry(free_, upper != 0, row0 + row, indices[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) cnt[colmap[row0 + row]] = c;
@@ -337,13 +373,13 @@ __global__ void k_compact_count(int64_t nrows, const int64_t* __restrict__ indpt
 
 // one warp per source row: kept entries written in order (ballot + prefix popcount keeps the column order)
 __global__ void k_compact_fill(int64_t nrows, const int64_t* __restrict__ indptr, const int64_t* __restrict__ indices,
-                               const double* __restrict__ vals, const unsigned char* __restrict__ free_, int64_t row0,
-                               const int64_t* __restrict__ colmap, const int64_t* __restrict__ out_ptr,
+                               const double* __restrict__ vals, const unsigned char* __restrict__ free_, int upper,
+                               int64_t row0, const int64_t* __restrict__ colmap, const int64_t* __restrict__ out_ptr,
                                int64_t* __restrict__ out_idx, double* __restrict__ out_val) {
   const int lane = threadIdx.x & 31;
   for (int64_t row = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5; row < nrows;
        row += (int64_t(gridDim.x) * blockDim.x) >> 5) {
-    if (!free_[row0 + row]) continue;
+    if (free_ != nullptr && !free_[row0 + row]) continue;
     int64_t o = out_ptr[colmap[row0 + row]];
     const int64_t a = indptr[row], e = indptr[row + 1];
     for (int64_t k0 = a; k0 < e; k0 += 32) {
@@ -352,7 +388,7 @@ __global__ void k_compact_fill(int64_t nrows, const int64_t* __restrict__ indptr
       bool keep = false;
       if (k < e) {
         col = indices[k];
-        keep = free_[col] != 0;
+        keep = keep_entry(free_, upper != 0, row0 + row, col);
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if (keep) {
@@ -375,8 +411,8 @@ unsigned rows_grid(int64_t nrows) {
 // colmap[ncols + 1]: exclusive scan of the free flags (colmap[ncols] = number of free DOFs); out_ptr[nfree_rows + 1].
 // Returns the number of kept rows and of kept entries through nkeep / nnz (host).
 int csr_compact_symbolic(cudaStream_t st, int64_t nrows, int64_t ncols, const int64_t* indptr, const int64_t* indices,
-                         const unsigned char* free_, int64_t row0, int64_t* colmap, int64_t* out_ptr, int64_t* nkeep,
-                         int64_t* nnz, int64_t* launches) {
+                         const unsigned char* free_, int upper, int64_t row0, int64_t* colmap, int64_t* out_ptr,
+                         int64_t* nkeep, int64_t* nnz, int64_t* launches) {
   if (nrows < 0 || ncols <= 0 || row0 < 0 || row0 + nrows > ncols) return PF3_E_BAD_ARG;
   // colmap = exclusive scan of the flags, in place
   k_flag_i64<<<cg_grid(ncols), kCgThreads, 0, st>>>(ncols, free_, colmap);
@@ -401,7 +437,7 @@ int csr_compact_symbolic(cudaStream_t st, int64_t nrows, int64_t ncols, const in
   PF3_CUDA(cudaMemsetAsync(out_ptr, 0, size_t(keep + 1) * sizeof(int64_t), st));
   if (nrows > 0 && keep > 0) {
     // colmap is global; the local rank is colmap[row0 + row] - lo: pass a shifted output pointer
-    k_compact_count<<<rows_grid(nrows), 256, 0, st>>>(nrows, indptr, indices, free_, row0, colmap, out_ptr - lo);
+    k_compact_count<<<rows_grid(nrows), 256, 0, st>>>(nrows, indptr, indices, free_, upper, row0, colmap, out_ptr - lo);
     ++*launches;
   }
   size_t tb2 = 0;
@@ -423,14 +459,14 @@ int csr_compact_symbolic(cudaStream_t st, int64_t nrows, int64_t ncols, const in
 }
 
 int csr_compact_fill(cudaStream_t st, int64_t nrows, int64_t ncols, const int64_t* indptr, const int64_t* indices,
-                     const double* vals, const unsigned char* free_, int64_t row0, const int64_t* colmap,
+                     const double* vals, const unsigned char* free_, int upper, int64_t row0, const int64_t* colmap,
                      const int64_t* out_ptr, int64_t* out_idx, double* out_val, int64_t* launches) {
   if (nrows <= 0) return PF3_OK;
   if (row0 < 0 || row0 + nrows > ncols) return PF3_E_BAD_ARG;
   int64_t lo = 0;
   PF3_CUDA(cudaMemcpyAsync(&lo, colmap + row0, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   PF3_CUDA(cudaStreamSynchronize(st));
-  k_compact_fill<<<rows_grid(nrows), 256, 0, st>>>(nrows, indptr, indices, vals, free_, row0, colmap, out_ptr - lo,
+  k_compact_fill<<<rows_grid(nrows), 256, 0, st>>>(nrows, indptr, indices, vals, free_, upper, row0, colmap, out_ptr - lo,
                                                    out_idx, out_val);
   ++*launches;
   return int(cudaGetLastError());

@@ -146,3 +146,37 @@ def stiffened_panel(nx, ny, nstiff=64, seed=0):
     beams = dict(kind="beamc", x=skin["x"], conn=bconn, props=p, vxy=np.tile(normal, (bconn.shape[0], 1)),
                  ndof=skin["ndof"], u=skin["u"])
     return skin, beams
+
+
+def batch_from_case(case, device=None):
+    """``ElementBatch`` for a case dict returned by the generators above."""
+    from .batch import ElementBatch
+    kind = case["kind"]
+    kw = dict(x=case.get("x"), props=case.get("props"), prop_id=case.get("prop_id"), u=case.get("u"),
+              nnodes=case["ndof"] // 6, device=device)
+    if kind in ("quad4", "quad4r", "tria3r"):
+        kw.update(xmat=case.get("xmat"), K6ROT=case.get("K6ROT"), alpha_shear_locking=case.get("alpha"),
+                  hgfactors=case.get("hg"))
+    elif kind in ("beamc", "beamlr"):
+        kw.update(vxy=case["vxy"])
+    elif kind == "spring":
+        kw.update(axes=case["axes"], k=case["k"])
+    return ElementBatch(kind, case["conn"], **kw)
+
+
+def static_case(side):
+    """The bounded static-solve workload both arms of bench.py's ``config.solve_e2e`` run: the workload mesh at
+    side x side elements, all six dofs clamped on the four edges, a unit load along the plate normal on every
+    interior node (the flow of tests/test_quad4_static_point_load.py:53-104 with the diagonal scaling of
+    tests/test_quad4r_linear_buckling_plate.py:135-146)."""
+    case = plate_quad4(side, side, with_u=False)
+    nny = side + 1
+    nn = case["ndof"] // 6
+    i, j = np.divmod(np.arange(nn), nny)
+    edge = (i == 0) | (i == side) | (j == 0) | (j == side)
+    free = np.repeat(~edge, 6)
+    normal = fixed_rotation(0)[:, 2]
+    f = np.zeros(case["ndof"])
+    for d in range(3):
+        f[d::6] = normal[d] * (~edge)
+    return case, free, f, normal

@@ -173,11 +173,13 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
 
 
 def plan_cg_native(plan, vals, b, free=None, rtol=1e-12, atol=0.0, maxiter=None, x0=None, extra=(),
-                   scaled_norm=False, check_every=16):
+                   scaled_norm=False, check_every=16, graph=None):
     """``pf3_plan_cg``: Jacobi-preconditioned CG for ``(P A P) x = P b`` entirely in native kernels on ONE device,
     ``A = vals + sum(c * v for plan_i, v, c in extra)``.  ``scaled_norm=True`` applies the stopping test
     ``|r| <= max(rtol |b|, atol)`` in the diagonally scaled norm, i.e. exactly what the reference's
     ``cg(D Kuu D, D fu, atol=...)`` measures (tests/test_quad4r_linear_buckling_plate.py:135-146).
+    ``graph``: replay each batch of ``check_every`` iterations as one CUDA graph (default: systems below 2 M dofs, which
+    are launch-bound); the solve then runs on a side stream ordered after / before the current torch stream.
     Returns (x[6*nnodes], iterations, status, residual norm, |b|); status 0 = converged, 1 = maxiter, 2 = breakdown."""
     dev = vals.device
     n = 6 * plan.nnodes
@@ -192,41 +194,77 @@ def plan_cg_native(plan, vals, b, free=None, rtol=1e-12, atol=0.0, maxiter=None,
     plans = [plan._plan] + [pe._plan for pe, _, _ in extra]
     vlist = [_ptr(vals)] + [_ptr(ve) for _, ve, _ in extra]
     coefs = [1.0] + [float(ce) for _, _, ce in extra]
-    flags = (1 if scaled_norm else 0) | (int(check_every) << 8)
-    it, status, res, bn = ctx.plan_cg(plans, vlist, coefs, _ptr(free_t) if free_t is not None else 0, _ptr(bt),
-                                      _ptr(x), x0 is not None, float(rtol), float(atol), int(maxiter or 0), flags)
+    if graph is None:
+        graph = n < 2000000
+    flags = (1 if scaled_norm else 0) | (2 if graph else 0) | (int(check_every) << 8)
+    args = (plans, vlist, coefs, _ptr(free_t) if free_t is not None else 0, _ptr(bt), _ptr(x), x0 is not None,
+            float(rtol), float(atol), int(maxiter or 0), flags)
+    if graph:
+        # stream capture is refused on the legacy default stream: run on a side stream ordered against the caller's
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ctx = context(dev)
+            it, status, res, bn = ctx.plan_cg(*args)
+        cur.wait_stream(side)
+        context(dev)
+    else:
+        it, status, res, bn = ctx.plan_cg(*args)
     return x, it, status, res, bn
 
 
-def compact_csr(indptr, indices, vals, free, row0=0, pattern=None):
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
+def compact_csr(indptr, indices, vals, free, row0=0, pattern=None, upper=False, ncols=None, out=None,
+                want_indices=True):
     """``K[bu, :][:, bu]`` (tests/test_quad4_static_point_load.py:84-99) as device CSR arrays from a device CSR matrix:
     rows / columns whose ``free`` flag is set are kept and renumbered by their rank among the free dofs.  ``row0``: the
-    global index of the matrix' first row (row-sharded plans).  Returns ((indptr_uu, indices_uu, vals_uu), pattern);
-    hand ``pattern`` back in to refresh only the values of a fixed pattern."""
+    global index of the matrix' first row (row-sharded plans).  ``free=None`` keeps every dof (``ncols`` is then
+    required); ``upper=True`` keeps only ``col >= row`` (``scipy.sparse.triu``: one triangle of a symmetric matrix, 5/9 of
+    the values).  Returns ((indptr_uu, indices_uu, vals_uu), pattern); hand ``pattern`` back in to refresh only the
+    values of a fixed pattern (``out``: preallocated value tensor)."""
     dev = indptr.device
     ctx = context(dev)
     nrows = indptr.numel() - 1
-    free = _dev(free, torch.uint8, dev)
-    ncols = free.numel()
+    free = _dev(free, torch.uint8, dev) if free is not None else None
+    if free is not None:
+        ncols = free.numel()
+    elif ncols is None:
+        raise ValueError("ncols is required without a dof mask")
+    flags = 1 if upper else 0
+    fptr = _ptr(free) if free is not None else 0
     if pattern is None:
         colmap = torch.empty(ncols + 1, dtype=torch.int64, device=dev)
         optr = torch.empty(nrows + 1, dtype=torch.int64, device=dev)
-        nkeep, nnz = ctx.csr_compact_symbolic(nrows, ncols, _ptr(indptr), _ptr(indices), _ptr(free), row0, _ptr(colmap),
-                                              _ptr(optr))
+        nkeep, nnz = ctx.csr_compact_symbolic(nrows, ncols, _ptr(indptr), _ptr(indices), fptr, flags, row0,
+                                              _ptr(colmap), _ptr(optr))
         optr = optr[:nkeep + 1]
-        oidx = torch.empty(nnz, dtype=torch.int64, device=dev)
-        pattern = (colmap, optr, oidx, nnz, False)
+        oidx = torch.empty(nnz, dtype=torch.int64, device=dev) if want_indices else None
+        pattern = (colmap, optr, oidx, nnz, not want_indices)
     colmap, optr, oidx, nnz, filled = pattern
-    oval = torch.empty(nnz, dtype=torch.float64, device=dev) if vals is not None else None
-    ctx.csr_compact_fill(nrows, ncols, _ptr(indptr), _ptr(indices), _ptr(vals) if vals is not None else 0, _ptr(free),
-                         row0, _ptr(colmap), _ptr(optr), 0 if filled else _ptr(oidx), _ptr(oval) if oval is not None else 0)
+    oval = None
+    if vals is not None:
+        oval = out if out is not None else torch.empty(nnz, dtype=torch.float64, device=dev)
+    ctx.csr_compact_fill(nrows, ncols, _ptr(indptr), _ptr(indices), _ptr(vals) if vals is not None else 0, fptr, flags,
+                         row0, _ptr(colmap), _ptr(optr), 0 if (filled or oidx is None) else _ptr(oidx),
+                         _ptr(oval) if oval is not None else 0)
     return (optr, oidx, oval), (colmap, optr, oidx, nnz, True)
 
 
-def plan_compact(plan, vals, free, pattern=None):
+def plan_compact(plan, vals, free, pattern=None, upper=False, out=None, want_indices=True):
     """``compact_csr`` on the CSR values of an ``AssemblyPlan`` (its own row block when row-sharded)."""
     indptr, indices = plan.pattern()
-    return compact_csr(indptr, indices, vals, free, row0=6 * plan.node_begin, pattern=pattern)
+    return compact_csr(indptr, indices, vals, free, row0=6 * plan.node_begin, pattern=pattern, upper=upper,
+                       ncols=6 * plan.nnodes, out=out, want_indices=want_indices)
 
 
 def shift_invert_operator(plan_a, a_vals, plan_m, m_vals, sigma, free, rtol=1e-13, maxiter=None):

@@ -1,0 +1,147 @@
+// Micro-benchmark: K2's store stream (see k2_store_stream.cu) PLUS its dependent reads and a dial of arithmetic, to
+// separate what costs the fused kernel its distance to the pure store stream (8.4 ms at 4 M Quad4):
+//   reads = 0: stores only (the k2_store_stream.cu figure)
+//   reads = 1: every CTA first loads its 128-byte node-record pair, then (dependent) the 256-byte records of its 8
+//              incident elements with cp.async, waits, and only then issues the stores -- K2's load chain, no arithmetic
+//   reads = 2: the same loads from ONE address (L1/L2 hits: the instructions and the wait, no DRAM / L2 traffic)
+//   reads = 3: node records only      reads = 4: element records only, address known up front (no dependent load)
+//   reads = 5: both, but independent (the element index does not wait for the node record: ONE load latency)
+//   reads = 6: as 1, and every CTA prefetches (prefetch.global.L2) the node record and the element records of the CTA
+//              `ahead` pairs later
+//   fma:   dependent DFMA chain of that many instructions per lane between the loads and the stores (K2 executes
+//          about 700 FP64 and 2000 instructions per warp)
+// One-warp CTAs, one node pair each, 12 resident CTAs per SM (dynamic shared memory), hardware CTA order.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o k2_stream_reads k2_stream_reads.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, double* c0, double* cg, double* cm,
+                                        const double* noderec, const double* erec, int n, int64_t npairs, int reads,
+                                        int nfma, int ahead) {
+  extern __shared__ __align__(128) double st[];   // 8 slabs x 152 doubles | 16 doubles node records | 8 x 34 element records
+  const int lane = threadIdx.x;
+  for (int i = lane; i < 8 * 152; i += 32) st[i] = double(i);
+  double* nrs = st + 8 * 152;
+  double* ers = nrs + 16;
+  const int64_t p = blockIdx.x;
+  if (p >= npairs) return;
+  const int nn1 = n + 1;
+  const int h = lane >> 4, l16 = lane & 15, kq = l16 >> 2;
+  const int64_t node = 2 * p + h;
+  const int64_t nnodes = int64_t(nn1) * nn1;
+  const bool valid = node < nnodes;
+  const int i = int(node / nn1), j = int(node - int64_t(i) * nn1);
+  const int ei = i - 1 + (kq & 1), ej = j - 1 + (kq >> 1);
+  const bool act = valid && ei >= 0 && ei < n && ej >= 0 && ej < n;
+  int64_t e = int64_t(ei) * n + ej;
+  const int a = (kq == 0) ? 2 : (kq == 1) ? 3 : (kq == 2) ? 1 : 0;
+  double acc = 1.0;
+  if (reads == 6 && p + ahead < npairs) {
+    // L2 prefetch for the CTA `ahead` pairs later: its node record and (same mesh arithmetic) its element records
+    const int64_t p2 = p + ahead;
+    if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(noderec + p2 * 16));
+    const int64_t node2 = 2 * p2 + h;
+    const int i2 = int(node2 / nn1), j2 = int(node2 - int64_t(i2) * nn1);
+    const int ei2 = i2 - 1 + (kq & 1), ej2 = j2 - 1 + (kq >> 1);
+    if (node2 < nnodes && ei2 >= 0 && ei2 < n && ej2 >= 0 && ej2 < n && (lane & 3) < 2)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(erec + (int64_t(ei2) * n + ej2) * 32 + (lane & 3) * 16));
+  }
+  if (reads == 4 || reads == 5) {
+    // element records first / independently of the node record
+    if (act) {
+      const char* src = reinterpret_cast<const char*>(erec + e * 32);
+      char* dst = reinterpret_cast<char*>(ers + (lane >> 2) * 34);
+      for (int c = (lane & 3) * 16; c < 256; c += 64)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (reads == 3 || reads == 5) {
+    if (lane < 8) {
+      const char* src = reinterpret_cast<const char*>(noderec + p * 16) + 16 * lane;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(nrs) + 16 * lane), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (reads >= 3 && reads <= 5) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    acc = nrs[lane & 15] + ers[(lane >> 2) * 34 + (lane & 3)] + 1.0;
+  }
+  if (reads == 1 || reads == 2 || reads == 6) {
+    if (lane < 8) {
+      const char* src = reinterpret_cast<const char*>(noderec + (reads == 2 ? 0 : p * 16)) + 16 * lane;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(nrs) + 16 * lane), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // the element index "comes from" the node record (dependent load)
+    const int64_t bias = int64_t(nrs[lane & 15] * 0.0);
+    if (act) {
+      const char* src = reinterpret_cast<const char*>(erec + (reads == 2 ? 0 : (e + bias) * 32));
+      char* dst = reinterpret_cast<char*>(ers + (lane >> 2) * 34);
+      for (int c = (lane & 3) * 16; c < 256; c += 64)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    acc = ers[(lane >> 2) * 34 + (lane & 3)] + 1.0;
+  }
+  for (int t = 0; t < nfma; ++t) acc = fma(acc, 1.0000001, 1e-9);
+  st[lane] = acc;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (act && (lane & 3) == 0) {
+    const uint32_t src = smem_u32(st + (lane >> 2) * 152);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kg + e * 144 + a * 36), "r"(src), "r"(288) : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(m + e * 480 + a * 120), "r"(src), "r"(960) : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kc0 + e * 576 + a * 144), "r"(src), "r"(1152) : "memory");
+  }
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  if (valid) {
+    const double2 v = make_double2(acc, 4.);
+    double2* o0 = reinterpret_cast<double2*>(c0 + node * 324);
+    for (int t = l16; t < 162; t += 16) o0[t] = v;
+    double2* o1 = reinterpret_cast<double2*>(cm + node * 270);
+    for (int t = l16; t < 135; t += 16) o1[t] = v;
+    double* o2 = cg + node * 81;
+    for (int t = l16; t < 81; t += 16) o2[t] = 5.;
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+int main() {
+  const int n = 2000;
+  const int64_t ne = int64_t(n) * n, nnodes = int64_t(n + 1) * (n + 1), npairs = (nnodes + 1) / 2;
+  const size_t sizes[8] = {size_t(ne) * 576, size_t(ne) * 144, size_t(ne) * 480, size_t(nnodes) * 324 + 16, size_t(nnodes) * 81 + 16,
+                           size_t(nnodes) * 270 + 16, size_t(npairs) * 16 + 16, size_t(ne) * 32 + 64};
+  double* b[8];
+  for (int i = 0; i < 8; ++i) { cudaMalloc(&b[i], sizes[i] * 8); cudaMemset(b[i], 0, sizes[i] * 8); }
+  const double coo = double(ne) * (576 + 144 + 480) * 8, csr = double(nnodes) * (324 + 81 + 270) * 8;
+  cudaEvent_t s, e;
+  cudaEventCreate(&s); cudaEventCreate(&e);
+  auto run = [&](int ctas, int reads, int nfma, int ahead) {
+    const size_t smem = (size_t(227) * 1024 / ctas - 1024) & ~size_t(127);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    float best = 1e9f;
+    for (int r = 0; r < 4; ++r) {
+      cudaEventRecord(s);
+      k<<<unsigned(npairs), 32, smem>>>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], n, npairs, reads, nfma, ahead);
+      cudaEventRecord(e);
+      cudaDeviceSynchronize();
+      float ms; cudaEventElapsedTime(&ms, s, e);
+      if (r > 0 && ms < best) best = ms;
+    }
+    printf("{\"ctas_per_sm\": %d, \"reads\": %d, \"dfma_per_lane\": %d, \"ahead\": %d, \"ms\": %.3f, \"store_GBps\": %.1f, \"err\": %d}\n",
+           ctas, reads, nfma, ahead, best, (coo + csr) / best / 1e6, int(cudaGetLastError()));
+  };
+  for (int reads : {0, 1, 2})
+    for (int nf : {0, 256, 1024}) run(12, reads, nf, 0);
+  for (int ctas : {12, 16, 20, 24, 32})
+    for (int reads : {1, 3, 4, 5}) run(ctas, reads, 0, 0);
+  for (int ahead : {256, 1024, 2048, 4096}) run(12, 6, 0, ahead);
+  for (int ctas : {16, 24}) run(ctas, 1, 1024, 0);
+  return 0;
+}

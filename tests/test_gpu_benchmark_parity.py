@@ -174,7 +174,7 @@ def test_north_star_plate_sampled_against_reference():
     # 16 patches: corners, edges, interior, and the tail of the element range (e >= 3.7 M: offsets > 2^31)
     spots = [(0, 0), (0, 1968), (500, 984), (996, 0), (1000, 1000), (1337, 411), (1500, 1968), (700, 1500),
              (250, 40), (1800, 900),
-             (1860, 0), (1900, 1000), (1950, 1968), (1992, 0), (1992, 984), (1992, 1968)]
+             (1870, 0), (1900, 1000), (1950, 1968), (1992, 0), (1992, 984), (1992, 1968)]
     rep = {"patches": len(spots), "elements": len(spots) * 256}
     tail = 0
     for (i0, j0) in spots:
