@@ -4,12 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # reference Cython loop on host cores
 
-One step = one pass of the hot path over the whole mesh: ONE fused element kernel writing the
-KC0/KG/M COO value arrays (values only — the steady-state `update_*v_only` case; the index
-arrays are a function of connectivity and are not re-written) + three numeric CSR assemblies
-through a precomputed plan.  N>1 (torchrun): weak scaling, the mesh grows to N x (side x side)
-elements, node rows are strip-partitioned, each rank evaluates the elements touching its
-rows (halo duplicated) and assembles its own CSR row block: no collective on the data path.
+One step = one pass of the hot path over the whole mesh: the record kernel + ONE fused node-centric kernel writing
+the KC0/KG/M COO value arrays (values only — the steady-state `update_*v_only` case; the index arrays are a function
+of connectivity and are not re-written) AND the three assembled CSR value arrays through a precomputed plan.
+N>1 (torchrun): node rows are strip-partitioned, each rank evaluates the elements touching its rows (halo duplicated)
+and assembles its own CSR row block: no collective on the data path.  The headline `value` is WEAK scaling (the mesh
+grows to N x side x side elements); the same line carries, under `details`,
+  * `strong`  : the metric's own size (side x side = 4.0 M elements in total) cut into N strips,
+  * `others`  : BASELINE configs 2-5 timed with the same clock (N=1: config 5 as one GPU's share; N>1: sharded),
+  * `solve_e2e`: a user-level end-to-end — host x in, KC0 assembled and the static problem solved by the native CG on the
+                device, only u back — next to the reference doing loop + tocsc + scipy cg on the same mesh,
+and a `parity` object: checksums that tie every rank's CSR block to its COO arrays and to closed forms, all-reduced, so
+that every line of a scaling run carries a correctness bit.
 Prints one JSON line (rank 0).
 """
 import argparse
@@ -40,6 +46,7 @@ def clocks_sampler(index, stop, out):
                               "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return
+
     def reader():
         for line in p.stdout:
             out.append(line.strip())
@@ -79,6 +86,10 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+L2_NOTE = ("every timed step writes >= 15 kB per element of fresh COO + CSR output (60 GB at 4.0 M elements), far more than "
+           "the 126 MB L2: inputs and outputs never stay cached between steps, no flush needed")
+
+
 def workload_name(side):
     """config.workload, shared by both arms (the reference arm times a bounded sample of it)."""
     return ("configs[1..] north-star mesh: %dx%d Quad4 structured plate per GPU (%d elements/GPU), rigidly rotated, "
@@ -86,6 +97,7 @@ def workload_name(side):
             % (side, side, side * side))
 
 
+# ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -105,10 +117,11 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(args.side), "elements_per_step": rb.ne,
-                       "note": "each step is a bounded sample of that workload (a %dx%d-element sub-plate of the same "
-                               "mesh, laminate and displacement field); the reference cannot hold 4M Quad4 in one COO "
-                               "array (int32 init_k, quad4.pyx:453)" % (args.cpu_side, args.cpu_side)},
+            "config": {"workload": workload_name(args.side), "l2": L2_NOTE},
+            "details": {"elements_per_step": rb.ne,
+                        "note": "each step is a bounded sample of that workload (a %dx%d-element sub-plate of the same "
+                                "mesh, laminate and displacement field); the reference cannot hold 4M Quad4 in one COO "
+                                "array (int32 init_k, quad4.pyx:453)" % (args.cpu_side, args.cpu_side)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": rb.nproc, "kind": "reference", "sample": rb.describe()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -116,32 +129,95 @@ def run_reference(args):
     return 0
 
 
-def run_ours(args):
+# ------------------------------------------------------------------------------------------------ our arm
+class Dist:
+    """torch.distributed plumbing of the bench (NCCL: barrier, max / sum reductions of a few scalars)."""
+
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op="sum"):
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX,
+                                        "min": self.dist.ReduceOp.MIN}[op])
+        return [float(v) for v in t.tolist()]
+
+    def gather(self, val):
+        t = self.torch.tensor([float(val)], dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return [float(val)]
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+
+def plate_shard(meshes, nx, ny, a, rank, world):
+    """Rank `rank`'s strip of the nx x ny plate: it owns nx/world element columns' worth of node columns."""
+    cols = nx // world
+    i0 = rank * cols + (1 if rank > 0 else 0)
+    i1 = (rank + 1) * cols + 1 if rank < world - 1 else nx + 1
+    return meshes.plate_quad4(nx, ny, a=a, b=1.0, i0=i0 if world > 1 else None, i1=i1 if world > 1 else None,
+                              local=True)
+
+
+def parity_checks(torch, D, case, batch, plans, coos, csr, a_len, ne_total):
+    """Correctness bits of this run, all-reduced over the ranks.
+      * csr_vs_coo[m]: |sum(CSR values of the owned rows) - sum(COO values of the owned (unique) elements)| / sum|CSR|.
+        Over all ranks both are the sum of every entry of the global matrix: a wrong halo, row cut or slot map breaks it.
+      * mass: sum(M e_x) over the x-translation dofs against intrho * a * b (closed form for the plate).
+      * rigid: max|KC0 e_x| / max|KC0| (a rigid translation produces no force).
+      * kc0_sum_per_element / m_sum_per_element: every element of this mesh has the same matrices, so these do not
+        depend on N: compare them between the lines of a scaling run (KG depends on u and is tied by csr_vs_coo)."""
+    lo, hi = case["owned_nodes"]
+    conn0 = batch.conn[:, 0]
+    owned = (conn0 >= lo) & (conn0 < hi)
+    ne = batch.ne
+    out, loc = {}, []
+    for m in ("KC0", "KG", "M"):
+        v = coos[m].v.view(ne, -1)
+        loc += [float(csr[m].sum()), float(csr[m].abs().sum()), float(v[owned].sum())]
+    loc.append(float(owned.sum()))
+    tot = D.reduce(loc)
+    worst = 0.
+    for i, m in enumerate(("KC0", "KG", "M")):
+        s_csr, s_abs, s_coo = tot[3 * i:3 * i + 3]
+        rel = abs(s_csr - s_coo) / s_abs if s_abs > 0 else float("inf")
+        out["csr_vs_coo_" + m] = rel
+        worst = max(worst, rel)
+    ne_unique = tot[9]
+    out["unique_elements"] = int(ne_unique)
+    out["kc0_sum_per_element"] = tot[2] / ne_unique
+    out["m_sum_per_element"] = tot[8] / ne_unique
+    nn = case["ndof"] // 6
+    ex = torch.zeros(6 * nn, dtype=torch.float64, device=csr["M"].device)
+    ex[0::6] = 1.0
+    ym = plans["M"].spmv(csr["M"], ex)
+    yk = plans["KC0"].spmv(csr["KC0"], ex)
+    mass = D.reduce([float(ym[0::6].sum())])[0]
+    kmax = D.reduce([float(yk.abs().max()), float(csr["KC0"].abs().max())], "max")
+    intrho = float(case["props"][0, 24])
+    out["mass_rel_err"] = abs(mass - intrho * a_len * 1.0) / (intrho * a_len)
+    out["rigid_translation_residual"] = kmax[0] / kmax[1]
+    out["ok"] = bool(worst <= 1e-11 and out["mass_rel_err"] <= 1e-10 and out["rigid_translation_residual"] <= 1e-10
+                     and int(ne_unique) == int(ne_total))
+    return out
+
+
+def measure_plate(torch, D, meshes, nx, ny, a_len, rank, world, dev, args, full):
+    """Plan + warm-up + timed steps of the fused path on this rank's strip of the nx x ny plate.  `full`: also the
+    host-buffer end-to-end steps.  Returns a dict (times are max over ranks)."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    from pyfe3d_b200 import meshes
     from pyfe3d_b200.batch import AssemblyPlan, ElementBatch, context
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    side = args.side
-    nx, ny = side * world, side
-    i0 = rank * side + (1 if rank > 0 else 0)
-    i1 = (rank + 1) * side + 1
-    case = meshes.plate_quad4(nx, ny, a=float(world), b=1.0, i0=i0 if world > 1 else None,
-                              i1=i1 if world > 1 else None, local=True)
+    case = plate_shard(meshes, nx, ny, a_len, rank, world)
     nnodes = case["ndof"] // 6
     ne_local = case["conn"].shape[0]
-    ne_unique_total = nx * ny
     batch = ElementBatch("quad4", case["conn"], case["x"], case["props"], u=case["u"], device=dev)
     ctx = context(dev)
     mats = ("KC0", "KG", "M")
@@ -170,50 +246,41 @@ def run_ours(args):
             if ev is not None:
                 ev[2 + i].record()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         step()
-    barrier()
+    D.barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     clk_lines, stop = [], threading.Event()
-    th = threading.Thread(target=clocks_sampler, args=(local, stop, clk_lines), daemon=True)
+    th = threading.Thread(target=clocks_sampler, args=(dev.index, stop, clk_lines), daemon=True)
     th.start()
     time.sleep(0.25)
     l0 = ctx.launch_count()
-    barrier()
+    D.barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     for k in range(args.steps):
         step(evs[k])
     end.record()
-    barrier()
+    D.barrier()
     launches = ctx.launch_count() - l0
     stop.set()
     th.join(timeout=3)
-    ms_total = start.elapsed_time(end)
     kern = np.zeros(4)
     for ev in evs:
         for i in range(4):
             kern[i] += ev[i].elapsed_time(ev[i + 1])
     kern /= args.steps                                         # ms per launch: eval, asm KC0, asm KG, asm M
-    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = float(tmax.item()) / args.steps
-    value = ne_unique_total / (ms_step * 1e-3)
+    ms_step = D.reduce([start.elapsed_time(end)], "max")[0] / args.steps
+    res = {"ms_step": ms_step, "kern": kern, "ne_local": ne_local, "ne_total": nx * ny, "launches": int(launches),
+           "symbolic_s": t_symbolic, "clocks": summarize_clocks(clk_lines), "fused": fused}
+    res["parity"] = parity_checks(torch, D, case, batch, plans, coos, csr, a_len, nx * ny)
 
     # ---- end to end through the public API with host buffers --------------------------------------
-    e2e = None
-    if args.e2e_steps > 0:
+    if full and args.e2e_steps > 0:
         try:
-            # pinned buffers are first-touched by a thread running on the GPU's own NUMA node, so that with several
-            # ranks the device->host copies do not all land in (or cross) one socket's memory
-            with numa_local(local) as numa:
+            # page-locked result buffers: portable (every context of the process may use them) and write-combined (the
+            # GPU's writes do not snoop the CPU caches).  numa_local first-touches them from the GPU's own NUMA node.
+            with numa_local(dev.index) as numa:
                 xh = torch.as_tensor(case["x"]).pin_memory()
                 uh = torch.as_tensor(case["u"]).pin_memory()
                 outh = {m: torch.empty(plans[m].nnz, dtype=torch.float64).pin_memory() for m in mats}
@@ -235,29 +302,273 @@ def run_ours(args):
                     outh[m].copy_(csr[m], non_blocking=True)
                 torch.cuda.synchronize()
             e2e_step()
-            barrier()
+            D.barrier()
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 e2e_step()
-            barrier()
-            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            e2e = {"value": ne_unique_total * args.e2e_steps / float(dt.item()), "unit": UNIT,
-                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "numa": numa,
-                   "what": "one pf3_eval_assemble_host call per step (C ABI, host buffers): H2D of x,u from pinned host "
-                           "memory -> record + fused kernels -> D2H of the KC0/KG/M CSR value arrays into pinned host "
-                           "memory (pattern is static; the COO value arrays are written on the device as in the timed steps)"}
+            torch.cuda.synchronize()
+            t_own = time.perf_counter() - t0
+            D.barrier()
+            dt = D.reduce([time.perf_counter() - t0], "max")[0]
+            per_rank = D.gather(d2h * args.e2e_steps / t_own / 1e9)
+            res["e2e"] = {"value": nx * ny * args.e2e_steps / dt, "unit": UNIT,
+                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "numa": numa,
+                          "d2h_gbs_per_rank": [round(v, 2) for v in per_rank],
+                          "what": "one pf3_eval_assemble_host call per step (C ABI, host buffers): H2D of x,u from pinned "
+                                  "host memory -> record + fused kernels -> D2H of the KC0/KG/M CSR value arrays into "
+                                  "pinned host memory (pattern is static; the COO value arrays are written on the device "
+                                  "as in the timed steps); d2h_gbs_per_rank names the limiter: the call is the PCIe copy"}
             del outh
+            # ---- the same step returning ONE TRIANGLE of each (symmetric) matrix: 5/9 of the bytes over PCIe.  Same
+            # C ABI: H2D of x, u -> pf3_eval_assemble (device) -> pf3_csr_compact_fill(PF3_COMPACT_UPPER) per matrix
+            # -> D2H of the compacted values.  Reported beside the headline, not instead of it: the default result of
+            # the path is the full scipy-shaped CSR matrix.
+            if fused and args.e2e_upper:
+                from pyfe3d_b200.solve import plan_compact
+                pats, up, uph = {}, {}, {}
+                for m in mats:
+                    (_, _, v), pats[m] = plan_compact(plans[m], csr[m], None, upper=True, want_indices=False)
+                    up[m] = v
+                with numa_local(dev.index):
+                    for m in mats:
+                        uph[m] = torch.empty(up[m].numel(), dtype=torch.float64).pin_memory()
+                d2h_up = sum(o.numel() * 8 for o in uph.values())
+
+                def upper_step():
+                    batch.x.copy_(xh, non_blocking=True)
+                    batch.u.copy_(uh, non_blocking=True)
+                    step()
+                    for m in mats:
+                        plan_compact(plans[m], csr[m], None, pattern=pats[m], upper=True, out=up[m])
+                        uph[m].copy_(up[m], non_blocking=True)
+                    torch.cuda.synchronize()
+                upper_step()
+                D.barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    upper_step()
+                D.barrier()
+                dtu = D.reduce([time.perf_counter() - t0], "max")[0]
+                res["e2e"]["symmetric_upper"] = {
+                    "value": nx * ny * args.e2e_steps / dtu, "unit": UNIT, "d2h_bytes_per_step": int(d2h_up),
+                    "what": "same step, only entries with col >= row of KC0/KG/M returned (scipy.sparse.triu layout, "
+                            "PF3_COMPACT_UPPER); for consumers that take a symmetric half"}
+                del up, uph, pats
+            del xh, uh
         except RuntimeError as exc:   # e.g. pinned allocation refused
-            e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+            res["e2e"] = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
+    del plans, coos, csr, batch
+    torch.cuda.empty_cache()
+    return res
+
+
+def time_steps(torch, D, fn, steps, warm=3):
+    for _ in range(warm):
+        fn()
+    D.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    D.barrier()
+    return D.reduce([a.elapsed_time(b)], "max")[0] / steps
+
+
+def other_config(torch, D, meshes, name, case, mats, peak, steps):
+    """BASELINE configs 2-4 on one GPU: evaluate + assemble (fused where the kind has it), values only."""
+    from pyfe3d_b200.batch import AssemblyPlan
+    b = meshes.batch_from_case(case)
+    nn = case["ndof"] // 6
+    kw = {}
+    for m in mats:
+        if m == "KGs":
+            kw["KG_given_stress"] = case.get("stress", (0., 0., 1.))
+        elif m.startswith("M"):
+            kw["M"] = True
+            kw["mtype"] = int(m[1])
+        else:
+            kw[m] = True
+    plan = AssemblyPlan("KC0", nn, [b])
+    coo, csr = plan.evaluate_assemble(**kw)
+    ms = time_steps(torch, D, lambda: plan.evaluate_assemble(coo=coo, csr=csr, **kw), steps)
+    alg = sum(coo[m].v.numel() * 8 for m in coo) + sum(csr[m].numel() * 8 for m in csr)
+    out = {"config": name, "kind": case["kind"], "elements": int(b.ne), "matrices": list(mats),
+           "ms_per_step": ms, "elements_per_s": b.ne / ms * 1e3, "algorithmic_bytes": int(alg),
+           "achieved_gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak,
+           "path": "two-pass" if getattr(plan, "_fused_unsupported", False) or case["kind"] not in ("quad4", "quad4r", "tria3r") else "fused"}
+    del plan, coo, csr, b
+    torch.cuda.empty_cache()
+    return out
+
+
+def config5(torch, D, meshes, rank, world, dev, cols, rows, lines, peak, steps):
+    """BASELINE config 5: stiffened panel, Quad4 skin + BeamC stiffeners in ONE matrix each (KC0, KG, M) + update_fint,
+    strip-sharded by DOF-row ownership.  N ranks x `cols` node columns x `rows`; `lines` stiffener lines per rank."""
+    import numpy as np
+    from pyfe3d_b200.batch import AssemblyPlan, Coo, ElementBatch
+    nx, ny = cols * world, rows
+    i0 = rank * cols + (1 if rank > 0 else 0)
+    i1 = (rank + 1) * cols + 1
+    skin = meshes.plate_quad4(nx, ny, a=float(world) * cols / rows, b=1.0, i0=i0 if world > 1 else None,
+                              i1=i1 if world > 1 else None, local=True)
+    nn = skin["ndof"] // 6
+    nny = ny + 1
+    lo, hi = skin["owned_nodes"]
+    c_lo, c_hi = lo // nny, hi // nny
+    ln = np.linspace(c_lo, c_hi, lines + 2)[1:-1].round().astype(int)
+    n1 = (np.repeat(ln, ny) * nny + np.tile(np.arange(ny), ln.size)).astype(np.int64)
+    bconn = np.stack([n1, n1 + 1], 1)
+    E, nu, rho, bb, hh = 70e9, 0.33, 2700., 0.002, 0.02
+    A, Iyy, Izz = bb * hh, bb * hh ** 3 / 12, hh * bb ** 3 / 12
+    p = np.zeros((1, 16))
+    p[0, :9] = [A, E, E / 2 / (1 + nu) * 5 / 6., Iyy, Izz, 0., Iyy + Izz, 0., 0.]
+    p[0, 9:15] = [rho * A, 0., 0., rho * Izz, rho * Iyy, 0.]
+    normal = meshes.fixed_rotation(0)[:, 2]
+    bs = [ElementBatch("quad4", skin["conn"], skin["x"], skin["props"], u=skin["u"], device=dev),
+          ElementBatch("beamc", bconn, skin["x"], p, u=skin["u"], vxy=np.tile(normal, (bconn.shape[0], 1)), nnodes=nn,
+                       device=dev)]
+    plan = AssemblyPlan("KC0", nn, bs, node_range=(lo, hi))
+    names = ("KC0", "KG", "M")
+    plans = {m: plan._sibling(m, 0) for m in names}
+    coo = {m: Coo(None, None, torch.zeros(plans[m].coo_size, dtype=torch.float64, device=dev), 6 * nn) for m in names}
+    csr = {m: torch.empty(plans[m].nnz, dtype=torch.float64, device=dev) for m in names}
+    fint = torch.zeros(6 * nn, dtype=torch.float64, device=dev)
+
+    def step():
+        plan.evaluate_assemble(KC0=True, KG=True, M=True, coo=coo, csr=csr)
+        plan.update_fint(fint)
+
+    ms = time_steps(torch, D, step, steps)
+    unique = nx * ny + lines * world * ny
+    alg = sum(coo[m].v.numel() * 8 + csr[m].numel() * 8 for m in names)
+    # correctness bit: sum of the assembled CSR entries of all ranks against the sum of the COO entries of the
+    # elements each rank owns (first node owned): the same global sum when halo and row cuts are right
+    loc = []
+    for m in names:
+        s = 0.
+        for g, b in enumerate(bs):
+            c0 = b.conn[:, 0]
+            own = (c0 >= lo) & (c0 < hi)
+            off = plans[m].coo_offsets[g]
+            s += float(coo[m].v[off:off + b.ne * b.sizes[m]].view(b.ne, -1)[own].sum())
+        loc += [float(csr[m].sum()), float(csr[m].abs().sum()), s]
+    tot = D.reduce(loc)
+    worst = max(abs(tot[3 * i] - tot[3 * i + 2]) / tot[3 * i + 1] for i in range(3))
+    out = {"config": "5: stiffened panel %d x %d Quad4 + %d BeamC in one matrix each, KC0+KG+M + update_fint, %s"
+                     % (nx, ny, lines * world * ny, "one GPU's share (1/8) of the 16M mesh" if world == 1 else
+                        "row-sharded over %d GPUs" % world),
+           "elements": int(unique), "elements_evaluated_per_gpu": int(bs[0].ne + bs[1].ne), "ms_per_step": ms,
+           "elements_per_s": unique / ms * 1e3, "achieved_gbs_per_gpu": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak,
+           "fused_quad_share": not getattr(plan, "_fused_unsupported", False),
+           "parity_csr_vs_coo": worst, "parity_ok": bool(worst <= 1e-11)}
+    del plan, plans, coo, csr, fint, bs
+    torch.cuda.empty_cache()
+    return out
+
+
+def solve_e2e(torch, meshes, dev, side):
+    """User-level end to end on one GPU: host x in -> KC0 evaluated + assembled -> static problem solved by the native
+    Jacobi-CG on the device -> only u back on the host (what a reference script does with its loop + tocsc + cg)."""
+    import numpy as np
+    from pyfe3d_b200.batch import AssemblyPlan
+    from pyfe3d_b200.solve import plan_cg_native
+    case, free, f, normal = meshes.static_case(side)
+    b = meshes.batch_from_case(case, device=dev)
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan("KC0", nn, [b])
+    free_t = torch.as_tensor(free.astype(np.uint8)).to(dev)
+    xh = torch.as_tensor(case["x"]).pin_memory()
+    fh = torch.as_tensor(f).pin_memory()
+    uh = torch.empty(6 * nn, dtype=torch.float64).pin_memory()
+
+    def run():
+        b.x.copy_(xh, non_blocking=True)
+        ft = fh.to(dev, non_blocking=True)
+        _, csr = plan.evaluate_assemble(KC0=True, write_coo=False)
+        x, it, status, res, bn = plan_cg_native(plan, csr["KC0"], ft, free=free_t, rtol=1e-9, scaled_norm=True)
+        uh.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+        return it, status
+    run()
+    t0 = time.perf_counter()
+    it, status = run()
+    dt = time.perf_counter() - t0
+    u = uh.numpy()
+    w = u[0::6] * normal[0] + u[1::6] * normal[1] + u[2::6] * normal[2]
+    return {"workload": "static solve, %dx%d Quad4 of the workload mesh, edges clamped, uniform normal load; "
+                        "diagonally scaled CG to 1e-9 (scaled norm)" % (side, side),
+            "elements": side * side, "dofs": 6 * nn, "seconds": dt, "cg_iterations": int(it), "cg_status": int(status),
+            "w_max": float(np.abs(w).max()), "h2d_bytes": int(xh.numel() * 8 + fh.numel() * 8),
+            "d2h_bytes": int(uh.numel() * 8)}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pyfe3d_b200 import meshes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    D = Dist(torch, dist, dev, world)
+    side = args.side
+    peak, peak_src = measured_peak()
+
+    # ---- headline: weak scaling, side x side elements per GPU
+    weak = measure_plate(torch, D, meshes, side * world, side, float(world), rank, world, dev, args, full=True)
+    # ---- the metric's own size cut into N strips
+    strong = None
+    if world > 1 and args.strong and side % world == 0:
+        s = measure_plate(torch, D, meshes, side, side, 1.0, rank, world, dev, args, full=False)
+        strong = {"elements_total": s["ne_total"], "elements_evaluated_per_gpu": s["ne_local"],
+                  "ms_per_step": s["ms_step"], "value": s["ne_total"] / (s["ms_step"] * 1e-3), "unit": UNIT,
+                  "parity_ok": s["parity"]["ok"], "kc0_sum_per_element": s["parity"]["kc0_sum_per_element"]}
+    elif world == 1:
+        strong = {"elements_total": weak["ne_total"], "elements_evaluated_per_gpu": weak["ne_local"],
+                  "ms_per_step": weak["ms_step"], "value": weak["ne_total"] / (weak["ms_step"] * 1e-3), "unit": UNIT,
+                  "note": "N=1: identical to the headline"}
+    # ---- the other BASELINE configurations under the same clock
+    others = []
+    if args.others:
+        try:
+            f = args.others_scale
+            if world == 1:
+                others.append(other_config(torch, D, meshes, "2: BeamC curved cantilever, 100k elements, KC0 + M(mtype 0)",
+                                           meshes.arc_beamc(int(100001 * f)), ("KC0", "M0"), peak, args.steps))
+                others.append(other_config(torch, D, meshes, "3: Quad4R cylinder 1760x571 (1.0M), material axes, KC0 + KG_given_stress",
+                                           meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)),
+                                           ("KC0", "KGs"), peak, args.steps))
+                others.append(other_config(torch, D, meshes, "4: Tria3R distorted plate 1415x1415x2 (4.0M), KC0 + M(mtype 1)",
+                                           meshes.plate_tria3r(int(1415 * f ** 0.5), int(1415 * f ** 0.5)),
+                                           ("KC0", "M1"), peak, args.steps))
+            others.append(config5(torch, D, meshes, rank, world, dev, max(2, int(496 * f)), max(2, int(3968 * f ** 0.5)) if f < 1 else 3968,
+                                  8, peak, args.steps))
+        except Exception as exc:  # reporting only: the headline stands without it
+            others.append({"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])})
+    # ---- user-level end to end (one GPU)
+    solve = None
+    if rank == 0 and args.solve_side > 0:
+        try:
+            solve = solve_e2e(torch, meshes, dev, args.solve_side)
+        except Exception as exc:
+            solve = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+    D.barrier()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = measured_peak()
+    fused = weak["fused"]
+    kern, ne_local, ms_step = weak["kern"], weak["ne_local"], weak["ms_step"]
     if fused:
         names = ["quad_record_kernel + quad_fused_kernel<QUAD4> (COO values of KC0,KG,M + their CSR values; 2 launches)"]
         alg = [BYTES_PATH * ne_local]
@@ -289,32 +600,45 @@ def run_ours(args):
         try:
             from oracle import ref_loop
             if ref_loop.available():
-                from oracle.cpu_bench import ReferenceBench
-                rb = ReferenceBench(side=args.cpu_side)
+                from oracle import cpu_bench
+                rb = cpu_bench.ReferenceBench(side=args.cpu_side)
                 rb.step()
                 dt = rb.step()
                 rb.close()
                 cpu = {"value": rb.ne / dt, "unit": UNIT, "cores": rb.nproc, "kind": "reference", "sample": rb.describe()}
+                # SURVEY 8(d) / BASELINE.md: the same loop on ONE core (a smaller sample of the same mesh)
+                r1 = cpu_bench.ReferenceBench(side=args.cpu_side_1core, nproc=1)
+                dt1 = r1.step()
+                r1.close()
+                cpu["one_core"] = {"value": r1.ne / dt1, "unit": UNIT, "cores": 1, "sample": r1.describe()}
+                if solve is not None and "seconds" in solve:
+                    dts, its, wmax, info = cpu_bench.reference_static_solve(args.solve_side)
+                    solve["reference_seconds"] = dts
+                    solve["reference_cg_iterations"] = its
+                    solve["reference_w_max"] = wmax
+                    solve["w_max_rel_diff"] = abs(wmax - solve["w_max"]) / abs(wmax)
+                    solve["speedup_vs_reference"] = dts / solve["seconds"]
+                    solve["reference_what"] = ("compiled reference on 1 host core: Cython loop (KC0) + coo_matrix.tocsc + "
+                                               "K[bu,:][:,bu] + diagonally scaled scipy cg, same mesh and tolerance")
         except Exception as exc:  # the CPU leg is reporting only
             cpu = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
 
+    value = weak["ne_total"] / (ms_step * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(side),
-                       "elements_total": ne_unique_total, "elements_evaluated_per_gpu": ne_local,
+            "config": {"workload": workload_name(side), "l2": L2_NOTE},   # identical in both arms; the rest: details
+            "details": {"elements_total": weak["ne_total"], "elements_evaluated_per_gpu": ne_local,
                        "halo": "row-ownership strips, halo elements duplicated, no collective on the data path",
-                       "l2": "COO+CSR outputs are %.1f GB per step, far larger than the 126 MB L2 (no flush needed)"
-                             % ((BYTES_ASM_READ + BYTES_CSR) * ne_local / 1e9),
-                       "symbolic_plan_s": t_symbolic, "indices": "values only (update_*v_only=1); plan built once",
-                       "path": args.path},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": summarize_clocks(clk_lines)}
+                       "output_gb_per_step_per_gpu": (BYTES_ASM_READ + BYTES_CSR) * ne_local / 1e9,
+                       "symbolic_plan_s": weak["symbolic_s"], "indices": "values only (update_*v_only=1); plan built once",
+                       "path": args.path, "strong": strong, "others": others, "solve_e2e": solve},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": weak.get("e2e"), "gpu_launches": weak["launches"],
+            "clocks": weak["clocks"], "parity": weak["parity"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
-
 
 
 class numa_local:
@@ -352,6 +676,7 @@ class numa_local:
             os.sched_setaffinity(0, self.saved)
         return False
 
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -363,6 +688,12 @@ def main():
     ap.add_argument("--path", default="fused", choices=["fused", "twopass"],
                     help="fused: one node-centric kernel writes COO + CSR; twopass: eval kernel then 3 assemblies")
     ap.add_argument("--cpu-side", type=int, default=256, help="side of the sub-plate the CPU arm evaluates")
+    ap.add_argument("--cpu-side-1core", type=int, default=96, help="side of the sub-plate of the one-core CPU figure")
+    ap.add_argument("--e2e-upper", type=int, default=1, help="also time the end-to-end step returning one triangle")
+    ap.add_argument("--strong", type=int, default=1, help="N>1: also time the metric's own size cut into N strips")
+    ap.add_argument("--others", type=int, default=1, help="also time BASELINE configs 2-5 (config.others)")
+    ap.add_argument("--others-scale", type=float, default=1.0, help="shrink the other configs (smoke tests)")
+    ap.add_argument("--solve-side", type=int, default=32, help="side of the static-solve end-to-end workload (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

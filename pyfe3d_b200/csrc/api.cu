@@ -52,9 +52,6 @@ int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st,
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches,
                               int phases);
 int fused_record_stride(const EvalArgs& A);
-bool fused_split_applies(const FusedArgs& F);
-cudaError_t launch_quad_fused_split(int kind, FusedArgs& F, double* rec, cudaStream_t st, cudaStream_t aux,
-                                    cudaEvent_t* ev, FusedSplit* S, int64_t* launches);
 int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_union_map(const pf3_plan* pl, int group, int matrix, int mtype, UnionMap* um);
@@ -98,9 +95,6 @@ struct pf3_context {
   cudaEvent_t chunk_done[PF3_HOST_CHUNKS] = {};
   char* stage_host = nullptr;           // pinned + device staging of the small host-pointer calls (per-element drop-in)
   char* stage_dev = nullptr;
-  cudaStream_t k1_stream = nullptr;     // high-priority side stream of the split fused launch (records of later ranges)
-  cudaEvent_t k1_done[pf3::kFusedMaxSplit] = {};
-  pf3::FusedSplit split;                // cached cut points of the last plan
   void* solve_work = nullptr;           // vectors + scalars of pf3_plan_cg / pf3_plan_spmv_scaled
   size_t solve_work_bytes = 0;
 };
@@ -290,9 +284,6 @@ int pf3_destroy(pf3_context* ctx) {
   if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
   if (ctx->stage_dev) cudaFree(ctx->stage_dev);
   if (ctx->solve_work) cudaFree(ctx->solve_work);
-  if (ctx->k1_stream) cudaStreamDestroy(ctx->k1_stream);
-  for (cudaEvent_t ev : ctx->k1_done)
-    if (ev) cudaEventDestroy(ev);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (cudaEvent_t ev : ctx->chunk_done)
     if (ev) cudaEventDestroy(ev);
@@ -677,17 +668,6 @@ int eval_assemble_impl(pf3_context* ctx, const pf3_batch* b, const pf3_plan* pla
     rc = fused_pipelined(ctx, b->kind, F, dev_out, host_out, per_block);
     if (rc) return rc;
     *copied = true;
-  } else if (!tria && pf3::fused_split_applies(F)) {
-    // K1 of the later node-pair ranges runs on a side stream behind K2 of the earlier ones
-    if (!ctx->k1_stream) {
-      int lo = 0, hi = 0;
-      PF3_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      PF3_CUDA(cudaStreamCreateWithPriority(&ctx->k1_stream, cudaStreamNonBlocking, hi));
-      for (cudaEvent_t& ev : ctx->k1_done) PF3_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    }
-    cudaError_t e = pf3::launch_quad_fused_split(b->kind, F, ctx->scratch, ctx->stream, ctx->k1_stream, ctx->k1_done,
-                                                 &ctx->split, &ctx->launches);
-    if (e != cudaSuccess) return int(e);
   } else {
     cudaError_t e = tria ? pf3::launch_tria_fused(F, ctx->scratch, ctx->stream, &ctx->launches)
                          : pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3);

@@ -60,6 +60,8 @@ struct pf3_plan {
   int32_t* d_inc_meta = nullptr;
   int32_t* d_slot = nullptr;
   mutable pf3::NodeRec* d_noderec = nullptr;   // built on first fused use
+  mutable int2* d_pftab = nullptr;             // L2 prefetch table of the fused quad kernel (common.cuh: kPfChunk)
+  mutable int64_t pf_nchunks = 0;
   mutable pf3::TriaRec* d_triarec = nullptr;   // ditto, Tria3R
   mutable int rmax = 0;
   mutable std::vector<pf3::NodeRec*> d_grecs;  // per-group records of the slab assembly (built on first use)
@@ -1194,6 +1196,36 @@ __global__ void k_max_valence(const int64_t* inc_ptr, int64_t nown, int* out) {
   for (int64_t n = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; n < nown; n += int64_t(gridDim.x) * blockDim.x)
     atomicMax(out, int(inc_ptr[n + 1] - inc_ptr[n]));
 }
+// L2 prefetch table (common.cuh: kPfChunk): first the lowest node pair that uses each element, then per chunk of pairs
+// the [min, max] of the elements used first there.
+__global__ void k_pf_first_use(const NodeRec* __restrict__ rec, int64_t total, int rmax, int* __restrict__ first_use) {
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int pair = int((t / rmax) >> 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int inc = rec[t].inc[k];
+      if (inc >= 0) atomicMin(first_use + (inc >> 4), pair);
+    }
+  }
+}
+__global__ void k_pf_ranges(const int* __restrict__ first_use, int64_t ne, int* __restrict__ lo, int* __restrict__ hi) {
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < ne; e += int64_t(gridDim.x) * blockDim.x) {
+    const int f = first_use[e];
+    if (f == 0x7f7f7f7f) continue;
+    const int c = f / kPfChunk;
+    atomicMin(lo + c, int(e));
+    atomicMax(hi + c, int(e));
+  }
+}
+__global__ void k_pf_table(const int* __restrict__ lo, const int* __restrict__ hi, int64_t nchunks, int2* __restrict__ tab) {
+  for (int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; c < nchunks; c += int64_t(gridDim.x) * blockDim.x) {
+    int2 t = make_int2(0, 0);
+    // a chunk of kPfChunk pairs of a quad mesh first-uses about 2 kPfChunk elements; a run much longer than that means
+    // the numbering scatters them (prefetching the hull would read far more than is used): no prefetch for this chunk
+    if (hi[c] >= lo[c] && hi[c] - lo[c] + 1 <= 8 * kPfChunk) t = make_int2(lo[c], hi[c] - lo[c] + 1);
+    tab[c] = t;
+  }
+}
 __global__ void k_node_records(const int64_t* __restrict__ brow_ptr, const int64_t* __restrict__ inc_ptr,
                                const int64_t* __restrict__ inc_pair0, const int32_t* __restrict__ slot, int64_t nown,
                                int rmax, NodeRec* __restrict__ out) {
@@ -1441,8 +1473,33 @@ int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st,
                                                                   pl->d_slot, pl->nown, pl->rmax, pl->d_noderec);
     *launches += 2;
     PF3_CUDA(cudaGetLastError());
+    // L2 prefetch table (only worth it when there are several chunks ahead to prefetch)
+    const int64_t npairs = (pl->nown + 1) / 2;
+    const int64_t nchunks = (npairs + kPfChunk - 1) / kPfChunk;
+    if (nchunks > 4 * kPfAhead && npairs < (int64_t(1) << 31)) {
+      int *d_first = nullptr, *d_lo = nullptr, *d_hi = nullptr;
+      PF3_CUDA(cudaMalloc((void**)&d_first, size_t(G.ne) * sizeof(int)));
+      PF3_CUDA(cudaMalloc((void**)&d_lo, size_t(nchunks) * sizeof(int)));
+      PF3_CUDA(cudaMalloc((void**)&d_hi, size_t(nchunks) * sizeof(int)));
+      PF3_CUDA(cudaMalloc((void**)&pl->d_pftab, size_t(nchunks) * sizeof(int2)));
+      PF3_CUDA(cudaMemsetAsync(d_first, 0x7f, size_t(G.ne) * sizeof(int), st));   // 0x7f7f7f7f: "never" (> any pair)
+      PF3_CUDA(cudaMemsetAsync(d_lo, 0x7f, size_t(nchunks) * sizeof(int), st));
+      PF3_CUDA(cudaMemsetAsync(d_hi, 0xff, size_t(nchunks) * sizeof(int), st));    // -1
+      k_pf_first_use<<<grid_for(pl->nown * pl->rmax), 256, 0, st>>>(pl->d_noderec, pl->nown * pl->rmax, pl->rmax, d_first);
+      k_pf_ranges<<<grid_for(G.ne), 256, 0, st>>>(d_first, G.ne, d_lo, d_hi);
+      k_pf_table<<<grid_for(nchunks), 256, 0, st>>>(d_lo, d_hi, nchunks, pl->d_pftab);
+      *launches += 3;
+      PF3_CUDA(cudaGetLastError());
+      PF3_CUDA(cudaStreamSynchronize(st));
+      cudaFree(d_first);
+      cudaFree(d_lo);
+      cudaFree(d_hi);
+      pl->pf_nchunks = nchunks;
+    }
   }
   F->noderec = pl->d_noderec;
+  F->pftab = pl->d_pftab;
+  F->pf_nchunks = pl->pf_nchunks;
   F->rmax = pl->rmax;
   F->brow_ptr = pl->d_brow_ptr;
   F->inc_ptr = pl->d_inc_ptr;
@@ -1500,7 +1557,7 @@ int64_t plan_nrows(const pf3_plan* pl) { return pl->nrows; }
 extern "C" int pf3_plan_destroy(pf3_plan* pl) {
   if (!pl) return PF3_OK;
   cudaFree(pl->d_brow_ptr); cudaFree(pl->d_bcol); cudaFree(pl->d_inc_ptr); cudaFree(pl->d_inc_src);
-  cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot); cudaFree(pl->d_noderec); cudaFree(pl->d_triarec); cudaFree(pl->d_frecs);
+  cudaFree(pl->d_inc_pair0); cudaFree(pl->d_inc_meta); cudaFree(pl->d_slot); cudaFree(pl->d_noderec); cudaFree(pl->d_pftab); cudaFree(pl->d_triarec); cudaFree(pl->d_frecs);
   for (auto* r : pl->d_grecs) cudaFree(r);
   for (auto* t : pl->d_tabs) cudaFree(t);
   cudaFree(pl->d_indptr); cudaFree(pl->d_indices); cudaFree(pl->d_perm); cudaFree(pl->d_seg);

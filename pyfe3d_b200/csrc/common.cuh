@@ -113,17 +113,16 @@ struct FusedArgs {
   int zero_empty;                         // multi-group plans: zero the rows of nodes this group does not touch
   int64_t pair_first;                     // quads: this launch covers node pairs [pair_first, pair_first + pair_count)
   int64_t pair_count;                     //        (pair_count == 0: all pairs) -- pf3_eval_assemble_host's pipeline
+  const int2* __restrict__ pftab;         // quads: L2 prefetch table (see kPfChunk), nullptr: no prefetch
+  int64_t pf_nchunks;
 };
 
-// cut points of the split launch of the fused quad kernels (quad_fused.cu: launch_quad_fused_split)
-constexpr int kFusedMaxSplit = 8;
-struct FusedSplit {
-  const void* key = nullptr;          // the plan's node records these cuts were computed for
-  int64_t nown = 0, ne = 0;
-  int n = 0;
-  int64_t pair_at[kFusedMaxSplit + 1];   // K2 of range r: node pairs [pair_at[r], pair_at[r+1])
-  int64_t elem_to[kFusedMaxSplit];       // K1 of range r: elements [elem_to[r-1], elem_to[r])
-};
+// L2 prefetch table of the fused quad kernel (quad_fused.cu): the node pairs are cut into chunks of kPfChunk; entry c
+// holds the contiguous run of element records that are used FIRST by a pair of chunk c (x = first element, y = count;
+// y = 0: no usable run).  The CTA of the first pair of chunk c issues bulk L2 prefetches for the node records and the
+// element records of chunk c + kPfAhead.
+constexpr int kPfChunk = 512;
+constexpr int kPfAhead = 8;
 
 struct Mat3 {
   double a[3][3];

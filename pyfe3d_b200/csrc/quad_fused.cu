@@ -37,8 +37,11 @@ constexpr double kGpF = 0.5773502691896257645092;
 #endif
 constexpr int kFusedWarps = PF3_FUSED_WARPS;
 
-#ifndef PF3_K1_SPLIT
-#define PF3_K1_SPLIT 4   // node-pair ranges of the split launch (1: K1 then K2, no overlap)
+#ifndef PF3_L2_HINTS
+#define PF3_L2_HINTS 1   // stores carry an L2 evict-first policy (nothing written here is read again by this step)
+#endif
+#ifndef PF3_L2_PREFETCH
+#define PF3_L2_PREFETCH 1   // bulk L2 prefetch of the node / element records kPfAhead chunks of node pairs ahead
 #endif
 constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path (NodeRec::gmap)
 // Element record (doubles): 0..5 the element x and y axes (R columns 0 and 1, row-major 3 x 2; z = x X y is recomputed
@@ -175,12 +178,36 @@ struct SlabShape {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+// L2 evict-first policy for everything this kernel writes: 60 GB per step stream through the L2 and are never read
+// again, while the element records are re-read by up to three later CTAs and the prefetched records must survive until
+// their CTAs run.  (Measured with scripts/micro/k2_stream_reads.cu: a DRAM read among the writes costs ~12x its bytes.)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void stg_stream(double2* p, double2 v, uint64_t pol) {
+#if PF3_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void stg_stream(double* p, double v, uint64_t pol) {
+#if PF3_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+
 // Lanes have written their block into slab (lane>>2).  Ship the slabs to the COO array and reduce the (up to)
 // 4 incidences of each half-warp's node into its CSR rows in the fixed order k = 0..3.
 template <int NR, int CNT>
 __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, double* __restrict__ coo,
                                            int64_t slab_base, bool act, double* __restrict__ csr, int64_t csr_base,
-                                           int nb, bool first_round, int lane, const UnionMap* um = nullptr) {
+                                           int nb, bool first_round, int lane, uint64_t pol,
+                                           const UnionMap* um = nullptr) {
   constexpr int kSlab = SlabShape<NR, CNT>::kSlab, kLd = SlabShape<NR, CNT>::kLd;
   const int h = lane >> 4, l16 = lane & 15;
 #if PF3_COO_TMA
@@ -188,9 +215,15 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
   __syncwarp();
   if (coo != nullptr && act && (lane & 3) == 0) {
     const uint32_t src = smem_u32(st + (lane >> 2) * kLd);
+#if PF3_L2_HINTS
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(coo + slab_base),
+                 "r"(src), "r"(kSlab * 8), "l"(pol)
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(coo + slab_base), "r"(src),
                  "r"(kSlab * 8)
                  : "memory");
+#endif
   }
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 #else
@@ -294,7 +327,7 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
             sum.x += t.x;
             sum.y += t.y;
           }
-          *o = sum;
+          stg_stream(o, sum, pol);
         }
       }
     } else {
@@ -320,7 +353,8 @@ __device__ __forceinline__ void emit_slabs(const double* st, const NodeRec* nr, 
             if (off[k2] >= 0) sum += sh[d * 4 * CNT + off[k2]];
 #endif
           double* o = out + d * w + x;
-          if (first_round) *o = sum; else *o += sum;
+          if (!first_round) sum += *o;
+          stg_stream(o, sum, pol);
         }
       }
     }
@@ -442,6 +476,27 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
   // static schedule: this warp owns CHUNK consecutive pairs
   const int64_t np0 = F.pair_first + (int64_t(blockIdx.x) * kFusedWarps + warp) * CHUNK;
   if (np0 >= npairs) return;
+  const uint64_t pol = l2_evict_first_policy();
+#if PF3_L2_PREFETCH
+  // The CTA of the first pair of a chunk pulls the node records and the first-use element records of the chunk
+  // kPfAhead chunks ahead into L2 with a few bulk prefetches: the DRAM reads of this kernel then arrive as long bursts
+  // instead of 128- and 256-byte reads scattered between its writes (each of which turns the DRAM bus around).
+  if (F.pftab != nullptr && lane == 0 && (np0 % kPfChunk) < CHUNK) {
+    const int64_t c = np0 / kPfChunk + kPfAhead;
+    if (c < F.pf_nchunks) {
+      constexpr unsigned kPiece = 32768;
+      const int64_t n0 = c * kPfChunk * 2;
+      const int64_t nn = min(int64_t(2 * kPfChunk), F.nown - n0);
+      const char* q = reinterpret_cast<const char*>(F.noderec + n0 * rmax);
+      for (int64_t left = nn * rmax * int64_t(sizeof(NodeRec)); left > 0; left -= kPiece, q += kPiece)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(unsigned(min(left, int64_t(kPiece)))) : "memory");
+      const int2 t = F.pftab[c];
+      q = reinterpret_cast<const char*>(rec + int64_t(t.x) * rstride);
+      for (int64_t left = int64_t(t.y) * rstride * 8; left > 0; left -= kPiece, q += kPiece)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(unsigned(min(left, int64_t(kPiece)))) : "memory");
+    }
+  }
+#endif
   const int nitems = int(min(int64_t(CHUNK), npairs - np0)) * rmax;   // item j = (pair np0 + j / rmax, round j % rmax)
 
   auto rec_fetch_pair = [&](int slot3, int64_t pair, int r) {
@@ -591,7 +646,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
 #pragma unroll
         for (int jj = 0; jj < 3; ++jj) sl[i * 12 + jj] = (R.a[i][2] * R.a[jj][2]) * ge;
       emit_slabs<3, 3>(st, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 144 + a * 36, act, F.csr_kg,
-                       umKG ? b0 * umKG->mc : b0 * 9, nb, first, lane, umKG);
+                       umKG ? b0 * umKG->mc : b0 * 9, nb, first, lane, pol, umKG);
     }
 
     // ---------------- M : H_ab * (T6 m_l T6^T)
@@ -633,7 +688,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
           sl[(3 + i) * 20 + 3] = H * rq[1];
           sl[(3 + i) * 20 + 4] = H * rq[2];
         }
-        emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, umM ? b0 * umM->mc : b0 * 30, nb, first, lane, umM);
+        emit_slabs<6, 5>(st, nr, coo, e * 480 + a * 120, act, F.csr_m, umM ? b0 * umM->mc : b0 * 30, nb, first, lane, pol, umM);
       } else {
         double* sl = st + (lane >> 2) * SlabShape<6, 3>::kLd + b * 3;
         stage_reuse_wait();
@@ -644,7 +699,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
             sl[i * 12 + jj] = H * (r0 * R.a[i][0] * R.a[jj][0] + r0 * R.a[i][1] * R.a[jj][1] + r0 * R.a[i][2] * R.a[jj][2]);
             sl[(3 + i) * 12 + jj] = H * (r2 * R.a[i][0] * R.a[jj][0] + r2 * R.a[i][1] * R.a[jj][1]);
           }
-        emit_slabs<6, 3>(st, nr, coo, e * 480 + a * 72, act, F.csr_m, umM ? b0 * umM->mc : b0 * 18, nb, first, lane, umM);
+        emit_slabs<6, 3>(st, nr, coo, e * 480 + a * 72, act, F.csr_m, umM ? b0 * umM->mc : b0 * 18, nb, first, lane, pol, umM);
       }
     }
 
@@ -744,7 +799,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
         sl2[(3 + i) * 12 + 2] = make_double2(o2[i][1], o2[i][2]);
       }
       emit_slabs<6, 6>(st, nr, A.kc0v ? A.kc0v + A.kc0_k0 : nullptr, e * 576 + a * 144, act, F.csr_kc0,
-                       umK ? b0 * umK->mc : b0 * 36, nb, first, lane, umK);
+                       umK ? b0 * umK->mc : b0 * 36, nb, first, lane, pol, umK);
     }
   }
   // the bulk copies read this CTA's shared memory: they must have done so before the CTA retires
@@ -777,27 +832,6 @@ cudaError_t launch_k1(int kind, const EvalArgs& A, double* rec, int stride, int6
     quad_record_kernel<PF3_QUAD4R><<<g1, 32 * warps, smem1, st>>>(A, rec, stride, e_begin, e_end);
   ++*launches;
   return cudaGetLastError();
-}
-
-// largest element index the node records of each pair range refer to
-struct PairCuts {
-  int n;
-  int64_t at[kFusedMaxSplit + 1];
-};
-__global__ void k_range_emax(const NodeRec* __restrict__ rec, int64_t nown, int rmax, PairCuts C, int* __restrict__ out) {
-  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < nown * rmax; t += int64_t(gridDim.x) * blockDim.x) {
-    const NodeRec& r = rec[t];
-    int m = -1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (r.inc[k] >= 0) m = max(m, r.inc[k] >> 4);
-    if (m < 0) continue;
-    const int64_t pair = (t / rmax) >> 1;
-    int g = 0;
-    for (int q = 1; q < C.n; ++q)
-      if (pair >= C.at[q]) g = q;
-    if (m > out[g]) atomicMax(out + g, m);
-  }
 }
 
 }  // namespace
@@ -841,80 +875,6 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   }
   ++*launches;
   return cudaGetLastError();
-}
-
-// The store-bound three-matrix call with K1 hidden behind K2: the node pairs are cut into S->n ranges; K1 runs on `st`
-// only for the elements the FIRST range needs, the records of the later ranges are produced on the high-priority side
-// stream `aux` by one-warp CTAs (the footprint of a K2 CTA, so they slot into the SMs as K2 CTAs retire) while K2 of
-// the earlier ranges is running; K2 of range r waits for its records through ev[r].  K1 is latency-bound on its gathers
-//  and K2 leaves issue slots and DRAM bandwidth unused, so the two overlap almost for free.
-// S caches the element cut points of a plan (they depend on the node records only).
-bool fused_split_applies(const FusedArgs& F) {
-  const int w = F.A.what;
-  const int vol = ((w & PF3_KC0) ? 900 : 0) + ((w & (PF3_KG | PF3_KG_STRESS)) ? 225 : 0) + ((w & PF3_M) ? 750 : 0);
-  const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
-  return PF3_K1_SPLIT > 1 && vol >= 1400 && !mapped && F.noderec != nullptr && F.pair_count == 0 &&
-         F.nown >= int64_t(PF3_K1_SPLIT) * 65536;
-}
-
-cudaError_t launch_quad_fused_split(int kind, FusedArgs& F, double* rec, cudaStream_t st, cudaStream_t aux,
-                                    cudaEvent_t* ev, FusedSplit* S, int64_t* launches) {
-  const int n = PF3_K1_SPLIT;
-  const int64_t npairs = (F.nown + 1) / 2;
-  if (S->key != F.noderec || S->nown != F.nown || S->ne != F.A.ne || S->n != n) {
-    PairCuts C;
-    C.n = n;
-    for (int r = 0; r <= n; ++r) C.at[r] = npairs * r / n;
-    int* d_out = nullptr;
-    cudaError_t e = cudaMalloc((void**)&d_out, sizeof(int) * kFusedMaxSplit);
-    if (e != cudaSuccess) return e;
-    cudaMemsetAsync(d_out, 0xff, sizeof(int) * kFusedMaxSplit, st);   // -1
-    k_range_emax<<<148 * 8, 256, 0, st>>>(F.noderec, F.nown, F.rmax, C, d_out);
-    ++*launches;
-    int h[kFusedMaxSplit];
-    e = cudaMemcpyAsync(h, d_out, sizeof(int) * kFusedMaxSplit, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_out);
-    if (e != cudaSuccess) return e;
-    int64_t upto = 0;
-    for (int r = 0; r < n; ++r) {
-      upto = std::max<int64_t>(upto, int64_t(h[r]) + 1);
-      S->pair_at[r] = C.at[r];
-      S->elem_to[r] = (r == n - 1) ? F.A.ne : std::min<int64_t>(upto, F.A.ne);
-    }
-    S->pair_at[n] = npairs;
-    S->key = F.noderec;
-    S->nown = F.nown;
-    S->ne = F.A.ne;
-    S->n = n;
-  }
-  const int stride = fused_record_stride(F.A);
-  cudaError_t e = cudaEventRecord(ev[0], st);   // the inputs (x, u, ...) and the previous call's K2 are ordered before this
-  if (e != cudaSuccess) return e;
-  e = cudaStreamWaitEvent(aux, ev[0], 0);
-  if (e != cudaSuccess) return e;
-  e = launch_k1(kind, F.A, rec, stride, 0, S->elem_to[0], 4, st, launches);
-  if (e != cudaSuccess) return e;
-  for (int r = 1; r < n; ++r) {
-    e = launch_k1(kind, F.A, rec, stride, S->elem_to[r - 1], S->elem_to[r], 1, aux, launches);
-    if (e != cudaSuccess) return e;
-    e = cudaEventRecord(ev[r], aux);
-    if (e != cudaSuccess) return e;
-  }
-  for (int r = 0; r < n; ++r) {
-    if (r > 0) {
-      e = cudaStreamWaitEvent(st, ev[r], 0);
-      if (e != cudaSuccess) return e;
-    }
-    F.pair_first = S->pair_at[r];
-    F.pair_count = S->pair_at[r + 1] - S->pair_at[r];
-    if (F.pair_count > 0) {
-      e = launch_quad_fused(kind, F, rec, st, launches, 2);
-      if (e != cudaSuccess) return e;
-    }
-  }
-  F.pair_first = F.pair_count = 0;
-  return cudaSuccess;
 }
 
 }  // namespace pf3

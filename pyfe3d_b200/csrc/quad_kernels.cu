@@ -107,8 +107,12 @@ struct QuadExtra {       // Quad4R only
   double hg[5];          // w0 * E_d * g^2 for d = u v w rx ry (quad4r.pyx:3088-3092)
 };
 
-template <int KIND>
-__global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
+// ONLY = 0: any subset of the outputs.  ONLY = PF3_FINT: the instantiation for update_fint / update_probe_finte / state
+// calls, which contains no matrix code (248 registers and no spills against 254 + 144 bytes of spills; forcing three
+// CTAs per SM costs 1.1 kB of spills, so occupancy stays at 8 warps per SM).
+template <int KIND, int ONLY>
+__global__ void __launch_bounds__(kThreads, ONLY ? 2 : 1) quad_eval_kernel(const EvalArgs A) {
+  const int what = ONLY ? (A.what & ONLY) : A.what;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t e0 = (int64_t(blockIdx.x) * kWarpsPerCta + warp) * 32;
@@ -118,13 +122,13 @@ __global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
   double* stage = smem + warp * 32 * kStageLd;
   double* my = stage + lane * kStageLd;
 
-  const bool need_u = (A.what & (PF3_KG | PF3_FINT)) != 0 || A.state_out != nullptr;
+  const bool need_u = (what & (PF3_KG | PF3_FINT)) != 0 || A.state_out != nullptr;
   double ue[24];
   ShellGeom<4> g;
   shell_geom<4>(A, e, g, need_u && (A.u != nullptr || A.state != nullptr) ? ue : nullptr);
   if (A.state_out != nullptr) {
     if (lane < nvalid) store_state<4>(A, e, g, (A.u != nullptr || A.state != nullptr) ? ue : nullptr);
-    if (A.what == 0) return;
+    if (what == 0) return;
   }
   ShellCoef c;
   shell_coef<4>(A, e, g, c);
@@ -175,9 +179,9 @@ __global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
   const double c44 = q.w0 * c.E44 * 0.0625, c45 = q.w0 * c.E45 * 0.0625, c55 = q.w0 * c.E55 * 0.0625;
 
   // ------------------------------------------------------------------ KG
-  if (A.what & (PF3_KG | PF3_KG_STRESS)) {
+  if (what & (PF3_KG | PF3_KG_STRESS)) {
     double Ge[4][4];
-    if (A.what & PF3_KG_STRESS) {
+    if (what & PF3_KG_STRESS) {
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
   }
 
   // ------------------------------------------------------------------ M
-  if (A.what & PF3_M) {
+  if (what & PF3_M) {
     double H[4][4];
     if (A.mtype == 0) {
 #pragma unroll
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
   }
 
   // ------------------------------------------------------------------ KC0
-  if (A.what & PF3_KC0) {
+  if (what & PF3_KC0) {
     double* out = A.kc0v + A.kc0_k0;
 #pragma unroll 1
     for (int a = 0; a < 4; ++a) {
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(kThreads) quad_eval_kernel(const EvalArgs A) {
   }
 
   // ------------------------------------------------------------------ fint / finte
-  if (A.what & PF3_FINT) {
+  if (what & PF3_FINT) {
     double f[24];
 #pragma unroll
     for (int i = 0; i < 24; ++i) f[i] = 0.;
@@ -656,20 +660,20 @@ cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st) {
   if (A.ne <= 0) return cudaSuccess;
   const int64_t per_cta = 32 * kWarpsPerCta;
   const unsigned grid = unsigned((A.ne + per_cta - 1) / per_cta);
+  static PerDeviceOnce once;
+  if (once.first()) {
+    cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4, PF3_FINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+    cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4R, PF3_FINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
+  }
+  const bool fint_only = (A.what & ~PF3_FINT) == 0;   // update_fint / update_probe_finte / state: no matrix code
   if (kind == PF3_QUAD4) {
-    static PerDeviceOnce once;
-    if (once.first()) {
-      cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-      cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-    }
-    quad_eval_kernel<PF3_QUAD4><<<grid, kThreads, kStageBytes, st>>>(A);
+    if (fint_only) quad_eval_kernel<PF3_QUAD4, PF3_FINT><<<grid, kThreads, kStageBytes, st>>>(A);
+    else quad_eval_kernel<PF3_QUAD4, 0><<<grid, kThreads, kStageBytes, st>>>(A);
   } else {
-    static PerDeviceOnce once;
-    if (once.first()) {
-      cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-      cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
-    }
-    quad_eval_kernel<PF3_QUAD4R><<<grid, kThreads, kStageBytes, st>>>(A);
+    if (fint_only) quad_eval_kernel<PF3_QUAD4R, PF3_FINT><<<grid, kThreads, kStageBytes, st>>>(A);
+    else quad_eval_kernel<PF3_QUAD4R, 0><<<grid, kThreads, kStageBytes, st>>>(A);
   }
   return cudaGetLastError();
 }

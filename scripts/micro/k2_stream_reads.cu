@@ -6,6 +6,10 @@
 //   reads = 2: the same loads from ONE address (L1/L2 hits: the instructions and the wait, no DRAM / L2 traffic)
 //   reads = 3: node records only      reads = 4: element records only, address known up front (no dependent load)
 //   reads = 5: both, but independent (the element index does not wait for the node record: ONE load latency)
+//   reads = 7: as 1, and every 64th CTA issues two BULK L2 prefetches (cp.async.bulk.prefetch.L2) `ahead` pairs ahead:
+//              64 node-record pairs (8 KB) and the 128 element records those pairs use first (32 KB): the same DRAM
+//              reads, batched into a few long bursts instead of 128/256-byte reads scattered between the writes
+//   reads = 8: as 1, but the element records come from a 1 MB window (L2 hits, no DRAM reads): the crossbar share
 //   reads = 6: as 1, and every CTA prefetches (prefetch.global.L2) the node record and the element records of the CTA
 //              `ahead` pairs later
 //   fma:   dependent DFMA chain of that many instructions per lane between the loads and the stores (K2 executes
@@ -18,7 +22,7 @@
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, double* c0, double* cg, double* cm,
                                         const double* noderec, const double* erec, int n, int64_t npairs, int reads,
-                                        int nfma, int ahead) {
+                                        int nfma, int ahead, int nrl, int erb, int hint, int chunkp) {
   extern __shared__ __align__(128) double st[];   // 8 slabs x 152 doubles | 16 doubles node records | 8 x 34 element records
   const int lane = threadIdx.x;
   for (int i = lane; i < 8 * 152; i += 32) st[i] = double(i);
@@ -35,8 +39,12 @@ __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, doub
   const int ei = i - 1 + (kq & 1), ej = j - 1 + (kq >> 1);
   const bool act = valid && ei >= 0 && ei < n && ej >= 0 && ej < n;
   int64_t e = int64_t(ei) * n + ej;
+  const int64_t e_store = e;
   const int a = (kq == 0) ? 2 : (kq == 1) ? 3 : (kq == 2) ? 1 : 0;
   double acc = 1.0;
+  uint64_t pol_first = 0, pol_last = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
   if (reads == 6 && p + ahead < npairs) {
     // L2 prefetch for the CTA `ahead` pairs later: its node record and (same mesh arithmetic) its element records
     const int64_t p2 = p + ahead;
@@ -47,19 +55,31 @@ __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, doub
     if (node2 < nnodes && ei2 >= 0 && ei2 < n && ej2 >= 0 && ej2 < n && (lane & 3) < 2)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(erec + (int64_t(ei2) * n + ej2) * 32 + (lane & 3) * 16));
   }
+  if (reads == 7 && (p % chunkp) == 0 && lane == 0) {
+    // pairs [p2, p2 + chunkp) are nodes [2 p2, 2 p2 + 2 chunkp): the elements they use FIRST are those with the same
+    // index (element (i, j) = i n + j, node (i, j) = i (n + 1) + j): a contiguous run of 2 chunkp records.  Issued
+    // in pieces of 64 pairs (8 KB of node records, 32 KB of element records per instruction).
+    for (int64_t p2 = p + ahead; p2 < p + ahead + chunkp && p2 + 64 <= npairs; p2 += 64) {
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(noderec + p2 * 16), "r"(64 * 128) : "memory");
+      const int64_t e2 = (2 * p2 / nn1) * n + (2 * p2 % nn1);
+      if (e2 + 128 <= int64_t(n) * n)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(erec + e2 * 32), "r"(128 * 256) : "memory");
+    }
+  }
+  if (reads == 8) e = e & 4095;
   if (reads == 4 || reads == 5) {
     // element records first / independently of the node record
     if (act) {
-      const char* src = reinterpret_cast<const char*>(erec + e * 32);
+      const char* src = reinterpret_cast<const char*>(erec) + e * erb;
       char* dst = reinterpret_cast<char*>(ers + (lane >> 2) * 34);
-      for (int c = (lane & 3) * 16; c < 256; c += 64)
+      for (int c = (lane & 3) * 16; c < erb; c += 64)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   if (reads == 3 || reads == 5) {
-    if (lane < 8) {
-      const char* src = reinterpret_cast<const char*>(noderec + p * 16) + 16 * lane;
+    if (lane < nrl) {
+      const char* src = reinterpret_cast<const char*>(noderec + p * 2 * nrl) + 16 * lane;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(nrs) + 16 * lane), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -69,7 +89,7 @@ __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, doub
     __syncwarp();
     acc = nrs[lane & 15] + ers[(lane >> 2) * 34 + (lane & 3)] + 1.0;
   }
-  if (reads == 1 || reads == 2 || reads == 6) {
+  if (reads == 1 || reads == 2 || reads >= 6) {
     if (lane < 8) {
       const char* src = reinterpret_cast<const char*>(noderec + (reads == 2 ? 0 : p * 16)) + 16 * lane;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(nrs) + 16 * lane), "l"(src) : "memory");
@@ -82,8 +102,12 @@ __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, doub
     if (act) {
       const char* src = reinterpret_cast<const char*>(erec + (reads == 2 ? 0 : (e + bias) * 32));
       char* dst = reinterpret_cast<char*>(ers + (lane >> 2) * 34);
-      for (int c = (lane & 3) * 16; c < 256; c += 64)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+      for (int c = (lane & 3) * 16; c < 256; c += 64) {
+        if (hint == 2)
+          asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + c)), "l"(src + c), "l"(pol_last) : "memory");
+        else
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + c)), "l"(src + c) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -96,19 +120,34 @@ __global__ void __launch_bounds__(32) k(double* kc0, double* kg, double* m, doub
   __syncwarp();
   if (act && (lane & 3) == 0) {
     const uint32_t src = smem_u32(st + (lane >> 2) * 152);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kg + e * 144 + a * 36), "r"(src), "r"(288) : "memory");
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(m + e * 480 + a * 120), "r"(src), "r"(960) : "memory");
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kc0 + e * 576 + a * 144), "r"(src), "r"(1152) : "memory");
+    if (hint) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(kg + e_store * 144 + a * 36), "r"(src), "r"(288), "l"(pol_first) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(m + e_store * 480 + a * 120), "r"(src), "r"(960), "l"(pol_first) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(kc0 + e_store * 576 + a * 144), "r"(src), "r"(1152), "l"(pol_first) : "memory");
+    } else {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kg + e_store * 144 + a * 36), "r"(src), "r"(288) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(m + e_store * 480 + a * 120), "r"(src), "r"(960) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(kc0 + e_store * 576 + a * 144), "r"(src), "r"(1152) : "memory");
+    }
   }
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   if (valid) {
     const double2 v = make_double2(acc, 4.);
     double2* o0 = reinterpret_cast<double2*>(c0 + node * 324);
-    for (int t = l16; t < 162; t += 16) o0[t] = v;
     double2* o1 = reinterpret_cast<double2*>(cm + node * 270);
-    for (int t = l16; t < 135; t += 16) o1[t] = v;
     double* o2 = cg + node * 81;
-    for (int t = l16; t < 81; t += 16) o2[t] = 5.;
+    if (hint) {
+      for (int t = l16; t < 162; t += 16)
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(o0 + t), "d"(v.x), "d"(v.y), "l"(pol_first) : "memory");
+      for (int t = l16; t < 135; t += 16)
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(o1 + t), "d"(v.x), "d"(v.y), "l"(pol_first) : "memory");
+      for (int t = l16; t < 81; t += 16)
+        asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(o2 + t), "d"(5.), "l"(pol_first) : "memory");
+    } else {
+      for (int t = l16; t < 162; t += 16) o0[t] = v;
+      for (int t = l16; t < 135; t += 16) o1[t] = v;
+      for (int t = l16; t < 81; t += 16) o2[t] = 5.;
+    }
   }
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
@@ -122,26 +161,25 @@ int main() {
   const double coo = double(ne) * (576 + 144 + 480) * 8, csr = double(nnodes) * (324 + 81 + 270) * 8;
   cudaEvent_t s, e;
   cudaEventCreate(&s); cudaEventCreate(&e);
-  auto run = [&](int ctas, int reads, int nfma, int ahead) {
+  auto run = [&](int ctas, int reads, int nfma, int ahead, int nrl, int erb, int hint, int chunkp) {
     const size_t smem = (size_t(227) * 1024 / ctas - 1024) & ~size_t(127);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     float best = 1e9f;
     for (int r = 0; r < 4; ++r) {
       cudaEventRecord(s);
-      k<<<unsigned(npairs), 32, smem>>>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], n, npairs, reads, nfma, ahead);
+      k<<<unsigned(npairs), 32, smem>>>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], n, npairs, reads, nfma, ahead, nrl, erb, hint, chunkp);
       cudaEventRecord(e);
       cudaDeviceSynchronize();
       float ms; cudaEventElapsedTime(&ms, s, e);
       if (r > 0 && ms < best) best = ms;
     }
-    printf("{\"ctas_per_sm\": %d, \"reads\": %d, \"dfma_per_lane\": %d, \"ahead\": %d, \"ms\": %.3f, \"store_GBps\": %.1f, \"err\": %d}\n",
-           ctas, reads, nfma, ahead, best, (coo + csr) / best / 1e6, int(cudaGetLastError()));
+    printf("{\"ctas_per_sm\": %d, \"reads\": %d, \"dfma_per_lane\": %d, \"ahead\": %d, \"noderec_bytes_per_pair\": %d, \"erec_bytes\": %d, \"l2_hint\": %d, \"prefetch_chunk_pairs\": %d, \"ms\": %.3f, \"store_GBps\": %.1f, \"err\": %d}\n",
+           ctas, reads, nfma, ahead, nrl * 16, erb, hint, chunkp, best, (coo + csr) / best / 1e6, int(cudaGetLastError()));
   };
-  for (int reads : {0, 1, 2})
-    for (int nf : {0, 256, 1024}) run(12, reads, nf, 0);
-  for (int ctas : {12, 16, 20, 24, 32})
-    for (int reads : {1, 3, 4, 5}) run(ctas, reads, 0, 0);
-  for (int ahead : {256, 1024, 2048, 4096}) run(12, 6, 0, ahead);
-  for (int ctas : {16, 24}) run(ctas, 1, 1024, 0);
+  for (int hint : {0, 1}) run(12, 0, 0, 0, 8, 256, hint, 64);
+  for (int hint : {0, 1, 2}) run(12, 1, 0, 0, 8, 256, hint, 64);
+  for (int hint : {0, 1})
+    for (int chunkp : {64, 512, 2048})
+      for (int ahead : {2048, 4096, 8192}) run(12, 7, 0, ahead, 8, 256, hint, chunkp);
   return 0;
 }
