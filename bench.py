@@ -169,32 +169,36 @@ def plate_shard(meshes, nx, ny, a, rank, world):
 
 def parity_checks(torch, D, case, batch, plans, coos, csr, a_len, ne_total):
     """Correctness bits of this run, all-reduced over the ranks.
-      * csr_vs_coo[m]: |sum(CSR values of the owned rows) - sum(COO values of the owned (unique) elements)| / sum|CSR|.
-        Over all ranks both are the sum of every entry of the global matrix: a wrong halo, row cut or slot map breaks it.
+      * csr_vs_coo[m]: |sum(CSR values of the owned rows) - sum(COO row slabs of the owned nodes)| / sum|CSR|.  A rank
+        writes the COO slab of an (element, local node) pair exactly when it owns that node's rows, so over all ranks
+        both are the sum of every entry of the global matrix: a wrong halo, row cut or slot map breaks the equality.
       * mass: sum(M e_x) over the x-translation dofs against intrho * a * b (closed form for the plate).
       * rigid: max|KC0 e_x| / max|KC0| (a rigid translation produces no force).
-      * kc0_sum_per_element / m_sum_per_element: every element of this mesh has the same matrices, so these do not
-        depend on N: compare them between the lines of a scaling run (KG depends on u and is tied by csr_vs_coo)."""
+      * kc0_abs_per_element / m_abs_per_element (sum of |entries| / elements): every element of this mesh has the
+        same matrices, so these do not depend on N: compare them between the lines of a scaling run (KG depends on u
+        and is tied by csr_vs_coo)."""
     lo, hi = case["owned_nodes"]
     conn0 = batch.conn[:, 0]
-    owned = (conn0 >= lo) & (conn0 < hi)
+    owned = (conn0 >= lo) & (conn0 < hi)                 # unique cover of the elements (first node owned)
+    own_slab = (batch.conn >= lo) & (batch.conn < hi)    # (element, local node) row slabs this rank writes
     ne = batch.ne
     out, loc = {}, []
     for m in ("KC0", "KG", "M"):
-        v = coos[m].v.view(ne, -1)
-        loc += [float(csr[m].sum()), float(csr[m].abs().sum()), float(v[owned].sum())]
+        v = coos[m].v.view(ne, batch.nn, -1)             # row slab of local node a = entries [a, a+1) * size / nn
+        loc += [float(csr[m].sum()), float(csr[m].abs().sum()), float(v[own_slab].sum()),
+                float(v[own_slab].abs().sum())]
     loc.append(float(owned.sum()))
     tot = D.reduce(loc)
     worst = 0.
     for i, m in enumerate(("KC0", "KG", "M")):
-        s_csr, s_abs, s_coo = tot[3 * i:3 * i + 3]
+        s_csr, s_abs, s_coo = tot[4 * i:4 * i + 3]
         rel = abs(s_csr - s_coo) / s_abs if s_abs > 0 else float("inf")
         out["csr_vs_coo_" + m] = rel
         worst = max(worst, rel)
-    ne_unique = tot[9]
+    ne_unique = tot[12]
     out["unique_elements"] = int(ne_unique)
-    out["kc0_sum_per_element"] = tot[2] / ne_unique
-    out["m_sum_per_element"] = tot[8] / ne_unique
+    out["kc0_abs_per_element"] = tot[3] / ne_unique
+    out["m_abs_per_element"] = tot[11] / ne_unique
     nn = case["ndof"] // 6
     ex = torch.zeros(6 * nn, dtype=torch.float64, device=csr["M"].device)
     ex[0::6] = 1.0
@@ -442,17 +446,16 @@ def config5(torch, D, meshes, rank, world, dev, cols, rows, lines, peak, steps):
     ms = time_steps(torch, D, step, steps)
     unique = nx * ny + lines * world * ny
     alg = sum(coo[m].v.numel() * 8 + csr[m].numel() * 8 for m in names)
-    # correctness bit: sum of the assembled CSR entries of all ranks against the sum of the COO entries of the
-    # elements each rank owns (first node owned): the same global sum when halo and row cuts are right
+    # correctness bit: sum of the assembled CSR entries of all ranks against the sum of the COO row slabs of the nodes
+    # each rank owns: the same global sum when halo and row cuts are right
     loc = []
     for m in names:
-        s = 0.
+        sm = 0.
         for g, b in enumerate(bs):
-            c0 = b.conn[:, 0]
-            own = (c0 >= lo) & (c0 < hi)
+            own = (b.conn >= lo) & (b.conn < hi)         # row slabs of the nodes this rank owns
             off = plans[m].coo_offsets[g]
-            s += float(coo[m].v[off:off + b.ne * b.sizes[m]].view(b.ne, -1)[own].sum())
-        loc += [float(csr[m].sum()), float(csr[m].abs().sum()), s]
+            sm += float(coo[m].v[off:off + b.ne * b.sizes[m]].view(b.ne, b.nn, -1)[own].sum())
+        loc += [float(csr[m].sum()), float(csr[m].abs().sum()), sm]
     tot = D.reduce(loc)
     worst = max(abs(tot[3 * i] - tot[3 * i + 2]) / tot[3 * i + 1] for i in range(3))
     out = {"config": "5: stiffened panel %d x %d Quad4 + %d BeamC in one matrix each, KC0+KG+M + update_fint, %s"
@@ -530,7 +533,7 @@ def run_ours(args):
         s = measure_plate(torch, D, meshes, side, side, 1.0, rank, world, dev, args, full=False)
         strong = {"elements_total": s["ne_total"], "elements_evaluated_per_gpu": s["ne_local"],
                   "ms_per_step": s["ms_step"], "value": s["ne_total"] / (s["ms_step"] * 1e-3), "unit": UNIT,
-                  "parity_ok": s["parity"]["ok"], "kc0_sum_per_element": s["parity"]["kc0_sum_per_element"]}
+                  "parity_ok": s["parity"]["ok"], "kc0_abs_per_element": s["parity"]["kc0_abs_per_element"]}
     elif world == 1:
         strong = {"elements_total": weak["ne_total"], "elements_evaluated_per_gpu": weak["ne_local"],
                   "ms_per_step": weak["ms_step"], "value": weak["ne_total"] / (weak["ms_step"] * 1e-3), "unit": UNIT,

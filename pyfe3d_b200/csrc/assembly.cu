@@ -1197,35 +1197,69 @@ __global__ void k_max_valence(const int64_t* inc_ptr, int64_t nown, int* out) {
     atomicMax(out, int(inc_ptr[n + 1] - inc_ptr[n]));
 }
 // L2 prefetch table (common.cuh: kPfChunk): first the lowest node pair that uses each element, then per chunk of pairs
-// the [min, max] of the elements used first there.
-__global__ void k_pf_first_use(const NodeRec* __restrict__ rec, int64_t total, int rmax, int* __restrict__ first_use) {
+// and quarter of the element range the [min, max] of the elements used first there.
+template <class REC, int NINC, int DIV>
+__global__ void k_pf_first_use(const REC* __restrict__ rec, int64_t total, int rmax, int* __restrict__ first_use) {
   for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
     const int pair = int((t / rmax) >> 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NINC; ++k) {
       const int inc = rec[t].inc[k];
-      if (inc >= 0) atomicMin(first_use + (inc >> 4), pair);
+      if (inc >= 0) atomicMin(first_use + inc / DIV, pair);
     }
   }
 }
-__global__ void k_pf_ranges(const int* __restrict__ first_use, int64_t ne, int* __restrict__ lo, int* __restrict__ hi) {
+__global__ void k_pf_ranges(const int* __restrict__ first_use, int64_t ne, int64_t seglen, int* __restrict__ lo,
+                            int* __restrict__ hi) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < ne; e += int64_t(gridDim.x) * blockDim.x) {
     const int f = first_use[e];
     if (f == 0x7f7f7f7f) continue;
-    const int c = f / kPfChunk;
-    atomicMin(lo + c, int(e));
-    atomicMax(hi + c, int(e));
+    const int64_t slot = int64_t(f / kPfChunk) * kPfRuns + min(int64_t(kPfRuns - 1), e / seglen);
+    atomicMin(lo + slot, int(e));
+    atomicMax(hi + slot, int(e));
   }
 }
-__global__ void k_pf_table(const int* __restrict__ lo, const int* __restrict__ hi, int64_t nchunks, int2* __restrict__ tab) {
-  for (int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; c < nchunks; c += int64_t(gridDim.x) * blockDim.x) {
+__global__ void k_pf_table(const int* __restrict__ lo, const int* __restrict__ hi, int64_t nslots, int2* __restrict__ tab) {
+  for (int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; c < nslots; c += int64_t(gridDim.x) * blockDim.x) {
     int2 t = make_int2(0, 0);
-    // a chunk of kPfChunk pairs of a quad mesh first-uses about 2 kPfChunk elements; a run much longer than that means
-    // the numbering scatters them (prefetching the hull would read far more than is used): no prefetch for this chunk
+    // a chunk of kPfChunk node pairs first-uses about 2 kPfChunk elements; a run much longer than that means the
+    // numbering scatters them (prefetching the hull would read far more than is used): no prefetch of this run
     if (hi[c] >= lo[c] && hi[c] - lo[c] + 1 <= 8 * kPfChunk) t = make_int2(lo[c], hi[c] - lo[c] + 1);
     tab[c] = t;
   }
 }
+}  // namespace
+
+// Build the prefetch table of a plan from its node records (quads: NodeRec, 4 incidences, pair id e*16+..; triangles:
+// TriaRec, 10 incidences, e*9+..).
+template <class REC, int NINC, int DIV>
+static int build_pf_table(const pf3_plan* pl, const REC* rec, int64_t ne, cudaStream_t st, int64_t* launches) {
+  const int64_t npairs = (pl->nown + 1) / 2;
+  const int64_t nchunks = (npairs + kPfChunk - 1) / kPfChunk;
+  if (nchunks <= 4 * kPfAhead || npairs >= (int64_t(1) << 31) || ne <= 0) return PF3_OK;   // too small to matter
+  const int64_t nslots = nchunks * kPfRuns;
+  int *d_first = nullptr, *d_lo = nullptr, *d_hi = nullptr;
+  PF3_CUDA(cudaMalloc((void**)&d_first, size_t(ne) * sizeof(int)));
+  PF3_CUDA(cudaMalloc((void**)&d_lo, size_t(nslots) * sizeof(int)));
+  PF3_CUDA(cudaMalloc((void**)&d_hi, size_t(nslots) * sizeof(int)));
+  PF3_CUDA(cudaMalloc((void**)&pl->d_pftab, size_t(nslots) * sizeof(int2)));
+  PF3_CUDA(cudaMemsetAsync(d_first, 0x7f, size_t(ne) * sizeof(int), st));   // 0x7f7f7f7f: "never" (> any pair)
+  PF3_CUDA(cudaMemsetAsync(d_lo, 0x7f, size_t(nslots) * sizeof(int), st));
+  PF3_CUDA(cudaMemsetAsync(d_hi, 0xff, size_t(nslots) * sizeof(int), st));    // -1
+  k_pf_first_use<REC, NINC, DIV><<<grid_for(pl->nown * pl->rmax), 256, 0, st>>>(rec, pl->nown * pl->rmax, pl->rmax, d_first);
+  k_pf_ranges<<<grid_for(ne), 256, 0, st>>>(d_first, ne, (ne + kPfRuns - 1) / kPfRuns, d_lo, d_hi);
+  k_pf_table<<<grid_for(nslots), 256, 0, st>>>(d_lo, d_hi, nslots, pl->d_pftab);
+  *launches += 3;
+  PF3_CUDA(cudaGetLastError());
+  PF3_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_first);
+  cudaFree(d_lo);
+  cudaFree(d_hi);
+  pl->pf_nchunks = nchunks;
+  return PF3_OK;
+}
+
+namespace {
 __global__ void k_node_records(const int64_t* __restrict__ brow_ptr, const int64_t* __restrict__ inc_ptr,
                                const int64_t* __restrict__ inc_pair0, const int32_t* __restrict__ slot, int64_t nown,
                                int rmax, NodeRec* __restrict__ out) {
@@ -1439,8 +1473,12 @@ int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int6
                                                                   pl->d_slot, pl->nown, pl->rmax, pl->d_triarec);
     *launches += 2;
     PF3_CUDA(cudaGetLastError());
+    int rc = build_pf_table<TriaRec, 10, 9>(pl, pl->d_triarec, G.ne, st, launches);
+    if (rc) return rc;
   }
   F->triarec = pl->d_triarec;
+  F->pftab = pl->d_pftab;
+  F->pf_nchunks = pl->pf_nchunks;
   F->rmax = pl->rmax;
   F->brow_ptr = pl->d_brow_ptr;
   F->inc_ptr = pl->d_inc_ptr;
@@ -1473,29 +1511,8 @@ int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st,
                                                                   pl->d_slot, pl->nown, pl->rmax, pl->d_noderec);
     *launches += 2;
     PF3_CUDA(cudaGetLastError());
-    // L2 prefetch table (only worth it when there are several chunks ahead to prefetch)
-    const int64_t npairs = (pl->nown + 1) / 2;
-    const int64_t nchunks = (npairs + kPfChunk - 1) / kPfChunk;
-    if (nchunks > 4 * kPfAhead && npairs < (int64_t(1) << 31)) {
-      int *d_first = nullptr, *d_lo = nullptr, *d_hi = nullptr;
-      PF3_CUDA(cudaMalloc((void**)&d_first, size_t(G.ne) * sizeof(int)));
-      PF3_CUDA(cudaMalloc((void**)&d_lo, size_t(nchunks) * sizeof(int)));
-      PF3_CUDA(cudaMalloc((void**)&d_hi, size_t(nchunks) * sizeof(int)));
-      PF3_CUDA(cudaMalloc((void**)&pl->d_pftab, size_t(nchunks) * sizeof(int2)));
-      PF3_CUDA(cudaMemsetAsync(d_first, 0x7f, size_t(G.ne) * sizeof(int), st));   // 0x7f7f7f7f: "never" (> any pair)
-      PF3_CUDA(cudaMemsetAsync(d_lo, 0x7f, size_t(nchunks) * sizeof(int), st));
-      PF3_CUDA(cudaMemsetAsync(d_hi, 0xff, size_t(nchunks) * sizeof(int), st));    // -1
-      k_pf_first_use<<<grid_for(pl->nown * pl->rmax), 256, 0, st>>>(pl->d_noderec, pl->nown * pl->rmax, pl->rmax, d_first);
-      k_pf_ranges<<<grid_for(G.ne), 256, 0, st>>>(d_first, G.ne, d_lo, d_hi);
-      k_pf_table<<<grid_for(nchunks), 256, 0, st>>>(d_lo, d_hi, nchunks, pl->d_pftab);
-      *launches += 3;
-      PF3_CUDA(cudaGetLastError());
-      PF3_CUDA(cudaStreamSynchronize(st));
-      cudaFree(d_first);
-      cudaFree(d_lo);
-      cudaFree(d_hi);
-      pl->pf_nchunks = nchunks;
-    }
+    int rc = build_pf_table<NodeRec, 4, 16>(pl, pl->d_noderec, G.ne, st, launches);
+    if (rc) return rc;
   }
   F->noderec = pl->d_noderec;
   F->pftab = pl->d_pftab;

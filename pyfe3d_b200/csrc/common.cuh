@@ -113,16 +113,49 @@ struct FusedArgs {
   int zero_empty;                         // multi-group plans: zero the rows of nodes this group does not touch
   int64_t pair_first;                     // quads: this launch covers node pairs [pair_first, pair_first + pair_count)
   int64_t pair_count;                     //        (pair_count == 0: all pairs) -- pf3_eval_assemble_host's pipeline
-  const int2* __restrict__ pftab;         // quads: L2 prefetch table (see kPfChunk), nullptr: no prefetch
+  const int2* __restrict__ pftab;         // L2 prefetch table [pf_nchunks][kPfRuns] (see kPfChunk), nullptr: no prefetch
   int64_t pf_nchunks;
 };
 
-// L2 prefetch table of the fused quad kernel (quad_fused.cu): the node pairs are cut into chunks of kPfChunk; entry c
-// holds the contiguous run of element records that are used FIRST by a pair of chunk c (x = first element, y = count;
-// y = 0: no usable run).  The CTA of the first pair of chunk c issues bulk L2 prefetches for the node records and the
-// element records of chunk c + kPfAhead.
+// L2 prefetch table of the fused shell kernels (quad_fused.cu, tria_fused.cu): the node pairs are cut into chunks of
+// kPfChunk; entry c holds kPfRuns contiguous runs of element records that are used FIRST by a node of chunk c, one per
+// quarter of the element range (x = first element, y = count; y = 0: none, or too scattered to be worth reading) --
+// structured meshes first-use one run per chunk, meshes built from several structured parts (config 4: the second
+// triangle of every cell is numbered ne/2 later) one run per part.  The CTA of the first node of chunk c issues bulk L2
+// prefetches for the node records and those element records of chunk c + kPfAhead.
+constexpr int kPfRuns = 4;
 constexpr int kPfChunk = 512;
-constexpr int kPfAhead = 8;
+constexpr int kPfAhead = 8;   // (4, 8 and 16 chunks ahead measure the same, 32 slightly worse)
+// Halving the node records to 32 bytes (per-incidence slot lists, expanded into gmap by the kernel) was measured and
+// rejected: 10.88 ms against 10.75 for these 64-byte records on the same box -- with the bulk prefetch in place their
+// DRAM reads are already batched, and the expansion sits on the critical path of every CTA.
+
+#ifndef PF3_L2_HINTS
+#define PF3_L2_HINTS 1   // stores of the fused kernels carry an L2 evict-first policy
+#endif
+// L2 evict-first policy for everything the fused kernels write: their output (60 GB per step for 4 M Quad4) streams
+// through the L2 and is never read again, while the element records are re-read by up to three later CTAs and the prefetched records must survive until
+// their CTAs run.  (Measured with scripts/micro/k2_stream_reads.cu: a DRAM read among the writes costs ~12x its bytes.)
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void stg_stream(double2* p, double2 v, uint64_t pol) {
+#if PF3_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void stg_stream(double* p, double v, uint64_t pol) {
+#if PF3_L2_HINTS
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+
 
 struct Mat3 {
   double a[3][3];

@@ -37,9 +37,6 @@ constexpr double kGpF = 0.5773502691896257645092;
 #endif
 constexpr int kFusedWarps = PF3_FUSED_WARPS;
 
-#ifndef PF3_L2_HINTS
-#define PF3_L2_HINTS 1   // stores carry an L2 evict-first policy (nothing written here is read again by this step)
-#endif
 #ifndef PF3_L2_PREFETCH
 #define PF3_L2_PREFETCH 1   // bulk L2 prefetch of the node / element records kPfAhead chunks of node pairs ahead
 #endif
@@ -177,29 +174,6 @@ struct SlabShape {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-// L2 evict-first policy for everything this kernel writes: 60 GB per step stream through the L2 and are never read
-// again, while the element records are re-read by up to three later CTAs and the prefetched records must survive until
-// their CTAs run.  (Measured with scripts/micro/k2_stream_reads.cu: a DRAM read among the writes costs ~12x its bytes.)
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void stg_stream(double2* p, double2 v, uint64_t pol) {
-#if PF3_L2_HINTS
-  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
-#else
-  *p = v;
-#endif
-}
-__device__ __forceinline__ void stg_stream(double* p, double v, uint64_t pol) {
-#if PF3_L2_HINTS
-  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
-#else
-  *p = v;
-#endif
-}
 
 // Lanes have written their block into slab (lane>>2).  Ship the slabs to the COO array and reduce the (up to)
 // 4 incidences of each half-warp's node into its CSR rows in the fixed order k = 0..3.
@@ -490,10 +464,12 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       const char* q = reinterpret_cast<const char*>(F.noderec + n0 * rmax);
       for (int64_t left = nn * rmax * int64_t(sizeof(NodeRec)); left > 0; left -= kPiece, q += kPiece)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(unsigned(min(left, int64_t(kPiece)))) : "memory");
-      const int2 t = F.pftab[c];
-      q = reinterpret_cast<const char*>(rec + int64_t(t.x) * rstride);
-      for (int64_t left = int64_t(t.y) * rstride * 8; left > 0; left -= kPiece, q += kPiece)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(unsigned(min(left, int64_t(kPiece)))) : "memory");
+      for (int run = 0; run < kPfRuns; ++run) {
+        const int2 t = F.pftab[c * kPfRuns + run];
+        q = reinterpret_cast<const char*>(rec + int64_t(t.x) * rstride);
+        for (int64_t left = int64_t(t.y) * rstride * 8; left > 0; left -= kPiece, q += kPiece)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(unsigned(min(left, int64_t(kPiece)))) : "memory");
+      }
     }
   }
 #endif

@@ -135,16 +135,22 @@ __device__ __forceinline__ void tstage_wait() {
 template <int NR, int CNT>
 __device__ __forceinline__ void tria_emit(const double* st, const TriaRec* nr, double* __restrict__ coo,
                                           int64_t slab_base, bool act, int b, double* __restrict__ csr,
-                                          int64_t csr_base, int nb, int v, bool first_round, int lane) {
+                                          int64_t csr_base, int nb, int v, bool first_round, int lane, uint64_t pol) {
   constexpr int kSlab = TSlab<NR, CNT>::kSlab, kLd = TSlab<NR, CNT>::kLd;
   if constexpr (TSlab<NR, CNT>::kBulk) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (coo != nullptr && act && b == 0) {
       const uint32_t src = smem_u32t(st + (lane / 3) * kLd);
+#if PF3_L2_HINTS
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(coo + slab_base),
+                   "r"(src), "r"(kSlab * 8), "l"(pol)
+                   : "memory");
+#else
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(coo + slab_base), "r"(src),
                    "r"(kSlab * 8)
                    : "memory");
+#endif
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   } else {
@@ -153,7 +159,7 @@ __device__ __forceinline__ void tria_emit(const double* st, const TriaRec* nr, d
     for (int k2 = 0; k2 < v; ++k2) {
       const int64_t base = __shfl_sync(0xffffffffu, slab_base, 3 * k2);
       const bool on = __shfl_sync(0xffffffffu, int(act), 3 * k2) != 0;
-      if (coo != nullptr && on && lane < kSlab) coo[base + lane] = st[k2 * kLd + lane];
+      if (coo != nullptr && on && lane < kSlab) stg_stream(coo + base + lane, st[k2 * kLd + lane], pol);
     }
   }
   if (nb > 0 && csr != nullptr) {
@@ -187,7 +193,7 @@ __device__ __forceinline__ void tria_emit(const double* st, const TriaRec* nr, d
             sum[d].x += t.x;
             sum[d].y += t.y;
           }
-          *o = sum[d];
+          stg_stream(o, sum[d], pol);
         }
       }
     } else {
@@ -209,7 +215,8 @@ __device__ __forceinline__ void tria_emit(const double* st, const TriaRec* nr, d
 #pragma unroll
         for (int d = 0; d < NR; ++d) {
           double* o = out + d * w + x;
-          if (first_round) *o = sum[d]; else *o += sum[d];
+          if (!first_round) sum[d] += *o;
+          stg_stream(o, sum[d], pol);
         }
       }
     }
@@ -247,10 +254,29 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
   TriaRec* ring = reinterpret_cast<TriaRec*>(st + kTStage);
   double* erec = st + kTStage + kTRing * 16;
   const int k = lane / 3, b = lane - 3 * k;     // lanes 30, 31: k = 10, never active
+  const uint64_t pol = l2_evict_first_policy();
   const int64_t n0 = (int64_t(blockIdx.x) * kTWarps + warp) * kTChunk;
   if (n0 >= F.nown) return;
   const int rmax = F.rmax;
   const int nitems = int(min(int64_t(kTChunk), F.nown - n0)) * rmax;   // items j = (node n0 + j / rmax, round j % rmax)
+  // bulk L2 prefetch of the node records and first-use element records kPfAhead chunks ahead (see quad_fused.cu)
+  if (F.pftab != nullptr && F.triarec != nullptr && lane == 0 && (n0 % (2 * kPfChunk)) < kTChunk) {
+    const int64_t c = n0 / (2 * kPfChunk) + kPfAhead;
+    if (c < F.pf_nchunks) {
+      constexpr unsigned kPiece = 32768;
+      const int64_t nn0 = c * kPfChunk * 2;
+      const int64_t nn = min(int64_t(2 * kPfChunk), F.nown - nn0);
+      const char* q = reinterpret_cast<const char*>(F.triarec + nn0 * rmax);
+      for (int64_t left = nn * rmax * int64_t(sizeof(TriaRec)); left > 0; left -= kPiece, q += kPiece)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(unsigned(min(left, int64_t(kPiece)))) : "memory");
+      for (int run = 0; run < kPfRuns; ++run) {
+        const int2 t = F.pftab[c * kPfRuns + run];
+        q = reinterpret_cast<const char*>(rec + int64_t(t.x) * rstride);
+        for (int64_t left = int64_t(t.y) * rstride * 8; left > 0; left -= kPiece, q += kPiece)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(unsigned(min(left, int64_t(kPiece)))) : "memory");
+      }
+    }
+  }
 
   auto rec_fetch = [&](int j) {
     if (j < nitems && F.triarec != nullptr) {
@@ -342,7 +368,7 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
           for (int jj = 0; jj < 3; ++jj) sl[i * 9 + jj] = (R.a[i][2] * R.a[jj][2]) * ge;
       }
       tria_emit<3, 3>(st, nr, A.kgv ? A.kgv + A.kg_k0 : nullptr, e * 81 + a * 27, act, b, F.csr_kg, b0 * 9, nb, v,
-                      first, lane);
+                      first, lane, pol);
     }
 
     // ---------------- M : H_ab * (T6 m_l T6^T) (tria3r.pyx:4063 ff.)
@@ -379,7 +405,7 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
             sl[(3 + i) * 15 + 4] = h * Mi.rr[i][2];
           }
         }
-        tria_emit<6, 5>(st, nr, coo, e * 270 + a * 90, act, b, F.csr_m, b0 * 30, nb, v, first, lane);
+        tria_emit<6, 5>(st, nr, coo, e * 270 + a * 90, act, b, F.csr_m, b0 * 30, nb, v, first, lane, pol);
       } else {
         if (stager) {
           double* sl = st + k * TSlab<6, 3>::kLd + b * 3;
@@ -391,7 +417,7 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
               sl[(3 + i) * 9 + jj] = h * Mi.rr[i][jj];
             }
         }
-        tria_emit<6, 3>(st, nr, coo, e * 270 + a * 54, act, b, F.csr_m, b0 * 18, nb, v, first, lane);
+        tria_emit<6, 3>(st, nr, coo, e * 270 + a * 54, act, b, F.csr_m, b0 * 18, nb, v, first, lane, pol);
       }
     }
 
@@ -447,7 +473,7 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
         }
       }
       tria_emit<6, 6>(st, nr, A.kc0v ? A.kc0v + A.kc0_k0 : nullptr, e * 324 + a * 108, act, b, F.csr_kc0, b0 * 36, nb, v,
-                      first, lane);
+                      first, lane, pol);
     }
   }
   tstage_wait();   // the bulk copies read this CTA's shared memory: they must have done so before it retires
