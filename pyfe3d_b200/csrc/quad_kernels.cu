@@ -109,9 +109,15 @@ struct QuadExtra {       // Quad4R only
 
 // ONLY = 0: any subset of the outputs.  ONLY = PF3_FINT: the instantiation for update_fint / update_probe_finte / state
 // calls, which contains no matrix code (248 registers and no spills against 254 + 144 bytes of spills; forcing three
-// CTAs per SM costs 1.1 kB of spills, so occupancy stays at 8 warps per SM).
+// CTAs per SM costs 1.1 kB of spills, so occupancy stays at 8 warps per SM).  A four-lanes-per-element variant (lane =
+// Gauss point during the integration, = node afterwards, 168 registers, no staging) was measured and rejected: every
+// lane has to form the frame and the laminate coefficients itself, and update_fint of 4 M Quad4 took 1.78 ms against
+// 1.37 ms with this kernel.
+#ifndef PF3_FINT_CTAS
+#define PF3_FINT_CTAS 2
+#endif
 template <int KIND, int ONLY>
-__global__ void __launch_bounds__(kThreads, ONLY ? 2 : 1) quad_eval_kernel(const EvalArgs A) {
+__global__ void __launch_bounds__(kThreads, ONLY ? PF3_FINT_CTAS : 1) quad_eval_kernel(const EvalArgs A) {
   const int what = ONLY ? (A.what & ONLY) : A.what;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -546,219 +552,6 @@ __global__ void __launch_bounds__(kThreads, ONLY ? 2 : 1) quad_eval_kernel(const
   }
 }
 
-// update_fint / update_probe_finte for a whole batch (quad4.pyx:1316-1362, :1174-1201; quad4r.pyx:4620-4679, :549-1143)
-// with FOUR LANES PER ELEMENT: lane q of an element's quad owns Gauss point q of the 2x2 rule during the integration
-// and node q afterwards.  Every lane forms the frame, the local displacements and the laminate coefficients itself
-// (the same addresses in four neighbouring lanes: one memory transaction), integrates its own Gauss point into a partial
-// 24-vector, and a two-step exchange inside the quad (xor 2, xor 1: 12 + 6 doubles) leaves every lane with the six
-// totals of ITS node, to which it adds the centre-point terms of that node.  Each lane then writes 48 contiguous
-// bytes: an element's 24 doubles are contiguous, a warp's 8 elements too -- no shared-memory staging.  The
-// thread-per-element instantiation of quad_eval_kernel needs 248 registers (8 warps per SM) for the same work.
-template <int KIND>
-__global__ void __launch_bounds__(128, 3) quad_fint_kernel(const EvalArgs A) {
-  const int lane = threadIdx.x & 31, q = lane & 3;
-  const int64_t e_raw = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 2;
-  const bool live = e_raw < A.ne;
-  const int64_t e = live ? e_raw : A.ne - 1;
-  double ue[24];
-  ShellGeom<4> g;
-  shell_geom<4>(A, e, g, ue);
-  ShellCoef c;
-  shell_coef<4>(A, e, g, c);
-  const Mat3& R = g.R;
-  // own Gauss point q = 2 ixi + ieta and the centre
-  const double xi = (q & 2) ? kGp : -kGp, eta = (q & 1) ? kGp : -kGp;
-  double wx[4], wy[4], dJ;
-  jac_at(g.X, g.Y, xi, eta, wx, wy, dJ);
-  const double idJ = 1. / dJ;
-  double w0x[4], w0y[4], dJ0;
-  jac_at(g.X, g.Y, 0., 0., w0x, w0y, dJ0);
-  const double i0 = 1. / dJ0, w0 = 4. * dJ0;
-  double N0x[4], N0y[4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    N0x[a] = w0x[a] * i0;
-    N0y[a] = w0y[a] * i0;
-  }
-  double kd = 1., hgq[5] = {0., 0., 0., 0., 0.};   // Quad4 ignores K6ROT (quad4.pyx:1069-1073)
-  if (KIND == PF3_QUAD4R) {
-    double K6ROT = 100., hgf[5] = {1., 1., 1., 1., 1.};
-    if (A.eparam != nullptr) {
-      const double* ep = A.eparam + e * PF3_EPARAM_STRIDE;
-      K6ROT = ep[0];
-#pragma unroll
-      for (int d = 0; d < 5; ++d) hgf[d] = ep[2 + d];
-    }
-    kd = 1e-6 * K6ROT * c.A[5];
-    const double A11 = c.A[0], A12 = c.A[1], A16 = c.A[2], A22 = c.A[3], A26 = c.A[4], A66 = c.A[5];
-    const double den = -A11 * A22 * A66 + A11 * A26 * A26 + A12 * A12 * A66 - 2 * A12 * A16 * A26 + A16 * A16 * A22;
-    const double a11 = (-A22 * A66 + A26 * A26) / den;
-    const double a22 = (-A11 * A66 + A16 * A16) / den;
-    const double E1eq = 1. / (c.h * a11), E2eq = 1. / (c.h * a22);
-    const double dd = 1.0 + 1.0 / g.area;
-    const double Eu = hgf[0] * 0.1 * E1eq * c.h / dd;
-    const double Ev = hgf[1] * 0.1 * E2eq * c.h / dd;
-    const double Erx = hgf[3] * 0.1 * E2eq * c.h * c.h * c.h / dd;
-    const double Ery = hgf[4] * 0.1 * E1eq * c.h * c.h * c.h / dd;
-    const double Ew = hgf[2] * 0.5 * (Erx + Ery);
-    const double j11 = 2. * (N0x[2] + N0x[1]), j12 = 2. * (N0x[2] - N0x[1]);
-    const double j21 = 2. * (N0y[2] + N0y[1]), j22 = 2. * (N0y[2] - N0y[1]);
-    const double gam = 0.25 * (j11 * j22 + j12 * j21);
-    const double wg2 = w0 * gam * gam;
-    hgq[0] = wg2 * Eu;
-    hgq[1] = wg2 * Ev;
-    hgq[2] = wg2 * Ew;
-    hgq[3] = wg2 * Erx;
-    hgq[4] = wg2 * Ery;
-  }
-  const bool thick = (KIND == PF3_QUAD4) && (c.h / sqrt(g.area) >= 1.);
-
-  // ---- this lane's Gauss point: partial forces on all four nodes
-  double f[24];
-#pragma unroll
-  for (int i = 0; i < 24; ++i) f[i] = 0.;
-  double nx[4], ny[4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    nx[a] = wx[a] * idJ;
-    ny[a] = wy[a] * idJ;
-  }
-  // stress resultants s = [A B; B D] eps from gradients (gx, gy); returns them in s[6]
-  auto resultants = [&](const double* gx, const double* gy, double* s) {
-    double eps[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      eps[0] += gx[a] * ue[6 * a];
-      eps[1] += gy[a] * ue[6 * a + 1];
-      eps[2] += gy[a] * ue[6 * a] + gx[a] * ue[6 * a + 1];
-      eps[3] += gx[a] * ue[6 * a + 4];
-      eps[4] -= gy[a] * ue[6 * a + 3];
-      eps[5] += gy[a] * ue[6 * a + 4] - gx[a] * ue[6 * a + 3];
-    }
-    s[0] = c.A[0] * eps[0] + c.A[1] * eps[1] + c.A[2] * eps[2] + c.B[0] * eps[3] + c.B[1] * eps[4] + c.B[2] * eps[5];
-    s[1] = c.A[1] * eps[0] + c.A[3] * eps[1] + c.A[4] * eps[2] + c.B[1] * eps[3] + c.B[3] * eps[4] + c.B[4] * eps[5];
-    s[2] = c.A[2] * eps[0] + c.A[4] * eps[1] + c.A[5] * eps[2] + c.B[2] * eps[3] + c.B[4] * eps[4] + c.B[5] * eps[5];
-    s[3] = c.B[0] * eps[0] + c.B[1] * eps[1] + c.B[2] * eps[2] + c.D[0] * eps[3] + c.D[1] * eps[4] + c.D[2] * eps[5];
-    s[4] = c.B[1] * eps[0] + c.B[3] * eps[1] + c.B[4] * eps[2] + c.D[1] * eps[3] + c.D[3] * eps[4] + c.D[4] * eps[5];
-    s[5] = c.B[2] * eps[0] + c.B[4] * eps[1] + c.B[5] * eps[2] + c.D[2] * eps[3] + c.D[4] * eps[4] + c.D[5] * eps[5];
-  };
-  if (KIND == PF3_QUAD4) {   // constitutive part at 2x2 Gauss; Quad4R integrates it at the centre (per node, below)
-    double s[6];
-    resultants(nx, ny, s);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      f[6 * a + 0] += wx[a] * s[0] + wy[a] * s[2];
-      f[6 * a + 1] += wy[a] * s[1] + wx[a] * s[2];
-      f[6 * a + 3] -= wy[a] * s[4] + wx[a] * s[5];
-      f[6 * a + 4] += wx[a] * s[3] + wy[a] * s[5];
-    }
-  }
-  {
-    double th = 0.;   // drilling penalty, 2x2 Gauss in both kinds
-#pragma unroll
-    for (int a = 0; a < 4; ++a) th += 0.5 * ny[a] * ue[6 * a] - 0.5 * nx[a] * ue[6 * a + 1] + kNgp[q][a] * ue[6 * a + 5];
-    th *= kd;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      f[6 * a + 0] += 0.5 * wy[a] * th;
-      f[6 * a + 1] -= 0.5 * wx[a] * th;
-      f[6 * a + 5] += dJ * kNgp[q][a] * th;
-    }
-  }
-  if (thick) {
-    double gyz = 0., gxz = 0.;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      gyz += ny[a] * ue[6 * a + 2];
-      gxz += nx[a] * ue[6 * a + 2];
-    }
-    const double ty = c.E44 * gyz + c.E45 * gxz, tx = c.E45 * gyz + c.E55 * gxz;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) f[6 * a + 2] += wy[a] * ty + wx[a] * tx;
-  }
-
-  // ---- exchange inside the quad: lane q ends with the totals of node q
-  double h12[12];
-  {
-    const bool up = (q & 2) != 0;   // lanes 2,3 keep nodes 2,3
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const double keep = up ? f[12 + i] : f[i];
-      const double send = up ? f[i] : f[12 + i];
-      h12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-  }
-  double fn[6];
-  {
-    const bool up = (q & 1) != 0;   // of its pair of nodes, the odd lane keeps the upper one
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const double keep = up ? h12[6 + i] : h12[i];
-      const double send = up ? h12[i] : h12[6 + i];
-      fn[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-  }
-
-  // ---- centre-point terms of node q
-  double n0x = N0x[0], n0y = N0y[0];
-#pragma unroll
-  for (int a = 1; a < 4; ++a) {
-    n0x = (q == a) ? N0x[a] : n0x;
-    n0y = (q == a) ? N0y[a] : n0y;
-  }
-  if (KIND == PF3_QUAD4R) {
-    double s[6];
-    resultants(N0x, N0y, s);
-    const double wxq = w0 * n0x, wyq = w0 * n0y;
-    fn[0] += wxq * s[0] + wyq * s[2];
-    fn[1] += wyq * s[1] + wxq * s[2];
-    fn[3] -= wyq * s[4] + wxq * s[5];
-    fn[4] += wxq * s[3] + wyq * s[5];
-    const double sgn = (q & 1) ? -1. : 1.;   // hourglass vector (+ - + -), quad4r.pyx:3116
-#pragma unroll
-    for (int d = 0; d < 5; ++d) fn[d] += sgn * hgq[d] * (ue[d] - ue[6 + d] + ue[12 + d] - ue[18 + d]);
-  }
-  {
-    double gyzg = 0., gxzg = 0., ry = 0., rx = 0.;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      gyzg += N0y[a] * ue[6 * a + 2];
-      gxzg += N0x[a] * ue[6 * a + 2];
-      rx += ue[6 * a + 3];
-      ry += ue[6 * a + 4];
-    }
-    const double gyz = gyzg - 0.25 * rx, gxz = gxzg + 0.25 * ry;
-    const double ty = w0 * (c.E44 * gyz + c.E45 * gxz), tx = w0 * (c.E45 * gyz + c.E55 * gxz);
-    double tyw = ty, txw = tx;
-    if (thick) {  // minus the gradient-gradient part already integrated at 2x2 (quad4.pyx:1152-1171)
-      tyw -= w0 * (c.E44 * gyzg + c.E45 * gxzg);
-      txw -= w0 * (c.E45 * gyzg + c.E55 * gxzg);
-    }
-    fn[2] += n0y * tyw + n0x * txw;
-    fn[3] -= 0.25 * ty;
-    fn[4] += 0.25 * tx;
-  }
-  if (!live) return;
-  if (A.finte != nullptr) {
-    double2* o = reinterpret_cast<double2*>(A.finte + e * 24 + 6 * q);
-    o[0] = make_double2(fn[0], fn[1]);
-    o[1] = make_double2(fn[2], fn[3]);
-    o[2] = make_double2(fn[4], fn[5]);
-  }
-  if (A.fe != nullptr) {
-    double gl[6];
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        gl[3 * t + i] = R.a[i][0] * fn[3 * t] + R.a[i][1] * fn[3 * t + 1] + R.a[i][2] * fn[3 * t + 2];
-    double2* o = reinterpret_cast<double2*>(A.fe + e * 24 + 6 * q);
-    o[0] = make_double2(gl[0], gl[1]);
-    o[1] = make_double2(gl[2], gl[3]);
-    o[2] = make_double2(gl[4], gl[5]);
-  }
-}
-
 // Piston-theory aerodynamic matrices (update_KA_beta quad4.pyx:9491, update_KA_gamma :10312, update_CA :11115;
 // Quad4R: quad4r.pyx:12789, :13605, :14403).  One element per thread.  All three are a 4x4 scalar matrix over the
 // node pairs times z z^T on the translations (z = third column of R), 2x2 Gauss with wij = 1:
@@ -881,14 +674,6 @@ cudaError_t launch_quad(int kind, const EvalArgs& A, cudaStream_t st) {
     cudaFuncSetAttribute(quad_eval_kernel<PF3_QUAD4R, PF3_FINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kStageBytes));
   }
   const bool fint_only = (A.what & ~PF3_FINT) == 0;   // update_fint / update_probe_finte / state: no matrix code
-  if (A.what == PF3_FINT && A.state == nullptr && A.state_out == nullptr && A.u != nullptr &&
-      ((((uintptr_t)A.finte) | ((uintptr_t)A.fe)) & 15) == 0) {
-    // four lanes per element (quad_fint_kernel)
-    const unsigned g4 = unsigned((A.ne * 4 + 127) / 128);
-    if (kind == PF3_QUAD4) quad_fint_kernel<PF3_QUAD4><<<g4, 128, 0, st>>>(A);
-    else quad_fint_kernel<PF3_QUAD4R><<<g4, 128, 0, st>>>(A);
-    return cudaGetLastError();
-  }
   if (kind == PF3_QUAD4) {
     if (fint_only) quad_eval_kernel<PF3_QUAD4, PF3_FINT><<<grid, kThreads, kStageBytes, st>>>(A);
     else quad_eval_kernel<PF3_QUAD4, 0><<<grid, kThreads, kStageBytes, st>>>(A);

@@ -98,6 +98,58 @@ def run_spmv(side):
                       "algorithmic_GBps": alg_csr / ms_csr / 1e6, "frac_of_6538.9": alg_csr / ms_csr / 1e6 / 6538.9}))
 
 
+def run_cg(side, iters=64, host_side=400):
+    """one iteration of the native Jacobi-CG (pf3_plan_cg) on KC0 of the north-star mesh against its
+    roofline (block SpMV: 8 B per nonzero + 8 B per 6x6 block; the three vector kernels: 13 vector passes), and scipy's
+    cg on the host cores on a smaller plate of the same mesh (per-iteration time scaled by the nonzero count)."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import cg
+    from pyfe3d_b200.solve import plan_cg_native
+    case, free, f, normal = meshes.static_case(side)
+    b = meshes.batch_from_case(case)
+    nn = case["ndof"] // 6
+    plan = AssemblyPlan("KC0", nn, [b])
+    _, csr = plan.evaluate_assemble(KC0=True, write_coo=False)
+    vals = csr["KC0"]
+    free_t = torch.as_tensor(free.astype(np.uint8)).cuda()
+    ft = torch.as_tensor(f).cuda()
+    plan_cg_native(plan, vals, ft, free=free_t, rtol=0., maxiter=8, graph=False)          # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, it, status, res, bn = plan_cg_native(plan, vals, ft, free=free_t, rtol=0., maxiter=iters, graph=False, check_every=iters)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n = 6 * nn
+    alg = plan.nnz * 8 + plan._plan.nblocks * 8 + 2 * n * 8 + 13 * n * 8
+    ms_it = dt / it * 1e3
+    out = {"config": "native CG iteration, KC0 of %dx%d Quad4 (%d dofs, %d nnz), clamped edges" % (side, side, n, plan.nnz),
+           "iterations_timed": it, "ms_per_iteration": ms_it, "algorithmic_bytes_per_iteration": alg,
+           "achieved_GBps": alg / ms_it / 1e6, "frac_of_6538.9": alg / ms_it / 1e6 / 6538.9}
+    nnz_dev = plan.nnz
+    del plan, vals, csr, b
+    torch.cuda.empty_cache()
+    # host: scipy cg on the diagonally scaled Kuu of a host_side x host_side plate of the same mesh
+    case, free, f, normal = meshes.static_case(host_side)
+    b = meshes.batch_from_case(case)
+    plan = AssemblyPlan("KC0", case["ndof"] // 6, [b])
+    _, csr = plan.evaluate_assemble(KC0=True, write_coo=False)
+    K = plan.to_scipy(csr["KC0"]).tocsr()
+    bu = free.astype(bool)
+    Kuu = K[bu, :][:, bu]
+    dis = 1.0 / np.sqrt(np.maximum(Kuu.diagonal(), 1e-30))
+    D = sp.diags(dis)
+    Ks = (D @ Kuu @ D).tocsr()
+    fs = D @ f[bu]
+    t0 = time.perf_counter()
+    cg(Ks, fs, rtol=0., atol=0., maxiter=iters)
+    dth = (time.perf_counter() - t0) / iters * 1e3
+    out["scipy_host_ms_per_iteration"] = dth
+    out["scipy_host_nnz"] = int(Ks.nnz)
+    out["scipy_host_ms_per_iteration_scaled_to_device_nnz"] = dth * nnz_dev / Ks.nnz
+    out["note"] = "host figure: scipy cg (1 thread SpMV) on the %dx%d plate; last field scales it by the nonzero count" % (host_side, host_side)
+    print(json.dumps(out))
+
+
 def run_mixed(side, nstiff=64):
     """Config 5 (per-GPU share): Quad4 skin + BeamC stiffeners in ONE matrix per KC0 / KG / M, plus update_fint.
     The groups have different masks for KG and M, so this is the two-pass path: one evaluation launch per group and
@@ -243,11 +295,17 @@ if __name__ == "__main__":
     if "--aero" in sys.argv:
         run_aero(200 if "--small" in sys.argv else 2000)
         sys.exit(0)
+    if "--cg" in sys.argv:
+        run_cg(100 if "--small" in sys.argv else 2000, host_side=50 if "--small" in sys.argv else 400)
+        sys.exit(0)
     if "--spmv" in sys.argv:
         run_spmv(200 if "--small" in sys.argv else 2000)
         sys.exit(0)
     small = "--small" in sys.argv
     f = 0.1 if small else 1.0
+    if "--config2" in sys.argv:
+        run("config2 BeamC arc 100k, KC0+M", meshes.arc_beamc(int(100001 * f)), ("KC0", "M0"), False)
+        sys.exit(0)
     if "--config3" in sys.argv:
         run("config3 Quad4R cylinder 1M, KC0+KG_given_stress", meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)),
             ("KC0", "KGs"), True)

@@ -176,10 +176,23 @@ int main() {
     printf("{\"ctas_per_sm\": %d, \"reads\": %d, \"dfma_per_lane\": %d, \"ahead\": %d, \"noderec_bytes_per_pair\": %d, \"erec_bytes\": %d, \"l2_hint\": %d, \"prefetch_chunk_pairs\": %d, \"ms\": %.3f, \"store_GBps\": %.1f, \"err\": %d}\n",
            ctas, reads, nfma, ahead, nrl * 16, erb, hint, chunkp, best, (coo + csr) / best / 1e6, int(cudaGetLastError()));
   };
-  for (int hint : {0, 1}) run(12, 0, 0, 0, 8, 256, hint, 64);
-  for (int hint : {0, 1, 2}) run(12, 1, 0, 0, 8, 256, hint, 64);
+  // 1. which reads cost what (12 CTAs/SM, no arithmetic)
+  for (int reads : {0, 3, 4, 1, 5, 2, 8}) run(12, reads, 0, 0, 8, 256, 0, 64);
+  // 2. occupancy
+  for (int reads : {1, 5}) run(16, reads, 0, 0, 8, 256, 0, 64);
+  // 3. per request or per byte?
+  for (int nrl : {4, 2}) run(12, 3, 0, 0, nrl, 256, 0, 64);
+  for (int erb : {192, 128, 64}) run(12, 4, 0, 0, 8, erb, 0, 64);
+  // 4. L2 policy on the stores, bulk prefetch in chunks
+  for (int hint : {1, 2}) run(12, 1, 0, 0, 8, 256, hint, 64);
   for (int hint : {0, 1})
     for (int chunkp : {64, 512, 2048})
       for (int ahead : {2048, 4096, 8192}) run(12, 7, 0, ahead, 8, 256, hint, chunkp);
+  // 5. with a dial of dependent arithmetic on top
+  for (int nf : {256, 1024}) {
+    run(12, 0, nf, 0, 8, 256, 0, 64);
+    run(12, 1, nf, 0, 8, 256, 0, 64);
+    run(12, 7, nf, 4096, 8, 256, 1, 512);
+  }
   return 0;
 }

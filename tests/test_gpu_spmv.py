@@ -136,3 +136,28 @@ def test_shift_invert_operator_reproduces_beam_frequencies():
     for i, k in enumerate(("omega1", "omega2", "omega3")):
         assert abs(om[i] - gold[k]) <= 1e-8 * gold[k], (k, om[i], gold[k])
     assert op.stats["solves"] > 0
+
+
+def test_spmv_csr_arbitrary_rows():
+    """pf3_spmv_csr on a CSR matrix with odd / empty / single-entry rows (the paired 16-byte path starts at the first
+    even position of a row and hands an odd first or last entry to single lanes)."""
+    import scipy.sparse as sp
+    import torch
+    from pyfe3d_b200.batch import spmv
+    rng = np.random.default_rng(21)
+    n = 777
+    A = sp.random(n, n, density=0.02, random_state=5, format="lil")
+    A[5, :] = 0.
+    A[6, :] = 0.
+    A[7, :] = 0.
+    A[7, 3] = 2.5                       # single entry
+    for r in (11, 12, 13):
+        A[r, rng.choice(n, size=65 + r, replace=False)] = rng.normal(size=65 + r)   # longer than one pass of the warp
+    A = A.tocsr()
+    A.sort_indices()
+    x = rng.normal(size=n)
+    y = spmv(torch.as_tensor(A.indptr.astype(np.int64)).cuda(), torch.as_tensor(A.indices.astype(np.int64)).cuda(),
+             torch.as_tensor(A.data).cuda(), torch.as_tensor(x).cuda()).cpu().numpy()
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1.)
+    assert y[5] == 0. and y[6] == 0. and y[7] == 2.5 * x[3]
