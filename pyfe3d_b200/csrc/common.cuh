@@ -124,6 +124,10 @@ struct FusedArgs {
 // triangle of every cell is numbered ne/2 later) one run per part.  The CTA of the first node of chunk c issues bulk L2
 // prefetches for the node records and those element records of chunk c + kPfAhead.
 constexpr int kPfRuns = 4;
+// Measured and rejected: a PRODUCER MODE without the record launch -- in block order every chunk preceded by the 40
+// one-warp producer CTAs (K1 for 32 elements each) of the chunk 8 chunks later, per-chunk completion flags, consumers
+// find the records in L2.  Parity-green, 10.82 ms against 10.48 ms for K1 + K2 on the same box: the producers' gathers
+// of conn / x / u are DRAM reads inside the write stream again, and their latency-bound warps hold K2's CTA slots.
 constexpr int kPfChunk = 512;
 constexpr int kPfAhead = 8;   // (4, 8 and 16 chunks ahead measure the same, 32 slightly worse)
 // Halving the node records to 32 bytes (per-incidence slot lists, expanded into gmap by the kernel) was measured and

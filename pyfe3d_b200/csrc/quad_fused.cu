@@ -59,20 +59,13 @@ __host__ __device__ constexpr int rec_ld(int stride) { return stride + ((stride 
 #ifndef PF3_K1_CTAS
 #define PF3_K1_CTAS 3
 #endif
+// The records of the 32 consecutive elements [e0, e0 + nvalid) by one warp: staged in shared memory (odd leading
+// dimension ld = stride + 1, 32 * ld doubles at `stage`) and written out as one contiguous run of nvalid x stride doubles.
 template <int KIND>
-__global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const EvalArgs A, double* __restrict__ rec, int stride,
-                                                                       int64_t e_begin, int64_t e_end) {
-  // records are staged per warp in shared memory (odd leading dimension) and written out as one contiguous
-  // run of 32 x stride doubles
-  extern __shared__ double k1_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // this launch covers elements [e_begin, e_end)
-  const int64_t e0 = e_begin + (int64_t(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
-  if (e0 >= e_end) return;
-  const int nvalid = int(min(int64_t(32), e_end - e0));
+__device__ __forceinline__ void record_warp(const EvalArgs& A, double* __restrict__ rec, int stride, int64_t e0, int nvalid,
+                                            double* stage, int lane) {
   const int64_t e = e0 + min(lane, nvalid - 1);
   const int ld = stride + 1;
-  double* stage = k1_smem + warp * 32 * ld;
   const bool kg_u = (A.what & PF3_KG) != 0;
   double ue[24];
   ShellGeom<4> g;
@@ -154,6 +147,17 @@ __global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const Eva
   } else {
     for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / stride) * ld + idx % stride];
   }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const EvalArgs A, double* __restrict__ rec, int stride,
+                                                                       int64_t e_begin, int64_t e_end) {
+  extern __shared__ double k1_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // this launch covers elements [e_begin, e_end)
+  const int64_t e0 = e_begin + (int64_t(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
+  if (e0 >= e_end) return;
+  record_warp<KIND>(A, rec, stride, e0, int(min(int64_t(32), e_end - e0)), k1_smem + warp * 32 * (stride + 1), lane);
 }
 
 // ------------------------------------------------------------------------------------------ K2
@@ -817,17 +821,17 @@ cudaError_t launch_k1(int kind, const EvalArgs& A, double* rec, int stride, int6
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases) {
   if (F.nown <= 0 || F.A.ne <= 0) return cudaSuccess;
   const int stride = fused_record_stride(F.A);
-  if (phases & 1) {
-    cudaError_t e1 = launch_k1(kind, F.A, rec, stride, 0, F.A.ne, 4, st, launches);
-    if (e1 != cudaSuccess) return e1;
-  }
-  if (!(phases & 2)) return cudaSuccess;
   // doubles written per element (COO + CSR share): the three-matrix north-star call is store-bound, smaller calls are
   // latency-bound and take the prefetching variant
   const int w = F.A.what;
   const int vol = ((w & PF3_KC0) ? 900 : 0) + ((w & (PF3_KG | PF3_KG_STRESS)) ? 225 : 0) + ((w & PF3_M) ? 750 : 0);
   const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
   const int chunk = (vol < 1400 && !mapped) ? kFChunkBig : 1;
+  if (phases & 1) {
+    cudaError_t e1 = launch_k1(kind, F.A, rec, stride, 0, F.A.ne, 4, st, launches);
+    if (e1 != cudaSuccess) return e1;
+  }
+  if (!(phases & 2)) return cudaSuccess;
   const size_t smem = fused_smem_bytes(stride, chunk);
   const int64_t npairs = F.pair_count ? F.pair_count : (F.nown + 1) / 2;
   const int64_t want = (npairs + int64_t(kFusedWarps) * chunk - 1) / (int64_t(kFusedWarps) * chunk);
