@@ -322,7 +322,6 @@ def measure_plate(torch, D, meshes, nx, ny, a_len, rank, world, dev, args, full)
                                   "host memory -> record + fused kernels -> D2H of the KC0/KG/M CSR value arrays into "
                                   "pinned host memory (pattern is static; the COO value arrays are written on the device "
                                   "as in the timed steps); d2h_gbs_per_rank names the limiter: the call is the PCIe copy"}
-            del outh
             # ---- the same step returning ONE TRIANGLE of each (symmetric) matrix: 5/9 of the bytes over PCIe.  Same
             # C ABI: H2D of x, u -> pf3_eval_assemble (device) -> pf3_csr_compact_fill(PF3_COMPACT_UPPER) per matrix
             # -> D2H of the compacted values.  Reported beside the headline, not instead of it: the default result of
@@ -333,9 +332,8 @@ def measure_plate(torch, D, meshes, nx, ny, a_len, rank, world, dev, args, full)
                 for m in mats:
                     (_, _, v), pats[m] = plan_compact(plans[m], csr[m], None, upper=True, want_indices=False)
                     up[m] = v
-                with numa_local(dev.index):
-                    for m in mats:
-                        uph[m] = torch.empty(up[m].numel(), dtype=torch.float64).pin_memory()
+                for m in mats:
+                    uph[m] = outh[m][:up[m].numel()]          # the pinned buffers of the full-matrix step, reused
                 d2h_up = sum(o.numel() * 8 for o in uph.values())
 
                 def upper_step():
@@ -358,7 +356,7 @@ def measure_plate(torch, D, meshes, nx, ny, a_len, rank, world, dev, args, full)
                     "what": "same step, only entries with col >= row of KC0/KG/M returned (scipy.sparse.triu layout, "
                             "PF3_COMPACT_UPPER); for consumers that take a symmetric half"}
                 del up, uph, pats
-            del xh, uh
+            del outh, xh, uh
         except RuntimeError as exc:   # e.g. pinned allocation refused
             res["e2e"] = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
     del plans, coos, csr, batch
