@@ -315,9 +315,17 @@ def measure_plate(torch, D, meshes, nx, ny, a_len, rank, world, dev, args, full)
             D.barrier()
             dt = D.reduce([time.perf_counter() - t0], "max")[0]
             per_rank = D.gather(d2h * args.e2e_steps / t_own / 1e9)
+            # the box's raw device->host rate for the same buffers (one plain copy of the KC0 values, nothing else
+            # running): what the end-to-end step is limited by
+            torch.cuda.synchronize()
+            t0r = time.perf_counter()
+            outh["KC0"].copy_(csr["KC0"], non_blocking=True)
+            torch.cuda.synchronize()
+            raw_gbs = outh["KC0"].numel() * 8 / (time.perf_counter() - t0r) / 1e9
             res["e2e"] = {"value": nx * ny * args.e2e_steps / dt, "unit": UNIT,
                           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "numa": numa,
                           "d2h_gbs_per_rank": [round(v, 2) for v in per_rank],
+                          "d2h_gbs_raw_copy_rank0": round(raw_gbs, 2),
                           "what": "one pf3_eval_assemble_host call per step (C ABI, host buffers): H2D of x,u from pinned "
                                   "host memory -> record + fused kernels -> D2H of the KC0/KG/M CSR value arrays into "
                                   "pinned host memory (pattern is static; the COO value arrays are written on the device "

@@ -51,7 +51,7 @@ int64_t plan_group_ne(const pf3_plan* pl);
 int plan_fused_args(const pf3_plan* pl, int kind, FusedArgs* F, cudaStream_t st, int64_t* launches);
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches,
                               int phases);
-int fused_record_stride(const EvalArgs& A);
+int fused_record_stride(int kind, const EvalArgs& A);
 int plan_fused_args_tria(const pf3_plan* pl, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_fused_args_group(const pf3_plan* pl, int group, FusedArgs* F, cudaStream_t st, int64_t* launches);
 int plan_union_map(const pf3_plan* pl, int group, int matrix, int mtype, UnionMap* um);
@@ -462,7 +462,7 @@ int pf3_eval(pf3_context* ctx, const pf3_batch* b, int what, const pf3_coo* kc0,
     F.A = A;
     F.nown = b->ne;
     F.rmax = 1;
-    rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
+    rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(b->kind, F.A) * sizeof(double));
     if (rc) return rc;
     cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3);
     return int(e);
@@ -658,7 +658,7 @@ int eval_assemble_impl(pf3_context* ctx, const pf3_batch* b, const pf3_plan* pla
   F.csr_kc0 = csr_kc0;
   F.csr_kg = csr_kg;
   F.csr_m = csr_m;
-  rc = ensure_scratch(ctx, size_t(b->ne) * (tria ? pf3::tria_fused_record_stride(F.A) : pf3::fused_record_stride(F.A)) *
+  rc = ensure_scratch(ctx, size_t(b->ne) * (tria ? pf3::tria_fused_record_stride(F.A) : pf3::fused_record_stride(b->kind, F.A)) *
                                sizeof(double));
   if (rc) return rc;
   // the pipeline pays off when the device->host copies dominate: enough node pairs for PF3_HOST_CHUNKS full waves
@@ -729,7 +729,7 @@ int pf3_eval_assemble_group(pf3_context* ctx, const pf3_batch* b, const pf3_plan
   F.csr_kc0 = csr_kc0;
   F.csr_kg = csr_kg;
   F.csr_m = csr_m;
-  rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(F.A) * sizeof(double));
+  rc = ensure_scratch(ctx, size_t(b->ne) * pf3::fused_record_stride(b->kind, F.A) * sizeof(double));
   if (rc) return rc;
   cudaError_t e = pf3::launch_quad_fused(b->kind, F, ctx->scratch, ctx->stream, &ctx->launches, 3);
   if (e != cudaSuccess) return int(e);

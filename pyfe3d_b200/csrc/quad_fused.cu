@@ -43,14 +43,20 @@ constexpr int kFusedWarps = PF3_FUSED_WARPS;
 constexpr int kMaxSlots = 16;               // column blocks per node row supported by the fused path (NodeRec::gmap)
 // Element record (doubles): 0..5 the element x and y axes (R columns 0 and 1, row-major 3 x 2; z = x X y is recomputed
 // by the consumer) | 6..13 the eight local edge differences | 14..17 1/detJ at the 2x2 Gauss points | 18 1/detJ at the
-// centre | 19 area | [KG from u: 12 membrane force resultants Nxx, Nyy, Nxy at the 4 Gauss points] | [material axes: the
-// rotated A, B, D, 18 doubles].  20 / 32 / 38 / 50 doubles = 160 / 256 / 304 / 400 B: the three-matrix north-star call
-// reads 256-byte records that never straddle a third 128-byte line.
+// centre | 19 area (Quad4: NEGATIVE when the element is "thick", h / sqrt(area) >= 1, quad4.pyx:1032) | [Quad4R: the
+// drilling coefficient 1e-6 K6ROT A66 and the five hourglass coefficients w0 gamma^2 E_d, quad4r.pyx:3088-3116 -- nine
+// divisions that every one of the 16 lanes working on an element would otherwise repeat] | [KG from u: 12 membrane force
+// resultants Nxx, Nyy, Nxy at the 4 Gauss points] | [material axes: the rotated A, B, D, 18 doubles].  Quad4: 20 / 32 /
+// 38 / 50 doubles (the three-matrix north-star call reads 256-byte records that never straddle a third 128-byte line);
+// Quad4R: 6 more.
 constexpr int kRecBase = 20;
+constexpr int kRecHg = 6;
 constexpr int kRecN = 12;
 constexpr int kRecABD = 18;
-constexpr int kRecMax = kRecBase + kRecN + kRecABD;
-__host__ __device__ constexpr int rec_stride(bool kg_u, bool rot) { return kRecBase + (kg_u ? kRecN : 0) + (rot ? kRecABD : 0); }
+constexpr int kRecMax = kRecBase + kRecHg + kRecN + kRecABD;
+__host__ __device__ constexpr int rec_stride(bool quad4r, bool kg_u, bool rot) {
+  return kRecBase + (quad4r ? kRecHg : 0) + (kg_u ? kRecN : 0) + (rot ? kRecABD : 0);
+}
 // shared-memory stride of a staged record: even (16-byte aligned) and = 2 mod 4, so that the 16-byte loads of the 8
 // incidences of a warp fall into disjoint banks
 __host__ __device__ constexpr int rec_ld(int stride) { return stride + ((stride & 3) == 2 ? 0 : 2); }
@@ -100,11 +106,45 @@ __device__ __forceinline__ void record_warp(const EvalArgs& A, double* __restric
   const double J21c = 0.25 * (d[2] + d[3]), J22c = 0.25 * (d[6] + d[7]);
   r[18] = 1. / (J11c * J22c - J12c * J21c);
   r[19] = g.area;
-  if (kg_u || rot) {
+  constexpr int kHg = (KIND == PF3_QUAD4R) ? kRecHg : 0;
+  if (KIND == PF3_QUAD4 && A.props != nullptr) {
+    const double hh = A.props[int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE + 23];
+    if (hh / sqrt(g.area) >= 1.) r[19] = -g.area;   // thick: transverse shear integrated at 2x2 (quad4.pyx:1032,1127)
+  }
+  if (kg_u || rot || KIND == PF3_QUAD4R) {
     ShellCoef c;
     shell_coef<4>(A, e, g, c);
+    if (KIND == PF3_QUAD4R) {
+      double K6ROT = 100., hgf[5] = {1., 1., 1., 1., 1.};
+      if (A.eparam != nullptr) {
+        const double* ep = A.eparam + e * PF3_EPARAM_STRIDE;
+        K6ROT = ep[0];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) hgf[q] = ep[2 + q];
+      }
+      const double* cA = c.A;
+      const double hh = c.h;
+      const double den = -cA[0] * cA[3] * cA[5] + cA[0] * cA[4] * cA[4] + cA[1] * cA[1] * cA[5] -
+                         2 * cA[1] * cA[2] * cA[4] + cA[2] * cA[2] * cA[3];
+      const double a11 = (-cA[3] * cA[5] + cA[4] * cA[4]) / den, a22 = (-cA[0] * cA[5] + cA[2] * cA[2]) / den;
+      const double E1eq = 1. / (hh * a11), E2eq = 1. / (hh * a22);
+      const double dd = 1.0 + 1.0 / g.area;
+      const double Eu = hgf[0] * 0.1 * E1eq * hh / dd, Ev = hgf[1] * 0.1 * E2eq * hh / dd;
+      const double Erx = hgf[3] * 0.1 * E2eq * hh * hh * hh / dd, Ery = hgf[4] * 0.1 * E1eq * hh * hh * hh / dd;
+      const double Ew = hgf[2] * 0.5 * (Erx + Ery);
+      // gamma_a = +-(j11 j22 + j12 j21)/4 with j = J0^-1 (quad4r.pyx:3116); the sign (+ - + -) stays with the lanes
+      const double w0 = 4. * (J11c * J22c - J12c * J21c);
+      const double gam = 0.25 * (J22c * J11c + J12c * J21c) * r[18] * r[18];
+      const double wg2 = w0 * gam * gam;
+      r[kRecBase + 0] = 1e-6 * K6ROT * cA[5];
+      r[kRecBase + 1] = wg2 * Eu;
+      r[kRecBase + 2] = wg2 * Ev;
+      r[kRecBase + 3] = wg2 * Ew;
+      r[kRecBase + 4] = wg2 * Erx;
+      r[kRecBase + 5] = wg2 * Ery;
+    }
     if (rot) {
-      double* ra = r + kRecBase + (kg_u ? kRecN : 0);
+      double* ra = r + kRecBase + kHg + (kg_u ? kRecN : 0);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         ra[i] = c.A[i];
@@ -132,17 +172,17 @@ __device__ __forceinline__ void record_warp(const EvalArgs& A, double* __restric
           kyy -= ny * ue[6 * cn + 3];
           kxy += ny * ue[6 * cn + 4] - nx * ue[6 * cn + 3];
         }
-        r[20 + gp] = c.A[0] * exx + c.A[1] * eyy + c.A[2] * gxy + c.B[0] * kxx + c.B[1] * kyy + c.B[2] * kxy;
-        r[24 + gp] = c.A[1] * exx + c.A[3] * eyy + c.A[4] * gxy + c.B[1] * kxx + c.B[3] * kyy + c.B[4] * kxy;
-        r[28 + gp] = c.A[2] * exx + c.A[4] * eyy + c.A[5] * gxy + c.B[2] * kxx + c.B[4] * kyy + c.B[5] * kxy;
+        r[20 + kHg + gp] = c.A[0] * exx + c.A[1] * eyy + c.A[2] * gxy + c.B[0] * kxx + c.B[1] * kyy + c.B[2] * kxy;
+        r[24 + kHg + gp] = c.A[1] * exx + c.A[3] * eyy + c.A[4] * gxy + c.B[1] * kxx + c.B[3] * kyy + c.B[4] * kxy;
+        r[28 + kHg + gp] = c.A[2] * exx + c.A[4] * eyy + c.A[5] * gxy + c.B[2] * kxx + c.B[4] * kyy + c.B[5] * kxy;
       }
     }
   }
   __syncwarp();
   double* out = rec + e0 * stride;
   const int total = nvalid * stride;
-  if (stride == rec_stride(true, false)) {   // the north-star call: division by a constant
-    constexpr int kS = rec_stride(true, false);
+  if (stride == rec_stride(false, true, false)) {   // the north-star call: division by a constant
+    constexpr int kS = rec_stride(false, true, false);
     for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / kS) * ld + idx % kS];
   } else {
     for (int idx = lane; idx < total; idx += 32) out[idx] = stage[(idx / stride) * ld + idx % stride];
@@ -573,10 +613,12 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     const double dX10 = rr_[6], dX23 = rr_[7], dX30 = rr_[8], dX21 = rr_[9];
     const double dY10 = rr_[10], dY23 = rr_[11], dY30 = rr_[12], dY21 = rr_[13];
     const double idJ[4] = {rr_[14], rr_[15], rr_[16], rr_[17]};
-    const double idJ0 = rr_[18], area = rr_[19];
+    const double idJ0 = rr_[18], area = fabs(rr_[19]);
+    const bool thick = (KIND == PF3_QUAD4) && rr_[19] < 0.;   // decided once per element by K1
+    constexpr int kHg = (KIND == PF3_QUAD4R) ? kRecHg : 0;
     const bool kg_u = (A.what & PF3_KG) != 0;
     const double* prow = A.props + int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE;
-    const double* abd = (A.evec != nullptr) ? re + kRecBase + (kg_u ? kRecN : 0) : prow;
+    const double* abd = (A.evec != nullptr) ? re + kRecBase + kHg + (kg_u ? kRecN : 0) : prow;
 
     // Jacobian rows: J11,J12 depend on eta only, J21,J22 on xi only (index 0: -p, 1: +p)
     double J11e[2], J12e[2], J21x[2], J22x[2];
@@ -611,7 +653,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       pxba += wxb * na;
       hab += (na * nbv) * (J11e[ie] * J22x[ix] - J12e[ie] * J21x[ix]);
       if (kg_u) {
-        const double nxx = re[20 + gp], nyy = re[24 + gp], nxy = re[28 + gp];
+        const double nxx = re[20 + kHg + gp], nyy = re[24 + kHg + gp], nxy = re[28 + kHg + gp];
         ge += wxb * (vax * nxx + vay * nxy) + wyb * (vax * nxy + vay * nyy);
       }
     }
@@ -699,37 +741,20 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
       const double N0ya = (-J21c * 0.25 * xia + J11c * 0.25 * etaa) * idJ0;
       const double N0xb = (J22c * 0.25 * xib - J12c * 0.25 * etab) * idJ0;
       const double N0yb = (-J21c * 0.25 * xib + J11c * 0.25 * etab) * idJ0;
-      const double k13 = prow[21], k23 = prow[22], hh = prow[23];
+      const double k13 = prow[21], k23 = prow[22];
       const double E44 = prow[18] * k23, E45 = prow[19] * 0.5 * (k13 + k23), E55 = prow[20] * k13;
       const double sgn = ((a ^ b) & 1) ? -1. : 1.;
       double kd = 1., hg0 = 0., hg1 = 0., hg2 = 0., hg3 = 0., hg4 = 0.;
-      if (KIND == PF3_QUAD4R) {
-        double K6ROT = 100., hgf[5] = {1., 1., 1., 1., 1.};
-        if (A.eparam != nullptr) {
-          const double* ep = A.eparam + e * PF3_EPARAM_STRIDE;
-          K6ROT = ep[0];
-#pragma unroll
-          for (int d = 0; d < 5; ++d) hgf[d] = ep[2 + d];
-        }
-        kd = 1e-6 * K6ROT * cA[5];
-        const double den = -cA[0] * cA[3] * cA[5] + cA[0] * cA[4] * cA[4] + cA[1] * cA[1] * cA[5] -
-                           2 * cA[1] * cA[2] * cA[4] + cA[2] * cA[2] * cA[3];
-        const double a11 = (-cA[3] * cA[5] + cA[4] * cA[4]) / den, a22 = (-cA[0] * cA[5] + cA[2] * cA[2]) / den;
-        const double E1eq = 1. / (hh * a11), E2eq = 1. / (hh * a22);
-        const double dd = 1.0 + 1.0 / area;
-        const double Eu = hgf[0] * 0.1 * E1eq * hh / dd, Ev = hgf[1] * 0.1 * E2eq * hh / dd;
-        const double Erx = hgf[3] * 0.1 * E2eq * hh * hh * hh / dd, Ery = hgf[4] * 0.1 * E1eq * hh * hh * hh / dd;
-        const double Ew = hgf[2] * 0.5 * (Erx + Ery);
-        // gamma_a = +-(j11 j22 + j12 j21)/4 with j = J0^-1 (quad4r.pyx:3116)
-        const double gam = 0.25 * (J22c * J11c + J12c * J21c) * idJ0 * idJ0;
-        const double wg2 = sgn * w0 * gam * gam;
-        hg0 = wg2 * Eu;
-        hg1 = wg2 * Ev;
-        hg2 = wg2 * Ew;
-        hg3 = wg2 * Erx;
-        hg4 = wg2 * Ery;
+      if (KIND == PF3_QUAD4R) {   // per-element constants from the record (K1), the sign of the hourglass vector here
+        const double2* hq = reinterpret_cast<const double2*>(re + kRecBase);
+        const double2 h01 = hq[0], h23 = hq[1], h45 = hq[2];
+        kd = h01.x;
+        hg0 = sgn * h01.y;
+        hg1 = sgn * h23.x;
+        hg2 = sgn * h23.y;
+        hg3 = sgn * h45.x;
+        hg4 = sgn * h45.y;
       }
-      const bool thick = (KIND == PF3_QUAD4) && (hh / sqrt(area) >= 1.);
       // constitutive Gram: 2x2 Gauss (Quad4) or centre point with weight 4 detJ0 (Quad4R)
       double cxx = gxx, cxy = gxy, cyx = gyx, cyy = gyy;
       if (KIND == PF3_QUAD4R) {
@@ -790,7 +815,9 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
 
 size_t fused_smem_bytes(int rstride, int chunk) { return size_t(kFusedWarps) * warp_smem_doubles(rstride, chunk) * sizeof(double); }
 int fused_max_slots() { return kMaxSlots; }
-int fused_record_stride(const EvalArgs& A) { return rec_stride((A.what & PF3_KG) != 0, A.evec != nullptr); }
+int fused_record_stride(int kind, const EvalArgs& A) {
+  return rec_stride(kind == PF3_QUAD4R, (A.what & PF3_KG) != 0, A.evec != nullptr);
+}
 
 namespace {
 
@@ -820,7 +847,7 @@ cudaError_t launch_k1(int kind, const EvalArgs& A, double* rec, int stride, int6
 // the node pairs [F.pair_first, F.pair_first + F.pair_count) (all pairs when pair_count == 0).
 cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStream_t st, int64_t* launches, int phases) {
   if (F.nown <= 0 || F.A.ne <= 0) return cudaSuccess;
-  const int stride = fused_record_stride(F.A);
+  const int stride = fused_record_stride(kind, F.A);
   // doubles written per element (COO + CSR share): the three-matrix north-star call is store-bound, smaller calls are
   // latency-bound and take the prefetching variant
   const int w = F.A.what;

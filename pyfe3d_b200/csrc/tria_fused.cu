@@ -374,13 +374,15 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
     // ---------------- M : H_ab * (T6 m_l T6^T) (tria3r.pyx:4063 ff.)
     if (A.what & PF3_M) {
       double hd, ho;
+      // (multiplications by the reciprocals: a double division is a ~15-instruction sequence per lane; the last-bit
+      // difference to detJ / 12 etc. is far inside the 1e-12 tolerance)
       if (A.mtype == 0) {
-        hd = dJ / 12.;
-        ho = dJ / 24.;
+        hd = dJ * (1. / 12.);
+        ho = dJ * (1. / 24.);
       } else if (A.mtype == 1) {
-        hd = ho = dJ / 18.;
+        hd = ho = dJ * (1. / 18.);
       } else {
-        hd = dJ / 6.;
+        hd = dJ * (1. / 6.);
         ho = 0.;
       }
       const double h = (a == b) ? hd : ho;

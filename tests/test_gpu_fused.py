@@ -353,3 +353,40 @@ def test_plan_rejects_out_of_range_connectivity_and_handles_hub_rows():
     want = driver.run(case, what=("KC0",))["KC0"]
     S = sp.coo_matrix((want[2], (want[0], want[1])), shape=(case["ndof"],) * 2).tocsr()
     assert abs(A - S).max() <= util.TOL_CSR * np.abs(S.data).max()
+
+
+@pytest.mark.parametrize("kind,numbering", [("quad4", "structured"), ("quad4", "scattered"), ("quad4r", "scattered"),
+                                            ("tria3r", "structured"), ("tria3r", "scattered")])
+def test_fused_with_l2_prefetch_table(kind, numbering):
+    """Meshes large enough (> 32 chunks of 512 node pairs) for the plan to build its L2 prefetch table (common.cuh:
+    kPfChunk): structured numbering (one first-use run per chunk; two for the triangles' split numbering) and a random
+    renumbering of nodes AND elements (runs scattered over the whole element range: the table drops them).  The fused
+    kernel must give what the two-pass path gives either way -- the prefetch only moves data into L2."""
+    import torch
+    from pyfe3d_b200.batch import AssemblyPlan
+    case = cases.shell_mesh(kind, 211, 187, seed=77)
+    nn = case["ndof"] // 6
+    if numbering == "scattered":
+        rng = np.random.default_rng(5)
+        pn = rng.permutation(nn)                       # new position of every node
+        inv = np.argsort(pn)
+        case["x"] = np.asarray(case["x"]).reshape(nn, 3)[inv].ravel()
+        case["u"] = np.asarray(case["u"]).reshape(nn, 6)[inv].ravel()
+        pe = rng.permutation(case["conn"].shape[0])
+        case["conn"] = np.ascontiguousarray(pn[case["conn"]][pe])
+        for k in ("prop_id", "xmat", "hg", "K6ROT", "alpha"):
+            if case.get(k) is not None and np.ndim(case[k]) >= 1 and np.shape(case[k])[0] == pe.size:
+                case[k] = np.ascontiguousarray(np.asarray(case[k])[pe])
+    b = util.batch_from_case(case)
+    plan = AssemblyPlan("KC0", nn, [b])
+    ne = case["conn"].shape[0]
+    coo, csr = plan.evaluate_assemble(KC0=True, KG=True, M=True)
+    two = b.evaluate(KC0=True, KG=True, M=True, indices=False)
+    for m in ("KC0", "KG", "M"):
+        assert util.block_relerr(coo[m].v.cpu().numpy(), two[m].v.cpu().numpy(), ne) <= 1e-13, m
+        ref_csr = AssemblyPlan(m, nn, [b]).assemble(two[m].v)
+        assert float((csr[m] - ref_csr).abs().max()) <= 1e-12 * float(ref_csr.abs().max()), m
+    # and a second step into the same arrays (records, prefetches and evict-first stores of a steady-state loop)
+    coo2, csr2 = plan.evaluate_assemble(KC0=True, KG=True, M=True, coo=coo, csr={k: v.clone() for k, v in csr.items()})
+    for m in ("KC0", "KG", "M"):
+        assert torch.equal(csr2[m], csr[m])
