@@ -614,12 +614,14 @@ def run_ours(args):
                 rb.step()
                 dt = rb.step()
                 rb.close()
-                cpu = {"value": rb.ne / dt, "unit": UNIT, "cores": rb.nproc, "kind": "reference", "sample": rb.describe()}
+                cpu = {"value": rb.ne / dt, "unit": UNIT, "cores": rb.nproc, "kind": "reference", "sample": rb.describe(),
+                       "element_loop_s": rb.loop_s, "scipy_tocsr_s": rb.tocsr_s}
                 # SURVEY 8(d) / BASELINE.md: the same loop on ONE core (a smaller sample of the same mesh)
                 r1 = cpu_bench.ReferenceBench(side=args.cpu_side_1core, nproc=1)
                 dt1 = r1.step()
                 r1.close()
-                cpu["one_core"] = {"value": r1.ne / dt1, "unit": UNIT, "cores": 1, "sample": r1.describe()}
+                cpu["one_core"] = {"value": r1.ne / dt1, "unit": UNIT, "cores": 1, "sample": r1.describe(),
+                                   "element_loop_s": r1.loop_s, "scipy_tocsr_s": r1.tocsr_s}
                 if solve is not None and "seconds" in solve:
                     dts, its, wmax, info = cpu_bench.reference_static_solve(args.solve_side)
                     solve["reference_seconds"] = dts
@@ -696,8 +698,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--path", default="fused", choices=["fused", "twopass"],
                     help="fused: one node-centric kernel writes COO + CSR; twopass: eval kernel then 3 assemblies")
-    ap.add_argument("--cpu-side", type=int, default=256, help="side of the sub-plate the CPU arm evaluates")
-    ap.add_argument("--cpu-side-1core", type=int, default=96, help="side of the sub-plate of the one-core CPU figure")
+    ap.add_argument("--cpu-side", type=int, default=448,
+                    help="side of the sub-plate the CPU arm evaluates (448^2 = 200 704 elements: BASELINE.md section 3)")
+    ap.add_argument("--cpu-side-1core", type=int, default=448, help="side of the sub-plate of the one-core CPU figure")
     ap.add_argument("--e2e-upper", type=int, default=1, help="also time the end-to-end step returning one triangle")
     ap.add_argument("--strong", type=int, default=1, help="N>1: also time the metric's own size cut into N strips")
     ap.add_argument("--others", type=int, default=1, help="also time BASELINE configs 2-5 (config.others)")

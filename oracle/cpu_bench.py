@@ -30,13 +30,15 @@ def _work(rng):
     import scipy.sparse as sp
     e0, e1 = rng
     case = _STATE["case"]
+    t0 = time.perf_counter()
     out = _STATE["ref_loop"].run(case, what=("KC0", "KG", "M0"), e0=e0, e1=e1)
+    t1 = time.perf_counter()
     n = case["ndof"]
     nnz = 0
     for k in ("KC0", "KG", "M0"):
         r, c, v = out[k]
         nnz += sp.coo_matrix((v, (r, c)), shape=(n, n)).tocsr().nnz
-    return nnz
+    return nnz, t1 - t0, time.perf_counter() - t1
 
 
 class ReferenceBench:
@@ -54,8 +56,12 @@ class ReferenceBench:
 
     def step(self):
         t0 = time.perf_counter()
-        self.pool.map(_work, self.slices, chunksize=1)
-        return time.perf_counter() - t0
+        res = self.pool.map(_work, self.slices, chunksize=1)
+        dt = time.perf_counter() - t0
+        # slowest worker's split: element loop against scipy coo -> csr
+        self.loop_s = max(r[1] for r in res)
+        self.tocsr_s = max(r[2] for r in res)
+        return dt
 
     def close(self):
         self.pool.close()
