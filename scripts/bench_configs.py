@@ -150,6 +150,49 @@ def run_cg(side, iters=64, host_side=400):
     print(json.dumps(out))
 
 
+def run_dropin(n=2000):
+    """Cost of the PER-ELEMENT drop-in classes (import pyfe3d_b200 as pyfe3d): the reference's own loop
+    (tests/test_quad4_static_point_load.py:53-78) over n Quad4 elements, one C-ABI round trip per method call, against
+    the batched API on the same mesh."""
+    import pyfe3d_b200 as pf
+    from pyfe3d_b200.shellprop_utils import isotropic_plate
+    side = int(n ** 0.5)
+    case = meshes.plate_quad4(side, side, with_u=True)
+    x = np.ascontiguousarray(case["x"], float)
+    u = np.ascontiguousarray(case["u"], float)
+    conn = case["conn"]
+    ne = conn.shape[0]
+    prop = isotropic_plate(thickness=0.005, E=200e9, nu=0.3, calc_scf=True, rho=7800.)
+    data, probe = pf.Quad4Data(), pf.Quad4Probe()
+    KC0r = np.zeros(data.KC0_SPARSE_SIZE * ne, pf.INT); KC0c = np.zeros_like(KC0r); KC0v = np.zeros(KC0r.size)
+    KGr = np.zeros(data.KG_SPARSE_SIZE * ne, pf.INT); KGc = np.zeros_like(KGr); KGv = np.zeros(KGr.size)
+    Mr = np.zeros(data.M_SPARSE_SIZE * ne, pf.INT); Mc = np.zeros_like(Mr); Mv = np.zeros(Mr.size)
+    t0 = time.perf_counter()
+    for e in range(ne):
+        q = pf.Quad4(probe)
+        q.n1, q.n2, q.n3, q.n4 = [int(t) for t in conn[e]]
+        q.c1, q.c2, q.c3, q.c4 = [int(6 * t) for t in conn[e]]
+        q.init_k_KC0, q.init_k_KG, q.init_k_M = e * data.KC0_SPARSE_SIZE, e * data.KG_SPARSE_SIZE, e * data.M_SPARSE_SIZE
+        q.update_rotation_matrix(x)
+        q.update_probe_xe(x)
+        q.update_KC0(KC0r, KC0c, KC0v, prop)
+        q.update_probe_ue(u)
+        q.update_KG(KGr, KGc, KGv, prop)
+        q.update_M(Mr, Mc, Mv, prop)
+    dt = time.perf_counter() - t0
+    b = ElementBatch("quad4", conn, x, prop, u=u)
+    b.evaluate(KC0=True, KG=True, M=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    coo = b.evaluate(KC0=True, KG=True, M=True)
+    v = coo["KC0"].v.cpu().numpy()
+    dtb = time.perf_counter() - t1
+    err = float(np.abs(v - KC0v).max() / np.abs(KC0v).max())
+    print(json.dumps({"config": "per-element drop-in loop, %d Quad4 (6 method calls per element)" % ne, "seconds": dt,
+                      "us_per_method_call": dt / (6 * ne) * 1e6, "elements_per_s": ne / dt,
+                      "batched_api_seconds_same_mesh_incl_indices_and_d2h": dtb, "KC0_max_rel_diff_loop_vs_batch": err}))
+
+
 def run_mixed(side, nstiff=64):
     """Config 5 (per-GPU share): Quad4 skin + BeamC stiffeners in ONE matrix per KC0 / KG / M, plus update_fint.
     The groups have different masks for KG and M, so this is the two-pass path: one evaluation launch per group and
@@ -294,6 +337,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--aero" in sys.argv:
         run_aero(200 if "--small" in sys.argv else 2000)
+        sys.exit(0)
+    if "--dropin" in sys.argv:
+        run_dropin(400 if "--small" in sys.argv else 2000)
         sys.exit(0)
     if "--cg" in sys.argv:
         run_cg(100 if "--small" in sys.argv else 2000, host_side=50 if "--small" in sys.argv else 400)
