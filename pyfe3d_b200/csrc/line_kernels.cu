@@ -47,6 +47,8 @@ __device__ __forceinline__ void sym(KS& K, int i, int j, double v) {
 template <class KS>
 __device__ __forceinline__ void beamc_Ke(const BeamP& p, double L, KS& K) {
   K.zero();
+  const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
+  (void)iL2; (void)iL3;
   const double L2 = L * L, L3 = L2 * L;
   const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
   const double by = 1 / (1. - ay), bz = 1 / (1. - az);
@@ -54,31 +56,31 @@ __device__ __forceinline__ void beamc_Ke(const BeamP& p, double L, KS& K) {
   const double Kz = bz * bz * (p.A * p.G * L2 * az * az + 12 * p.E * p.Iyy);
   const double Kyz = p.E * p.Iyz * by * bz;
   const double Sy = p.Az * p.G * ay * by, Sz = p.Ay * p.G * az * bz;
-  const double cz = p.Az * p.E * bz * (1 - az) / L, cy = p.Ay * p.E * by * (ay - 1) / L;
-  const double EA = p.A * p.E / L, GJ = p.G * p.J / L;
+  const double cz = p.Az * p.E * bz * (1 - az) * iL, cy = p.Ay * p.E * by * (ay - 1) * iL;
+  const double EA = p.A * p.E * iL, GJ = p.G * p.J * iL;
   sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
   sym(K, 0, 4, cz); sym(K, 6, 10, cz); sym(K, 0, 10, -cz); sym(K, 4, 6, -cz);
   sym(K, 0, 5, cy); sym(K, 6, 11, cy); sym(K, 0, 11, -cy); sym(K, 5, 6, -cy);
-  sym(K, 1, 1, Ky / L3); sym(K, 7, 7, Ky / L3); sym(K, 1, 7, -Ky / L3);
-  sym(K, 1, 5, Ky / (2 * L2)); sym(K, 1, 11, Ky / (2 * L2)); sym(K, 5, 7, -Ky / (2 * L2)); sym(K, 7, 11, -Ky / (2 * L2));
-  sym(K, 2, 2, Kz / L3); sym(K, 8, 8, Kz / L3); sym(K, 2, 8, -Kz / L3);
-  sym(K, 2, 4, -Kz / (2 * L2)); sym(K, 2, 10, -Kz / (2 * L2)); sym(K, 4, 8, Kz / (2 * L2)); sym(K, 8, 10, Kz / (2 * L2));
-  sym(K, 1, 2, 12 * Kyz / L3); sym(K, 7, 8, 12 * Kyz / L3); sym(K, 1, 8, -12 * Kyz / L3); sym(K, 2, 7, -12 * Kyz / L3);
-  sym(K, 1, 4, -6 * Kyz / L2); sym(K, 1, 10, -6 * Kyz / L2); sym(K, 5, 8, -6 * Kyz / L2); sym(K, 8, 11, -6 * Kyz / L2);
-  sym(K, 2, 5, 6 * Kyz / L2); sym(K, 2, 11, 6 * Kyz / L2); sym(K, 4, 7, 6 * Kyz / L2); sym(K, 7, 10, 6 * Kyz / L2);
+  sym(K, 1, 1, Ky * iL3); sym(K, 7, 7, Ky * iL3); sym(K, 1, 7, -Ky * iL3);
+  sym(K, 1, 5, Ky * (0.5 * iL2)); sym(K, 1, 11, Ky * (0.5 * iL2)); sym(K, 5, 7, -Ky * (0.5 * iL2)); sym(K, 7, 11, -Ky * (0.5 * iL2));
+  sym(K, 2, 2, Kz * iL3); sym(K, 8, 8, Kz * iL3); sym(K, 2, 8, -Kz * iL3);
+  sym(K, 2, 4, -Kz * (0.5 * iL2)); sym(K, 2, 10, -Kz * (0.5 * iL2)); sym(K, 4, 8, Kz * (0.5 * iL2)); sym(K, 8, 10, Kz * (0.5 * iL2));
+  sym(K, 1, 2, 12 * Kyz * iL3); sym(K, 7, 8, 12 * Kyz * iL3); sym(K, 1, 8, -12 * Kyz * iL3); sym(K, 2, 7, -12 * Kyz * iL3);
+  sym(K, 1, 4, -6 * Kyz * iL2); sym(K, 1, 10, -6 * Kyz * iL2); sym(K, 5, 8, -6 * Kyz * iL2); sym(K, 8, 11, -6 * Kyz * iL2);
+  sym(K, 2, 5, 6 * Kyz * iL2); sym(K, 2, 11, 6 * Kyz * iL2); sym(K, 4, 7, 6 * Kyz * iL2); sym(K, 7, 10, 6 * Kyz * iL2);
   sym(K, 3, 3, GJ); sym(K, 9, 9, GJ); sym(K, 3, 9, -GJ);
-  sym(K, 1, 3, Sy / L); sym(K, 7, 9, Sy / L); sym(K, 1, 9, -Sy / L); sym(K, 3, 7, -Sy / L);
+  sym(K, 1, 3, Sy * iL); sym(K, 7, 9, Sy * iL); sym(K, 1, 9, -Sy * iL); sym(K, 3, 7, -Sy * iL);
   sym(K, 3, 5, Sy / 2); sym(K, 3, 11, Sy / 2); sym(K, 5, 9, -Sy / 2); sym(K, 9, 11, -Sy / 2);
-  sym(K, 2, 3, -Sz / L); sym(K, 8, 9, -Sz / L); sym(K, 2, 9, Sz / L); sym(K, 3, 8, Sz / L);
+  sym(K, 2, 3, -Sz * iL); sym(K, 8, 9, -Sz * iL); sym(K, 2, 9, Sz * iL); sym(K, 3, 8, Sz * iL);
   sym(K, 3, 4, Sz / 2); sym(K, 3, 10, Sz / 2); sym(K, 4, 9, -Sz / 2); sym(K, 9, 10, -Sz / 2);
   const double EIy = p.E * p.Iyy, EIz = p.E * p.Izz, AGL2 = p.A * p.G * L2;
-  const double k44 = bz * bz * (AGL2 * az * az / 4 + EIy * az * az - 2 * EIy * az + 4 * EIy) / L;
-  const double k55 = by * by * (AGL2 * ay * ay / 4 + EIz * ay * ay - 2 * EIz * ay + 4 * EIz) / L;
+  const double k44 = bz * bz * (AGL2 * az * az / 4 + EIy * az * az - 2 * EIy * az + 4 * EIy) * iL;
+  const double k55 = by * by * (AGL2 * ay * ay / 4 + EIz * ay * ay - 2 * EIz * ay + 4 * EIz) * iL;
   sym(K, 4, 4, k44); sym(K, 10, 10, k44);
-  sym(K, 4, 10, bz * bz * (AGL2 * az * az / 4 - EIy * az * az + 2 * EIy * az + 2 * EIy) / L);
+  sym(K, 4, 10, bz * bz * (AGL2 * az * az / 4 - EIy * az * az + 2 * EIy * az + 2 * EIy) * iL);
   sym(K, 5, 5, k55); sym(K, 11, 11, k55);
-  sym(K, 5, 11, by * by * (AGL2 * ay * ay / 4 - EIz * ay * ay + 2 * EIz * ay + 2 * EIz) / L);
-  const double k45 = Kyz * (-ay * az + ay + az - 4) / L, k411 = Kyz * (ay * az - ay - az - 2) / L;
+  sym(K, 5, 11, by * by * (AGL2 * ay * ay / 4 - EIz * ay * ay + 2 * EIz * ay + 2 * EIz) * iL);
+  const double k45 = Kyz * (-ay * az + ay + az - 4) * iL, k411 = Kyz * (ay * az - ay - az - 2) * iL;
   sym(K, 4, 5, k45); sym(K, 10, 11, k45); sym(K, 4, 11, k411); sym(K, 5, 10, k411);
 }
 
@@ -86,33 +88,35 @@ __device__ __forceinline__ void beamc_Ke(const BeamP& p, double L, KS& K) {
 template <class KS>
 __device__ __forceinline__ void beamc_KGe(const BeamP& p, double L, const double* ue, KS& K) {
   K.zero();
+  const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
+  (void)iL2; (void)iL3;
   const double L2 = L * L;
   const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
   const double by = 1 / (1. - ay), bz = 1 / (1. - az);
-  const double N = p.A * p.E * (-ue[0] + ue[6]) / L;
-  double v = N * by * by * (5 * ay * ay - 10 * ay + 6) / (5 * L);
+  const double N = p.A * p.E * (-ue[0] + ue[6]) * iL;
+  double v = N * by * by * (5 * ay * ay - 10 * ay + 6) * (0.2 * iL);
   sym(K, 1, 1, v); sym(K, 7, 7, v); sym(K, 1, 7, -v);
-  v = N * bz * bz * (5 * az * az - 10 * az + 6) / (5 * L);
+  v = N * bz * bz * (5 * az * az - 10 * az + 6) * (0.2 * iL);
   sym(K, 2, 2, v); sym(K, 8, 8, v); sym(K, 2, 8, -v);
-  v = N * by * bz * (5 * ay * az - 5 * ay - 5 * az + 6) / (5 * L);
+  v = N * by * bz * (5 * ay * az - 5 * ay - 5 * az + 6) * (0.2 * iL);
   sym(K, 1, 2, v); sym(K, 7, 8, v); sym(K, 1, 8, -v); sym(K, 2, 7, -v);
-  v = N * by * by / 10;
+  v = N * by * by * (1. / 10);
   sym(K, 1, 5, v); sym(K, 1, 11, v); sym(K, 5, 7, -v); sym(K, 7, 11, -v);
-  v = -N * bz * bz / 10;
+  v = -N * bz * bz * (1. / 10);
   sym(K, 2, 4, v); sym(K, 2, 10, v); sym(K, 4, 8, -v); sym(K, 8, 10, -v);
-  v = -N * by * bz / 10;
+  v = -N * by * bz * (1. / 10);
   sym(K, 1, 4, v); sym(K, 1, 10, v); sym(K, 4, 7, -v); sym(K, 7, 10, -v);
-  v = N * by * bz / 10;
+  v = N * by * bz * (1. / 10);
   sym(K, 2, 5, v); sym(K, 2, 11, v); sym(K, 5, 8, -v); sym(K, 8, 11, -v);
-  v = L * N * bz * bz * (5 * az * az - 10 * az + 8) / 60;
+  v = L * N * bz * bz * (5 * az * az - 10 * az + 8) * (1. / 60);
   sym(K, 4, 4, v); sym(K, 10, 10, v);
-  v = L * N * by * by * (5 * ay * ay - 10 * ay + 8) / 60;
+  v = L * N * by * by * (5 * ay * ay - 10 * ay + 8) * (1. / 60);
   sym(K, 5, 5, v); sym(K, 11, 11, v);
-  sym(K, 4, 10, L * N * bz * bz * (-5 * az * az + 10 * az - 2) / 60);
-  sym(K, 5, 11, L * N * by * by * (-5 * ay * ay + 10 * ay - 2) / 60);
-  v = L * N * by * bz * (-5 * ay * az + 5 * ay + 5 * az - 8) / 60;
+  sym(K, 4, 10, L * N * bz * bz * (-5 * az * az + 10 * az - 2) * (1. / 60));
+  sym(K, 5, 11, L * N * by * by * (-5 * ay * ay + 10 * ay - 2) * (1. / 60));
+  v = L * N * by * bz * (-5 * ay * az + 5 * ay + 5 * az - 8) * (1. / 60);
   sym(K, 4, 5, v); sym(K, 10, 11, v);
-  v = L * N * by * bz * (5 * ay * az - 5 * ay - 5 * az + 2) / 60;
+  v = L * N * by * bz * (5 * ay * az - 5 * ay - 5 * az + 2) * (1. / 60);
   sym(K, 4, 11, v); sym(K, 5, 10, v);
 }
 
@@ -120,6 +124,8 @@ __device__ __forceinline__ void beamc_KGe(const BeamP& p, double L, const double
 template <class KS>
 __device__ __forceinline__ void beamc_Me(const BeamP& p, double L, int mtype, KS& K) {
   K.zero();
+  const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
+  (void)iL2; (void)iL3;
   const double L2 = L * L;
   const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
   const double by = 1 / (1. - ay), bz = 1 / (1. - az);
@@ -137,72 +143,76 @@ __device__ __forceinline__ void beamc_Me(const BeamP& p, double L, int mtype, KS
   }
   const double by2 = by * by, bz2 = bz * bz, ay2 = ay * ay, az2 = az * az, bb = by * bz;
   double v;
-  sym(K, 0, 0, L * r0 / 3); sym(K, 6, 6, L * r0 / 3); sym(K, 0, 6, L * r0 / 6);
+  sym(K, 0, 0, L * r0 * (1. / 3)); sym(K, 6, 6, L * r0 * (1. / 3)); sym(K, 0, 6, L * r0 * (1. / 6));
   v = by * ry / 2; sym(K, 0, 1, v); sym(K, 1, 6, v); sym(K, 0, 7, -v); sym(K, 6, 7, -v);
   v = bz * rz / 2; sym(K, 0, 2, v); sym(K, 2, 6, v); sym(K, 0, 8, -v); sym(K, 6, 8, -v);
-  v = L * bz * rz * (1 - 4 * az) / 12; sym(K, 0, 4, v); sym(K, 6, 10, v);
-  v = L * by * ry * (4 * ay - 1) / 12; sym(K, 0, 5, v); sym(K, 6, 11, v);
-  v = -L * bz * rz * (2 * az + 1) / 12; sym(K, 0, 10, v); sym(K, 4, 6, v);
-  v = L * by * ry * (2 * ay + 1) / 12; sym(K, 0, 11, v); sym(K, 5, 6, v);
-  v = by2 * (70 * L2 * ay2 * r0 - 147 * L2 * ay * r0 + 78 * L2 * r0 + 252 * ry2) / (210 * L); sym(K, 1, 1, v); sym(K, 7, 7, v);
-  sym(K, 1, 7, by2 * (35 * L2 * ay2 * r0 - 63 * L2 * ay * r0 + 27 * L2 * r0 - 252 * ry2) / (210 * L));
-  v = bz2 * (70 * L2 * az2 * r0 - 147 * L2 * az * r0 + 78 * L2 * r0 + 252 * rz2) / (210 * L); sym(K, 2, 2, v); sym(K, 8, 8, v);
-  sym(K, 2, 8, bz2 * (35 * L2 * az2 * r0 - 63 * L2 * az * r0 + 27 * L2 * r0 - 252 * rz2) / (210 * L));
-  v = 6 * bb * ryz / (5 * L); sym(K, 1, 2, v); sym(K, 7, 8, v); sym(K, 1, 8, -v); sym(K, 2, 7, -v);
-  v = L * by * rz * (20 * ay - 21) / 60; sym(K, 1, 3, v); sym(K, 7, 9, v);
-  v = L * by * rz * (10 * ay - 9) / 60; sym(K, 1, 9, v); sym(K, 3, 7, v);
-  v = L * bz * ry * (21 - 20 * az) / 60; sym(K, 2, 3, v); sym(K, 8, 9, v);
-  v = L * bz * ry * (9 - 10 * az) / 60; sym(K, 2, 9, v); sym(K, 3, 8, v);
-  v = -bb * ryz * (5 * az + 1) / 10; sym(K, 1, 4, v); sym(K, 1, 10, v); sym(K, 4, 7, -v); sym(K, 7, 10, -v);
-  v = bb * ryz * (5 * ay + 1) / 10; sym(K, 2, 5, v); sym(K, 2, 11, v); sym(K, 5, 8, -v); sym(K, 8, 11, -v);
-  v = by2 * (35 * L2 * ay2 * r0 - 77 * L2 * ay * r0 + 44 * L2 * r0 + 420 * ay * ry2 + 84 * ry2) / 840; sym(K, 1, 5, v); sym(K, 7, 11, -v);
-  v = by2 * (-35 * L2 * ay2 * r0 + 63 * L2 * ay * r0 - 26 * L2 * r0 + 420 * ay * ry2 + 84 * ry2) / 840; sym(K, 1, 11, v); sym(K, 5, 7, -v);
-  v = bz2 * (-35 * L2 * az2 * r0 + 77 * L2 * az * r0 - 44 * L2 * r0 - 420 * az * rz2 - 84 * rz2) / 840; sym(K, 2, 4, v); sym(K, 8, 10, -v);
-  v = bz2 * (35 * L2 * az2 * r0 - 63 * L2 * az * r0 + 26 * L2 * r0 - 420 * az * rz2 - 84 * rz2) / 840; sym(K, 2, 10, v); sym(K, 4, 8, -v);
-  v = L * (ry2 + rz2) / 3; sym(K, 3, 3, v); sym(K, 9, 9, v); sym(K, 3, 9, L * (ry2 + rz2) / 6);
-  v = L2 * bz * ry * (5 * az - 6) / 120; sym(K, 3, 4, v); sym(K, 9, 10, -v);
-  v = L2 * by * rz * (5 * ay - 6) / 120; sym(K, 3, 5, v); sym(K, 9, 11, -v);
-  v = L2 * bz * ry * (4 - 5 * az) / 120; sym(K, 3, 10, v); sym(K, 4, 9, -v);
-  v = L2 * by * rz * (4 - 5 * ay) / 120; sym(K, 3, 11, v); sym(K, 5, 9, -v);
-  v = L * bz2 * (7 * L2 * az2 * r0 - 14 * L2 * az * r0 + 8 * L2 * r0 + 280 * az2 * rz2 - 140 * az * rz2 + 112 * rz2) / 840; sym(K, 4, 4, v); sym(K, 10, 10, v);
-  v = L * by2 * (7 * L2 * ay2 * r0 - 14 * L2 * ay * r0 + 8 * L2 * r0 + 280 * ay2 * ry2 - 140 * ay * ry2 + 112 * ry2) / 840; sym(K, 5, 5, v); sym(K, 11, 11, v);
-  sym(K, 4, 10, L * bz2 * (-7 * L2 * az2 * r0 + 14 * L2 * az * r0 - 6 * L2 * r0 + 140 * az2 * rz2 + 140 * az * rz2 - 28 * rz2) / 840);
-  sym(K, 5, 11, L * by2 * (-7 * L2 * ay2 * r0 + 14 * L2 * ay * r0 - 6 * L2 * r0 + 140 * ay2 * ry2 + 140 * ay * ry2 - 28 * ry2) / 840);
-  v = L * bb * ryz * (-20 * ay * az + 5 * ay + 5 * az - 8) / 60; sym(K, 4, 5, v); sym(K, 10, 11, v);
-  v = L * bb * ryz * (-10 * ay * az - 5 * ay - 5 * az + 2) / 60; sym(K, 4, 11, v); sym(K, 5, 10, v);
+  v = L * bz * rz * (1 - 4 * az) * (1. / 12); sym(K, 0, 4, v); sym(K, 6, 10, v);
+  v = L * by * ry * (4 * ay - 1) * (1. / 12); sym(K, 0, 5, v); sym(K, 6, 11, v);
+  v = -L * bz * rz * (2 * az + 1) * (1. / 12); sym(K, 0, 10, v); sym(K, 4, 6, v);
+  v = L * by * ry * (2 * ay + 1) * (1. / 12); sym(K, 0, 11, v); sym(K, 5, 6, v);
+  v = by2 * (70 * L2 * ay2 * r0 - 147 * L2 * ay * r0 + 78 * L2 * r0 + 252 * ry2) * (iL * (1. / 210)); sym(K, 1, 1, v); sym(K, 7, 7, v);
+  sym(K, 1, 7, by2 * (35 * L2 * ay2 * r0 - 63 * L2 * ay * r0 + 27 * L2 * r0 - 252 * ry2) * (iL * (1. / 210)));
+  v = bz2 * (70 * L2 * az2 * r0 - 147 * L2 * az * r0 + 78 * L2 * r0 + 252 * rz2) * (iL * (1. / 210)); sym(K, 2, 2, v); sym(K, 8, 8, v);
+  sym(K, 2, 8, bz2 * (35 * L2 * az2 * r0 - 63 * L2 * az * r0 + 27 * L2 * r0 - 252 * rz2) * (iL * (1. / 210)));
+  v = 6 * bb * ryz * (0.2 * iL); sym(K, 1, 2, v); sym(K, 7, 8, v); sym(K, 1, 8, -v); sym(K, 2, 7, -v);
+  v = L * by * rz * (20 * ay - 21) * (1. / 60); sym(K, 1, 3, v); sym(K, 7, 9, v);
+  v = L * by * rz * (10 * ay - 9) * (1. / 60); sym(K, 1, 9, v); sym(K, 3, 7, v);
+  v = L * bz * ry * (21 - 20 * az) * (1. / 60); sym(K, 2, 3, v); sym(K, 8, 9, v);
+  v = L * bz * ry * (9 - 10 * az) * (1. / 60); sym(K, 2, 9, v); sym(K, 3, 8, v);
+  v = -bb * ryz * (5 * az + 1) * (1. / 10); sym(K, 1, 4, v); sym(K, 1, 10, v); sym(K, 4, 7, -v); sym(K, 7, 10, -v);
+  v = bb * ryz * (5 * ay + 1) * (1. / 10); sym(K, 2, 5, v); sym(K, 2, 11, v); sym(K, 5, 8, -v); sym(K, 8, 11, -v);
+  v = by2 * (35 * L2 * ay2 * r0 - 77 * L2 * ay * r0 + 44 * L2 * r0 + 420 * ay * ry2 + 84 * ry2) * (1. / 840); sym(K, 1, 5, v); sym(K, 7, 11, -v);
+  v = by2 * (-35 * L2 * ay2 * r0 + 63 * L2 * ay * r0 - 26 * L2 * r0 + 420 * ay * ry2 + 84 * ry2) * (1. / 840); sym(K, 1, 11, v); sym(K, 5, 7, -v);
+  v = bz2 * (-35 * L2 * az2 * r0 + 77 * L2 * az * r0 - 44 * L2 * r0 - 420 * az * rz2 - 84 * rz2) * (1. / 840); sym(K, 2, 4, v); sym(K, 8, 10, -v);
+  v = bz2 * (35 * L2 * az2 * r0 - 63 * L2 * az * r0 + 26 * L2 * r0 - 420 * az * rz2 - 84 * rz2) * (1. / 840); sym(K, 2, 10, v); sym(K, 4, 8, -v);
+  v = L * (ry2 + rz2) * (1. / 3); sym(K, 3, 3, v); sym(K, 9, 9, v); sym(K, 3, 9, L * (ry2 + rz2) * (1. / 6));
+  v = L2 * bz * ry * (5 * az - 6) * (1. / 120); sym(K, 3, 4, v); sym(K, 9, 10, -v);
+  v = L2 * by * rz * (5 * ay - 6) * (1. / 120); sym(K, 3, 5, v); sym(K, 9, 11, -v);
+  v = L2 * bz * ry * (4 - 5 * az) * (1. / 120); sym(K, 3, 10, v); sym(K, 4, 9, -v);
+  v = L2 * by * rz * (4 - 5 * ay) * (1. / 120); sym(K, 3, 11, v); sym(K, 5, 9, -v);
+  v = L * bz2 * (7 * L2 * az2 * r0 - 14 * L2 * az * r0 + 8 * L2 * r0 + 280 * az2 * rz2 - 140 * az * rz2 + 112 * rz2) * (1. / 840); sym(K, 4, 4, v); sym(K, 10, 10, v);
+  v = L * by2 * (7 * L2 * ay2 * r0 - 14 * L2 * ay * r0 + 8 * L2 * r0 + 280 * ay2 * ry2 - 140 * ay * ry2 + 112 * ry2) * (1. / 840); sym(K, 5, 5, v); sym(K, 11, 11, v);
+  sym(K, 4, 10, L * bz2 * (-7 * L2 * az2 * r0 + 14 * L2 * az * r0 - 6 * L2 * r0 + 140 * az2 * rz2 + 140 * az * rz2 - 28 * rz2) * (1. / 840));
+  sym(K, 5, 11, L * by2 * (-7 * L2 * ay2 * r0 + 14 * L2 * ay * r0 - 6 * L2 * r0 + 140 * ay2 * ry2 + 140 * ay * ry2 - 28 * ry2) * (1. / 840));
+  v = L * bb * ryz * (-20 * ay * az + 5 * ay + 5 * az - 8) * (1. / 60); sym(K, 4, 5, v); sym(K, 10, 11, v);
+  v = L * bb * ryz * (-10 * ay * az - 5 * ay - 5 * az + 2) * (1. / 60); sym(K, 4, 11, v); sym(K, 5, 10, v);
 }
 
 // linear Timoshenko beam, one-point reduced integration; beamlr.pyx:460-1186
 template <class KS>
 __device__ __forceinline__ void beamlr_Ke(const BeamP& p, double L, KS& K) {
   K.zero();
-  const double EA = p.E * p.A / L, EAz = p.E * p.Az / L, EAy = p.E * p.Ay / L;
-  const double GA = p.G * p.A, GAy = p.G * p.Ay, GAz = p.G * p.Az, GJ = p.G * p.J / L;
+  const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
+  (void)iL2; (void)iL3;
+  const double EA = p.E * p.A * iL, EAz = p.E * p.Az * iL, EAy = p.E * p.Ay * iL;
+  const double GA = p.G * p.A, GAy = p.G * p.Ay, GAz = p.G * p.Az, GJ = p.G * p.J * iL;
   sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
   sym(K, 0, 4, EAz); sym(K, 6, 10, EAz); sym(K, 0, 10, -EAz); sym(K, 4, 6, -EAz);
   sym(K, 0, 5, -EAy); sym(K, 6, 11, -EAy); sym(K, 0, 11, EAy); sym(K, 5, 6, EAy);
-  sym(K, 1, 1, GA / L); sym(K, 7, 7, GA / L); sym(K, 2, 2, GA / L); sym(K, 8, 8, GA / L);
-  sym(K, 1, 7, -GA / L); sym(K, 2, 8, -GA / L);
-  sym(K, 1, 3, -GAz / L); sym(K, 7, 9, -GAz / L); sym(K, 1, 9, GAz / L); sym(K, 3, 7, GAz / L);
+  sym(K, 1, 1, GA * iL); sym(K, 7, 7, GA * iL); sym(K, 2, 2, GA * iL); sym(K, 8, 8, GA * iL);
+  sym(K, 1, 7, -GA * iL); sym(K, 2, 8, -GA * iL);
+  sym(K, 1, 3, -GAz * iL); sym(K, 7, 9, -GAz * iL); sym(K, 1, 9, GAz * iL); sym(K, 3, 7, GAz * iL);
   sym(K, 1, 5, GA / 2); sym(K, 1, 11, GA / 2); sym(K, 5, 7, -GA / 2); sym(K, 7, 11, -GA / 2);
-  sym(K, 2, 3, GAy / L); sym(K, 8, 9, GAy / L); sym(K, 2, 9, -GAy / L); sym(K, 3, 8, -GAy / L);
+  sym(K, 2, 3, GAy * iL); sym(K, 8, 9, GAy * iL); sym(K, 2, 9, -GAy * iL); sym(K, 3, 8, -GAy * iL);
   sym(K, 2, 4, -GA / 2); sym(K, 2, 10, -GA / 2); sym(K, 4, 8, GA / 2); sym(K, 8, 10, GA / 2);
   sym(K, 3, 3, GJ); sym(K, 9, 9, GJ); sym(K, 3, 9, -GJ);
   sym(K, 3, 4, -GAy / 2); sym(K, 3, 10, -GAy / 2); sym(K, 4, 9, GAy / 2); sym(K, 9, 10, GAy / 2);
   sym(K, 3, 5, -GAz / 2); sym(K, 3, 11, -GAz / 2); sym(K, 5, 9, GAz / 2); sym(K, 9, 11, GAz / 2);
-  sym(K, 4, 4, GA * L / 4 + p.E * p.Iyy / L); sym(K, 10, 10, GA * L / 4 + p.E * p.Iyy / L);
-  sym(K, 4, 10, GA * L / 4 - p.E * p.Iyy / L);
-  sym(K, 5, 5, GA * L / 4 + p.E * p.Izz / L); sym(K, 11, 11, GA * L / 4 + p.E * p.Izz / L);
-  sym(K, 5, 11, GA * L / 4 - p.E * p.Izz / L);
-  sym(K, 4, 5, -p.E * p.Iyz / L); sym(K, 10, 11, -p.E * p.Iyz / L);
-  sym(K, 4, 11, p.E * p.Iyz / L); sym(K, 5, 10, p.E * p.Iyz / L);
+  sym(K, 4, 4, GA * L / 4 + p.E * p.Iyy * iL); sym(K, 10, 10, GA * L / 4 + p.E * p.Iyy * iL);
+  sym(K, 4, 10, GA * L / 4 - p.E * p.Iyy * iL);
+  sym(K, 5, 5, GA * L / 4 + p.E * p.Izz * iL); sym(K, 11, 11, GA * L / 4 + p.E * p.Izz * iL);
+  sym(K, 5, 11, GA * L / 4 - p.E * p.Izz * iL);
+  sym(K, 4, 5, -p.E * p.Iyz * iL); sym(K, 10, 11, -p.E * p.Iyz * iL);
+  sym(K, 4, 11, p.E * p.Iyz * iL); sym(K, 5, 10, p.E * p.Iyz * iL);
 }
 
 // beamlr.pyx:1388-1462 (literal 0.333.. / 0.1666.. constants of the reference kept)
 template <class KS>
 __device__ __forceinline__ void beamlr_KGe(const BeamP& p, double L, const double* ue, KS& K) {
   K.zero();
-  const double N = p.A * p.E * (-ue[0] + ue[6]) / L;
+  const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
+  (void)iL2; (void)iL3;
+  const double N = p.A * p.E * (-ue[0] + ue[6]) * iL;
   const double t = 0.333333333333333 * L * N, s = 0.166666666666667 * L * N;
   sym(K, 4, 4, t); sym(K, 5, 5, t); sym(K, 10, 10, t); sym(K, 11, 11, t);
   sym(K, 4, 5, -t); sym(K, 10, 11, -t);
@@ -214,6 +224,8 @@ __device__ __forceinline__ void beamlr_KGe(const BeamP& p, double L, const doubl
 template <class KS>
 __device__ __forceinline__ void beamlr_Me(const BeamP& p, double L, int mtype, bool truss, KS& K) {
   K.zero();
+  const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
+  (void)iL2; (void)iL3;
   double mb[6][6];
 #pragma unroll
   for (int i = 0; i < 6; ++i)
@@ -243,7 +255,7 @@ __device__ __forceinline__ void beamlr_Me(const BeamP& p, double L, int mtype, b
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) K.set(6 * a + i, 6 * b + j, ((a == b) ? L / 3 : L / 6) * mb[i][j]);
+          for (int j = 0; j < 6; ++j) K.set(6 * a + i, 6 * b + j, ((a == b) ? L / 3 : L * (1. / 6)) * mb[i][j]);
   } else {
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -255,7 +267,9 @@ __device__ __forceinline__ void beamlr_Me(const BeamP& p, double L, int mtype, b
 template <class KS>
 __device__ __forceinline__ void truss_Ke(const BeamP& p, double L, KS& K) {
   K.zero();
-  const double EA = p.E * p.A / L, GJ = p.G * p.J / L;
+  const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
+  (void)iL2; (void)iL3;
+  const double EA = p.E * p.A * iL, GJ = p.G * p.J * iL;
   sym(K, 0, 0, EA); sym(K, 6, 6, EA); sym(K, 0, 6, -EA);
   sym(K, 3, 3, GJ); sym(K, 9, 9, GJ); sym(K, 3, 9, -GJ);
 }
