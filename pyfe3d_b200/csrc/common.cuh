@@ -174,10 +174,14 @@ __device__ __forceinline__ void cross3(const double* a, const double* b, double*
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
 __device__ __forceinline__ double normalize3(double* v) {
+  // one division and three multiplications (the reference divides each component, quad4.pyx:548-552: the components
+  // differ from that in the last bit at most; a double division is a ~15-instruction sequence and every frame has three
+  // of these)
   double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-  v[0] /= n;
-  v[1] /= n;
-  v[2] /= n;
+  const double inv = 1. / n;
+  v[0] *= inv;
+  v[1] *= inv;
+  v[2] *= inv;
   return n;
 }
 

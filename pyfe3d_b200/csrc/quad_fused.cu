@@ -525,7 +525,11 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     else
       asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto rec_fetch = [&](int j) { rec_fetch_pair(j % kFRing, j < nitems ? np0 + j / rmax : int64_t(-1), j % rmax); };
+  // (rounds: rmax == 1 unless a node has more than 4 incident elements -- no runtime integer divisions then)
+  const bool one_round = rmax == 1;
+  auto rec_fetch = [&](int j) {
+    rec_fetch_pair(j % kFRing, j < nitems ? np0 + (one_round ? j : j / rmax) : int64_t(-1), one_round ? 0 : j % rmax);
+  };
   auto erec_prefetch = [&](int j, bool valid) {
     if (valid)
       erec_fetch(rec, rstride, erec + (j % kFBufs) * 8 * eld, (ring + (j % kFRing) * 2 + h)->inc[k], lane);
@@ -542,7 +546,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
 
   for (int j = 0;; ++j) {
     if (j >= nitems) break;
-    const int r = j % rmax;
+    const int r = one_round ? 0 : j % rmax;
     if constexpr (CHUNK > 1) {
       rec_fetch(j + 2);
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // node records j+1 and element records j have landed

@@ -66,9 +66,10 @@ __device__ __forceinline__ void material_axes(ShellGeom<NN>& g, const double* xm
   double v[3] = {xm[0], xm[1], xm[2]};
   double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
   if (!(n > tol)) return;
-  v[0] /= n;
-  v[1] /= n;
-  v[2] /= n;
+  const double inv = 1. / n;
+  v[0] *= inv;
+  v[1] *= inv;
+  v[2] *= inv;
   const double z[3] = {g.R.a[0][2], g.R.a[1][2], g.R.a[2][2]};
   const double xh[3] = {g.R.a[0][0], g.R.a[1][0], g.R.a[2][0]};
   const double yh[3] = {g.R.a[0][1], g.R.a[1][1], g.R.a[2][1]};

@@ -281,7 +281,8 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
   auto rec_fetch = [&](int j) {
     if (j < nitems && F.triarec != nullptr) {
       if (lane < 8) {
-        const char* src = reinterpret_cast<const char*>(F.triarec + (n0 + j / rmax) * rmax + j % rmax) + 16 * lane;
+        const int64_t rec_index = rmax == 1 ? n0 + j : (n0 + j / rmax) * rmax + j % rmax;   // no runtime division when
+        const char* src = reinterpret_cast<const char*>(F.triarec + rec_index) + 16 * lane;    // every node has one round
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32t(reinterpret_cast<char*>(ring + j % kTRing) + 16 * lane)),
                      "l"(src)
                      : "memory");
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
     const int nb = nr->nb, v = nr->v;
     const int64_t e = act ? (pair0 / 9) : 0;
     const int a = act ? ((pair0 - int(e) * 9) / 3) : 0;
-    const bool first = (j % rmax == 0);
+    const bool first = rmax == 1 || (j % rmax == 0);
     const int kk = (k < kTInc) ? k : 0;   // idle lanes compute on slab 0's record but never stage or store
 
     const double* re = erec + ((j & 1) * kTInc + kk) * eld;
