@@ -395,7 +395,10 @@ constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1216 doubles: the 
 // CTA scheduler alone orders the work; measured 10.4 ms against 11.0 / 11.5 ms for chunks of 2 / 4, which widen the
 // window of nodes in flight and take L1 away).  4: the next pair's records arrive by cp.async while this one is
 // computed (the latency-bound one- and two-matrix calls: config 3 2.46 -> 2.14 ms).
-constexpr int kFChunkBig = 4;
+#ifndef PF3_CHUNK_BIG
+#define PF3_CHUNK_BIG 4
+#endif
+constexpr int kFChunkBig = PF3_CHUNK_BIG;
 __host__ __device__ constexpr int fring(int chunk) { return chunk > 1 ? 3 : 1; }
 __host__ __device__ constexpr int fbufs(int chunk) { return chunk > 1 ? 2 : 1; }
 // per warp: slab staging | ring of node-record pairs (64 B each) | element records of 8 incidences (x2 when
@@ -857,7 +860,11 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
   const int w = F.A.what;
   const int vol = ((w & PF3_KC0) ? 900 : 0) + ((w & (PF3_KG | PF3_KG_STRESS)) ? 225 : 0) + ((w & PF3_M) ? 750 : 0);
   const bool mapped = F.um[0].active || F.um[1].active || F.um[2].active;
+#ifdef PF3_FORCE_CHUNK4
+  const int chunk = !mapped ? kFChunkBig : 1;
+#else
   const int chunk = (vol < 1400 && !mapped) ? kFChunkBig : 1;
+#endif
   if (phases & 1) {
     cudaError_t e1 = launch_k1(kind, F.A, rec, stride, 0, F.A.ne, 4, st, launches);
     if (e1 != cudaSuccess) return e1;
