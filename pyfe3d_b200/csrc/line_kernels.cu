@@ -410,6 +410,12 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
       P0[i] = A.x[3 * n0 + i];
       P1[i] = A.x[3 * n1 + i];
     }
+  double U[2][6];   // gathered with the coordinates, not after the frame: one exposed memory round trip less
+  if (need_u)
+    for (int i = 0; i < 6; ++i) {
+      U[0][i] = A.u[6 * n0 + i];
+      U[1][i] = A.u[6 * n1 + i];
+    }
   if (from_state) {
     const double* s = A.state + e * PF3_STATE_STRIDE;
     for (int i = 0; i < 3; ++i)
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
   if (need_u) {
     for (int a = 0; a < 2; ++a)
       for (int t = 0; t < 2; ++t) {
-        const double* ug = A.u + 6 * (a ? n1 : n0) + 3 * t;
+        const double* ug = U[a] + 3 * t;
         ue[6 * a + 3 * t + 0] = xh[0] * ug[0] + xh[1] * ug[1] + xh[2] * ug[2];
         ue[6 * a + 3 * t + 1] = yh[0] * ug[0] + yh[1] * ug[1] + yh[2] * ug[2];
         ue[6 * a + 3 * t + 2] = zh[0] * ug[0] + zh[1] * ug[1] + zh[2] * ug[2];

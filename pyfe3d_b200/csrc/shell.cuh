@@ -96,13 +96,18 @@ __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGe
   const bool need_x = !from_state || (A.state_flags & PF3_STATE_REFRESH_XE);
   const bool need_u = ue != nullptr && (!from_state || (A.state_flags & PF3_STATE_REFRESH_UE));
   int64_t cn[NN];
-  double P[NN][3];
+  double P[NN][3], U[NN][6];
 #pragma unroll
   for (int a = 0; a < NN; ++a) {
     cn[a] = A.conn[e * NN + a];
     if (need_x) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) P[a][i] = A.x[3 * cn[a] + i];
+    }
+    // the displacement gather is issued with the coordinate gather, not after the frame: one exposed DRAM round trip less
+    if (need_u) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) U[a][i] = A.u[6 * cn[a] + i];
     }
   }
   double xh[3], yh[3], zh[3];
@@ -200,8 +205,7 @@ __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGe
     for (int a = 0; a < NN; ++a)
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const double* ug = A.u + 6 * cn[a] + 3 * t;
-        double u0 = ug[0], u1 = ug[1], u2 = ug[2];
+        const double u0 = U[a][3 * t], u1 = U[a][3 * t + 1], u2 = U[a][3 * t + 2];
         ue[6 * a + 3 * t + 0] = xh[0] * u0 + xh[1] * u1 + xh[2] * u2;
         ue[6 * a + 3 * t + 1] = yh[0] * u0 + yh[1] * u1 + yh[2] * u2;
         ue[6 * a + 3 * t + 2] = zh[0] * u0 + zh[1] * u1 + zh[2] * u2;
