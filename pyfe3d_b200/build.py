@@ -47,7 +47,7 @@ def build_lib(force=False, verbose=True):
         src = os.path.join(CSRC, cu)
         obj = os.path.join(OBJDIR, cu[:-3] + ".o")
         if force or _newer(obj, [src] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("PF3_EXTRA_NVCC_FLAGS", "").split() + ["-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)

@@ -128,6 +128,23 @@ constexpr int kPfRuns = 4;
 // one-warp producer CTAs (K1 for 32 elements each) of the chunk 8 chunks later, per-chunk completion flags, consumers
 // find the records in L2.  Parity-green, 10.82 ms against 10.48 ms for K1 + K2 on the same box: the producers' gathers
 // of conn / x / u are DRAM reads inside the write stream again, and their latency-bound warps hold K2's CTA slots.
+// Thread-per-element kernels: the connectivity of the 32 elements a warp will gather through is streamed from DRAM and
+// heads a chain of dependent round trips (connectivity -> coordinates / displacements).  One lane per warp asks L2 for the
+// connectivity rows of the warp PF3_CONN_AHEAD elements further on, so that the first trip is an L2 hit.
+#ifndef PF3_CONN_AHEAD
+#define PF3_CONN_AHEAD 65536
+#endif
+__device__ __forceinline__ void conn_prefetch(const int64_t* conn, int nn, int64_t e0, int64_t ne, int lane) {
+#if PF3_CONN_AHEAD > 0
+  const int64_t e1 = e0 + PF3_CONN_AHEAD;
+  if (lane == 0 && e1 + 32 <= ne) {
+    const char* q = reinterpret_cast<const char*>(conn + e1 * nn);
+    const unsigned bytes = unsigned(32 * nn * 8);
+    if ((reinterpret_cast<uintptr_t>(q) & 15) == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(bytes) : "memory");
+  }
+#endif
+}
 constexpr int kPfChunk = 512;
 constexpr int kPfAhead = 8;   // (4, 8 and 16 chunks ahead measure the same, 32 slightly worse)
 // Halving the node records to 32 bytes (per-incidence slot lists, expanded into gmap by the kernel) was measured and

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(128, PF3_K1_CTAS) quad_record_kernel(const Eva
   // this launch covers elements [e_begin, e_end)
   const int64_t e0 = e_begin + (int64_t(blockIdx.x) * (blockDim.x >> 5) + warp) * 32;
   if (e0 >= e_end) return;
+  conn_prefetch(A.conn, 4, e0, e_end, lane);
   record_warp<KIND>(A, rec, stride, e0, int(min(int64_t(32), e_end - e0)), k1_smem + warp * 32 * (stride + 1), lane);
 }
 

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(128) tria_record_kernel(const EvalArgs A, doub
   if (e0 >= A.ne) return;
   const int nvalid = int(min(int64_t(32), A.ne - e0));
   const int64_t e = e0 + min(lane, nvalid - 1);
+  conn_prefetch(A.conn, 3, e0, A.ne, lane);
   const int ld = stride + 1;
   double* stage = k1_smem + warp * 32 * ld;
   const bool kg_u = (A.what & PF3_KG) != 0;

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(kThreads) tria_eval_kernel(const EvalArgs A) {
   if (e0 >= A.ne) return;
   const int nvalid = int(min(int64_t(32), A.ne - e0));
   const int64_t e = e0 + min(lane, nvalid - 1);
+  if (A.state == nullptr) conn_prefetch(A.conn, 3, e0, A.ne, lane);
   double* stage = smem + warp * 32 * kStageLd;
   double* my = stage + lane * kStageLd;
 

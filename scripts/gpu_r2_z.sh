@@ -1,6 +1,13 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python scripts/bench_configs.py --fint 2>&1 | tail -2 | cut -c1-130
-python scripts/bench_configs.py --kinds 2>&1 | tail -7 | cut -c1-330
-python scripts/bench_configs.py --config2 2>&1 | tail -1 | cut -c1-330
-python bench.py --steps 20 --warmup 3 --e2e-steps 0 --cpu-side 0 --others 0 --solve-side 0 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['roofline']['frac'], d['parity']['ok'])"
+python -m pytest tests -m gpu -x -q -k "fint or finte or config5 or mixed or elements_api or reference" 2>&1 | tail -3
+cp pyfe3d_b200/lib/libpyfe3d_b200.so /tmp/lib_default.so
+: > gpurun_out/r2z_pipe.txt
+for r in 1 2 3; do
+for name in default nopipe; do
+  if [ "$name" = "default" ]; then cp /tmp/lib_default.so pyfe3d_b200/lib/libpyfe3d_b200.so; else cp pyfe3d_b200/lib/variants/$name/libpyfe3d_b200.so pyfe3d_b200/lib/libpyfe3d_b200.so; fi
+  echo "== $name $r" >> gpurun_out/r2z_pipe.txt
+  python scripts/bench_configs.py --fint 2>&1 | tail -2 | cut -c1-130 >> gpurun_out/r2z_pipe.txt
+done
+done
+cp /tmp/lib_default.so pyfe3d_b200/lib/libpyfe3d_b200.so
+cat gpurun_out/r2z_pipe.txt
