@@ -7,9 +7,12 @@ leaves the GPU.  What it replaces in a reference script (tests/test_quad4_static
 
 Single device: ``plan_cg_solve`` runs ``pf3_plan_cg`` -- the whole iteration in native kernels (block SpMV + three fused
 vector kernels, deterministic reductions, convergence flag on the device).  Row-sharded over several GPUs it keeps the
-loop here, because the search direction is exchanged between ranks every iteration (NCCL all_gather).
+loop here, because the halo of the search direction is exchanged between ranks every iteration (grouped NCCL
+send / recv between the ranks whose row blocks meet: ``halo_plan`` / ``halo_exchange``).
 ``compact_csr`` / ``plan_compact`` return ``K[bu, :][:, bu]`` itself as a CSR matrix for callers that hand Kuu to scipy's
 ``spsolve`` / ``eigsh``."""
+import os
+
 import torch
 
 from .batch import _dev, _ptr, context
@@ -72,7 +75,8 @@ def cg_solve(indptr, indices, vals, b, free=None, rtol=1e-12, maxiter=None, x0=N
     return x, -maxiter
 
 
-def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, group=None, extra=()):
+def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, group=None, extra=(), check_every=16,
+                  graph=None):
     """Jacobi-preconditioned CG on the CSR values of a structured ``AssemblyPlan`` through its block SpMV
     (``pf3_plan_spmv``: no per-entry indices, 8.2 B per nonzero).
 
@@ -82,9 +86,12 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
 
     Single GPU: the plan owns every row.  Multi GPU (``group`` = a torch.distributed process group, one rank per
     GPU): every rank owns the row block of its plan (``node_range``) and holds vectors of its own rows; the search
-    direction is the only vector every rank needs in full, so each iteration does ONE all_gather of the owned
-    slices of p (the halo exchange of SURVEY 8(e)) and two scalar all_reduces.  ``b``/``free``/``x0`` are global
-    [6*nnodes] arrays; returns (x_global, info)."""
+    direction is the only vector a rank needs beyond its rows, and only at the columns its elements touch, so each
+    iteration does ONE point-to-point halo exchange of p (the halo exchange of SURVEY 8(e): grouped NCCL send/recv
+    between the ranks whose row blocks meet) and two small all_reduces; the iteration is allocation-free and the host looks at the residual
+    once per batch of ``check_every`` iterations.  ``graph=True`` replays each batch as one CUDA graph with the NCCL
+    operations captured; measured slower than eager launches on 2 B200 (1.87 against 0.44 ms per iteration at 6 M dofs),
+    so it is off by default.  ``b``/``free``/``x0`` are global [6*nnodes] arrays; returns (x_global, info)."""
     import torch.distributed as dist
     dev = vals.device
     n = 6 * plan.nnodes
@@ -113,63 +120,149 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
             out.add_(tmp, alpha=ce)
         return out
 
+    # Halo exchange.  A rank's rows read the columns of the nodes its elements touch: [need_lo, need_hi) is that range
+    # (from the connectivity), and what lies outside the own rows comes from the ranks that own it -- point-to-point
+    # (NCCL send / recv grouped into one launch), straight between the global-length direction vectors: on a banded
+    # numbering that is one mesh line of dofs per neighbour instead of an all_gather of the whole vector.
+    world, me = dist.get_world_size(group), dist.get_rank(group)
+    cmin = min(int(bb.conn.min()) for pp in (plan,) + tuple(e[0] for e in extra) for bb in pp.batches)
+    cmax = max(int(bb.conn.max()) for pp in (plan,) + tuple(e[0] for e in extra) for bb in pp.batches)
+    mine = torch.tensor([lo, hi, min(6 * cmin, lo), max(6 * cmax + 6, hi)], dtype=torch.int64, device=dev)
+    table = torch.empty(4 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(table, mine, group=group)
+    table = table.view(world, 4).tolist()
+    halo = halo_plan(table, me)
+    pg = torch.zeros(n, dtype=torch.float64, device=dev)          # direction, global length: own rows + halo are current
+
+    full_gather = os.environ.get("PF3_CG_EXCHANGE", "halo") == "all_gather"    # A/B switch for scripts/bench_cg_multi.py
+
+    def exchange():
+        if full_gather:
+            pg.copy_(gather_all(p.clone()))
+            return pg
+        return halo_exchange(pg, halo, group)
+
     def allsum(t):
-        if multi:
-            dist.all_reduce(t, group=group)
+        dist.all_reduce(t, group=group)
         return t
 
-    if multi:
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(dist.get_world_size(group))]
-        dist.all_gather(sizes, torch.tensor([hi - lo], dtype=torch.int64, device=dev), group=group)
-        sizes = [int(t.item()) for t in sizes]
-        same = len(set(sizes)) == 1
-
-    pg = torch.zeros(n, dtype=torch.float64, device=dev)          # global search direction
-
-    def gather(local):
-        if not multi:
-            pg.copy_(local)
-        elif same:
-            dist.all_gather_into_tensor(pg, local.contiguous(), group=group)
+    def gather_all(local):
+        sizes = [row[1] - row[0] for row in table]
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        if len(set(sizes)) == 1:
+            dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         else:
             parts = [torch.empty(sz, dtype=torch.float64, device=dev) for sz in sizes]
             dist.all_gather(parts, local.contiguous(), group=group)
-            torch.cat(parts, out=pg)
-        return pg
+            torch.cat(parts, out=out)
+        return out
 
+    p = pg[lo:hi]                                                 # the own slice IS the local direction vector
     x = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+    ap = torch.empty_like(x)
     if x0 is not None:
         x = _dev(x0, torch.float64, dev)[lo:hi] * fl
-    ap = torch.empty_like(x)
-    r = bl - matvec(gather(x), ap)
+        p.copy_(x)
+        r = bl - matvec(exchange(), ap)
+    else:
+        r = bl.clone()
     z = minv * r
-    p = z.clone()
-    rz = allsum(torch.dot(r, z))
-    bnorm = float(allsum(torch.dot(bl, bl)).sqrt())
-    if bnorm == 0.0:
-        return gather(x).clone(), 0
+    p.copy_(z)
+    sc = allsum(torch.stack([torch.dot(r, z), torch.dot(r, r), torch.dot(bl, bl)]))
+    rz = sc[0].clone()
+    bnorm = float(sc[2].sqrt())
     maxiter = maxiter or 10 * n
-    info = -maxiter
-    if float(allsum(torch.dot(r, r)).sqrt()) <= rtol * bnorm or float(rz) == 0.0:
-        return gather(x).clone(), 0
-    for it in range(1, maxiter + 1):
-        matvec(gather(p), ap)
-        pap = allsum(torch.dot(p, ap))
-        if it % 8 == 1 and not float(pap) > 0.0:           # breakdown: not positive definite on the free dofs
+    if bnorm == 0.0 or float(sc[1].sqrt()) <= rtol * bnorm or float(rz) == 0.0:
+        return gather_all(x), 0
+    two = torch.zeros(2, dtype=torch.float64, device=dev)
+    pap, alpha, beta = (torch.zeros((), dtype=torch.float64, device=dev) for _ in range(3))
+
+    def iterate():
+        # one iteration, allocation-free and without host synchronisation: every operand is a fixed buffer, so a batch of
+        # iterations can be captured into a CUDA graph (NCCL operations included) and replayed
+        matvec(exchange(), ap)
+        torch.dot(p, ap, out=pap)
+        allsum(pap)
+        torch.div(rz, pap, out=alpha)
+        x.addcmul_(alpha, p)
+        r.addcmul_(alpha, ap, value=-1.0)
+        torch.mul(minv, r, out=z)
+        two[0].copy_(torch.dot(r, z))
+        two[1].copy_(torch.dot(r, r))
+        allsum(two)                                        # one all_reduce for both scalars
+        torch.div(two[0], rz, out=beta)
+        torch.addcmul(z, beta, p, out=p)                   # p = z + beta p, in place in the global vector
+        rz.copy_(two[0])
+
+    def state():
+        # (breakdown, converged) from the scalars of the last iteration -- the only host synchronisation of a batch
+        t = torch.stack([pap, two[1], two[0]]).tolist()
+        return (not t[0] > 0.0), (t[1] ** 0.5 <= rtol * bnorm or t[2] == 0.0)
+
+    it, info = 0, -maxiter
+    graph_obj = None
+    want_graph = bool(graph)
+    while it < maxiter:
+        k = min(check_every, maxiter - it)
+        if want_graph and graph_obj is None and it >= check_every and k == check_every:
+            # the first batch ran eagerly (warm-up: NCCL channels, allocator); capture the second one
+            try:
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for _ in range(check_every):
+                        iterate()
+                graph_obj = g                              # capture does not execute: replay below runs this batch
+            except Exception:                              # NCCL / driver without capture support: stay eager
+                want_graph = False
+                torch.cuda.synchronize(dev)
+        if graph_obj is not None and k == check_every:
+            graph_obj.replay()
+        else:
+            for _ in range(k):
+                iterate()
+        it += k
+        broke, conv = state()
+        if broke:                                          # not positive definite on the free dofs (or NaN)
             info = -it
             break
-        alpha = rz / pap
-        x += alpha * p
-        r -= alpha * ap
-        z = minv * r
-        rz_new = allsum(torch.dot(r, z))
-        if (it % 8 == 0 or it == maxiter) and (float(allsum(torch.dot(r, r)).sqrt()) <= rtol * bnorm
-                                               or float(rz_new) == 0.0):
+        if conv:
             info = it
             break
-        p = z + (rz_new / rz) * p
-        rz = rz_new
-    return gather(x).clone(), info
+    return gather_all(x), info
+
+
+def halo_exchange(vec, halo, group):
+    """One halo exchange of the global-length vector ``vec`` (own rows current on entry, own rows + halo on return):
+    every (send, recv) pair of ``halo_plan`` as grouped point-to-point operations (one NCCL launch)."""
+    import torch.distributed as dist
+    ops = []
+    for r, (s0, s1), (r0, r1) in halo:
+        peer = dist.get_global_rank(group, r) if group is not None and group is not dist.group.WORLD else r
+        if s1 > s0:
+            ops.append(dist.P2POp(dist.isend, vec[s0:s1], peer, group=group))
+        if r1 > r0:
+            ops.append(dist.P2POp(dist.irecv, vec[r0:r1], peer, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return vec
+
+
+def halo_plan(table, me):
+    """Who sends what to whom: ``table[r] = (lo, hi, need_lo, need_hi)`` (dof ranges: rows owned by rank r, columns its
+    rows read).  Returns [(r, (send_lo, send_hi), (recv_lo, recv_hi))] for every rank r != me with something to move:
+    rank `me` sends the part of ITS rows that r reads and receives the part of r's rows that IT reads."""
+    lo, hi, need_lo, need_hi = table[me]
+    out = []
+    for r, (rlo, rhi, rneed_lo, rneed_hi) in enumerate(table):
+        if r == me:
+            continue
+        send = (max(rneed_lo, lo), min(rneed_hi, hi))
+        recv = (max(need_lo, rlo), min(need_hi, rhi))
+        if send[1] > send[0] or recv[1] > recv[0]:
+            out.append((r, send if send[1] > send[0] else (0, 0), recv if recv[1] > recv[0] else (0, 0)))
+    return out
 
 
 def plan_cg_native(plan, vals, b, free=None, rtol=1e-12, atol=0.0, maxiter=None, x0=None, extra=(),

@@ -1,6 +1,6 @@
 """GPU, world_size 2, NCCL (skipped with fewer than two GPUs): config 1 evaluated, assembled and solved with the rows
 sharded over two ranks -- each rank runs the fused kernel on the elements touching its node range, keeps its own
-CSR row block, and the Jacobi-CG exchanges only the search direction (one all_gather per iteration)."""
+CSR row block, and the Jacobi-CG exchanges only the halo of the search direction (grouped NCCL send / recv per iteration)."""
 import json
 import os
 import socket
