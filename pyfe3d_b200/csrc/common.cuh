@@ -57,6 +57,23 @@ struct EvalArgs {
   int acc_kc0, acc_kg, acc_m;
 };
 
+// Property-table row of element e.  Under compute-sanitizer's memcheck the SASS this compiles to (a predicated-off LDG +
+// CS2R + predicated IMAD.WIDE) is executed with garbage row offsets -- false out-of-bounds reports at the property loads
+// that follow, although the hardware runs it correctly (goldens match to 1e-12, and a build with a printf next to it is
+// clean under the tool).  -DPF3_MEMCHECK_BUILD (scripts/build_memcheck_lib.sh, used by scripts/gpu_sanitizer.sh) selects
+// a form with an unconditional index load and selects, which keeps memcheck usable on the whole library; it costs about
+// 1 % on update_fint / config 4 (one more dependent load in front of the property loads), so it is not the default.
+__device__ __forceinline__ int64_t prop_index(const EvalArgs& A, int64_t e) {
+#ifdef PF3_MEMCHECK_BUILD
+  const bool has = A.prop_id != nullptr;
+  const int32_t* pp = has ? A.prop_id + e : reinterpret_cast<const int32_t*>(A.conn);
+  const int v = *pp;
+  return has ? int64_t(v) : int64_t(0);
+#else
+  return A.prop_id ? int64_t(A.prop_id[e]) : int64_t(0);
+#endif
+}
+
 // destinations of the piston-theory matrices (quad_aero_kernel): 0 KA_beta, 1 KA_gamma, 2 CA
 struct AeroOut {
   double* v[3];

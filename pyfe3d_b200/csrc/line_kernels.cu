@@ -506,8 +506,7 @@ __global__ void __launch_bounds__(kThreads) line_eval_kernel(const EvalArgs A) {
   if (KIND == PF3_SPRING) {
     for (int i = 0; i < 6; ++i) kspr[i] = A.eparam[e * PF3_EPARAM_STRIDE + i];
   } else {
-    const int pid = A.prop_id ? A.prop_id[e] : 0;
-    const double* q = A.props + int64_t(pid) * PF3_BEAMPROP_STRIDE;
+    const double* q = A.props + prop_index(A, e) * PF3_BEAMPROP_STRIDE;
     p.A = q[0]; p.E = q[1]; p.G = q[2]; p.Iyy = q[3]; p.Izz = q[4]; p.Iyz = q[5]; p.J = q[6]; p.Ay = q[7];
     p.Az = q[8]; p.r0 = q[9]; p.ry = q[10]; p.rz = q[11]; p.ry2 = q[12]; p.rz2 = q[13]; p.ryz = q[14];
   }

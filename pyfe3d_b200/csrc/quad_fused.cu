@@ -75,7 +75,7 @@ __device__ __forceinline__ void record_warp(const EvalArgs& A, double* __restric
   const bool kg_u = (A.what & PF3_KG) != 0;
   double ue[24];
   ShellGeom<4> g;
-  shell_geom<4>(A, e, g, kg_u ? ue : nullptr);
+  shell_geom<4, true>(A, e, g, kg_u ? ue : nullptr);
   double* r = stage + lane * ld;
   const bool rot = A.evec != nullptr;
 #pragma unroll
@@ -108,7 +108,7 @@ __device__ __forceinline__ void record_warp(const EvalArgs& A, double* __restric
   r[19] = g.area;
   constexpr int kHg = (KIND == PF3_QUAD4R) ? kRecHg : 0;
   if (KIND == PF3_QUAD4 && A.props != nullptr) {
-    const double hh = A.props[int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE + 23];
+    const double hh = A.props[prop_index(A, e) * PF3_SHELLPROP_STRIDE + 23];
     if (hh / sqrt(g.area) >= 1.) r[19] = -g.area;   // thick: transverse shear integrated at 2x2 (quad4.pyx:1032,1127)
   }
   if (kg_u || rot || KIND == PF3_QUAD4R) {
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(32 * kFusedWarps, PF3_FUSED_CTAS) quad_fused_k
     const bool thick = (KIND == PF3_QUAD4) && rr_[19] < 0.;   // decided once per element by K1
     constexpr int kHg = (KIND == PF3_QUAD4R) ? kRecHg : 0;
     const bool kg_u = (A.what & PF3_KG) != 0;
-    const double* prow = A.props + int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE;
+    const double* prow = A.props + prop_index(A, e) * PF3_SHELLPROP_STRIDE;
     const double* abd = (A.evec != nullptr) ? re + kRecBase + kHg + (kg_u ? kRecN : 0) : prow;
 
     // Jacobian rows: J11,J12 depend on eta only, J21,J22 on xi only (index 0: -p, 1: +p)

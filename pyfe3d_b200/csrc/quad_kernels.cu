@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, ONLY ? PF3_FINT_CTAS : 1) quad_eval_
   const bool need_u = (what & (PF3_KG | PF3_FINT)) != 0 || A.state_out != nullptr;
   double ue[24];
   ShellGeom<4> g;
-  shell_geom<4>(A, e, g, need_u && (A.u != nullptr || A.state != nullptr) ? ue : nullptr);
+  shell_geom<4, true>(A, e, g, need_u && (A.u != nullptr || A.state != nullptr) ? ue : nullptr);
   if (A.state_out != nullptr) {
     if (lane < nvalid) store_state<4>(A, e, g, (A.u != nullptr || A.state != nullptr) ? ue : nullptr);
     if (what == 0) return;

@@ -90,7 +90,9 @@ __device__ __forceinline__ void material_axes(ShellGeom<NN>& g, const double* xm
 
 // Quad4/Quad4R.update_rotation_matrix + update_probe_xe + update_area
 // (quad4.pyx:491-624, 682-752); Tria3R: tria3r.pyx:294-424, 480-547.
-template <int NN>
+// EARLY_U: gather the displacements together with the coordinates instead of after the frame (one exposed DRAM round
+// trip less: update_fint 0.99 -> 0.92 ms at 4 M Quad4).
+template <int NN, bool EARLY_U = false>
 __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGeom<NN>& g, double* ue) {
   const bool from_state = A.state != nullptr;
   const bool need_x = !from_state || (A.state_flags & PF3_STATE_REFRESH_XE);
@@ -104,8 +106,7 @@ __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGe
 #pragma unroll
       for (int i = 0; i < 3; ++i) P[a][i] = A.x[3 * cn[a] + i];
     }
-    // the displacement gather is issued with the coordinate gather, not after the frame: one exposed DRAM round trip less
-    if (need_u) {
+    if (EARLY_U && need_u) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) U[a][i] = A.u[6 * cn[a] + i];
     }
@@ -205,7 +206,13 @@ __device__ __forceinline__ void shell_geom(const EvalArgs& A, int64_t e, ShellGe
     for (int a = 0; a < NN; ++a)
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const double u0 = U[a][3 * t], u1 = U[a][3 * t + 1], u2 = U[a][3 * t + 2];
+        double u0, u1, u2;
+        if (EARLY_U) {
+          u0 = U[a][3 * t], u1 = U[a][3 * t + 1], u2 = U[a][3 * t + 2];
+        } else {
+          const double* ug = A.u + 6 * cn[a] + 3 * t;
+          u0 = ug[0], u1 = ug[1], u2 = ug[2];
+        }
         ue[6 * a + 3 * t + 0] = xh[0] * u0 + xh[1] * u1 + xh[2] * u2;
         ue[6 * a + 3 * t + 1] = yh[0] * u0 + yh[1] * u1 + yh[2] * u2;
         ue[6 * a + 3 * t + 2] = zh[0] * u0 + zh[1] * u1 + zh[2] * u2;
@@ -255,8 +262,7 @@ __device__ __forceinline__ void rotate_sym3(const double (*T)[3], const double* 
 template <int NN>
 __device__ __forceinline__ void shell_coef(const EvalArgs& A, int64_t e, const ShellGeom<NN>& g,
                                            ShellCoef& c) {
-  const int pid = A.prop_id ? A.prop_id[e] : 0;
-  const double* p = A.props + int64_t(pid) * PF3_SHELLPROP_STRIDE;
+  const double* p = A.props + prop_index(A, e) * PF3_SHELLPROP_STRIDE;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     c.A[i] = p[i];

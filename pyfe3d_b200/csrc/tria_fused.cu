@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) tria_record_kernel(const EvalArgs A, doub
   const bool kg_u = (A.what & PF3_KG) != 0;
   double ue[18];
   ShellGeom<3> g;
-  shell_geom<3>(A, e, g, kg_u ? ue : nullptr);
+  shell_geom<3, true>(A, e, g, kg_u ? ue : nullptr);
   ShellCoef c;
   shell_coef<3>(A, e, g, c);
   double K6ROT = 100., alpha = 0.7;
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(32 * kTWarps, PF3_TFUSED_CTAS) tria_fused_kern
       for (int jj = 0; jj < 3; ++jj) R.a[i][jj] = re[3 * i + jj];
     const double Nxa = re[9 + a], Nya = re[12 + a], Nxb = re[9 + b], Nyb = re[12 + b];
     const double w = re[15], kd = re[16], E44 = re[17], E45 = re[18], E55 = re[19], dJ = re[20];
-    const double* prow = A.props + int64_t(A.prop_id ? A.prop_id[e] : 0) * PF3_SHELLPROP_STRIDE;
+    const double* prow = A.props + prop_index(A, e) * PF3_SHELLPROP_STRIDE;
     const double* abd = (rstride == kTRecRot) ? re + 24 : prow;
     const bool stager = act && k < kTInc;
 

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kThreads) tria_eval_kernel(const EvalArgs A) {
   const bool have_u = (A.u != nullptr || A.state != nullptr);
   double ue[18];
   ShellGeom<3> g;
-  shell_geom<3>(A, e, g, have_u ? ue : nullptr);
+  shell_geom<3, true>(A, e, g, have_u ? ue : nullptr);
   if (A.state_out != nullptr) {
     if (lane < nvalid) store_state<3>(A, e, g, have_u ? ue : nullptr);
     if (A.what == 0) return;
