@@ -14,6 +14,9 @@ grows to N x side x side elements); the same line carries, under `details`,
   * `others`  : BASELINE configs 2-5 timed with the same clock (N=1: config 5 as one GPU's share; N>1: sharded),
   * `solve_e2e`: a user-level end-to-end — host x in, KC0 assembled and the static problem solved by the native CG on the
                 device, only u back — next to the reference doing loop + tocsc + scipy cg on the same mesh,
+  * `sharded_cg`: (N>1) the one downstream exchange step — Jacobi-CG on KC0 with the rows sharded over the ranks: block SpMV
+                on the own rows + point-to-point halo exchange of the search direction (grouped NCCL send / recv), ms per
+                iteration, with the all_gather it replaces beside it and the true residual as a correctness bit,
 and a `parity` object: checksums that tie every rank's CSR block to its COO arrays and to closed forms, all-reduced, so
 that every line of a scaling run carries a correctness bit.
 Prints one JSON line (rank 0).
@@ -512,6 +515,58 @@ def solve_e2e(torch, meshes, dev, side):
             "d2h_bytes": int(uh.numel() * 8)}
 
 
+def sharded_cg(torch, dist, meshes, rank, world, dev, side, k1=64, k2=256):
+    """N > 1: the one downstream exchange step of the path -- Jacobi-CG on KC0 of the side x side plate with the rows
+    sharded over the ranks (SURVEY 8(e) + 8(f) rank 1): fused assembly of the own row block, then
+    ``plan_cg_solve(group=WORLD)``: block SpMV on the own rows, point-to-point halo exchange of the search direction
+    (grouped NCCL send / recv), two small all_reduces per iteration.  ms per iteration = slope between two iteration
+    counts, device-timed, max over ranks; the same with an all_gather of the whole direction beside it."""
+    import numpy as np
+    from pyfe3d_b200 import sharding
+    from pyfe3d_b200.batch import AssemblyPlan
+    from pyfe3d_b200.solve import plan_cg_solve
+    case, free, f, normal = meshes.static_case(side)
+    n = case["ndof"]
+    sub = sharding.shard_case(case, rank, world)
+    b = meshes.batch_from_case(sub, device=dev)
+    plan = AssemblyPlan("KC0", n // 6, [b], node_range=sub["owned_nodes"])
+    _, csr = plan.evaluate_assemble(KC0=True, write_coo=False)
+    vals = csr["KC0"]
+    free_t = torch.as_tensor(free.astype(np.uint8)).to(dev)
+    ft = torch.as_tensor(f).to(dev)
+
+    def timed(iters):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x, info = plan_cg_solve(plan, vals, ft, free=free_t, rtol=0., maxiter=iters, group=dist.group.WORLD)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), x
+
+    out = {"what": "row-sharded Jacobi-CG on KC0 of the %dx%d plate (%d dofs, clamped edges): ms per iteration over %d ranks"
+                   % (side, side, n, world), "rows_per_rank": plan.nrows, "nnz_per_rank": plan.nnz}
+    xs = {}
+    for mode in ("halo", "all_gather"):
+        os.environ["PF3_CG_EXCHANGE"] = mode
+        timed(32)
+        t1, _ = timed(k1)
+        t2, xs[mode] = timed(k2)
+        out["ms_per_iteration_" + ("halo_p2p" if mode == "halo" else "all_gather")] = (t2 - t1) / (k2 - k1)
+    os.environ["PF3_CG_EXCHANGE"] = "halo"
+    # correctness bit: the iterates do not depend on HOW the direction reaches the other ranks -- after k2 iterations the
+    # solution of the halo exchange must equal the one of the all_gather (a wrong or missing halo entry changes it at once)
+    lo, hi = 6 * plan.node_begin, 6 * plan.node_end
+    d = torch.stack([(xs["halo"][lo:hi] - xs["all_gather"][lo:hi]).abs().max(), xs["all_gather"][lo:hi].abs().max()])
+    dist.all_reduce(d, op=dist.ReduceOp.MAX)
+    out["halo_vs_all_gather_rel_diff_after_%d_iterations" % k2] = float(d[0] / d[1])
+    out["ok"] = bool(float(d[0]) <= 1e-12 * float(d[1]))
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -562,6 +617,13 @@ def run_ours(args):
                                   8, peak, args.steps))
         except Exception as exc:  # reporting only: the headline stands without it
             others.append({"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])})
+    # ---- the downstream exchange step: row-sharded CG with a point-to-point halo exchange (N > 1)
+    cg = None
+    if world > 1 and args.cg_side > 0:
+        try:
+            cg = sharded_cg(torch, dist, meshes, rank, world, dev, args.cg_side)
+        except Exception as exc:  # reporting only
+            cg = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     # ---- user-level end to end (one GPU)
     solve = None
     if rank == 0 and args.solve_side > 0:
@@ -643,7 +705,7 @@ def run_ours(args):
                        "halo": "row-ownership strips, halo elements duplicated, no collective on the data path",
                        "output_gb_per_step_per_gpu": (BYTES_ASM_READ + BYTES_CSR) * ne_local / 1e9,
                        "symbolic_plan_s": weak["symbolic_s"], "indices": "values only (update_*v_only=1); plan built once",
-                       "path": args.path, "strong": strong, "others": others, "solve_e2e": solve},
+                       "path": args.path, "strong": strong, "others": others, "solve_e2e": solve, "sharded_cg": cg},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": weak.get("e2e"), "gpu_launches": weak["launches"],
             "clocks": weak["clocks"], "parity": weak["parity"]}
     print(json.dumps(line))
@@ -705,6 +767,7 @@ def main():
     ap.add_argument("--strong", type=int, default=1, help="N>1: also time the metric's own size cut into N strips")
     ap.add_argument("--others", type=int, default=1, help="also time BASELINE configs 2-5 (config.others)")
     ap.add_argument("--others-scale", type=float, default=1.0, help="shrink the other configs (smoke tests)")
+    ap.add_argument("--cg-side", type=int, default=2000, help="N>1: side of the plate of the row-sharded CG leg (0: skip)")
     ap.add_argument("--solve-side", type=int, default=32, help="side of the static-solve end-to-end workload (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -6,7 +6,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
     python bench.py --steps 5 --warmup 3 --e2e-steps 0 --cpu-side 0 --others 0 --solve-side 0 > gpurun_out/r02_launches_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'quad_fused|quad_record' -s 6 -c 2 -o gpurun_out/r02_prof \
     python bench.py --steps 2 --warmup 3 --e2e-steps 0 --cpu-side 0 --others 0 --solve-side 0 > gpurun_out/r02_prof_bench.log 2>&1
-ncu --set full --clock-control none -k regex:'quad_fused|quad_record' -s 8 -c 2 -o gpurun_out/r02_prof_cfg3 \
+ncu --set full --clock-control none -k regex:quad_fused -s 4 -c 1 -o gpurun_out/r02_prof_cfg3 \
     python scripts/bench_configs.py --config3 > gpurun_out/r02_prof_cfg3.log 2>&1
 ncu --set full --clock-control none -k regex:'tria_fused|tria_record' -s 8 -c 2 -o gpurun_out/r02_prof_cfg4 \
     python scripts/bench_configs.py --config4 > gpurun_out/r02_prof_cfg4.log 2>&1
