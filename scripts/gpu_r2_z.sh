@@ -5,5 +5,5 @@ import json
 d=json.loads(open("gpurun_out/r02_bench_line_2gpu.json").read().strip().splitlines()[-1])
 print(d["value"], d["ms_per_step"], d["parity"]["ok"], d["details"]["strong"])
 print(d["details"]["sharded_cg"])
-print(d["e2e"]["value"], d["e2e"].get("d2h_gbs_per_rank"))
+print(d["e2e"]["value"], d["e2e"].get("d2h_gbs_per_rank"), d["e2e"]["symmetric_upper"]["value"])
 PY
