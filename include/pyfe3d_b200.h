@@ -308,6 +308,20 @@ int pf3_plan_cg(pf3_context* ctx, int nops, const pf3_plan* const* plans, const 
 int pf3_plan_spmv_scaled(pf3_context* ctx, const pf3_plan* plan, const double* vals, const unsigned char* free_dof,
                          const double* scale, const double* x, double* y);
 
+/* The vector kernels of ONE iteration of the Jacobi-CG on a rank's OWN rows, for the row-sharded multi-GPU solve
+ * (pyfe3d_b200/solve.py plan_cg_solve with a process group: block SpMV on the own rows, point-to-point halo exchange of
+ * the search direction, these three fused kernels with two small all_reduces between them).  n: own rows.
+ *   sc (device, 4 doubles): [0] p.Ap   [1] new r.M^-1.r   [2] r.r   [3] current r.M^-1.r
+ *   _dot   : sc[0] = sum p*ap over the own rows                          -> caller all-reduces sc[0]
+ *   _update: a = sc[3]/sc[0]; x += a p; r -= a ap; sc[1] = sum r*minv*r; sc[2] = sum r*r   -> caller all-reduces sc[1..2]
+ *   _dir   : p = minv r + (sc[1]/sc[3]) p; then sc[3] = sc[1]
+ * Reductions are deterministic (fixed block order).  work: pf3_cg_shard_work_bytes() bytes on the device, zeroed once. */
+size_t pf3_cg_shard_work_bytes(void);
+int pf3_cg_shard_dot(pf3_context* ctx, int64_t n, const double* p, const double* ap, double* sc, void* work);
+int pf3_cg_shard_update(pf3_context* ctx, int64_t n, const double* p, const double* ap, const double* minv, double* x,
+                        double* r, double* sc, void* work);
+int pf3_cg_shard_dir(pf3_context* ctx, int64_t n, const double* r, const double* minv, double* p, double* sc, void* work);
+
 /* K[bu, :][:, bu] as an explicit CSR matrix (tests/test_quad4_static_point_load.py:84-99) from a device CSR matrix whose
  * rows are the global rows [row0, row0 + nrows) (row0 = 6*node_begin of a row-sharded plan, else 0) and whose column
  * indices are global in [0, ncols): rows / columns with free_dof[.] != 0 are kept and renumbered by their rank among

@@ -86,6 +86,12 @@ cdef extern from "pyfe3d_b200.h":
     int pf3_plan_cg(pf3_context*, int nops, const pf3_plan* const* plans, const double* const* vals,
                     const double* coefs, const unsigned char* free_dof, const double* b, double* x, int use_x0,
                     double rtol, double atol, int maxiter, int flags, pf3_cg_info* info) nogil
+    size_t pf3_cg_shard_work_bytes() nogil
+    int pf3_cg_shard_dot(pf3_context*, int64_t n, const double* p, const double* ap, double* sc, void* work) nogil
+    int pf3_cg_shard_update(pf3_context*, int64_t n, const double* p, const double* ap, const double* minv, double* x,
+                            double* r, double* sc, void* work) nogil
+    int pf3_cg_shard_dir(pf3_context*, int64_t n, const double* r, const double* minv, double* p, double* sc,
+                         void* work) nogil
     int pf3_plan_spmv_scaled(pf3_context*, const pf3_plan*, const double* vals, const unsigned char* free_dof,
                              const double* scale, const double* x, double* y) nogil
     int pf3_csr_compact_symbolic(pf3_context*, int64_t nrows, int64_t ncols, const int64_t* indptr,
@@ -133,6 +139,10 @@ cdef int _check(int rc) except -1:
     if rc == -1:
         raise ValueError(msg)
     raise Pf3Error("%s (code %d)" % (msg, rc))
+
+
+def cg_shard_work_bytes():
+    return pf3_cg_shard_work_bytes()
 
 
 def version():
@@ -369,6 +379,27 @@ cdef class Context:
                              use_x0, rtol, atol, maxiter, flags, &info)
         _check(rc)
         return info.iterations, info.status, info.residual, info.bnorm
+
+    def cg_shard_dot(self, int64_t n, uintptr_t p, uintptr_t ap, uintptr_t sc, uintptr_t work):
+        cdef int rc
+        with nogil:
+            rc = pf3_cg_shard_dot(self.ctx, n, <const double*>p, <const double*>ap, <double*>sc, <void*>work)
+        _check(rc)
+
+    def cg_shard_update(self, int64_t n, uintptr_t p, uintptr_t ap, uintptr_t minv, uintptr_t x, uintptr_t r,
+                        uintptr_t sc, uintptr_t work):
+        cdef int rc
+        with nogil:
+            rc = pf3_cg_shard_update(self.ctx, n, <const double*>p, <const double*>ap, <const double*>minv, <double*>x,
+                                     <double*>r, <double*>sc, <void*>work)
+        _check(rc)
+
+    def cg_shard_dir(self, int64_t n, uintptr_t r, uintptr_t minv, uintptr_t p, uintptr_t sc, uintptr_t work):
+        cdef int rc
+        with nogil:
+            rc = pf3_cg_shard_dir(self.ctx, n, <const double*>r, <const double*>minv, <double*>p, <double*>sc,
+                                  <void*>work)
+        _check(rc)
 
     def memcpy_h2d(self, uintptr_t dst, uintptr_t src, size_t n):
         cdef int rc

@@ -44,6 +44,12 @@ int fint_gather(cudaStream_t st, int64_t ne, int nn, int64_t nnodes, const int64
                 double* fint, int64_t* launches);
 int64_t plan_nnz(const pf3_plan* pl);
 int64_t plan_nblocks(const pf3_plan* pl);
+size_t cg_shard_work_bytes();
+int cg_shard_dot(cudaStream_t st, int64_t n, const double* p, const double* ap, double* sc, void* work, int64_t* launches);
+int cg_shard_update(cudaStream_t st, int64_t n, const double* p, const double* ap, const double* minv, double* x, double* r,
+                    double* sc, void* work, int64_t* launches);
+int cg_shard_dir(cudaStream_t st, int64_t n, const double* r, const double* minv, double* p, double* sc, void* work,
+                 int64_t* launches);
 int plan_fint_gather(const pf3_plan* pl, cudaStream_t st, int group, const double* fe, double* fint, int64_t* launches);
 int plan_group_kind_nn(const pf3_plan* pl, int group);
 int64_t plan_group_ne_of(const pf3_plan* pl, int group);
@@ -947,6 +953,30 @@ int pf3_plan_cg(pf3_context* ctx, int nops, const pf3_plan* const* plans, const 
     info->bnorm = bnorm;
   }
   return rc;
+}
+
+size_t pf3_cg_shard_work_bytes(void) { return pf3::cg_shard_work_bytes(); }
+
+int pf3_cg_shard_dot(pf3_context* ctx, int64_t n, const double* p, const double* ap, double* sc, void* work) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (n <= 0 || !p || !ap || !sc || !work) return PF3_E_BAD_ARG;
+  return pf3::cg_shard_dot(ctx->stream, n, p, ap, sc, work, &ctx->launches);
+}
+
+int pf3_cg_shard_update(pf3_context* ctx, int64_t n, const double* p, const double* ap, const double* minv, double* x,
+                        double* r, double* sc, void* work) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (n <= 0 || !p || !ap || !minv || !x || !r || !sc || !work) return PF3_E_BAD_ARG;
+  return pf3::cg_shard_update(ctx->stream, n, p, ap, minv, x, r, sc, work, &ctx->launches);
+}
+
+int pf3_cg_shard_dir(pf3_context* ctx, int64_t n, const double* r, const double* minv, double* p, double* sc, void* work) {
+  int rc = use_device(ctx);
+  if (rc) return rc;
+  if (n <= 0 || !r || !minv || !p || !sc || !work) return PF3_E_BAD_ARG;
+  return pf3::cg_shard_dir(ctx->stream, n, r, minv, p, sc, work, &ctx->launches);
 }
 
 int pf3_plan_spmv_scaled(pf3_context* ctx, const pf3_plan* plan, const double* vals, const unsigned char* free_dof,

@@ -205,12 +205,81 @@ __global__ void __launch_bounds__(kCgThreads) k_cg_dir(int64_t n, const double* 
   }
 }
 
+// ---- row-sharded CG: the same three passes on a rank's own rows, scalars in a caller-owned array (all-reduced by the
+// caller between the passes): sc[0] p.Ap, sc[1] new r.z, sc[2] r.r, sc[3] current r.z
+__global__ void __launch_bounds__(kCgThreads) k_shard_dot(int64_t n, const double* __restrict__ p,
+                                                          const double* __restrict__ ap, double* partial,
+                                                          unsigned* ticket, double* sc) {
+  double acc[1] = {0.};
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    acc[0] += p[i] * ap[i];
+  grid_reduce<1>(acc, partial, ticket, [&](const double* t) { sc[0] = t[0]; });
+}
+__global__ void __launch_bounds__(kCgThreads) k_shard_update(int64_t n, const double* __restrict__ p,
+                                                             const double* __restrict__ ap,
+                                                             const double* __restrict__ minv, double* __restrict__ x,
+                                                             double* __restrict__ r, double* partial, unsigned* ticket,
+                                                             double* sc) {
+  const double alpha = sc[3] / sc[0];
+  double acc[2] = {0., 0.};
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * ap[i];
+    r[i] = ri;
+    acc[0] += ri * minv[i] * ri;
+    acc[1] += ri * ri;
+  }
+  grid_reduce<2>(acc, partial, ticket, [&](const double* t) {
+    sc[1] = t[0];
+    sc[2] = t[1];
+  });
+}
+__global__ void __launch_bounds__(kCgThreads) k_shard_dir(int64_t n, const double* __restrict__ r,
+                                                          const double* __restrict__ minv, double* __restrict__ p,
+                                                          unsigned* ticket, double* sc) {
+  const double beta = sc[1] / sc[3];
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    p[i] = minv[i] * r[i] + beta * p[i];
+  __syncthreads();   // every thread of the block has read sc[3] (through beta) before the ticket is taken
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {   // the last block: nobody reads the old sc[3] any more
+      *ticket = 0u;
+      sc[3] = sc[1];
+    }
+  }
+}
+
 unsigned cg_grid(int64_t n) {
   const int64_t want = (n + kCgThreads - 1) / kCgThreads;
   return unsigned(std::max<int64_t>(1, std::min<int64_t>(want, kCgMaxBlocks)));
 }
 
 }  // namespace
+
+// work layout of the row-sharded kernels: partial sums (2 per block) | three tickets
+size_t cg_shard_work_bytes() { return size_t(2) * kCgMaxBlocks * sizeof(double) + 64; }
+namespace {
+inline unsigned* shard_tickets(void* work) { return reinterpret_cast<unsigned*>(static_cast<double*>(work) + 2 * kCgMaxBlocks); }
+}
+int cg_shard_dot(cudaStream_t st, int64_t n, const double* p, const double* ap, double* sc, void* work, int64_t* launches) {
+  k_shard_dot<<<cg_grid(n), kCgThreads, 0, st>>>(n, p, ap, static_cast<double*>(work), shard_tickets(work), sc);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+int cg_shard_update(cudaStream_t st, int64_t n, const double* p, const double* ap, const double* minv, double* x, double* r,
+                    double* sc, void* work, int64_t* launches) {
+  k_shard_update<<<cg_grid(n), kCgThreads, 0, st>>>(n, p, ap, minv, x, r, static_cast<double*>(work),
+                                                    shard_tickets(work) + 1, sc);
+  ++*launches;
+  return int(cudaGetLastError());
+}
+int cg_shard_dir(cudaStream_t st, int64_t n, const double* r, const double* minv, double* p, double* sc, void* work,
+                 int64_t* launches) {
+  k_shard_dir<<<cg_grid(n), kCgThreads, 0, st>>>(n, r, minv, p, shard_tickets(work) + 2, sc);
+  ++*launches;
+  return int(cudaGetLastError());
+}
 
 struct CgOp {
   const pf3_plan* plan;

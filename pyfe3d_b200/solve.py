@@ -90,8 +90,8 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
     iteration does ONE point-to-point halo exchange of p (the halo exchange of SURVEY 8(e): grouped NCCL send/recv
     between the ranks whose row blocks meet) and two small all_reduces; the iteration is allocation-free and the host looks at the residual
     once per batch of ``check_every`` iterations.  ``graph=True`` replays each batch as one CUDA graph with the NCCL
-    operations captured; measured slower than eager launches on 2 B200 (1.87 against 0.44 ms per iteration at 6 M dofs),
-    so it is off by default.  ``b``/``free``/``x0`` are global [6*nnodes] arrays; returns (x_global, info)."""
+    operations captured; it measures the same as eager launches (0.46 against 0.45 ms per iteration on 8 B200 at 24 M
+    dofs), so it is off by default.  ``b``/``free``/``x0`` are global [6*nnodes] arrays; returns (x_global, info)."""
     import torch.distributed as dist
     dev = vals.device
     n = 6 * plan.nnodes
@@ -174,30 +174,29 @@ def plan_cg_solve(plan, vals, b, free=None, rtol=1e-12, maxiter=None, x0=None, g
     maxiter = maxiter or 10 * n
     if bnorm == 0.0 or float(sc[1].sqrt()) <= rtol * bnorm or float(rz) == 0.0:
         return gather_all(x), 0
-    two = torch.zeros(2, dtype=torch.float64, device=dev)
-    pap, alpha, beta = (torch.zeros((), dtype=torch.float64, device=dev) for _ in range(3))
+    # sc = [p.Ap, new r.z, r.r, current r.z] on the device; the three fused vector kernels of the iteration are native
+    # (pf3_cg_shard_dot / _update / _dir, csrc/solve.cu: deterministic reductions), NCCL all-reduces the scalars between
+    from . import _cabi
+    nl = hi - lo
+    sc = torch.zeros(4, dtype=torch.float64, device=dev)
+    sc[3] = rz
+    work = torch.zeros(_cabi.cg_shard_work_bytes() // 8 + 1, dtype=torch.float64, device=dev)
+    del z
 
     def iterate():
-        # one iteration, allocation-free and without host synchronisation: every operand is a fixed buffer, so a batch of
-        # iterations can be captured into a CUDA graph (NCCL operations included) and replayed
+        # one iteration, allocation-free and without host synchronisation
         matvec(exchange(), ap)
-        torch.dot(p, ap, out=pap)
-        allsum(pap)
-        torch.div(rz, pap, out=alpha)
-        x.addcmul_(alpha, p)
-        r.addcmul_(alpha, ap, value=-1.0)
-        torch.mul(minv, r, out=z)
-        two[0].copy_(torch.dot(r, z))
-        two[1].copy_(torch.dot(r, r))
-        allsum(two)                                        # one all_reduce for both scalars
-        torch.div(two[0], rz, out=beta)
-        torch.addcmul(z, beta, p, out=p)                   # p = z + beta p, in place in the global vector
-        rz.copy_(two[0])
+        ctx = context(dev)
+        ctx.cg_shard_dot(nl, _ptr(p), _ptr(ap), _ptr(sc), _ptr(work))
+        allsum(sc[0:1])
+        ctx.cg_shard_update(nl, _ptr(p), _ptr(ap), _ptr(minv), _ptr(x), _ptr(r), _ptr(sc), _ptr(work))
+        allsum(sc[1:3])                                    # one all_reduce for both scalars
+        ctx.cg_shard_dir(nl, _ptr(r), _ptr(minv), _ptr(p), _ptr(sc), _ptr(work))
 
     def state():
         # (breakdown, converged) from the scalars of the last iteration -- the only host synchronisation of a batch
-        t = torch.stack([pap, two[1], two[0]]).tolist()
-        return (not t[0] > 0.0), (t[1] ** 0.5 <= rtol * bnorm or t[2] == 0.0)
+        t = sc.tolist()
+        return (not t[0] > 0.0), (t[2] ** 0.5 <= rtol * bnorm or t[1] == 0.0)
 
     it, info = 0, -maxiter
     graph_obj = None

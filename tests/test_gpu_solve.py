@@ -218,3 +218,35 @@ def test_compact_upper_triangle_is_scipy_triu(masked):
     (ip3, ix3, v3), _ = plan_compact(plan, vals, None if free is None else torch.as_tensor(free).cuda(), upper=True,
                                      want_indices=False)
     assert ix3 is None and np.array_equal(v3.cpu().numpy(), want.data)
+
+
+def test_cg_shard_step_kernels_match_torch():
+    """pf3_cg_shard_dot / _update / _dir (the fused vector kernels of the row-sharded CG) against the same algebra in torch."""
+    import torch
+    from pyfe3d_b200 import _cabi
+    from pyfe3d_b200.batch import context
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for n in (1, 37, 100003, 3000001):
+        p, ap, r, x = (torch.randn(n, dtype=torch.float64, generator=g).to(dev) for _ in range(4))
+        minv = torch.rand(n, dtype=torch.float64, generator=g).to(dev) + 0.5
+        sc = torch.tensor([0., 0., 0., 1.7], dtype=torch.float64, device=dev)
+        work = torch.zeros(_cabi.cg_shard_work_bytes() // 8 + 1, dtype=torch.float64, device=dev)
+        ctx = context(dev)
+        p0, x0, r0 = p.clone(), x.clone(), r.clone()
+        for _ in range(2):   # twice: the tickets must have been reset
+            ctx.cg_shard_dot(n, p.data_ptr(), ap.data_ptr(), sc.data_ptr(), work.data_ptr())
+        want_pap = torch.dot(p0, ap)
+        assert abs(float(sc[0]) - float(want_pap)) <= 1e-12 * float(p0.abs() @ ap.abs())
+        sc[0] = 2.5                                                     # as if all-reduced
+        ctx.cg_shard_update(n, p.data_ptr(), ap.data_ptr(), minv.data_ptr(), x.data_ptr(), r.data_ptr(), sc.data_ptr(),
+                            work.data_ptr())
+        alpha = 1.7 / 2.5
+        xr, rr = x0 + alpha * p0, r0 - alpha * ap
+        assert torch.allclose(x, xr, rtol=1e-14, atol=1e-14) and torch.allclose(r, rr, rtol=1e-14, atol=1e-14)
+        assert abs(float(sc[1]) - float((rr * minv) @ rr)) <= 1e-12 * float((rr * minv) @ rr)
+        assert abs(float(sc[2]) - float(rr @ rr)) <= 1e-12 * float(rr @ rr)
+        rzn = float(sc[1])
+        ctx.cg_shard_dir(n, r.data_ptr(), minv.data_ptr(), p.data_ptr(), sc.data_ptr(), work.data_ptr())
+        assert torch.allclose(p, minv * rr + (rzn / 1.7) * p0, rtol=1e-13, atol=1e-13)
+        assert float(sc[3]) == rzn                                      # r.z rolled over for the next iteration
