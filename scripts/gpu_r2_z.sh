@@ -1,2 +1,10 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 scripts/bench_cg_multi.py 2000 2>&1 | tail -2 | tee gpurun_out/r2z_cgmulti8.txt
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py > gpurun_out/preflight_bench.json 2> gpurun_out/preflight_bench.err; tail -1 gpurun_out/preflight_bench.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/preflight_bench.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["traffic"], d["e2e"]["value"], d["parity"]["ok"], d["gpu_launches"], d["clocks"])
+print([ (o.get("config","")[:12], o.get("ms_per_step"), o.get("frac")) for o in d["details"]["others"]])
+PY
