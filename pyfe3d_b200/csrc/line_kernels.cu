@@ -50,6 +50,7 @@ __device__ __forceinline__ void beamc_Ke(const BeamP& p, double L, KS& K) {
   const double iL = 1. / L, iL2 = iL * iL, iL3 = iL2 * iL;   // reciprocals: a double division costs ~15 instructions
   (void)iL2; (void)iL3;
   const double L2 = L * L, L3 = L2 * L;
+  (void)L3;
   const double ay = 12 * p.E * p.Izz / (p.G * p.A * L2), az = 12 * p.E * p.Iyy / (p.G * p.A * L2);
   const double by = 1 / (1. - ay), bz = 1 / (1. - az);
   const double Ky = by * by * (p.A * p.G * L2 * ay * ay + 12 * p.E * p.Izz);

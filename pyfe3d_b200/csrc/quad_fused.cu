@@ -394,12 +394,16 @@ __device__ __forceinline__ void stage_reuse_wait() {
 constexpr int kStageV4 = 8 * SlabShape<6, 6>::kLd;         // 1216 doubles: the largest matrix (KC0)
 // CHUNK = consecutive node pairs per warp.  1: one pair per warp, no prefetch (the store-bound three-matrix call: the
 // CTA scheduler alone orders the work; measured 10.4 ms against 11.0 / 11.5 ms for chunks of 2 / 4, which widen the
-// window of nodes in flight and take L1 away).  4: the next pair's records arrive by cp.async while this one is
-// computed (the latency-bound one- and two-matrix calls: config 3 2.46 -> 2.14 ms).
+// window of nodes in flight and take L1 away).  kFChunkBig = 2: the next pair's records arrive by cp.async while this
+// one is computed (the latency-bound one- and two-matrix calls; with the L2 prefetch in place 2 pairs beat 4, 8 and 1:
+// config 3 1.68 ms against 1.77 / 1.84 / 1.69, KC0 only at 4 M Quad4 4.84 against 5.01 / - / 5.07).
 #ifndef PF3_CHUNK_BIG
-#define PF3_CHUNK_BIG 4
+#define PF3_CHUNK_BIG 2
 #endif
 constexpr int kFChunkBig = PF3_CHUNK_BIG;
+#ifndef PF3_CHUNK_VOL
+#define PF3_CHUNK_VOL 1400   // calls that write less than this per node (two-matrix calls) take kFChunkBig pairs per CTA
+#endif
 __host__ __device__ constexpr int fring(int chunk) { return chunk > 1 ? 3 : 1; }
 __host__ __device__ constexpr int fbufs(int chunk) { return chunk > 1 ? 2 : 1; }
 // per warp: slab staging | ring of node-record pairs (64 B each) | element records of 8 incidences (x2 when
@@ -864,7 +868,7 @@ cudaError_t launch_quad_fused(int kind, const FusedArgs& F, double* rec, cudaStr
 #ifdef PF3_FORCE_CHUNK4
   const int chunk = !mapped ? kFChunkBig : 1;
 #else
-  const int chunk = (vol < 1400 && !mapped) ? kFChunkBig : 1;
+  const int chunk = (vol < PF3_CHUNK_VOL && !mapped) ? kFChunkBig : 1;
 #endif
   if (phases & 1) {
     cudaError_t e1 = launch_k1(kind, F.A, rec, stride, 0, F.A.ne, 4, st, launches);

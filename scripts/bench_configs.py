@@ -356,6 +356,14 @@ if __name__ == "__main__":
         run("config3 Quad4R cylinder 1M, KC0+KG_given_stress", meshes.cylinder_quad4r(int(1760 * f ** 0.5), int(571 * f ** 0.5)),
             ("KC0", "KGs"), True)
         sys.exit(0)
+    if "--subsets" in sys.argv:   # one- and two-matrix calls on the north-star mesh (the calls that take several node pairs per CTA)
+        side = int(2000 * f ** 0.5)
+        for kind, mk in (("quad4", meshes.plate_quad4), ("quad4r", meshes.plate_quad4)):
+            case = mk(side, side, kind=kind)
+            run("%s %dx%d KC0" % (kind, side, side), case, ("KC0",), True)
+            run("%s %dx%d KC0+KG" % (kind, side, side), case, ("KC0", "KG"), True)
+            run("%s %dx%d KC0+M0" % (kind, side, side), case, ("KC0", "M0"), True)
+        sys.exit(0)
     if "--config4" in sys.argv:
         run("config4 Tria3R distorted plate 4M, KC0+M(mtype1)", meshes.plate_tria3r(int(1415 * f ** 0.5), int(1415 * f ** 0.5)),
             ("KC0", "M1"), True)

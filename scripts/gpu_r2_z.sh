@@ -1,10 +1,14 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-python bench.py > gpurun_out/preflight_bench.json 2> gpurun_out/preflight_bench.err; tail -1 gpurun_out/preflight_bench.err
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/preflight_bench.json").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"]["traffic"], d["e2e"]["value"], d["parity"]["ok"], d["gpu_launches"], d["clocks"])
-print([ (o.get("config","")[:12], o.get("ms_per_step"), o.get("frac")) for o in d["details"]["others"]])
-PY
+cp pyfe3d_b200/lib/libpyfe3d_b200.so /tmp/lib_default.so
+: > gpurun_out/r2z_t.txt
+for r in 1 2 3; do
+for name in default t1 t2 t8; do
+  if [ "$name" = "default" ]; then cp /tmp/lib_default.so pyfe3d_b200/lib/libpyfe3d_b200.so; else cp pyfe3d_b200/lib/variants/$name/libpyfe3d_b200.so pyfe3d_b200/lib/libpyfe3d_b200.so; fi
+  echo -n "$name $r " >> gpurun_out/r2z_t.txt
+  python scripts/bench_configs.py --config4 2>&1 | tail -1 | grep -o '"ms_per_step": [0-9.]*' >> gpurun_out/r2z_t.txt
+done
+done
+cp /tmp/lib_default.so pyfe3d_b200/lib/libpyfe3d_b200.so
+sort gpurun_out/r2z_t.txt
+python -m pytest tests/test_gpu_fused.py tests/test_gpu_benchmark_parity.py -m gpu -x -q 2>&1 | tail -2
+python scripts/bench_configs.py --config3 2>&1 | tail -1 | cut -c1-60,150-330
