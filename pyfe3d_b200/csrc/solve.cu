@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(kCgThreads) k_shard_update(int64_t n, const do
                                                              const double* __restrict__ minv, double* __restrict__ x,
                                                              double* __restrict__ r, double* partial, unsigned* ticket,
                                                              double* sc) {
-  const double alpha = sc[3] / sc[0];
+  // p.Ap <= 0 (breakdown, or an exactly converged system iterated on inside a batch): freeze the iterate instead of
+  // spreading NaN; the host sees p.Ap and the residual at the end of the batch
+  const double alpha = sc[0] > 0. ? sc[3] / sc[0] : 0.;
   double acc[2] = {0., 0.};
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     x[i] += alpha * p[i];
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(kCgThreads) k_shard_update(int64_t n, const do
 __global__ void __launch_bounds__(kCgThreads) k_shard_dir(int64_t n, const double* __restrict__ r,
                                                           const double* __restrict__ minv, double* __restrict__ p,
                                                           unsigned* ticket, double* sc) {
-  const double beta = sc[1] / sc[3];
+  const double beta = sc[3] != 0. ? sc[1] / sc[3] : 0.;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     p[i] = minv[i] * r[i] + beta * p[i];
   __syncthreads();   // every thread of the block has read sc[3] (through beta) before the ticket is taken

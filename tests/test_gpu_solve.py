@@ -250,3 +250,24 @@ def test_cg_shard_step_kernels_match_torch():
         ctx.cg_shard_dir(n, r.data_ptr(), minv.data_ptr(), p.data_ptr(), sc.data_ptr(), work.data_ptr())
         assert torch.allclose(p, minv * rr + (rzn / 1.7) * p0, rtol=1e-13, atol=1e-13)
         assert float(sc[3]) == rzn                                      # r.z rolled over for the next iteration
+
+
+def test_cg_shard_step_kernels_freeze_on_zero_denominators():
+    """p.Ap = 0 / r.z = 0 (an exactly converged system iterated on inside a batch) must not spread NaN."""
+    import torch
+    from pyfe3d_b200 import _cabi
+    from pyfe3d_b200.batch import context
+    dev = torch.device("cuda", 0)
+    n = 1000
+    p, ap, minv = torch.ones(n, dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev), \
+        torch.ones(n, dtype=torch.float64, device=dev)
+    x, r = torch.full((n,), 3.0, dtype=torch.float64, device=dev), torch.zeros(n, dtype=torch.float64, device=dev)
+    sc = torch.zeros(4, dtype=torch.float64, device=dev)
+    work = torch.zeros(_cabi.cg_shard_work_bytes() // 8 + 1, dtype=torch.float64, device=dev)
+    ctx = context(dev)
+    ctx.cg_shard_dot(n, p.data_ptr(), ap.data_ptr(), sc.data_ptr(), work.data_ptr())
+    ctx.cg_shard_update(n, p.data_ptr(), ap.data_ptr(), minv.data_ptr(), x.data_ptr(), r.data_ptr(), sc.data_ptr(),
+                        work.data_ptr())
+    ctx.cg_shard_dir(n, r.data_ptr(), minv.data_ptr(), p.data_ptr(), sc.data_ptr(), work.data_ptr())
+    assert torch.isfinite(x).all() and torch.isfinite(p).all() and torch.isfinite(sc).all()
+    assert torch.equal(x, torch.full_like(x, 3.0)) and float(sc[2]) == 0.0
