@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_solve.py -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -2
